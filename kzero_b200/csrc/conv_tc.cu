@@ -1,0 +1,346 @@
+// K1: the conv tower's workhorse -- implicit-GEMM conv3x3 / conv1x1 on the 5th-gen tensor cores.
+//
+// Replaces the per-layer `cudnnConvolutionBiasActivationForward` (fp32 NCHW) + separate residual-add
+// and relu autokernels of the reference's CUDA executor (kn-cuda-eval 0.7.3 planner, evidence
+// docs/conv_bn_sm_flow.svg; call site rust/kz-core/src/network/cudnn.rs:73).
+//
+// GEMM view (per layer):  D[M=positions, N=cout] = sum_{tap, ci} A_tap[M, ci] * W[N, tap*cin + ci]
+//   * activations are channels-last bf16 rows [position][cin_pad]; one M tile = 128 positions
+//   * A_tap is never materialised: the TMA engine loads the tile *shifted by the tap* and zero-fills
+//     everything that falls off the board:
+//       mode 1 (8x8 boards, dense rows): 4-D tensor map (c, x, y, board), box (64, 8, 8, 2) at (c0, dx, dy, b0)
+//       mode 0 (any board, padded rows): 2-D tensor map (c, row), box (64, 128) at (c0, row0 + dy*rank_pitch + dx);
+//              the padded row layout (kernels.cuh RowLayout) guarantees the shifted row is a zero row
+//   * both operands land in shared memory in the canonical K-major SWIZZLE_128B layout, tcgen05.mma
+//     (cta_group::1, kind::f16, M=128, N=cout_pad, K=16) accumulates fp32 in TMEM
+//   * epilogue (4 warps): tcgen05.ld -> +bias (BN folded on the host) -> relu -> +residual -> bf16 store.
+//     Order matters: the reference block is x + relu(bn(conv(...))), relu BEFORE the add
+//     (python/lib/model/post_act.py:218-228).
+//   * persistent CTAs, warp-specialised: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner),
+//     warps 2..5 epilogue; smem ring of `stages` (A,B) slots; two TMEM accumulators so the epilogue of
+//     tile i overlaps the MMAs of tile i+1.
+#include "kernels.cuh"
+
+namespace kzb {
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;                       // bf16 elements per smem row = 128 bytes = one swizzle span
+constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KiB
+constexpr int kThreads = 192;
+constexpr int kEpilogueWarp0 = 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+            "r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "SmemDescriptor"):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) | [32,46) SBO >> 4
+//   [46,48) version = 1 | [49,52) base offset = 0 | [61,64) layout type: 2 = SWIZZLE_128B
+// 8-row groups are 1024 B apart (SBO), rows inside a group 128 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+    d |= uint64_t(1) << 16;
+    d |= uint64_t(1024 >> 4) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(2) << 61;
+    return d;
+}
+
+// Instruction descriptor, kind::f16: c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1, both K-major,
+// N>>3 at [17,23), M>>4 at [24,29).
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct SmemLayout {
+    uint8_t* stage_base;
+    uint64_t* full;
+    uint64_t* empty;
+    uint64_t* tmem_full;
+    uint64_t* tmem_empty;
+    uint32_t* tmem_ptr;
+    float* bias;
+};
+
+__device__ __forceinline__ SmemLayout carve(uint8_t* base, int n, int stages) {
+    SmemLayout s;
+    s.stage_base = base;
+    uint8_t* p = base + size_t(stages) * (kABytes + n * 128);
+    s.full = reinterpret_cast<uint64_t*>(p);
+    s.empty = s.full + stages;
+    s.tmem_full = s.empty + stages;
+    s.tmem_empty = s.tmem_full + 2;
+    s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tmem_empty + 2);
+    s.bias = reinterpret_cast<float*>(s.tmem_ptr + 4);
+    return s;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+    conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const ConvTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B atoms need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const SmemLayout sm = carve(smem, p.n, p.stages);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int stage_bytes = kABytes + p.n * 128;
+    const int iters_per_tile = p.taps * p.kblocks;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+        for (int i = 0; i < p.stages; i++) {
+            mbar_init(&sm.full[i], 1);
+            mbar_init(&sm.empty[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&sm.tmem_full[i], 1);
+            mbar_init(&sm.tmem_empty[i], 4);  // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem_ptr)),
+                     "r"(uint32_t(p.tmem_cols))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < p.n; i += kThreads) sm.bias[i] = p.bias[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sm.tmem_ptr;
+    const uint32_t acc_stride = uint32_t(p.tmem_cols / 2);
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                for (int tap = 0; tap < p.taps; tap++) {
+                    const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
+                    const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
+                    for (int kb = 0; kb < p.kblocks; kb++) {
+                        mbar_wait(&sm.empty[stage], phase ^ 1);
+                        uint8_t* a_dst = sm.stage_base + size_t(stage) * stage_bytes;
+                        uint8_t* b_dst = a_dst + kABytes;
+                        mbar_expect_tx(&sm.full[stage], uint32_t(stage_bytes));
+                        if (p.mode == 1)
+                            tma_load_4d(&tmap_a, &sm.full[stage], a_dst, kb * kBlockK, dx, dy, tile * p.boards_per_tile);
+                        else
+                            tma_load_2d(&tmap_a, &sm.full[stage], a_dst, kb * kBlockK,
+                                        tile * kTileM + dy * p.lay.rank_pitch + dx);
+                        tma_load_2d(&tmap_b, &sm.full[stage], b_dst, tap * p.cin_pad + kb * kBlockK, 0);
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(kTileM, p.n);
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, local++) {
+                const int buf = local & 1;
+                const uint32_t buf_phase = (local >> 1) & 1;
+                mbar_wait(&sm.tmem_empty[buf], buf_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * acc_stride;
+                for (int it = 0; it < iters_per_tile; it++) {
+                    mbar_wait(&sm.full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sm.stage_base + size_t(stage) * stage_bytes);
+                    const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; k++) {
+                        // advancing 16 bf16 = 32 bytes along K stays inside the 128-byte swizzle span
+                        uint64_t a_desc = umma_desc_sw128(a_addr + k * 32);
+                        uint64_t b_desc = umma_desc_sw128(b_addr + k * 32);
+                        umma_bf16(tmem_d, a_desc, b_desc, idesc, (it | k) != 0);
+                    }
+                    umma_commit(&sm.empty[stage]);  // frees the smem slot once these MMAs have read it
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&sm.tmem_full[buf]);  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp % 4;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, local++) {
+            const int buf = local & 1;
+            const uint32_t buf_phase = (local >> 1) & 1;
+            const int row = tile * kTileM + quarter * 32 + lane;
+            bool on_board = true;
+            if (p.mode == 0) {
+                int r = row % p.lay.board_pitch;
+                on_board = (r % p.lay.rank_pitch) < p.lay.W && (r / p.lay.rank_pitch) < p.lay.H;
+            }
+            const bool store = row < p.valid_rows;
+
+            mbar_wait(&sm.tmem_full[buf], buf_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * acc_stride + (uint32_t(quarter * 32) << 16);
+
+            for (int c0 = 0; c0 < p.n_store; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + c0, r);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    float f = __uint_as_float(r[j]) + sm.bias[c0 + j];
+                    if (c0 + j < p.relu_n) f = fmaxf(f, 0.0f);
+                    v[j] = f;
+                }
+                if (p.res != nullptr && store) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.res + size_t(row) * p.res_stride + c0);
+                    uint4 q0 = rp[0], q1 = rp[1];
+                    const __nv_bfloat16* h0 = reinterpret_cast<const __nv_bfloat16*>(&q0);
+                    const __nv_bfloat16* h1 = reinterpret_cast<const __nv_bfloat16*>(&q1);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        v[j] += __bfloat162float(h0[j]);
+                        v[8 + j] += __bfloat162float(h1[j]);
+                    }
+                }
+                if (!on_board) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) v[j] = 0.0f;  // keep the padding rows zero for the next layer
+                }
+                if (store) {
+                    if (p.out_f32) {
+                        float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + size_t(row) * p.out_stride + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+                        uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + size_t(row) * p.out_stride + c0);
+                        op[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                        op[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.tmem_empty[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(p.tmem_cols))
+                     : "memory");
+    }
+}
+
+}  // namespace
+
+size_t conv_tc_smem_bytes(int n, int stages) {
+    return 1024 /*alignment slack*/ + size_t(stages) * (kABytes + size_t(n) * 128) + (2 * stages + 4) * 8 + 16 + size_t(n) * 4;
+}
+
+int conv_tc_pick_stages(int n) {
+    const size_t budget = 227 * 1024;
+    int stages = 8;
+    while (stages > 2 && conv_tc_smem_bytes(n, stages) > budget) stages--;
+    return stages;
+}
+
+void launch_conv_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ConvTcParams& p, int grid,
+                    cudaStream_t s) {
+    if (p.num_tiles <= 0) return;
+    size_t smem = conv_tc_smem_bytes(p.n, p.stages);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_set = true;
+    }
+    conv_tc_kernel<<<std::min(grid, p.num_tiles), kThreads, smem, s>>>(tmap_a, tmap_b, p);
+}
+
+}  // namespace kzb

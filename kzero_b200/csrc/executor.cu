@@ -1,0 +1,564 @@
+#include "executor.hpp"
+
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+namespace kzb {
+
+// ---------------------------------------------------------------------------------------------- utils
+namespace {
+
+thread_local std::string g_last_error;
+
+void cuda_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+#define CK(expr) cuda_check((expr), #expr)
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+size_t align16(size_t v) { return (v + 15) / 16 * 16; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cuda_check(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q), "cudaGetDriverEntryPoint");
+        if (q != cudaDriverEntryPointSuccess || !p) throw std::runtime_error("cuTensorMapEncodeTiled not available in this driver");
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// bf16 tensor map, SWIZZLE_128B, zero OOB fill.  dims/box innermost first; strides in bytes for dims 1..rank-1.
+CUtensorMap make_tmap(void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    CUtensorMap m;
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; i++) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+    }
+    CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cuuint32_t(rank), base, gdim, gstr, bdim, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+    return m;
+}
+
+}  // namespace
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const char* last_error() { return g_last_error.c_str(); }
+
+DeviceBuffer::~DeviceBuffer() {
+    if (ptr) cudaFree(ptr);
+}
+void DeviceBuffer::alloc(size_t n, bool zero) {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = n;
+    if (n == 0) return;
+    CK(cudaMalloc(&ptr, n));
+    if (zero) CK(cudaMemset(ptr, 0, n));
+}
+PinnedBuffer::~PinnedBuffer() {
+    if (ptr) cudaFreeHost(ptr);
+}
+void PinnedBuffer::alloc(size_t n) {
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    bytes = n;
+    if (n == 0) return;
+    CK(cudaMallocHost(&ptr, n));
+}
+
+template <typename T>
+static void upload(DeviceBuffer& buf, const std::vector<T>& host) {
+    buf.alloc(host.size() * sizeof(T), false);
+    if (!host.empty()) CK(cudaMemcpy(buf.ptr, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+}
+
+// ---------------------------------------------------------------------------------------------- Net
+Net::Net(int device, const void* onnx, size_t len, int max_batch, int precision)
+    : device_(device), max_batch_(max_batch), precision_(precision) {
+    if (max_batch < 1) throw std::runtime_error("max_batch must be >= 1");
+    if (precision != 0 && precision != 1) throw std::runtime_error("precision must be 0 (fp32) or 1 (bf16)");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw std::runtime_error("no CUDA device available (this library has no CPU fallback): " + std::string(cudaGetErrorString(e)));
+    if (device < 0 || device >= count) throw std::runtime_error("device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) throw std::runtime_error("libkzb200 is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+    num_sms_ = prop.multiProcessorCount;
+
+    spec_ = build_net_spec(parse_onnx(onnx, len));
+    if (spec_.scalar_conv.cout + (spec_.has_extra ? 1 : 0) > 16) throw std::runtime_error("scalar head with more than 15 hidden channels is not supported");
+    if (spec_.fc1.out > 128) throw std::runtime_error("scalar head hidden size > 128 is not supported");
+    if (spec_.has_extra && spec_.extra_fc.out != 1) throw std::runtime_error("policy head with more than one extra move is not supported");
+    if (spec_.channels > 256 || spec_.policy_conv1.cout > 256 || spec_.policy_conv2.cout > 256)
+        throw std::runtime_error("more than 256 channels is not supported");
+
+    CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    if (precision_ == 1)
+        build_bf16();
+    else
+        build_f32();
+
+    // tail parameters (shared by both precisions)
+    const int area = spec_.area(), hs = spec_.fc1.out, hc = spec_.scalar_conv.cout;
+    std::vector<float> fc1_t(size_t(hc) * area * hs);
+    for (int j = 0; j < hs; j++)
+        for (int i = 0; i < hc * area; i++) fc1_t[size_t(i) * hs + j] = spec_.fc1.w[size_t(j) * hc * area + i];
+    upload(d_fc1_t_, fc1_t);
+    upload(d_fc1_b_, spec_.fc1.b);
+    upload(d_fc2_w_, spec_.fc2.w);
+    upload(d_fc2_b_, spec_.fc2.b);
+    if (spec_.has_extra) upload(d_extra_w_, spec_.extra_fc.w);
+    upload(d_policy_src_, spec_.policy_src);
+
+    d_nchw_.alloc(size_t(max_batch_) * spec_.cin * area * 4, false);
+    d_out_scalars_.alloc(size_t(max_batch_) * 5 * 4, false);
+    d_out_logits_.alloc(size_t(max_batch_) * spec_.policy_len * 4, false);
+    CK(cudaStreamSynchronize(stream_));
+}
+
+Net::~Net() {
+    cudaSetDevice(device_);
+    if (stream_) {
+        cudaStreamSynchronize(stream_);
+        cudaStreamDestroy(stream_);
+    }
+}
+
+static std::vector<float> padded_bias(const std::vector<float>& b, int n) {
+    std::vector<float> out(n, 0.0f);
+    std::copy(b.begin(), b.end(), out.begin());
+    return out;
+}
+
+// the scalar-head conv and the optional extra policy conv read the same input: one launch, cout <= 16
+static ConvParams merged_small_conv(const NetSpec& s) {
+    ConvParams m = s.scalar_conv;
+    if (s.has_extra) {
+        m.w.insert(m.w.end(), s.extra_conv.w.begin(), s.extra_conv.w.end());
+        m.b.insert(m.b.end(), s.extra_conv.b.begin(), s.extra_conv.b.end());
+        m.cout += 1;
+    }
+    return m;
+}
+
+void Net::build_bf16() {
+    act_bf16_ = true;
+    const int W = spec_.board_w, H = spec_.board_h, C = spec_.channels;
+    const char* force = std::getenv("KZB_FORCE_LINEAR");
+    mode_ = (W == 8 && H == 8 && !(force && force[0] == '1')) ? 1 : 0;
+    if (mode_ == 1)
+        lay_ = RowLayout{W, H, W, W * H};
+    else
+        lay_ = RowLayout{W, H, W + 1, (W + 1) * (H + 1)};
+    const int boards_per_tile = mode_ == 1 ? 128 / (W * H) : 0;
+    const int boards_alloc = mode_ == 1 ? round_up(max_batch_, boards_per_tile) : max_batch_;
+    rows_alloc_ = round_up(boards_alloc * lay_.board_pitch, 128);
+    cin_pad_ = round_up(spec_.cin, 64);
+    c_pad_ = round_up(C, 64);
+    cp_pad_ = round_up(spec_.policy_conv1.cout, 64);
+    pm_stride_ = round_up(spec_.policy_conv2.cout, 16);
+    s1_stride_ = 16;
+
+    act_in_.alloc(size_t(rows_alloc_) * cin_pad_ * 2);
+    act_x_.alloc(size_t(rows_alloc_) * c_pad_ * 2);
+    act_t_.alloc(size_t(rows_alloc_) * c_pad_ * 2);
+    act_h1_.alloc(size_t(rows_alloc_) * cp_pad_ * 2);
+    act_s1_.alloc(size_t(rows_alloc_) * s1_stride_ * 4);
+    act_pm_.alloc(size_t(rows_alloc_) * pm_stride_ * 4);
+
+    auto add = [&](const std::string& name, const ConvParams& c, DeviceBuffer& in, int in_stride, const DeviceBuffer* res,
+                   DeviceBuffer& out, int out_stride, bool out_f32, int n, int relu_n) {
+        auto st = std::make_unique<ConvStep>();
+        st->name = name;
+        st->taps = c.ksize * c.ksize;
+        const int cin_pad = in_stride;
+        const int ktot = st->taps * cin_pad;
+        std::vector<__nv_bfloat16> w(size_t(n) * ktot, __float2bfloat16_rn(0.0f));
+        for (int co = 0; co < c.cout; co++)
+            for (int ci = 0; ci < c.cin; ci++)
+                for (int t = 0; t < st->taps; t++)
+                    w[size_t(co) * ktot + size_t(t) * cin_pad + ci] = __float2bfloat16_rn(c.w[(size_t(co) * c.cin + ci) * st->taps + t]);
+        upload(st->w_bf16, w);
+        upload(st->bias, padded_bias(c.b, n));
+
+        {
+            uint64_t dims[2] = {uint64_t(ktot), uint64_t(n)};
+            uint64_t strides[1] = {uint64_t(ktot) * 2};
+            uint32_t box[2] = {64, uint32_t(n)};
+            st->tmap_b = make_tmap(st->w_bf16.ptr, 2, dims, strides, box);
+        }
+        if (mode_ == 1) {
+            uint64_t dims[4] = {uint64_t(in_stride), uint64_t(W), uint64_t(H), uint64_t(rows_alloc_ / (W * H))};
+            uint64_t strides[3] = {uint64_t(in_stride) * 2, uint64_t(in_stride) * 2 * W, uint64_t(in_stride) * 2 * W * H};
+            uint32_t box[4] = {64, uint32_t(W), uint32_t(H), uint32_t(boards_per_tile)};
+            st->tmap_a = make_tmap(in.ptr, 4, dims, strides, box);
+        } else {
+            uint64_t dims[2] = {uint64_t(in_stride), uint64_t(rows_alloc_)};
+            uint64_t strides[1] = {uint64_t(in_stride) * 2};
+            uint32_t box[2] = {64, 128};
+            st->tmap_a = make_tmap(in.ptr, 2, dims, strides, box);
+        }
+        ConvTcParams& p = st->tc;
+        p.taps = st->taps;
+        p.cin_pad = cin_pad;
+        p.kblocks = cin_pad / 64;
+        p.n = n;
+        p.mode = mode_;
+        p.boards_per_tile = boards_per_tile;
+        p.lay = lay_;
+        p.bias = st->bias.as<float>();
+        p.relu_n = relu_n;
+        p.res = res ? res->as<__nv_bfloat16>() : nullptr;
+        p.res_stride = c_pad_;
+        p.out = out.ptr;
+        p.out_stride = out_stride;
+        p.out_f32 = out_f32 ? 1 : 0;
+        p.n_store = n;
+        p.stages = conv_tc_pick_stages(n);
+        int cols = 32;
+        while (cols < 2 * n) cols *= 2;
+        p.tmem_cols = cols;
+        convs_.push_back(std::move(st));
+    };
+
+    add("conv_first", spec_.first, act_in_, cin_pad_, nullptr, act_x_, c_pad_, false, c_pad_, 0);
+    for (int d = 0; d < spec_.depth; d++) {
+        add("block" + std::to_string(d) + "_conv1", spec_.blocks[2 * d], act_x_, c_pad_, nullptr, act_t_, c_pad_, false, c_pad_, c_pad_);
+        add("block" + std::to_string(d) + "_conv2", spec_.blocks[2 * d + 1], act_t_, c_pad_, &act_x_, act_x_, c_pad_, false, c_pad_, c_pad_);
+    }
+    add("policy_conv1", spec_.policy_conv1, act_x_, c_pad_, nullptr, act_h1_, cp_pad_, false, cp_pad_, cp_pad_);
+    add("scalar_conv", merged_small_conv(spec_), act_x_, c_pad_, nullptr, act_s1_, s1_stride_, true, 16, spec_.scalar_conv.cout);
+    add("policy_conv2", spec_.policy_conv2, act_h1_, cp_pad_, nullptr, act_pm_, pm_stride_, true, pm_stride_, 0);
+}
+
+void Net::build_f32() {
+    act_bf16_ = false;
+    const int W = spec_.board_w, H = spec_.board_h, C = spec_.channels;
+    mode_ = -1;
+    lay_ = RowLayout{W, H, W, W * H};
+    rows_alloc_ = max_batch_ * lay_.board_pitch;
+    cin_pad_ = round_up(spec_.cin, 8);
+    c_pad_ = round_up(C, 8);
+    cp_pad_ = round_up(spec_.policy_conv1.cout, 8);
+    pm_stride_ = round_up(spec_.policy_conv2.cout, 4);
+    s1_stride_ = 16;
+
+    act_in_.alloc(size_t(rows_alloc_) * cin_pad_ * 4);
+    act_x_.alloc(size_t(rows_alloc_) * c_pad_ * 4);
+    act_t_.alloc(size_t(rows_alloc_) * c_pad_ * 4);
+    act_h1_.alloc(size_t(rows_alloc_) * cp_pad_ * 4);
+    act_s1_.alloc(size_t(rows_alloc_) * s1_stride_ * 4);
+    act_pm_.alloc(size_t(rows_alloc_) * pm_stride_ * 4);
+
+    auto add = [&](const std::string& name, const ConvParams& c, DeviceBuffer& in, int in_stride, const DeviceBuffer* res,
+                   DeviceBuffer& out, int out_stride, int relu_n) {
+        auto st = std::make_unique<ConvStep>();
+        st->name = name;
+        st->taps = c.ksize * c.ksize;
+        std::vector<float> w(size_t(st->taps) * c.cin * c.cout);
+        for (int co = 0; co < c.cout; co++)
+            for (int ci = 0; ci < c.cin; ci++)
+                for (int t = 0; t < st->taps; t++)
+                    w[(size_t(t) * c.cin + ci) * c.cout + co] = c.w[(size_t(co) * c.cin + ci) * st->taps + t];
+        upload(st->w_f32, w);
+        upload(st->bias, c.b);
+        ConvF32Params& p = st->f32;
+        p.in = in.as<float>();
+        p.in_stride = in_stride;
+        p.w = st->w_f32.as<float>();
+        p.bias = st->bias.as<float>();
+        p.res = res ? res->as<float>() : nullptr;
+        p.res_stride = c_pad_;
+        p.out = out.as<float>();
+        p.out_stride = out_stride;
+        p.cin = c.cin;
+        p.cout = c.cout;
+        p.taps = st->taps;
+        p.relu_n = relu_n;
+        p.lay = lay_;
+        convs_.push_back(std::move(st));
+    };
+    add("conv_first", spec_.first, act_in_, cin_pad_, nullptr, act_x_, c_pad_, 0);
+    for (int d = 0; d < spec_.depth; d++) {
+        add("block" + std::to_string(d) + "_conv1", spec_.blocks[2 * d], act_x_, c_pad_, nullptr, act_t_, c_pad_, C);
+        add("block" + std::to_string(d) + "_conv2", spec_.blocks[2 * d + 1], act_t_, c_pad_, &act_x_, act_x_, c_pad_, C);
+    }
+    add("policy_conv1", spec_.policy_conv1, act_x_, c_pad_, nullptr, act_h1_, cp_pad_, spec_.policy_conv1.cout);
+    add("scalar_conv", merged_small_conv(spec_), act_x_, c_pad_, nullptr, act_s1_, s1_stride_, spec_.scalar_conv.cout);
+    add("policy_conv2", spec_.policy_conv2, act_h1_, cp_pad_, nullptr, act_pm_, pm_stride_, 0);
+}
+
+void Net::bind_mapper(int scalar_count, int bool_channels, int h, int w, int policy_len) {
+    // twin of check_graph_shapes, rust/kz-core/src/network/common.rs:165-198
+    if (scalar_count < 0 || bool_channels < 0) throw std::runtime_error("negative channel count");
+    if (scalar_count + bool_channels != spec_.cin || h != spec_.board_h || w != spec_.board_w)
+        throw std::runtime_error("Input shape mismatch between graph and mapper: graph [BATCH, " + std::to_string(spec_.cin) + ", " +
+                                 std::to_string(spec_.board_h) + ", " + std::to_string(spec_.board_w) + "] vs mapper [BATCH, " +
+                                 std::to_string(scalar_count + bool_channels) + ", " + std::to_string(h) + ", " + std::to_string(w) + "]");
+    if (policy_len != spec_.policy_len)
+        throw std::runtime_error("Wrong policy shape: graph has " + std::to_string(spec_.policy_len) + " entries, mapper " + std::to_string(policy_len));
+    CK(cudaSetDevice(device_));
+    scalar_count_ = scalar_count;
+    bool_channels_ = bool_channels;
+    bits_stride_ = (bool_channels * h * w + 7) / 8;
+    mv_cap_ = size_t(max_batch_) * spec_.policy_len;
+    // one contiguous input block [mv_off | scalars | bits | mv_idx] -> a single H2D copy per batch
+    size_t in_bytes = align16(size_t(max_batch_ + 1) * 4) + align16(size_t(max_batch_) * scalar_count_ * 4) +
+                      align16(size_t(max_batch_) * bits_stride_) + mv_cap_ * 4;
+    d_mv_off_.alloc(in_bytes, true);
+    h_in_.alloc(in_bytes);
+    // one contiguous output block [err(16) | values | probs] -> a single D2H copy per batch
+    size_t out_bytes = 16 + align16(size_t(max_batch_) * 5 * 4) + mv_cap_ * 4;
+    d_err_.alloc(out_bytes, true);
+    h_out_.alloc(out_bytes);
+}
+
+void Net::check_batch(int batch) const {
+    // cudnn.rs:58 assert!(batch_size <= max_batch_size)
+    if (batch < 0 || batch > max_batch_)
+        throw std::runtime_error("batch size " + std::to_string(batch) + " exceeds max_batch_size " + std::to_string(max_batch_));
+}
+void Net::require_mapper() const {
+    if (scalar_count_ < 0) throw std::runtime_error("kzb_net_bind_mapper must be called before packed evaluation");
+}
+
+// offsets inside the contiguous input/output blocks
+struct InBlock {
+    size_t off_scalars, off_bits, off_idx;
+};
+static InBlock in_block(int max_batch, int scalar_count, int bits_stride) {
+    InBlock b;
+    b.off_scalars = align16(size_t(max_batch + 1) * 4);
+    b.off_bits = b.off_scalars + align16(size_t(max_batch) * scalar_count * 4);
+    b.off_idx = b.off_bits + align16(size_t(max_batch) * bits_stride);
+    return b;
+}
+
+void Net::upload_packed(const uint8_t* bits, const float* scalars, int batch, const uint32_t* mv_idx, const uint32_t* mv_off) {
+    InBlock ib = in_block(max_batch_, scalar_count_, bits_stride_);
+    uint8_t* h = h_in_.as<uint8_t>();
+    size_t moves = 0;
+    if (mv_off) {
+        if (mv_off[0] != 0) throw std::runtime_error("mv_off[0] must be 0");
+        for (int i = 0; i < batch; i++)
+            if (mv_off[i + 1] < mv_off[i]) throw std::runtime_error("mv_off must be non-decreasing");
+        moves = mv_off[batch];
+        if (moves > mv_cap_) throw std::runtime_error("more legal moves than batch * policy_len");
+        std::memcpy(h, mv_off, size_t(batch + 1) * 4);
+        if (moves) std::memcpy(h + ib.off_idx, mv_idx, moves * 4);
+    } else {
+        std::memset(h, 0, size_t(batch + 1) * 4);
+    }
+    std::memcpy(h + ib.off_scalars, scalars, size_t(batch) * scalar_count_ * 4);
+    std::memcpy(h + ib.off_bits, bits, size_t(batch) * bits_stride_);
+    // the gaps between the segments are small; copy the used prefix in one go
+    size_t used = ib.off_idx + moves * 4;
+    CK(cudaMemcpyAsync(d_mv_off_.ptr, h, used, cudaMemcpyHostToDevice, stream_));
+    staged_batch_ = batch;
+    staged_moves_ = moves;
+}
+
+void Net::run_encode(int batch, const StepHook& hook) {
+    InBlock ib = in_block(max_batch_, scalar_count_, bits_stride_);
+    EncodeParams p;
+    p.bits = d_mv_off_.as<uint8_t>() + ib.off_bits;
+    p.scalars = reinterpret_cast<const float*>(d_mv_off_.as<uint8_t>() + ib.off_scalars);
+    p.batch = batch;
+    p.bits_stride = bits_stride_;
+    p.scalar_count = scalar_count_;
+    p.bool_channels = bool_channels_;
+    p.lay = lay_;
+    p.c_pad = cin_pad_;
+    p.out = act_in_.ptr;
+    launch_encode_nhwc(p, act_bf16_, stream_);
+    if (hook) hook("encode");
+}
+
+void Net::run_network(int batch, const StepHook& hook) {
+    for (auto& st : convs_) {
+        if (precision_ == 1) {
+            ConvTcParams p = st->tc;
+            if (mode_ == 1) {
+                p.num_tiles = (batch + p.boards_per_tile - 1) / p.boards_per_tile;
+                p.valid_rows = batch * lay_.board_pitch;
+            } else {
+                p.valid_rows = batch * lay_.board_pitch;
+                p.num_tiles = (p.valid_rows + 127) / 128;
+            }
+            launch_conv_tc(st->tmap_a, st->tmap_b, p, num_sms_, stream_);
+        } else {
+            ConvF32Params p = st->f32;
+            p.batch = batch;
+            launch_conv_fp32(p, stream_);
+        }
+        if (hook) hook(st->name.c_str());
+    }
+}
+
+void Net::run_tail(int batch, bool packed, const StepHook& hook) {
+    HeadsTailParams p{};
+    p.batch = batch;
+    p.lay = lay_;
+    p.s1 = act_s1_.as<float>();
+    p.s1_stride = s1_stride_;
+    p.hc = spec_.scalar_conv.cout;
+    p.pm = act_pm_.as<float>();
+    p.pm_stride = pm_stride_;
+    p.fc1_t = d_fc1_t_.as<float>();
+    p.fc1_b = d_fc1_b_.as<float>();
+    p.fc2_w = d_fc2_w_.as<float>();
+    p.fc2_b = d_fc2_b_.as<float>();
+    p.hs = spec_.fc1.out;
+    p.extra_w = spec_.has_extra ? d_extra_w_.as<float>() : nullptr;
+    p.extra_b = spec_.has_extra ? spec_.extra_fc.b[0] : 0.0f;
+    p.policy_src = d_policy_src_.as<int32_t>();
+    p.policy_len = spec_.policy_len;
+    p.out_scalars = d_out_scalars_.as<float>();
+    p.out_logits = d_out_logits_.as<float>();
+    if (packed) {
+        InBlock ib = in_block(max_batch_, scalar_count_, bits_stride_);
+        p.mv_off = d_mv_off_.as<uint32_t>();
+        p.mv_idx = reinterpret_cast<const uint32_t*>(d_mv_off_.as<uint8_t>() + ib.off_idx);
+        p.err_flag = d_err_.as<int>();
+        p.out_values = reinterpret_cast<float*>(d_err_.as<uint8_t>() + 16);
+        p.out_probs = reinterpret_cast<float*>(d_err_.as<uint8_t>() + 16 + align16(size_t(max_batch_) * 5 * 4));
+    }
+    launch_heads_tail(p, packed, stream_);
+    if (hook) hook("heads_tail");
+}
+
+void Net::eval_planes(const float* nchw, int batch, float* out_scalars, float* out_logits) {
+    check_batch(batch);
+    if (batch == 0) return;
+    CK(cudaSetDevice(device_));
+    const int area = spec_.area();
+    CK(cudaMemcpyAsync(d_nchw_.ptr, nchw, size_t(batch) * spec_.cin * area * 4, cudaMemcpyHostToDevice, stream_));
+    launch_nchw_to_rows(d_nchw_.as<float>(), batch, spec_.cin, lay_, cin_pad_, act_in_.ptr, act_bf16_, stream_);
+    run_network(batch, nullptr);
+    run_tail(batch, false, nullptr);
+    CK(cudaMemcpyAsync(out_scalars, d_out_scalars_.ptr, size_t(batch) * 5 * 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(out_logits, d_out_logits_.ptr, size_t(batch) * spec_.policy_len * 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+}
+
+void Net::eval_packed(const uint8_t* bits, const float* scalars, int batch, const uint32_t* mv_idx, const uint32_t* mv_off,
+                      float* out_values, float* out_policy) {
+    check_batch(batch);
+    require_mapper();
+    if (batch == 0) return;
+    CK(cudaSetDevice(device_));
+    upload_packed(bits, scalars, batch, mv_idx, mv_off);
+    CK(cudaMemsetAsync(d_err_.ptr, 0, 16, stream_));
+    run_encode(batch, nullptr);
+    run_network(batch, nullptr);
+    run_tail(batch, true, nullptr);
+    const size_t probs_off = 16 + align16(size_t(max_batch_) * 5 * 4);
+    // values are right behind the error word; probabilities start at a fixed offset: two spans, one stream
+    CK(cudaMemcpyAsync(h_out_.ptr, d_err_.ptr, 16 + size_t(batch) * 5 * 4, cudaMemcpyDeviceToHost, stream_));
+    if (staged_moves_)
+        CK(cudaMemcpyAsync(h_out_.as<uint8_t>() + probs_off, d_err_.as<uint8_t>() + probs_off, staged_moves_ * 4,
+                           cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+    int err = *h_out_.as<int>();
+    if (err != 0)
+        throw std::runtime_error("Softmax input sum must be strictly positive (board " + std::to_string(err - 1) +
+                                 "): the network produced NaN/inf logits");
+    std::memcpy(out_values, h_out_.as<uint8_t>() + 16, size_t(batch) * 5 * 4);
+    if (staged_moves_) std::memcpy(out_policy, h_out_.as<uint8_t>() + probs_off, staged_moves_ * 4);
+}
+
+void Net::encode_planes(const uint8_t* bits, const float* scalars, int batch, float* out_nchw) {
+    check_batch(batch);
+    require_mapper();
+    if (batch == 0) return;
+    CK(cudaSetDevice(device_));
+    upload_packed(bits, scalars, batch, nullptr, nullptr);
+    InBlock ib = in_block(max_batch_, scalar_count_, bits_stride_);
+    launch_encode_nchw_f32(d_mv_off_.as<uint8_t>() + ib.off_bits, reinterpret_cast<const float*>(d_mv_off_.as<uint8_t>() + ib.off_scalars),
+                           batch, bits_stride_, scalar_count_, bool_channels_, spec_.area(), d_nchw_.as<float>(), stream_);
+    CK(cudaMemcpyAsync(out_nchw, d_nchw_.ptr, size_t(batch) * spec_.cin * spec_.area() * 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+}
+
+void Net::stage_packed(const uint8_t* bits, const float* scalars, int batch, const uint32_t* mv_idx, const uint32_t* mv_off) {
+    check_batch(batch);
+    require_mapper();
+    CK(cudaSetDevice(device_));
+    upload_packed(bits, scalars, batch, mv_idx, mv_off);
+    CK(cudaStreamSynchronize(stream_));
+}
+
+void Net::flush_l2() {
+    const size_t bytes = size_t(256) << 20;  // > 126 MB L2
+    if (!d_flush_.ptr) d_flush_.alloc(bytes, false);
+    CK(cudaMemsetAsync(d_flush_.ptr, 1, bytes, stream_));
+}
+
+void Net::time_staged(int iters, bool flush, float* ms_out) {
+    require_mapper();
+    if (staged_batch_ <= 0) throw std::runtime_error("no staged batch: call kzb_stage_packed first");
+    CK(cudaSetDevice(device_));
+    std::vector<cudaEvent_t> ev(size_t(iters) * 2);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    for (int i = 0; i < iters; i++) {
+        if (flush) flush_l2();
+        CK(cudaEventRecord(ev[2 * i], stream_));
+        run_encode(staged_batch_, nullptr);
+        run_network(staged_batch_, nullptr);
+        run_tail(staged_batch_, true, nullptr);
+        CK(cudaEventRecord(ev[2 * i + 1], stream_));
+    }
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+    for (int i = 0; i < iters; i++) CK(cudaEventElapsedTime(&ms_out[i], ev[2 * i], ev[2 * i + 1]));
+    for (auto& e : ev) cudaEventDestroy(e);
+}
+
+void Net::profile_staged(bool flush, std::vector<std::string>& names, std::vector<float>& ms) {
+    require_mapper();
+    if (staged_batch_ <= 0) throw std::runtime_error("no staged batch: call kzb_stage_packed first");
+    CK(cudaSetDevice(device_));
+    std::vector<cudaEvent_t> ev;
+    names.clear();
+    auto mark = [&]() {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        CK(cudaEventRecord(e, stream_));
+        ev.push_back(e);
+    };
+    StepHook hook = [&](const char* name) {
+        names.push_back(name);
+        mark();
+    };
+    if (flush) flush_l2();
+    mark();
+    run_encode(staged_batch_, hook);
+    run_network(staged_batch_, hook);
+    run_tail(staged_batch_, true, hook);
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+    ms.resize(names.size());
+    for (size_t i = 0; i < names.size(); i++) CK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    for (auto& e : ev) cudaEventDestroy(e);
+}
+
+}  // namespace kzb

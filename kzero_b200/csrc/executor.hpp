@@ -1,0 +1,119 @@
+// The network object behind the C ABI: device buffers, packed weights, TMA tensor maps and the fixed
+// launch schedule for one AlphaZero ResNet.  The B200 build's counterpart of kn-cuda-eval's
+// `CudaExecutor` (planner + executor; call sites rust/kz-core/src/network/cudnn.rs:32,73).
+#pragma once
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "net_spec.hpp"
+
+namespace kzb {
+
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    DeviceBuffer() = default;
+    DeviceBuffer(const DeviceBuffer&) = delete;
+    DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+    ~DeviceBuffer();
+    void alloc(size_t n, bool zero = true);
+    template <typename T>
+    T* as() const {
+        return static_cast<T*>(ptr);
+    }
+};
+
+struct PinnedBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    PinnedBuffer() = default;
+    PinnedBuffer(const PinnedBuffer&) = delete;
+    PinnedBuffer& operator=(const PinnedBuffer&) = delete;
+    ~PinnedBuffer();
+    void alloc(size_t n);
+    template <typename T>
+    T* as() const {
+        return static_cast<T*>(ptr);
+    }
+};
+
+// one conv launch of the schedule
+struct ConvStep {
+    std::string name;
+    int taps = 9;
+    // bf16 tensor-core form
+    CUtensorMap tmap_a{}, tmap_b{};
+    ConvTcParams tc{};
+    DeviceBuffer w_bf16;  // [n][taps*cin_pad]
+    // fp32 form
+    ConvF32Params f32{};
+    DeviceBuffer w_f32;  // [taps][cin][cout]
+    DeviceBuffer bias;   // [n] f32
+};
+
+class Net {
+public:
+    Net(int device, const void* onnx, size_t len, int max_batch, int precision);
+    ~Net();
+
+    void bind_mapper(int scalar_count, int bool_channels, int h, int w, int policy_len);
+    void eval_planes(const float* nchw, int batch, float* out_scalars, float* out_logits);
+    void eval_packed(const uint8_t* bits, const float* scalars, int batch, const uint32_t* mv_idx, const uint32_t* mv_off,
+                     float* out_values, float* out_policy);
+    void encode_planes(const uint8_t* bits, const float* scalars, int batch, float* out_nchw);
+    void stage_packed(const uint8_t* bits, const float* scalars, int batch, const uint32_t* mv_idx, const uint32_t* mv_off);
+    void time_staged(int iters, bool flush_l2, float* ms_out);
+    void profile_staged(bool flush_l2, std::vector<std::string>& names, std::vector<float>& ms);
+    int launches_per_eval() const { return int(convs_.size()) + 2; }
+
+    const NetSpec& spec() const { return spec_; }
+    int device() const { return device_; }
+    int max_batch() const { return max_batch_; }
+    int precision() const { return precision_; }
+    int conv_mode() const { return precision_ == 1 ? mode_ : -1; }
+
+private:
+    using StepHook = std::function<void(const char*)>;
+    void build_bf16();
+    void build_f32();
+    void check_batch(int batch) const;
+    void require_mapper() const;
+    void upload_packed(const uint8_t* bits, const float* scalars, int batch, const uint32_t* mv_idx, const uint32_t* mv_off);
+    void run_encode(int batch, const StepHook& hook);
+    void run_network(int batch, const StepHook& hook);
+    void run_tail(int batch, bool packed, const StepHook& hook);
+    void flush_l2();
+
+    int device_, max_batch_, precision_;
+    NetSpec spec_;
+    cudaStream_t stream_ = nullptr;
+    int num_sms_ = 148;
+
+    int scalar_count_ = -1, bool_channels_ = -1, bits_stride_ = 0;
+    RowLayout lay_{};
+    int mode_ = 0;       // bf16 path: 0 padded rows / 2-D TMA, 1 dense 8x8 / 4-D TMA
+    int rows_alloc_ = 0; // multiple of 128
+    int cin_pad_ = 0, c_pad_ = 0, cp_pad_ = 0, s1_stride_ = 16, pm_stride_ = 0;
+    bool act_bf16_ = true;
+
+    DeviceBuffer d_bits_, d_scalars_, d_mv_idx_, d_mv_off_, d_nchw_;
+    DeviceBuffer act_in_, act_x_, act_t_, act_h1_, act_s1_, act_pm_;
+    DeviceBuffer d_fc1_t_, d_fc1_b_, d_fc2_w_, d_fc2_b_, d_extra_w_, d_policy_src_;
+    DeviceBuffer d_out_scalars_, d_out_logits_, d_out_values_, d_out_probs_, d_err_;
+    DeviceBuffer d_flush_;
+    PinnedBuffer h_in_, h_out_;
+    size_t mv_cap_ = 0;
+    int staged_batch_ = 0;
+    size_t staged_moves_ = 0;
+
+    std::vector<std::unique_ptr<ConvStep>> convs_;
+};
+
+// thread-local error plumbing for the C ABI
+void set_last_error(const std::string& msg);
+const char* last_error();
+
+}  // namespace kzb

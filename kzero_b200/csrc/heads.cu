@@ -1,0 +1,146 @@
+// K3: everything after the head convolutions, one warp per position, warp-shuffle reductions.
+//
+// Replaces, for this path:
+//   - the scalar head's Flatten/Gemm/Relu/Gemm steps (python/lib/model/post_act.py:15-19), which the
+//     reference executes as separate cuBLAS launches,
+//   - the policy Flatten/Gather/Concat plumbing (post_act.py:76-88, 102-112),
+//   - and, in packed mode, the CPU-side decode_output (rust/kz-core/src/network/common.rs:16-100):
+//     value = tanh(s0), wdl = softmax(s1..3), moves_left = s4, policy = softmax over the LEGAL moves only
+//     (gathered by the host-supplied move_to_index list), so only n_legal probabilities per position cross
+//     PCIe instead of the full [B, P] logit matrix.
+// HBM/latency-bound: algorithmic bytes per position = hc*A*4 + (n_legal or P)*4 read, (5 + n_legal or P)*4 written.
+#include "kernels.cuh"
+
+namespace kzb {
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kMaxHiddenPerLane = 4;  // hs <= 128
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) heads_tail_kernel(HeadsTailParams p) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int b = blockIdx.x * kWarpsPerBlock + warp;
+    if (b >= p.batch) return;  // whole warp exits together, no block-level sync below
+
+    const int area = p.lay.W * p.lay.H;
+    const int n_in = p.hc * area;
+    float* s_in = smem + size_t(warp) * n_in;  // flatten order (channel, y, x), post_act.py:16
+
+    for (int i = lane; i < n_in; i += 32) {
+        int c = i / area, sq = i % area;
+        s_in[i] = p.s1[size_t(p.lay.row(b, sq)) * p.s1_stride + c];
+    }
+    float extra = 0.0f;
+    if (p.extra_w) {
+        float e = 0.0f;
+        for (int sq = lane; sq < area; sq += 32) e += p.extra_w[sq] * p.s1[size_t(p.lay.row(b, sq)) * p.s1_stride + p.hc];
+        extra = warp_sum(e) + p.extra_b;
+    }
+    __syncwarp();
+
+    // fc1 + relu: lane owns hidden units lane, lane+32, ...
+    float h[kMaxHiddenPerLane];
+#pragma unroll
+    for (int u = 0; u < kMaxHiddenPerLane; u++) h[u] = 0.0f;
+    for (int i = 0; i < n_in; i++) {
+        float v = s_in[i];
+#pragma unroll
+        for (int u = 0; u < kMaxHiddenPerLane; u++) {
+            int j = lane + 32 * u;
+            if (j < p.hs) h[u] = fmaf(p.fc1_t[size_t(i) * p.hs + j], v, h[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kMaxHiddenPerLane; u++) {
+        int j = lane + 32 * u;
+        h[u] = j < p.hs ? fmaxf(h[u] + p.fc1_b[j], 0.0f) : 0.0f;
+    }
+    // fc2: 5 outputs
+    float sc[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        float part = 0.0f;
+#pragma unroll
+        for (int u = 0; u < kMaxHiddenPerLane; u++) {
+            int j = lane + 32 * u;
+            if (j < p.hs) part = fmaf(p.fc2_w[k * p.hs + j], h[u], part);
+        }
+        sc[k] = warp_sum(part) + p.fc2_b[k];
+    }
+
+    auto logit = [&](int i) -> float {
+        int src = p.policy_src[i];
+        if (src >= 0) return p.pm[size_t(p.lay.row(b, src % area)) * p.pm_stride + src / area];
+        return src == -1 ? 0.0f : extra;
+    };
+
+    if (!PACKED) {
+        if (lane < 5) p.out_scalars[size_t(b) * 5 + lane] = sc[lane];
+        for (int i = lane; i < p.policy_len; i += 32) p.out_logits[size_t(b) * p.policy_len + i] = logit(i);
+        return;
+    }
+
+    // decode_output, common.rs:59-74
+    if (lane == 0) {
+        float* ov = p.out_values + size_t(b) * 5;
+        ov[0] = tanhf(sc[0]);
+        float mx = fmaxf(sc[1], fmaxf(sc[2], sc[3]));
+        float e0 = expf(sc[1] - mx), e1 = expf(sc[2] - mx), e2 = expf(sc[3] - mx);
+        float sum = (e0 + e1) + e2;
+        if (!(sum > 0.0f)) atomicCAS(p.err_flag, 0, 1 + b);
+        ov[1] = e0 / sum;
+        ov[2] = e1 / sum;
+        ov[3] = e2 / sum;
+        ov[4] = sc[4];
+    }
+    // masked softmax over the legal moves only, common.rs:76-86 + softmax_in_place :102-114
+    const uint32_t o0 = p.mv_off[b], o1 = p.mv_off[b + 1];
+    const int n = int(o1 - o0);
+    if (n <= 0) return;  // terminal board: empty policy (common.rs:77)
+    float mx = -INFINITY;
+    for (int j = lane; j < n; j += 32) {
+        uint32_t idx = p.mv_idx[o0 + j];
+        float l = idx < uint32_t(p.policy_len) ? logit(int(idx)) : NAN;
+        p.out_probs[o0 + j] = l;  // stage the gathered logit; each lane re-reads only its own entries
+        mx = fmaxf(mx, l);
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int j = lane; j < n; j += 32) {
+        float e = expf(p.out_probs[o0 + j] - mx);
+        p.out_probs[o0 + j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (!(sum > 0.0f)) {  // NaN logits: the reference panics here (common.rs:110)
+        if (lane == 0) atomicCAS(p.err_flag, 0, 1 + b);
+    }
+    for (int j = lane; j < n; j += 32) p.out_probs[o0 + j] /= sum;
+}
+
+}  // namespace
+
+void launch_heads_tail(const HeadsTailParams& p, bool packed, cudaStream_t s) {
+    if (p.batch <= 0) return;
+    int blocks = (p.batch + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    size_t smem = size_t(kWarpsPerBlock) * p.hc * p.lay.W * p.lay.H * sizeof(float);
+    if (packed)
+        heads_tail_kernel<true><<<blocks, kWarpsPerBlock * 32, smem, s>>>(p);
+    else
+        heads_tail_kernel<false><<<blocks, kWarpsPerBlock * 32, smem, s>>>(p);
+}
+
+}  // namespace kzb

@@ -1,0 +1,118 @@
+// Device-side parameter blocks and host launchers for the hot path's kernels (sm_100a only).
+//   K2  encode      packed bitboards + scalars -> input planes          (encode.cu)      HBM-bound
+//   K1  conv tower  implicit-GEMM conv3x3/1x1 on tcgen05 + TMA + TMEM   (conv_tc.cu)     tensor-bound
+//       conv fp32   CUDA-core fp32 implicit GEMM, the <=1e-4 parity mode (conv_fp32.cu)
+//   K3  heads tail  scalar-head FCs, policy gather, masked softmax      (heads.cu)       HBM/latency-bound
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+namespace kzb {
+
+// Row index of square (y, x) of board b inside an activation matrix [rows][channels]:
+//   row = b * board_pitch + y * rank_pitch + x
+// dense  layout: rank_pitch = W,   board_pitch = H*W        (no padding rows)
+// padded layout: rank_pitch = W+1, board_pitch = (H+1)*(W+1): one zero column after every rank and one
+//   zero rank after every board, so every 3x3 tap is a pure row shift dy*rank_pitch+dx that lands on a
+//   zero row whenever it leaves the board.
+struct RowLayout {
+    int W, H, rank_pitch, board_pitch;
+    __host__ __device__ int row(int b, int sq) const { return b * board_pitch + (sq / W) * rank_pitch + (sq % W); }
+    __host__ __device__ bool padded() const { return rank_pitch != W; }
+};
+
+// ---------------------------------------------------------------------------------------------- K2
+struct EncodeParams {
+    const uint8_t* bits;   // [batch][bits_stride]   LSB-first (bit_buffer.rs:27-35)
+    const float* scalars;  // [batch][scalar_count]
+    int batch, bits_stride, scalar_count, bool_channels;
+    RowLayout lay;
+    int c_pad;  // channels per row in the output (>= scalar_count + bool_channels, multiple of 8)
+    void* out;  // [batch*board_pitch][c_pad] bf16 or f32
+};
+void launch_encode_nhwc(const EncodeParams& p, bool out_bf16, cudaStream_t s);
+// exact twin of InputMapper::encode_input_full (mapping/mod.rs:40-63): out [batch][Cs+Cb][H*W] f32
+void launch_encode_nchw_f32(const uint8_t* bits, const float* scalars, int batch, int bits_stride, int scalar_count,
+                            int bool_channels, int area, float* out, cudaStream_t s);
+// f32 NCHW [batch][C][H*W] -> rows [batch*board_pitch][c_pad] (bf16 or f32), zero pad rows / channels
+void launch_nchw_to_rows(const float* in, int batch, int channels, RowLayout lay, int c_pad, void* out, bool out_bf16,
+                         cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------- conv fp32
+struct ConvF32Params {
+    const float* in;  // [rows][in_stride]
+    int in_stride;
+    const float* w;     // [taps][cin][cout]
+    const float* bias;  // [cout]
+    const float* res;   // optional [rows][res_stride], added AFTER the relu (post_act.py:227-228)
+    int res_stride;
+    float* out;  // [rows][out_stride]
+    int out_stride;
+    int cin, cout, taps;  // taps 1 or 9
+    int relu_n;           // relu on output channels < relu_n
+    int batch;
+    RowLayout lay;  // dense
+};
+void launch_conv_fp32(const ConvF32Params& p, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------- K1
+struct ConvTcParams {
+    int num_tiles;  // 128-row M tiles
+    int taps;       // 1 or 9
+    int kblocks;    // cin_pad / 64
+    int cin_pad;
+    int n;     // UMMA N = padded cout, multiple of 16, <= 256
+    int mode;  // 0: rows are a padded linear layout, 2-D TMA; 1: dense 8x8 boards, 4-D TMA box (c,x,y,b)
+    int boards_per_tile;
+    RowLayout lay;
+    int valid_rows;  // rows >= valid_rows are not stored
+    const float* bias;  // [n]
+    int relu_n;
+    const __nv_bfloat16* res;  // optional [rows][res_stride]
+    int res_stride;
+    void* out;  // [rows][out_stride] bf16 or f32
+    int out_stride;
+    int out_f32;
+    int n_store;  // channels written per row (multiple of 16, <= n)
+    int stages;
+    int tmem_cols;
+};
+void launch_conv_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ConvTcParams& p, int grid,
+                    cudaStream_t s);
+size_t conv_tc_smem_bytes(int n, int stages);
+int conv_tc_pick_stages(int n);
+
+// ---------------------------------------------------------------------------------------------- K3
+struct HeadsTailParams {
+    int batch;
+    RowLayout lay;
+    const float* s1;  // [rows][s1_stride]: ch 0..hc-1 relu(scalar conv), ch hc = extra policy conv (no relu)
+    int s1_stride, hc;
+    const float* pm;  // [rows][pm_stride]: policy conv map, channel pc at [row][pc]
+    int pm_stride;
+    const float* fc1_t;  // [hc*A][hs]  (transposed fc1 weight)
+    const float* fc1_b;  // [hs]
+    const float* fc2_w;  // [5][hs]
+    const float* fc2_b;  // [5]
+    int hs;
+    const float* extra_w;  // [A] or null
+    float extra_b;
+    const int32_t* policy_src;  // [P]
+    int policy_len;
+    // planes mode (twin of CudaExecutor::evaluate, network/cudnn.rs:73)
+    float* out_scalars;  // [batch][5] raw
+    float* out_logits;   // [batch][P]
+    // packed mode (fused decode_output, network/common.rs:16-100)
+    const uint32_t* mv_idx;
+    const uint32_t* mv_off;  // [batch+1]
+    float* out_values;       // [batch][5]: tanh(v), softmax(wdl), moves_left
+    float* out_probs;        // CSR-aligned with mv_idx
+    int* err_flag;           // set to 1+board when a softmax sum is not > 0 (common.rs:110)
+};
+void launch_heads_tail(const HeadsTailParams& p, bool packed, cudaStream_t s);
+
+}  // namespace kzb

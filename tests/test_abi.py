@@ -1,0 +1,86 @@
+"""C-ABI surface and host-side logic that needs no GPU: the library loads, exports every symbol the
+header declares, recognises the reference's exports, rejects what it must, and refuses to run without CUDA."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, NET_NAMES, load_net_fixture, structure
+from kzero_b200 import _abi, netgen
+from kzero_b200.build import build
+from kzero_b200.network import B200Network, KzbError, inspect_onnx, mapper_for
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    build()
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "kzb200.h").read_text()
+    declared = set(re.findall(r"\b(kzb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_abi.SYMBOLS), declared ^ set(_abi.SYMBOLS)
+    lib = ctypes.CDLL(str(_abi.lib_path()))
+    for name in declared:
+        assert hasattr(lib, name), f"libkzb200.so does not export {name}"
+
+
+@pytest.mark.parametrize("name", [n for n in NET_NAMES if "att" not in n])
+def test_inspect_recognises_reference_exports(name):
+    onnx_bytes, x, _, policy = load_net_fixture(name)
+    info = inspect_onnx(onnx_bytes)
+    s = structure()[name]
+    assert [info.input_channels, info.board_h, info.board_w] == s["input_shape"]
+    assert info.policy_len == policy.shape[1]
+    depth = s["ops"].count("Add")
+    assert info.depth == depth
+    assert info.channels in (16, 32)
+
+
+def test_inspect_flops_match_survey_formula():
+    # chess 16x128 = 610.45 MFLOP / position, ataxx-7 8x64 = 58.57
+    chess = inspect_onnx(netgen.build_onnx(netgen.game_spec("chess"), 16, 128))
+    assert abs(chess.flops_per_position / 1e6 - 610.45) < 0.05
+    ataxx = inspect_onnx(netgen.build_onnx(netgen.game_spec("ataxx-7"), 8, 64))
+    assert abs(ataxx.flops_per_position / 1e6 - 58.57) < 0.05
+
+
+def test_inspect_accepts_unfolded_bn():
+    info = inspect_onnx(netgen.build_onnx(netgen.game_spec("ataxx-7"), 3, 16, fold_bn=False))
+    assert info.depth == 3 and info.channels == 16
+
+
+def test_inspect_rejects_attention_head_with_message():
+    onnx_bytes, *_ = load_net_fixture("chess_att_2x32")
+    with pytest.raises(KzbError, match="policy head"):
+        inspect_onnx(onnx_bytes)
+
+
+def test_inspect_rejects_garbage():
+    with pytest.raises(KzbError):
+        inspect_onnx(b"\x00\x01\x02 definitely not onnx")
+    with pytest.raises(KzbError):
+        inspect_onnx(netgen.build_onnx(netgen.game_spec("chess"), 1, 16)[:2000])
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product must fail loudly (never fall back to the oracle or any CPU path)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert _abi.lib().kzb_device_count() == 0
+    spec = netgen.game_spec("ataxx-7")
+    with pytest.raises(KzbError, match="no CUDA device|CPU fallback"):
+        B200Network(mapper_for(spec), netgen.build_onnx(spec, 1, 16), 4)
+
+
+def test_product_does_not_import_oracle():
+    for path in (ROOT / "kzero_b200").rglob("*"):
+        if path.suffix in (".py", ".cu", ".cpp", ".hpp", ".cuh", ".h"):
+            text = path.read_text()
+            assert "import oracle" not in text and "from oracle" not in text and "kz_oracle" not in text, path

@@ -1,0 +1,241 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference-derived golden files.
+
+Bars (BASELINE.json north_star):
+  input planes            bit-exact
+  fp32 path               <= 1e-4 max-abs on scalars and policy logits
+  bf16 tensor-core path   <= 2e-2 max-abs on policy logits, value sign agreement reported/checked
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle.graph_exec import OnnxOracle
+from helpers import GOLDEN, load_net_fixture
+from kzero_b200 import netgen
+from kzero_b200.network import (B200Network, EncodedBoard, KzbError, Mapper, PRECISION_BF16, PRECISION_FP32,
+                                mapper_for)
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_POLICY_TOL = 2e-2
+
+FIXTURE_GAMES = {"ataxx7_2x32": "ataxx-7", "chess_conv_2x32": "chess", "go9_2x32": "go-9",
+                 "ataxx5_scripted_1x16": "ataxx-5"}
+
+
+def _oracle_planes(spec, bits, scalars):
+    return oracle.expand_planes(bits, scalars, (spec.bool_channels, spec.board_size, spec.board_size),
+                                spec.scalar_channels)
+
+
+def _tiny_net(spec, **kw):
+    return netgen.build_onnx(spec, 1, 16, seed=11, **kw)
+
+
+# ------------------------------------------------------------------------------------------- K2 encode
+@pytest.mark.parametrize("game", ["chess", "ataxx-7", "go-9", "ataxx-3", "go-19"])
+def test_encode_bit_exact_vs_reference_golden(game):
+    d = np.load(GOLDEN / f"planes_{game}.npz")
+    cb, h, w = (int(v) for v in d["bool_shape"])
+    cs = int(d["scalar_count"])
+    spec = netgen.game_spec(game)
+    assert (spec.bool_channels, spec.scalar_channels) == (cb, cs)
+    with B200Network(mapper_for(spec), _tiny_net(spec), 8, precision=PRECISION_FP32) as net:
+        out = net.encode_planes(d["bits"], d["scalars"])
+    assert np.array_equal(out.view(np.uint32), d["planes"].view(np.uint32))
+
+
+@pytest.mark.parametrize("game,n", [("chess", 1024), ("ataxx-7", 256), ("go-9", 333)])
+def test_encode_bit_exact_vs_oracle_full_batch(game, n):
+    spec = netgen.game_spec(game)
+    bits, scalars, _, _ = netgen.synthetic_positions(spec, n, seed=3)
+    rng = np.random.default_rng(4)
+    bits[: n // 2] = rng.integers(0, 256, size=bits[: n // 2].shape, dtype=np.uint8)  # dense random bits too
+    scalars[: n // 2] = rng.standard_normal(scalars[: n // 2].shape).astype(np.float32)
+    with B200Network(mapper_for(spec), _tiny_net(spec), n, precision=PRECISION_FP32) as net:
+        out = net.encode_planes(bits, scalars)
+    ref = _oracle_planes(spec, bits, scalars)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------- fp32 path
+@pytest.mark.parametrize("name", list(FIXTURE_GAMES))
+def test_fp32_planes_vs_reference_pytorch_golden(name):
+    """kzb_eval_planes (twin of CudaExecutor::evaluate) against the PyTorch outputs the reference's own
+    check files hold (save_onnx.py:94-102)."""
+    onnx_bytes, x, scalars, policy = load_net_fixture(name)
+    spec = netgen.game_spec(FIXTURE_GAMES[name])
+    with B200Network(mapper_for(spec), onnx_bytes, 8, precision=PRECISION_FP32) as net:
+        s, p = net.evaluate_planes(x)
+    assert np.abs(s - scalars).max() <= FP32_TOL
+    assert np.abs(p - policy).max() <= FP32_TOL
+
+
+@pytest.mark.parametrize("name", list(FIXTURE_GAMES))
+def test_bf16_planes_vs_reference_pytorch_golden(name):
+    onnx_bytes, x, scalars, policy = load_net_fixture(name)
+    spec = netgen.game_spec(FIXTURE_GAMES[name])
+    with B200Network(mapper_for(spec), onnx_bytes, 8, precision=PRECISION_BF16) as net:
+        s, p = net.evaluate_planes(x)
+    assert np.abs(p - policy).max() <= BF16_POLICY_TOL
+    assert np.abs(s - scalars).max() <= 5e-2
+
+
+@pytest.mark.parametrize("game,depth,ch,n", [("ataxx-7", 8, 64, 64), ("chess", 4, 64, 33), ("go-9", 3, 48, 17)])
+@pytest.mark.parametrize("fold_bn", [True, False])
+def test_fp32_planes_vs_oracle(game, depth, ch, n, fold_bn):
+    spec = netgen.game_spec(game)
+    onnx_bytes = netgen.build_onnx(spec, depth, ch, seed=5, fold_bn=fold_bn)
+    x = np.random.default_rng(6).standard_normal((n, spec.input_channels, spec.board_size, spec.board_size)).astype(np.float32)
+    ref_s, ref_p = OnnxOracle(onnx_bytes).run(x)
+    with B200Network(mapper_for(spec), onnx_bytes, n, precision=PRECISION_FP32) as net:
+        s, p = net.evaluate_planes(x)
+    assert np.abs(s - ref_s).max() <= FP32_TOL
+    assert np.abs(p - ref_p).max() <= FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------- packed path
+def _oracle_packed(spec, onnx_bytes, bits, scalars, mv_idx, mv_off):
+    planes = _oracle_planes(spec, bits, scalars)
+    s, p = OnnxOracle(onnx_bytes).run(planes)
+    values, probs = oracle.decode_output(s, p, mv_idx, mv_off)
+    return s, p, values, probs
+
+
+def _check_packed(values, probs, ref_values, ref_probs, mv_off, tol_v, tol_p):
+    assert np.abs(values - ref_values).max() <= tol_v
+    if probs.size:
+        assert np.abs(probs - ref_probs).max() <= tol_p
+    for i in range(len(mv_off) - 1):
+        seg = probs[mv_off[i]:mv_off[i + 1]]
+        if seg.size:
+            assert abs(float(seg.sum()) - 1.0) < 1e-4
+
+
+@pytest.mark.parametrize("game,depth,ch,n", [("ataxx-7", 8, 64, 256), ("chess", 2, 32, 50), ("go-9", 2, 32, 31)])
+def test_fp32_packed_vs_oracle(game, depth, ch, n):
+    """Full fused call (encode -> tower -> heads -> masked softmax) vs oracle expand + graph + decode_output.
+    ataxx-7 8x64 batch 256 is BASELINE.json configs[0]."""
+    spec = netgen.game_spec(game)
+    onnx_bytes = netgen.build_onnx(spec, depth, ch, seed=7)
+    bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, n, seed=8)
+    _, _, ref_values, ref_probs = _oracle_packed(spec, onnx_bytes, bits, scalars, mv_idx, mv_off)
+    with B200Network(mapper_for(spec), onnx_bytes, n, precision=PRECISION_FP32) as net:
+        values, probs = net.evaluate_packed(bits, scalars, mv_idx, mv_off)
+    _check_packed(values, probs, ref_values, ref_probs, mv_off, FP32_TOL, FP32_TOL)
+
+
+@pytest.mark.parametrize("force_linear", ["0", "1"])
+@pytest.mark.parametrize("game,depth,ch,n", [("ataxx-7", 8, 64, 256), ("chess", 16, 128, 64), ("go-9", 4, 64, 40),
+                                              ("chess", 2, 32, 7)])
+def test_bf16_packed_vs_oracle(game, depth, ch, n, force_linear, monkeypatch):
+    """The tensor-core path, both im2col modes (4-D TMA box for 8x8 boards / padded-row 2-D)."""
+    if force_linear == "1" and game != "chess":
+        pytest.skip("non-8x8 boards always use the padded-row mode")
+    monkeypatch.setenv("KZB_FORCE_LINEAR", force_linear)
+    spec = netgen.game_spec(game)
+    onnx_bytes = netgen.build_onnx(spec, depth, ch, seed=9)
+    bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, n, seed=10)
+    ref_s, ref_p, ref_values, ref_probs = _oracle_packed(spec, onnx_bytes, bits, scalars, mv_idx, mv_off)
+    with B200Network(mapper_for(spec), onnx_bytes, n, precision=PRECISION_BF16) as net:
+        assert net.info().conv_mode == (1 if (game == "chess" and force_linear == "0") else 0)
+        values, probs = net.evaluate_packed(bits, scalars, mv_idx, mv_off)
+        planes = _oracle_planes(spec, bits, scalars)
+        s, p = net.evaluate_planes(planes)
+    err_p = np.abs(p - ref_p).max()
+    assert err_p <= BF16_POLICY_TOL, err_p
+    # value sign agreement wherever the oracle's value is not within rounding distance of zero
+    clear = np.abs(ref_s[:, 0]) > 0.05
+    agree = np.sign(s[clear, 0]) == np.sign(ref_s[clear, 0])
+    assert agree.all(), f"value sign agreement {agree.mean():.4f}"
+    _check_packed(values, probs, ref_values, ref_probs, mv_off, 5e-2, 1e-2)
+
+
+# ------------------------------------------------------------------------------------------- contract edges
+@pytest.mark.parametrize("precision", [PRECISION_FP32, PRECISION_BF16])
+def test_rows_independent_of_batch(precision):
+    """Result for row i must not depend on the other rows or on `batch` (SURVEY.md 8(b) batch semantics)."""
+    spec = netgen.game_spec("chess")
+    onnx_bytes = netgen.build_onnx(spec, 2, 32, seed=12)
+    bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, 37, seed=13)
+    with B200Network(mapper_for(spec), onnx_bytes, 64, precision=precision) as net:
+        v_all, p_all = net.evaluate_packed(bits, scalars, mv_idx, mv_off)
+        for i in [0, 5, 36]:
+            sl = slice(int(mv_off[i]), int(mv_off[i + 1]))
+            v1, p1 = net.evaluate_packed(bits[i:i + 1], scalars[i:i + 1], mv_idx[sl], np.array([0, sl.stop - sl.start], np.uint32))
+            assert np.array_equal(v1[0], v_all[i])
+            assert np.array_equal(p1, p_all[sl])
+
+
+def test_evaluate_batch_interface_and_terminal_board():
+    spec = netgen.game_spec("ataxx-7")
+    onnx_bytes = netgen.build_onnx(spec, 2, 32, seed=14)
+    bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, 5, seed=15)
+    boards = [EncodedBoard(bits[i], scalars[i], mv_idx[mv_off[i]:mv_off[i + 1]]) for i in range(5)]
+    boards[2] = EncodedBoard(bits[2], scalars[2], np.zeros(0, np.uint32))  # terminal: no available moves
+    with B200Network(mapper_for(spec), onnx_bytes, 8, precision=PRECISION_FP32) as net:
+        assert net.max_batch_size() == 8
+        evals = net.evaluate_batch(boards)
+        single = net.evaluate(boards[3])
+    assert len(evals) == 5
+    assert evals[2].policy.shape == (0,)  # common.rs:77
+    for i, e in enumerate(evals):
+        assert -1 < e.values.value < 1 and abs(sum(e.values.wdl) - 1) < 1e-5
+        if i != 2:
+            assert e.policy.shape == (len(boards[i].policy_indices),) and abs(e.policy.sum() - 1) < 1e-5
+    assert np.array_equal(single.policy, evals[3].policy)
+
+
+def test_errors_match_reference_panics():
+    spec = netgen.game_spec("ataxx-7")
+    onnx_bytes = netgen.build_onnx(spec, 1, 16, seed=16)
+    bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, 9, seed=17)
+    with B200Network(mapper_for(spec), onnx_bytes, 8, precision=PRECISION_FP32) as net:
+        with pytest.raises(KzbError, match="max_batch_size"):  # cudnn.rs:58
+            net.evaluate_packed(bits, scalars, mv_idx, mv_off)
+        bad = scalars[:4].copy()
+        bad[1, 0] = np.nan  # NaN input -> NaN logits -> the reference panics in softmax (common.rs:110)
+        with pytest.raises(KzbError, match="strictly positive"):
+            net.evaluate_packed(bits[:4], bad, mv_idx[: mv_off[4]], mv_off[:5])
+        # the handle stays usable after an error
+        v, p = net.evaluate_packed(bits[:4], scalars[:4], mv_idx[: mv_off[4]], mv_off[:5])
+        assert np.isfinite(v).all() and np.isfinite(p).all()
+    wrong = Mapper((spec.bool_channels + 1, 7, 7), spec.scalar_channels, (spec.policy_size,))
+    with pytest.raises(KzbError, match="Input shape mismatch"):  # common.rs:171-174
+        B200Network(wrong, onnx_bytes, 8)
+    wrong = Mapper((spec.bool_channels, 7, 7), spec.scalar_channels, (spec.policy_size + 1,))
+    with pytest.raises(KzbError, match="policy shape"):  # common.rs:182
+        B200Network(wrong, onnx_bytes, 8)
+
+
+def test_concurrent_instances_match(tmp_path):
+    """Pattern of rust/kz-misc/src/bin/test_concurrent.rs:32-145: several executors on one device, each in
+    its own thread, must keep reproducing the same outputs."""
+    import threading
+
+    spec = netgen.game_spec("chess")
+    onnx_bytes = netgen.build_onnx(spec, 2, 32, seed=18)
+    bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, 48, seed=19)
+    with B200Network(mapper_for(spec), onnx_bytes, 48) as net:
+        ref_v, ref_p = net.evaluate_packed(bits, scalars, mv_idx, mv_off)
+    failures = []
+
+    def worker():
+        try:
+            with B200Network(mapper_for(spec), onnx_bytes, 48) as n2:
+                for _ in range(10):
+                    v, p = n2.evaluate_packed(bits, scalars, mv_idx, mv_off)
+                    if not (np.array_equal(v, ref_v) and np.array_equal(p, ref_p)):
+                        failures.append("mismatch")
+        except Exception as e:  # noqa: BLE001
+            failures.append(repr(e))
+
+    threads = [threading.Thread(target=worker) for _ in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not failures, failures
