@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(THREADS) conv_fp32_kernel(ConvF32Params p) {
             int co = n0 + tx * 4 + j;
             if (co >= p.cout) continue;
             float v = acc[i][j] + p.bias[co];
-            if (co < p.relu_n) v = fmaxf(v, 0.0f);
+            if (co < p.relu_n) v = v < 0.0f ? 0.0f : v;  // NaN stays NaN, like torch/ONNX Relu
             if (p.res) v += p.res[row * p.res_stride + co];
             p.out[row * p.out_stride + co] = v;
         }

@@ -28,7 +28,7 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-template <bool PACKED>
+template <bool PACKED, int HPL>  // HPL = hidden units per lane = ceil(hs / 32)
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) heads_tail_kernel(HeadsTailParams p) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -51,22 +51,34 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) heads_tail_kernel(HeadsTa
     }
     __syncwarp();
 
-    // fc1 + relu: lane owns hidden units lane, lane+32, ...
-    float h[kMaxHiddenPerLane];
+    // fc1 + relu: lane owns hidden units lane, lane+32, ...; 8 inputs per step so 8*HPL independent
+    // weight loads are in flight (the loop is latency-bound otherwise); accumulation order stays i-ascending
+    float h[HPL];
 #pragma unroll
-    for (int u = 0; u < kMaxHiddenPerLane; u++) h[u] = 0.0f;
-    for (int i = 0; i < n_in; i++) {
-        float v = s_in[i];
+    for (int u = 0; u < HPL; u++) h[u] = 0.0f;
+    for (int i0 = 0; i0 < n_in; i0 += 8) {
+        float w[8][HPL], v[8];
 #pragma unroll
-        for (int u = 0; u < kMaxHiddenPerLane; u++) {
-            int j = lane + 32 * u;
-            if (j < p.hs) h[u] = fmaf(p.fc1_t[size_t(i) * p.hs + j], v, h[u]);
+        for (int k = 0; k < 8; k++) {
+            const int i = i0 + k;
+            const bool ok = i < n_in;
+            v[k] = ok ? s_in[i] : 0.0f;
+#pragma unroll
+            for (int u = 0; u < HPL; u++) {
+                const int j = lane + 32 * u;
+                w[k][u] = (ok && j < p.hs) ? __ldg(p.fc1_t + size_t(i) * p.hs + j) : 0.0f;
+            }
         }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+#pragma unroll
+            for (int u = 0; u < HPL; u++) h[u] = fmaf(w[k][u], v[k], h[u]);
     }
 #pragma unroll
-    for (int u = 0; u < kMaxHiddenPerLane; u++) {
-        int j = lane + 32 * u;
-        h[u] = j < p.hs ? fmaxf(h[u] + p.fc1_b[j], 0.0f) : 0.0f;
+    for (int u = 0; u < HPL; u++) {
+        const int j = lane + 32 * u;
+        float t = j < p.hs ? h[u] + p.fc1_b[j] : 0.0f;
+        h[u] = t < 0.0f ? 0.0f : t;
     }
     // fc2: 5 outputs
     float sc[5];
@@ -74,7 +86,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) heads_tail_kernel(HeadsTa
     for (int k = 0; k < 5; k++) {
         float part = 0.0f;
 #pragma unroll
-        for (int u = 0; u < kMaxHiddenPerLane; u++) {
+        for (int u = 0; u < HPL; u++) {
             int j = lane + 32 * u;
             if (j < p.hs) part = fmaf(p.fc2_w[k * p.hs + j], h[u], part);
         }
@@ -110,6 +122,41 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) heads_tail_kernel(HeadsTa
     const uint32_t o0 = p.mv_off[b], o1 = p.mv_off[b + 1];
     const int n = int(o1 - o0);
     if (n <= 0) return;  // terminal board: empty policy (common.rs:77)
+    constexpr int kRegMoves = 12;  // up to 384 legal moves stay in registers (chess <= 218, go-19 <= 362)
+    if (n <= 32 * kRegMoves) {
+        float l[kRegMoves];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < kRegMoves; k++) {
+            const int j = lane + 32 * k;
+            l[k] = -INFINITY;
+            if (j < n) {
+                uint32_t idx = p.mv_idx[o0 + j];
+                l[k] = idx < uint32_t(p.policy_len) ? logit(int(idx)) : NAN;
+                mx = fmaxf(mx, l[k]);
+            }
+        }
+        mx = warp_max(mx);
+        float sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kRegMoves; k++) {
+            const int j = lane + 32 * k;
+            if (j < n) {
+                l[k] = expf(l[k] - mx);
+                sum += l[k];
+            }
+        }
+        sum = warp_sum(sum);
+        if (!(sum > 0.0f)) {  // NaN logits: the reference panics here (common.rs:110)
+            if (lane == 0) atomicCAS(p.err_flag, 0, 1 + b);
+        }
+#pragma unroll
+        for (int k = 0; k < kRegMoves; k++) {
+            const int j = lane + 32 * k;
+            if (j < n) p.out_probs[o0 + j] = l[k] / sum;
+        }
+        return;
+    }
     float mx = -INFINITY;
     for (int j = lane; j < n; j += 32) {
         uint32_t idx = p.mv_idx[o0 + j];
@@ -125,7 +172,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) heads_tail_kernel(HeadsTa
         sum += e;
     }
     sum = warp_sum(sum);
-    if (!(sum > 0.0f)) {  // NaN logits: the reference panics here (common.rs:110)
+    if (!(sum > 0.0f)) {
         if (lane == 0) atomicCAS(p.err_flag, 0, 1 + b);
     }
     for (int j = lane; j < n; j += 32) p.out_probs[o0 + j] /= sum;
@@ -137,10 +184,18 @@ void launch_heads_tail(const HeadsTailParams& p, bool packed, cudaStream_t s) {
     if (p.batch <= 0) return;
     int blocks = (p.batch + kWarpsPerBlock - 1) / kWarpsPerBlock;
     size_t smem = size_t(kWarpsPerBlock) * p.hc * p.lay.W * p.lay.H * sizeof(float);
-    if (packed)
-        heads_tail_kernel<true><<<blocks, kWarpsPerBlock * 32, smem, s>>>(p);
-    else
-        heads_tail_kernel<false><<<blocks, kWarpsPerBlock * 32, smem, s>>>(p);
+    const int hpl = (p.hs + 31) / 32;
+#define KZB_TAIL(PACKED, HPL) heads_tail_kernel<PACKED, HPL><<<blocks, kWarpsPerBlock * 32, smem, s>>>(p)
+    if (packed) {
+        if (hpl <= 1) KZB_TAIL(true, 1);
+        else if (hpl == 2) KZB_TAIL(true, 2);
+        else KZB_TAIL(true, 4);
+    } else {
+        if (hpl <= 1) KZB_TAIL(false, 1);
+        else if (hpl == 2) KZB_TAIL(false, 2);
+        else KZB_TAIL(false, 4);
+    }
+#undef KZB_TAIL
 }
 
 }  // namespace kzb
