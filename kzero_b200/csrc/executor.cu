@@ -1,5 +1,6 @@
 #include "executor.hpp"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -167,7 +168,11 @@ void Net::build_bf16() {
     else
         lay_ = RowLayout{W, H, W + 1, (W + 1) * (H + 1)};
     const int boards_per_tile = mode_ == 1 ? 128 / (W * H) : 0;
-    const int boards_alloc = mode_ == 1 ? round_up(max_batch_, boards_per_tile) : max_batch_;
+    const int boards_alloc = mode_ == 1 ? round_up(max_batch_, 4) : max_batch_;
+    const char* no_tc8 = std::getenv("KZB_NO_CONV8");
+    const bool allow_tc8 = mode_ == 1 && !(no_tc8 && no_tc8[0] == '1');
+    conv_tc_prepare();
+    conv_tc8_prepare();
     rows_alloc_ = round_up(boards_alloc * lay_.board_pitch, 128);
     cin_pad_ = round_up(spec_.cin, 64);
     c_pad_ = round_up(C, 64);
@@ -214,6 +219,18 @@ void Net::build_bf16() {
             uint32_t box[2] = {64, 128};
             st->tmap_a = make_tmap(in.ptr, 2, dims, strides, box);
         }
+        if (allow_tc8 && st->taps == 9 && n <= 128 && !out_f32) {
+            // (c, x, board, y)-ordered view of the same rows, box (64, 8, 4 boards, 10 ranks incl. halo)
+            uint64_t dims[4] = {uint64_t(in_stride), 8, uint64_t(rows_alloc_ / 64), 8};
+            uint64_t strides[3] = {uint64_t(in_stride) * 2, uint64_t(in_stride) * 2 * 64, uint64_t(in_stride) * 2 * 8};
+            uint32_t box[4] = {64, 8, 4, 10};
+            st->tmap_a8 = make_tmap(in.ptr, 4, dims, strides, box);
+            st->use_tc8 = true;
+            st->tc8_b_slots = conv_tc8_pick_b_slots(n);
+            int c8 = 32;
+            while (c8 < 4 * n) c8 *= 2;
+            st->tc8_tmem_cols = c8;
+        }
         ConvTcParams& p = st->tc;
         p.taps = st->taps;
         p.cin_pad = cin_pad;
@@ -245,6 +262,65 @@ void Net::build_bf16() {
     add("policy_conv1", spec_.policy_conv1, act_x_, c_pad_, nullptr, act_h1_, cp_pad_, false, cp_pad_, cp_pad_);
     add("scalar_conv", merged_small_conv(spec_), act_x_, c_pad_, nullptr, act_s1_, s1_stride_, true, 16, spec_.scalar_conv.cout);
     add("policy_conv2", spec_.policy_conv2, act_h1_, cp_pad_, nullptr, act_pm_, pm_stride_, true, pm_stride_, 0);
+
+    // whole-tower persistent kernel: all 2*depth+1 conv3x3 layers in one launch (tower8.cu)
+    const char* no_t8 = std::getenv("KZB_NO_TOWER8");
+    const int units_max = (max_batch_ + 3) / 4;
+    if (allow_tc8 && c_pad_ <= 128 && !(no_t8 && no_t8[0] == '1') &&
+        (units_max + num_sms_ - 1) / num_sms_ <= tower8_max_local_units()) {
+        tower8_prepare();
+        tower_layers_ = 1 + 2 * spec_.depth;
+        const int n = c_pad_;
+        auto amap = [&](DeviceBuffer& buf, int stride) {
+            uint64_t dims[4] = {uint64_t(stride), 8, uint64_t(rows_alloc_ / 64), 8};
+            uint64_t strides[3] = {uint64_t(stride) * 2, uint64_t(stride) * 2 * 64, uint64_t(stride) * 2 * 8};
+            uint32_t box[4] = {64, 8, 4, 8};
+            return make_tmap(buf.ptr, 4, dims, strides, box);
+        };
+        tower_maps_.a[0] = amap(act_in_, cin_pad_);
+        tower_maps_.a[1] = amap(act_x_, c_pad_);
+        tower_maps_.a[2] = amap(act_t_, c_pad_);
+        tower_maps_.w[0] = convs_[0]->tmap_b;
+        const size_t layer_w_bytes = size_t(n) * 9 * c_pad_ * 2;
+        w_tower_.alloc(std::max<size_t>(layer_w_bytes * 2 * spec_.depth, 256), true);
+        for (int i = 0; i < 2 * spec_.depth; i++)
+            CK(cudaMemcpy(w_tower_.as<uint8_t>() + layer_w_bytes * i, convs_[1 + i]->w_bf16.ptr, layer_w_bytes, cudaMemcpyDeviceToDevice));
+        {
+            uint64_t dims[2] = {uint64_t(9 * c_pad_), uint64_t(std::max(1, 2 * spec_.depth) * n)};
+            uint64_t strides[1] = {uint64_t(9 * c_pad_) * 2};
+            uint32_t box[2] = {64, uint32_t(n)};
+            tower_maps_.w[1] = make_tmap(w_tower_.ptr, 2, dims, strides, box);
+        }
+        std::vector<TowerLayerDev> layers(tower_layers_);
+        for (int i = 0; i < tower_layers_; i++) {
+            TowerLayerDev& l = layers[i];
+            const bool first = i == 0, conv2 = !first && (i % 2 == 0);
+            l.a_map = first ? 0 : (conv2 ? 2 : 1);
+            l.w_map = first ? 0 : 1;
+            l.w_row0 = first ? 0 : (i - 1) * n;
+            l.cin_pad = first ? cin_pad_ : c_pad_;
+            l.kblocks = l.cin_pad / 64;
+            l.relu_n = first ? 0 : n;
+            l.has_res = conv2 ? 1 : 0;
+            l.out_buf = (first || conv2) ? 1 : 2;
+            l.bias = convs_[i]->bias.as<float>();
+        }
+        upload(d_tower_layers_, layers);
+        Tower8Params& tp = tower_params_;
+        tp.num_layers = tower_layers_;
+        tp.layers = d_tower_layers_.as<TowerLayerDev>();
+        tp.n = n;
+        tp.n_store = n;
+        tp.x = act_x_.as<__nv_bfloat16>();
+        tp.t = act_t_.as<__nv_bfloat16>();
+        tp.stride = c_pad_;
+        tp.b_slots = tower8_pick_b_slots(n);
+        int cols = 32;
+        while (cols < 4 * n) cols *= 2;
+        tp.tmem_cols = cols;
+        tp.timeline = nullptr;
+        use_tower8_ = true;
+    }
 }
 
 void Net::build_f32() {
@@ -391,9 +467,31 @@ void Net::run_encode(int batch, const StepHook& hook) {
 }
 
 void Net::run_network(int batch, const StepHook& hook) {
-    for (auto& st : convs_) {
+    size_t first_step = 0;
+    if (use_tower8_) {
+        Tower8Params tp = tower_params_;
+        tp.num_units = (batch + 3) / 4;
+        tp.valid_rows = batch * 64;
+        if (timeline_step_ == "tower8") tp.timeline = d_timeline_.as<unsigned long long>();
+        launch_tower8(tower_maps_, tp, num_sms_, stream_);
+        if (hook) hook("tower8");
+        first_step = size_t(tower_layers_);
+    }
+    for (size_t si = first_step; si < convs_.size(); si++) {
+        auto& st = convs_[si];
         if (precision_ == 1) {
             ConvTcParams p = st->tc;
+            p.timeline = nullptr;
+            if (st->use_tc8) {
+                if (timeline_step_ == st->name) p.timeline = d_timeline_.as<unsigned long long>();
+                p.num_tiles = (batch + 3) / 4;
+                p.valid_rows = batch * 64;
+                p.stages = st->tc8_b_slots;
+                p.tmem_cols = st->tc8_tmem_cols;
+                launch_conv_tc8(st->tmap_a8, st->tmap_b, p, num_sms_, stream_);
+                if (hook) hook(st->name.c_str());
+                continue;
+            }
             if (mode_ == 1) {
                 p.num_tiles = (batch + p.boards_per_tile - 1) / p.boards_per_tile;
                 p.valid_rows = batch * lay_.board_pitch;
@@ -537,6 +635,11 @@ void Net::profile_staged(bool flush, std::vector<std::string>& names, std::vecto
     require_mapper();
     if (staged_batch_ <= 0) throw std::runtime_error("no staged batch: call kzb_stage_packed first");
     CK(cudaSetDevice(device_));
+    const char* tl_env = std::getenv("KZB_TIMELINE");  // development aid: per-CTA clock stamps of one conv step
+    if (tl_env && tl_env[0]) {
+        timeline_step_ = tl_env;
+        d_timeline_.alloc(size_t(num_sms_) * 16 * 8, true);
+    }
     std::vector<cudaEvent_t> ev;
     names.clear();
     auto mark = [&]() {
@@ -559,6 +662,18 @@ void Net::profile_staged(bool flush, std::vector<std::string>& names, std::vecto
     ms.resize(names.size());
     for (size_t i = 0; i < names.size(); i++) CK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
     for (auto& e : ev) cudaEventDestroy(e);
+    if (!timeline_step_.empty()) {
+        std::vector<unsigned long long> h(size_t(num_sms_) * 16);
+        CK(cudaMemcpy(h.data(), d_timeline_.ptr, h.size() * 8, cudaMemcpyDeviceToHost));
+        if (FILE* f = std::fopen("gpurun_out/timeline.txt", "w")) {
+            for (int c = 0; c < num_sms_; c++) {
+                for (int j = 0; j < 13; j++) std::fprintf(f, "%lld ", h[c * 16 + j] ? (long long)(h[c * 16 + j] - h[c * 16]) : -1LL);
+                std::fprintf(f, "\n");
+            }
+            std::fclose(f);
+        }
+        timeline_step_.clear();
+    }
 }
 
 }  // namespace kzb

@@ -47,6 +47,9 @@ struct ConvStep {
     // bf16 tensor-core form
     CUtensorMap tmap_a{}, tmap_b{};
     ConvTcParams tc{};
+    bool use_tc8 = false;  // 8x8-board specialisation (conv_tc8.cu)
+    CUtensorMap tmap_a8{};
+    int tc8_b_slots = 0, tc8_tmem_cols = 0;
     DeviceBuffer w_bf16;  // [n][taps*cin_pad]
     // fp32 form
     ConvF32Params f32{};
@@ -67,7 +70,7 @@ public:
     void stage_packed(const uint8_t* bits, const float* scalars, int batch, const uint32_t* mv_idx, const uint32_t* mv_off);
     void time_staged(int iters, bool flush_l2, float* ms_out);
     void profile_staged(bool flush_l2, std::vector<std::string>& names, std::vector<float>& ms);
-    int launches_per_eval() const { return int(convs_.size()) + 2; }
+    int launches_per_eval() const { return int(convs_.size()) + 2 - (use_tower8_ ? tower_layers_ - 1 : 0); }
 
     const NetSpec& spec() const { return spec_; }
     int device() const { return device_; }
@@ -103,13 +106,21 @@ private:
     DeviceBuffer act_in_, act_x_, act_t_, act_h1_, act_s1_, act_pm_;
     DeviceBuffer d_fc1_t_, d_fc1_b_, d_fc2_w_, d_fc2_b_, d_extra_w_, d_policy_src_;
     DeviceBuffer d_out_scalars_, d_out_logits_, d_out_values_, d_out_probs_, d_err_;
-    DeviceBuffer d_flush_;
+    DeviceBuffer d_flush_, d_timeline_;
+    std::string timeline_step_;
     PinnedBuffer h_in_, h_out_;
     size_t mv_cap_ = 0;
     int staged_batch_ = 0;
     size_t staged_moves_ = 0;
 
     std::vector<std::unique_ptr<ConvStep>> convs_;
+
+    // whole-tower persistent kernel (8x8 boards): covers convs_[0 .. tower_layers_)
+    bool use_tower8_ = false;
+    int tower_layers_ = 0;
+    Tower8Maps tower_maps_{};
+    Tower8Params tower_params_{};
+    DeviceBuffer d_tower_layers_, w_tower_;
 };
 
 // thread-local error plumbing for the C ABI

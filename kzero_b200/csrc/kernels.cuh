@@ -80,11 +80,55 @@ struct ConvTcParams {
     int n_store;  // channels written per row (multiple of 16, <= n)
     int stages;
     int tmem_cols;
+    // development aid: when non-null, each CTA writes 16 clock64() stamps (see conv_tc8.cu) -- KZB_TIMELINE=1
+    unsigned long long* timeline;
 };
 void launch_conv_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ConvTcParams& p, int grid,
                     cudaStream_t s);
 size_t conv_tc_smem_bytes(int n, int stages);
 int conv_tc_pick_stages(int n);
+void conv_tc_prepare();  // per-device: opt in to 227 KB dynamic shared memory
+
+// 8x8-board specialisation (conv_tc8.cu): p.num_tiles counts 4-board work units, p.stages is the number
+// of weight-ring slots, tmap_a is the (c, x, board, y)-ordered map with box (64, 8, 4, 10).
+void launch_conv_tc8(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ConvTcParams& p, int grid,
+                     cudaStream_t s);
+size_t conv_tc8_smem_bytes(int n, int b_slots);
+int conv_tc8_pick_b_slots(int n);
+void conv_tc8_prepare();
+
+// whole-tower persistent kernel for 8x8 boards (tower8.cu)
+struct TowerLayerDev {
+    int a_map;   // input activations: 0 = encoded planes, 1 = X (residual stream), 2 = T (block-internal)
+    int w_map;   // 0 = first-layer weights, 1 = concatenated block weights
+    int w_row0;  // first row of this layer inside its weight matrix
+    int kblocks, cin_pad;
+    int relu_n;
+    int has_res;  // add X (same rows) after the relu
+    int out_buf;  // 1 = X, 2 = T
+    const float* bias;
+};
+struct Tower8Maps {
+    CUtensorMap a[3];
+    CUtensorMap w[2];
+};
+struct Tower8Params {
+    int num_layers;
+    const TowerLayerDev* layers;  // device memory
+    int num_units;                // 4-board work units
+    int valid_rows;
+    int n, n_store;
+    __nv_bfloat16* x;
+    __nv_bfloat16* t;
+    int stride;  // elements per row of X / T
+    int b_slots, tmem_cols;
+    unsigned long long* timeline;
+};
+void launch_tower8(const Tower8Maps& maps, const Tower8Params& p, int grid, cudaStream_t s);
+size_t tower8_smem_bytes(int n, int b_slots);
+int tower8_pick_b_slots(int n);
+int tower8_max_local_units();
+void tower8_prepare();
 
 // ---------------------------------------------------------------------------------------------- K3
 struct HeadsTailParams {
