@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- NN positions/sec of the self-play inference hot path on B200 (contract: see the task prompt).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config chess|ataxx|go9]
+
+A "step" = one pass of the hot path over one batch of synthetic positions: packed (bits, scalars) ->
+plane encoding -> conv tower -> heads -> legal-move-masked softmax.  Default workload = BASELINE.json
+configs[1]: chess 8x8 ResNet 16x128, kz-core chess mapping (21 planes in, 1880-move policy), batch 1024, bf16
+tensor-core path.  Multi-GPU = independent replicas sharded by game (no collective on the data path), so
+--gpus N under torchrun is weak scaling: every rank evaluates its own batches.
+
+Printed JSON (one line, rank 0):
+  value      positions/s, whole job, device-timed (CUDA events on the network's stream), inputs resident in HBM
+  e2e        positions/s through the public call (kzb_eval_packed via B200Network.evaluate_packed) with HOST
+             buffers: H2D of the packed batch and D2H of values + legal-move probabilities inside the timed region
+  roofline   dominant kernel (the conv tower) algorithmic TFLOP/s vs the measured bf16 peak
+  cpu_baseline  the oracle (CPU restatement of the reference's CPU executor) on a bounded sample, host cores
+`--impl reference` times that CPU restatement (the reference's own crates cannot be built here: no Rust
+toolchain, kn-graph is an un-vendored crates.io dependency) on all host threads, same workload and metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from kzero_b200 import netgen  # noqa: E402
+
+CONFIGS = {
+    # BASELINE.json configs[1] -- the configuration the metric is quoted on
+    "chess": dict(game="chess", depth=16, channels=128, batch=1024,
+                  workload="chess 8x8 ResNet 16x128 (kz-core chess mapping: 21x8x8 planes, 1880-move policy, "
+                           "conv policy head), batch 1024"),
+    # BASELINE.json configs[0] -- the reference's own CPU-runnable case
+    "ataxx": dict(game="ataxx-7", depth=8, channels=64, batch=256,
+                  workload="ataxx 7x7 ResNet 8x64, batch 256"),
+    "go9": dict(game="go-9", depth=20, channels=256, batch=4096,
+                workload="go 9x9 ResNet 20x256, batch 4096"),
+}
+N_INPUT_SETS = 4  # distinct synthetic batches rotated through the e2e loop
+
+
+def measured_peaks():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        d = json.loads(path.read_text())
+        return dict(tflops_sustained=float(d["bf16_tflops_sustained"]), tflops_burst=float(d["bf16_tflops"]),
+                    hbm_gbs=float(d["hbm_gbs"]), source="MEASURED_PEAKS.json")
+    # fallback stated in /opt/skills/guides/B200_PROFILING.md
+    return dict(tflops_sustained=1400.0, tflops_burst=1590.0, hbm_gbs=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                power.append(float(r[3]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, pw in zip(sm, power) if pw >= 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power))}
+
+
+def cpu_restatement_rate(cfg, onnx_bytes, spec, seconds_target: float, threads: int):
+    """positions/s of the oracle (expand planes -> ONNX graph in f32 -> decode_output) on `threads` host threads."""
+    import oracle
+    from oracle.graph_exec import OnnxOracle
+
+    oracle.set_threads(threads)
+    net = OnnxOracle(onnx_bytes)
+
+    def run(n, seed):
+        bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, n, seed=seed)
+        t0 = time.perf_counter()
+        planes = oracle.expand_planes(bits, scalars, (spec.bool_channels, spec.board_size, spec.board_size),
+                                      spec.scalar_channels)
+        s, p = net.run(planes)
+        oracle.decode_output(s, p, mv_idx, mv_off)
+        return time.perf_counter() - t0
+
+    probe_n = max(2, min(cfg["batch"], threads))
+    dt = run(probe_n, 100)
+    n = int(max(probe_n, min(cfg["batch"], seconds_target / max(dt / probe_n, 1e-9))))
+    dt = run(n, 101)
+    return n / dt, n, dt
+
+
+def run_reference(args, cfg, spec, onnx_bytes):
+    """--impl reference: the reference's CPU implementation of the path (restated; see module docstring)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rates = []
+    sample = 0
+    total = args.steps + args.warmup
+    per_step_seconds = max(2.0, min(20.0, 120.0 / total))
+    t_steps = []
+    for i in range(total):
+        rate, n, dt = cpu_restatement_rate(cfg, onnx_bytes, spec, per_step_seconds, threads)
+        if i >= args.warmup:
+            rates.append(rate)
+            t_steps.append(dt)
+            sample = n
+    value = float(np.mean(rates))
+    desc = (f"{sample} positions per step of the same workload (bounded sample; rate is per position so it "
+            f"extrapolates linearly to batch {cfg['batch']})")
+    line = {
+        "impl": "reference", "metric": "NN positions/sec", "value": value, "unit": "positions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean(t_steps) * 1e3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "batch_per_gpu": cfg["batch"], "sample_positions_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "positions/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement of kn-graph's CPU executor path (oracle/): the reference's Rust crates cannot be "
+                "built in this image (no cargo/rustc; kn-graph 0.7.3 is not vendored)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="chess", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    cfg = CONFIGS[args.config]
+    spec = netgen.game_spec(cfg["game"])
+    onnx_bytes = netgen.build_onnx(spec, cfg["depth"], cfg["channels"], seed=0)
+
+    if args.impl == "reference":
+        run_reference(args, cfg, spec, onnx_bytes)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from kzero_b200.network import B200Network, PRECISION_BF16, mapper_for
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batch = cfg["batch"]
+    net = B200Network(mapper_for(spec), onnx_bytes, batch, device=local_rank, precision=PRECISION_BF16)
+    info = net.info()
+    inputs = [netgen.synthetic_positions(spec, batch, seed=1000 * rank + i) for i in range(N_INPUT_SETS)]
+
+    # ---- device-resident throughput ("value"): K steps, each timed with CUDA events on the net's stream,
+    #      L2 flushed (256 MiB memset) before every step outside the timed region
+    for i in range(args.warmup):
+        net.evaluate_packed(*inputs[i % N_INPUT_SETS])
+    net.stage_packed(*inputs[0])
+    net.time_staged(args.warmup, True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    step_ms = net.time_staged(args.steps, True)
+    torch.cuda.synchronize()
+    wall_value = time.perf_counter() - wall0
+    barrier()
+
+    # ---- per-launch durations for the roofline of the dominant kernel (same staged batch, same stream)
+    tower_ms, all_ms = [], []
+    for _ in range(10):
+        names, ms = net.profile_staged(True)
+        all_ms.append(ms)
+        tower_ms.append(sum(m for n, m in zip(names, ms) if n == "tower8" or n.startswith("conv_first") or n.startswith("block")))
+    tower_launches = sum(1 for n in names if n == "tower8" or n.startswith("conv_first") or n.startswith("block"))
+    share = {n: float(np.mean([m[i] for m in all_ms])) for i, n in enumerate(names)}
+
+    # ---- end to end through the public call, host buffers in, host buffers out
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        net.evaluate_packed(*inputs[i % N_INPUT_SETS])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+
+    dev_s = float(step_ms.sum()) * 1e-3
+    times = torch.tensor([dev_s, e2e_s, wall_value], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_s, e2e_s, wall_value = (float(v) for v in times.tolist())
+
+    if rank == 0:
+        peaks = measured_peaks()
+        a = spec.area
+        tower_flops = batch * (2.0 * a * 9 * spec.input_channels * cfg["channels"]
+                               + cfg["depth"] * 2 * (2.0 * a * 9 * cfg["channels"] ** 2))
+        tower_s = float(np.mean(tower_ms)) * 1e-3
+        achieved = tower_flops / tower_s / 1e12
+        bits, scalars, mv_idx, mv_off = inputs[0]
+        h2d = int((batch + 1) * 4 + scalars.nbytes + bits.nbytes + mv_idx.nbytes)
+        d2h = int(16 + batch * 5 * 4 + mv_idx.nbytes)
+        traffic = None
+        tpath = ROOT / "profiles" / "tower_dram_traffic.json"
+        if tpath.exists() and args.config == "chess":
+            traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
+        line = {
+            "metric": "NN positions/sec", "value": world * batch * args.steps / dev_s, "unit": "positions/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "batch_per_gpu": batch, "parallelism": f"replicas x{world} (sharded by game, no collective)",
+                       "l2": "flushed before every timed step (256 MiB memset, untimed)", "conv_mode": int(info.conv_mode),
+                       "flops_per_position": float(info.flops_per_position)},
+            "e2e": {"value": world * batch * args.steps / e2e_s, "unit": "positions/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "inputs": f"{N_INPUT_SETS} distinct synthetic batches rotated, host numpy buffers"},
+            "gpu_launches": int(net.launches_per_eval() * args.steps),
+            "launches_per_step": int(net.launches_per_eval()),
+            "tflops_whole_step": float(info.flops_per_position) * batch * args.steps / dev_s / 1e12,
+            "roofline": {"bound": "tensor", "kernel": "tower8_kernel" if "tower8" in share else "conv_tc_kernel",
+                         "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["tflops_sustained"], "frac_of_burst_peak": achieved / peaks["tflops_burst"],
+                         "peak_source": peaks["source"] + " (bf16_tflops_sustained)", "traffic": traffic,
+                         "launches_per_step": tower_launches, "avg_launch_ms": tower_s * 1e3 / max(tower_launches, 1),
+                         "algorithmic_flops_per_launch": tower_flops / max(tower_launches, 1)},
+            "step_breakdown_ms": share,
+            "clocks": clocks,
+            "wall_ms_per_step_incl_flush": wall_value / args.steps * 1e3,
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rate, n, dt = cpu_restatement_rate(cfg, onnx_bytes, spec, 15.0, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "positions/s", "cores": threads, "kind": "port",
+                                    "sample": f"{n} positions of the same workload in {dt:.1f} s (oracle/: f32 ONNX graph "
+                                              "interpreter with C/OpenMP conv loops + plane expansion + decode_output)"}
+        print(json.dumps(line), flush=True)
+    net.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

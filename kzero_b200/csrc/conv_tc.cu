@@ -122,37 +122,40 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(kTileM, p.n);
-            int stage = 0;
-            uint32_t phase = 0;
-            int local = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, local++) {
-                const int buf = local & 1;
-                const uint32_t buf_phase = (local >> 1) & 1;
-                mbar_wait(&sm.tmem_empty[buf], buf_phase ^ 1);
+        // whole warp walks the loops (uniform datapath for the address arithmetic); lane 0 issues MMAs + commits
+        const uint32_t idesc = umma_idesc_bf16(kTileM, p.n);
+        const uint64_t desc_hi = umma_desc_sw128_hi();
+        int stage = 0;
+        uint32_t phase = 0;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, local++) {
+            const int buf = local & 1;
+            const uint32_t buf_phase = (local >> 1) & 1;
+            mbar_wait(&sm.tmem_empty[buf], buf_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + buf * acc_stride;
+            for (int it = 0; it < iters_per_tile; it++) {
+                mbar_wait(&sm.full[stage], phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + buf * acc_stride;
-                for (int it = 0; it < iters_per_tile; it++) {
-                    mbar_wait(&sm.full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sm.stage_base + size_t(stage) * stage_bytes);
-                    const uint32_t b_addr = a_addr + kABytes;
+                const uint32_t a_lo = umma_desc_lo(smem_u32(sm.stage_base + size_t(stage) * stage_bytes));
+                const uint32_t b_lo = a_lo + (kABytes >> 4);
+                if (lane == 0) {
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; k++) {
                         // advancing 16 bf16 = 32 bytes along K stays inside the 128-byte swizzle span
-                        uint64_t a_desc = umma_desc_sw128(a_addr + k * 32);
-                        uint64_t b_desc = umma_desc_sw128(b_addr + k * 32);
-                        umma_bf16(tmem_d, a_desc, b_desc, idesc, (it | k) != 0);
+                        umma_bf16(tmem_d, desc_hi | uint64_t(a_lo + 2 * k), desc_hi | uint64_t(b_lo + 2 * k), idesc,
+                                  (it | k) != 0);
                     }
                     umma_commit(&sm.empty[stage]);  // frees the smem slot once these MMAs have read it
-                    if (++stage == p.stages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
                 }
-                umma_commit(&sm.tmem_full[buf]);  // accumulator complete -> epilogue
+                __syncwarp();
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
+            if (lane == 0) umma_commit(&sm.tmem_full[buf]);  // accumulator complete -> epilogue
+            __syncwarp();
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)

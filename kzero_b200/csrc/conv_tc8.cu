@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int b_bytes = p.n * 128;
     const int num_units = p.num_tiles;  // here: 4-board units
-    unsigned long long* tl = p.timeline ? p.timeline + size_t(blockIdx.x) * 16 : nullptr;
+    unsigned long long* tl = p.timeline ? p.timeline + size_t(blockIdx.x) * 1024 : nullptr;
     if (tl && threadIdx.x == 0) tl[0] = clock64();
 
     if (warp == 0 && lane == 0) {
@@ -134,52 +134,58 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, p.n);
-            int a_slot = 0, b_slot = 0;
-            uint32_t a_phase = 0, b_phase = 0;
-            int local = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, local++) {
-                const int buf = local & 1;
-                mbar_wait(&sm.tmem_empty[buf], ((local >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + uint32_t(buf * 2) * acc_cols;
-                bool first = true;
-                for (int kb = 0; kb < p.kblocks; kb++) {
-                    for (int dx = -1; dx <= 1; dx++) {
-                        mbar_wait(&sm.a_full[a_slot], a_phase);
-                        if (tl && first && local < 2) tl[4 + local] = clock64();  // first operands of the unit landed
-                        const uint32_t a_addr = smem_u32(sm.a + size_t(a_slot) * kASlotBytes);
-                        for (int dy = -1; dy <= 1; dy++) {
-                            mbar_wait(&sm.b_full[b_slot], b_phase);
-                            tc_fence_after();
-                            const uint32_t b_addr = smem_u32(sm.b + size_t(b_slot) * b_bytes);
+        // whole warp walks the loops (uniform datapath for the address arithmetic); lane 0 issues MMAs + commits
+        const uint32_t idesc = umma_idesc_bf16(128, p.n);
+        const uint64_t desc_hi = umma_desc_sw128_hi();
+        int a_slot = 0, b_slot = 0;
+        uint32_t a_phase = 0, b_phase = 0;
+        int local = 0;
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, local++) {
+            const int buf = local & 1;
+            mbar_wait(&sm.tmem_empty[buf], ((local >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + uint32_t(buf * 2) * acc_cols;
+            bool first = true;
+            for (int kb = 0; kb < p.kblocks; kb++) {
+                for (int dx = -1; dx <= 1; dx++) {
+                    mbar_wait(&sm.a_full[a_slot], a_phase);
+                    if (tl && first && local < 2 && lane == 0) tl[4 + local] = clock64();  // first operands of the unit landed
+                    const uint32_t a_lo = umma_desc_lo(smem_u32(sm.a + size_t(a_slot) * kASlotBytes));
+                    for (int dy = -1; dy <= 1; dy++) {
+                        mbar_wait(&sm.b_full[b_slot], b_phase);
+                        tc_fence_after();
+                        const uint32_t b_lo = umma_desc_lo(smem_u32(sm.b + size_t(b_slot) * b_bytes));
+                        if (lane == 0) {
 #pragma unroll
                             for (int t = 0; t < 2; t++) {
-                                const uint32_t a_tile = a_addr + uint32_t((4 * t + 1 + dy) * kBoards) * 1024u;
+                                const uint32_t a_t = a_lo + uint32_t((4 * t + 1 + dy) * kBoards * (1024 >> 4));
 #pragma unroll
                                 for (int k = 0; k < 4; k++) {
-                                    umma_bf16(tmem_d + uint32_t(t) * acc_cols, umma_desc_sw128(a_tile + k * 32),
-                                              umma_desc_sw128(b_addr + k * 32), idesc, (!first || k != 0) ? 1u : 0u);
+                                    umma_bf16(tmem_d + uint32_t(t) * acc_cols, desc_hi | uint64_t(a_t + 2 * k),
+                                              desc_hi | uint64_t(b_lo + 2 * k), idesc, (!first || k != 0) ? 1u : 0u);
                                 }
                             }
-                            first = false;
                             umma_commit(&sm.b_empty[b_slot]);
-                            if (++b_slot == b_slots) {
-                                b_slot = 0;
-                                b_phase ^= 1;
-                            }
+                            if (dy == 1) umma_commit(&sm.a_empty[a_slot]);
                         }
-                        umma_commit(&sm.a_empty[a_slot]);
-                        if (++a_slot == kASlots) {
-                            a_slot = 0;
-                            a_phase ^= 1;
+                        __syncwarp();
+                        first = false;
+                        if (++b_slot == b_slots) {
+                            b_slot = 0;
+                            b_phase ^= 1;
                         }
                     }
+                    if (++a_slot == kASlots) {
+                        a_slot = 0;
+                        a_phase ^= 1;
+                    }
                 }
+            }
+            if (lane == 0) {
                 umma_commit(&sm.tmem_full[buf]);
                 if (tl && local < 2) tl[6 + local] = clock64();  // all MMAs of the unit issued
             }
+            __syncwarp();
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)

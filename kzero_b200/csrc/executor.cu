@@ -319,6 +319,10 @@ void Net::build_bf16() {
         while (cols < 4 * n) cols *= 2;
         tp.tmem_cols = cols;
         tp.timeline = nullptr;
+        const char* dbg = std::getenv("KZB_DEBUG");
+        tp.debug = dbg ? std::atoi(dbg) : 0;
+        const char* bs = std::getenv("KZB_B_SLOTS");
+        if (bs && std::atoi(bs) >= 2 && std::atoi(bs) <= tp.b_slots) tp.b_slots = std::atoi(bs);
         use_tower8_ = true;
     }
 }
@@ -638,7 +642,7 @@ void Net::profile_staged(bool flush, std::vector<std::string>& names, std::vecto
     const char* tl_env = std::getenv("KZB_TIMELINE");  // development aid: per-CTA clock stamps of one conv step
     if (tl_env && tl_env[0]) {
         timeline_step_ = tl_env;
-        d_timeline_.alloc(size_t(num_sms_) * 16 * 8, true);
+        d_timeline_.alloc(size_t(num_sms_) * 1024 * 8, true);
     }
     std::vector<cudaEvent_t> ev;
     names.clear();
@@ -663,11 +667,11 @@ void Net::profile_staged(bool flush, std::vector<std::string>& names, std::vecto
     for (size_t i = 0; i < names.size(); i++) CK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
     for (auto& e : ev) cudaEventDestroy(e);
     if (!timeline_step_.empty()) {
-        std::vector<unsigned long long> h(size_t(num_sms_) * 16);
+        std::vector<unsigned long long> h(size_t(num_sms_) * 1024);
         CK(cudaMemcpy(h.data(), d_timeline_.ptr, h.size() * 8, cudaMemcpyDeviceToHost));
         if (FILE* f = std::fopen("gpurun_out/timeline.txt", "w")) {
             for (int c = 0; c < num_sms_; c++) {
-                for (int j = 0; j < 13; j++) std::fprintf(f, "%lld ", h[c * 16 + j] ? (long long)(h[c * 16 + j] - h[c * 16]) : -1LL);
+                for (int j = 0; j < 1024; j++) std::fprintf(f, "%lld ", h[c * 1024 + j] ? (long long)(h[c * 1024 + j] - h[c * 1024]) : -1LL);
                 std::fprintf(f, "\n");
             }
             std::fclose(f);

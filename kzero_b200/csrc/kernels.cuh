@@ -123,6 +123,7 @@ struct Tower8Params {
     int stride;  // elements per row of X / T
     int b_slots, tmem_cols;
     unsigned long long* timeline;
+    int debug;  // development aid (KZB_DEBUG): 1 = skip A loads, 2 = skip B loads, 4 = skip epilogue memory traffic
 };
 void launch_tower8(const Tower8Maps& maps, const Tower8Params& p, int grid, cudaStream_t s);
 size_t tower8_smem_bytes(int n, int b_slots);

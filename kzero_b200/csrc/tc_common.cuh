@@ -62,6 +62,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// Same descriptor split into its address-independent upper part and the 14-bit start-address field, so the MMA
+// issue loop only does one integer add per operand (the issue thread is otherwise the bottleneck: measured
+// ~100 cycles per tcgen05.mma when the full descriptor is rebuilt each time vs 64 cycles of tensor work).
+__device__ __forceinline__ uint64_t umma_desc_sw128_hi() {
+    return (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return (smem_addr >> 4) & 0x3FFF; }
+
 // Instruction descriptor, kind::f16: c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1, both K-major,
 // N>>3 at [17,23), M>>4 at [24,29).
 __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {

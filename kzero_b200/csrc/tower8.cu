@@ -82,7 +82,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     const SmemT sm = carve_t(smem, p.n, p.b_slots);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int b_bytes = p.n * 128;
-    unsigned long long* tl = p.timeline ? p.timeline + size_t(blockIdx.x) * 16 : nullptr;
+    // development aid (KZB_TIMELINE=tower8): 1024 clock64() stamps per CTA, 8 per work item:
+    //   [0] tmem_empty acquired  [1] first operands landed  [2] MMAs issued  [3] accumulators complete
+    //   [4] epilogue done        [5] producer: ready acquired  [6] producer: unit's loads issued
+    unsigned long long* tl = p.timeline ? p.timeline + size_t(blockIdx.x) * 1024 : nullptr;
+#define KZB_STAMP(item, k) do { if (tl && (item) < 127) tl[8 + (item) * 8 + (k)] = clock64(); } while (0)
     if (tl && threadIdx.x == 0) tl[0] = clock64();
 
     if (warp == 0 && lane == 0) {
@@ -127,20 +131,26 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (lane == 0) {
             int a_slot = 0, b_slot = 0;
             uint32_t a_phase = 0, b_phase = 0;
+            int pitem = 0;
             for (int L = 0; L < p.num_layers; L++) {
                 const TowerLayerDev ld = p.layers[L];
                 const CUtensorMap* amap = &maps.a[ld.a_map];
                 const CUtensorMap* wmap = &maps.w[ld.w_map];
                 int ul = 0;
-                for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ul++) {
+                for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ul++, pitem++) {
                     // rows of this unit written by layer L-1's epilogue must be complete and visible
                     if (L > 0) mbar_wait(&sm.ready[ul], uint32_t(L - 1) & 1);
+                    KZB_STAMP(pitem, 5);
                     for (int kb = 0; kb < ld.kblocks; kb++) {
                         for (int dx = -1; dx <= 1; dx++) {
                             mbar_wait(&sm.a_empty[a_slot], a_phase ^ 1);
-                            mbar_expect_tx(&sm.a_full[a_slot], kABox);
-                            tma_load_4d(amap, &sm.a_full[a_slot], sm.a + kRankBytes + size_t(a_slot) * kAStride, kb * 64, dx,
-                                        unit * kBoards, 0);
+                            if (p.debug & 1) {
+                                mbar_arrive(&sm.a_full[a_slot]);
+                            } else {
+                                mbar_expect_tx(&sm.a_full[a_slot], kABox);
+                                tma_load_4d(amap, &sm.a_full[a_slot], sm.a + kRankBytes + size_t(a_slot) * kAStride, kb * 64, dx,
+                                            unit * kBoards, 0);
+                            }
                             if (++a_slot == kASlots) {
                                 a_slot = 0;
                                 a_phase ^= 1;
@@ -148,9 +158,13 @@ __global__ void __launch_bounds__(kThreads, 1)
                             for (int dy = -1; dy <= 1; dy++) {
                                 const int tap = (dy + 1) * 3 + (dx + 1);
                                 mbar_wait(&sm.b_empty[b_slot], b_phase ^ 1);
-                                mbar_expect_tx(&sm.b_full[b_slot], uint32_t(b_bytes));
-                                tma_load_2d(wmap, &sm.b_full[b_slot], sm.b + size_t(b_slot) * b_bytes,
-                                            tap * ld.cin_pad + kb * 64, ld.w_row0);
+                                if (p.debug & 2) {
+                                    mbar_arrive(&sm.b_full[b_slot]);
+                                } else {
+                                    mbar_expect_tx(&sm.b_full[b_slot], uint32_t(b_bytes));
+                                    tma_load_2d(wmap, &sm.b_full[b_slot], sm.b + size_t(b_slot) * b_bytes,
+                                                tap * ld.cin_pad + kb * 64, ld.w_row0);
+                                }
                                 if (++b_slot == p.b_slots) {
                                     b_slot = 0;
                                     b_phase ^= 1;
@@ -158,58 +172,69 @@ __global__ void __launch_bounds__(kThreads, 1)
                             }
                         }
                     }
+                    KZB_STAMP(pitem, 6);
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, p.n);
-            int a_slot = 0, b_slot = 0;
-            uint32_t a_phase = 0, b_phase = 0;
-            int item = 0;
-            for (int L = 0; L < p.num_layers; L++) {
-                const int kblocks = p.layers[L].kblocks;
-                for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, item++) {
-                    const int buf = item & 1;
-                    mbar_wait(&sm.tmem_empty[buf], ((item >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + uint32_t(buf * 2) * acc_cols;
-                    bool first = true;
-                    for (int kb = 0; kb < kblocks; kb++) {
-                        for (int dx = -1; dx <= 1; dx++) {
-                            mbar_wait(&sm.a_full[a_slot], a_phase);
-                            const uint32_t a_addr = smem_u32(sm.a + kRankBytes + size_t(a_slot) * kAStride);
-                            for (int dy = -1; dy <= 1; dy++) {
-                                mbar_wait(&sm.b_full[b_slot], b_phase);
-                                tc_fence_after();
-                                const uint32_t b_addr = smem_u32(sm.b + size_t(b_slot) * b_bytes);
+        // The whole warp walks the loops (warp-uniform control flow keeps the address arithmetic on the uniform
+        // datapath); lane 0 alone issues tcgen05.mma and the commits that track them.
+        const uint32_t idesc = umma_idesc_bf16(128, p.n);
+        const uint64_t desc_hi = umma_desc_sw128_hi();
+        int a_slot = 0, b_slot = 0;
+        uint32_t a_phase = 0, b_phase = 0;
+        int item = 0;
+        for (int L = 0; L < p.num_layers; L++) {
+            const int kblocks = p.layers[L].kblocks;
+            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, item++) {
+                const int buf = item & 1;
+                mbar_wait(&sm.tmem_empty[buf], ((item >> 1) & 1) ^ 1);
+                tc_fence_after();
+                if (lane == 0) KZB_STAMP(item, 0);
+                const uint32_t tmem_d = tmem_base + uint32_t(buf * 2) * acc_cols;
+                bool first = true;
+                for (int kb = 0; kb < kblocks; kb++) {
+                    for (int dx = -1; dx <= 1; dx++) {
+                        mbar_wait(&sm.a_full[a_slot], a_phase);
+                        if (first && lane == 0) KZB_STAMP(item, 1);
+                        const uint32_t a_lo = umma_desc_lo(smem_u32(sm.a + kRankBytes + size_t(a_slot) * kAStride));
+                        for (int dy = -1; dy <= 1; dy++) {
+                            mbar_wait(&sm.b_full[b_slot], b_phase);
+                            tc_fence_after();
+                            const uint32_t b_lo = umma_desc_lo(smem_u32(sm.b + size_t(b_slot) * b_bytes));
+                            if (lane == 0) {
 #pragma unroll
                                 for (int t = 0; t < 2; t++) {
                                     // tile t = ranks 4t..4t+3; tap dy starts dy ranks away (rank -1 / 8 = zero atoms)
-                                    const uint32_t a_tile = a_addr + uint32_t((4 * t + dy) * kRankBytes);
+                                    const uint32_t a_t = a_lo + uint32_t((4 * t + dy) * (kRankBytes >> 4));
 #pragma unroll
                                     for (int k = 0; k < 4; k++) {
-                                        umma_bf16(tmem_d + uint32_t(t) * acc_cols, umma_desc_sw128(a_tile + k * 32),
-                                                  umma_desc_sw128(b_addr + k * 32), idesc, (!first || k != 0) ? 1u : 0u);
+                                        umma_bf16(tmem_d + uint32_t(t) * acc_cols, desc_hi | uint64_t(a_t + 2 * k),
+                                                  desc_hi | uint64_t(b_lo + 2 * k), idesc, (!first || k != 0) ? 1u : 0u);
                                     }
                                 }
-                                first = false;
                                 umma_commit(&sm.b_empty[b_slot]);
-                                if (++b_slot == p.b_slots) {
-                                    b_slot = 0;
-                                    b_phase ^= 1;
-                                }
+                                if (dy == 1) umma_commit(&sm.a_empty[a_slot]);
                             }
-                            umma_commit(&sm.a_empty[a_slot]);
-                            if (++a_slot == kASlots) {
-                                a_slot = 0;
-                                a_phase ^= 1;
+                            __syncwarp();
+                            first = false;
+                            if (++b_slot == p.b_slots) {
+                                b_slot = 0;
+                                b_phase ^= 1;
                             }
                         }
+                        if (++a_slot == kASlots) {
+                            a_slot = 0;
+                            a_phase ^= 1;
+                        }
                     }
-                    umma_commit(&sm.tmem_full[buf]);
                 }
+                if (lane == 0) {
+                    umma_commit(&sm.tmem_full[buf]);
+                    KZB_STAMP(item, 2);
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -230,7 +255,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                 // tile t, TMEM lane quarter*32+lane  <->  rank 4t+quarter, board lane/8, file lane%8
                 const int row0 = board * 64 + quarter * 8 + (lane % 8);
                 const int row1 = row0 + 32;
-                const bool store0 = row0 < p.valid_rows, store1 = row1 < p.valid_rows;
+                const bool live = !(p.debug & 4);
+                const bool store0 = live && row0 < p.valid_rows, store1 = live && row1 < p.valid_rows;
 
                 // residual rows (bf16) fetched before the accumulator is waited for: latency hides behind the MMAs
                 uint32_t res[2][64];
@@ -248,6 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 }
                 mbar_wait(&sm.tmem_full[buf], (item >> 1) & 1);
                 tc_fence_after();
+                if (warp == 2 && lane == 0) KZB_STAMP(item, 3);
 
 #pragma unroll
                 for (int t = 0; t < 2; t++) {
@@ -299,6 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 if (lane == 0) {
                     mbar_arrive(&sm.tmem_empty[buf]);
                     mbar_arrive(&sm.ready[ul]);
+                    if (warp == 2) KZB_STAMP(item, 4);
                 }
             }
         }
