@@ -36,7 +36,8 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // bf16 tensor map, SWIZZLE_128B, zero OOB fill.  dims/box innermost first; strides in bytes for dims 1..rank-1.
-CUtensorMap make_tmap(void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+CUtensorMap make_tmap(void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                      bool swizzle128 = true) {
     CUtensorMap m;
     cuuint64_t gdim[5], gstr[4];
     cuuint32_t bdim[5], estr[5];
@@ -47,7 +48,8 @@ CUtensorMap make_tmap(void* base, int rank, const uint64_t* dims, const uint64_t
         if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
     }
     CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cuuint32_t(rank), base, gdim, gstr, bdim, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
     return m;
@@ -280,6 +282,15 @@ void Net::build_bf16() {
         tower_maps_.a[0] = amap(act_in_, cin_pad_);
         tower_maps_.a[1] = amap(act_x_, c_pad_);
         tower_maps_.a[2] = amap(act_t_, c_pad_);
+        auto omap = [&](DeviceBuffer& buf) {  // TMA store of one rank of a 4-board unit: [4 boards][8 x][c_pad]
+            uint64_t dims[4] = {uint64_t(c_pad_), 8, uint64_t(rows_alloc_ / 64), 8};
+            uint64_t strides[3] = {uint64_t(c_pad_) * 2, uint64_t(c_pad_) * 2 * 64, uint64_t(c_pad_) * 2 * 8};
+            uint32_t box[4] = {uint32_t(c_pad_), 8, 4, 1};
+            return make_tmap(buf.ptr, 4, dims, strides, box, false);
+        };
+        tower_maps_.out[0] = omap(act_x_);
+        tower_maps_.out[1] = omap(act_t_);
+        act_xt_.alloc(size_t(rows_alloc_ / 256 + 1) * 128 * 256 * 2);
         tower_maps_.w[0] = convs_[0]->tmap_b;
         const size_t layer_w_bytes = size_t(n) * 9 * c_pad_ * 2;
         w_tower_.alloc(std::max<size_t>(layer_w_bytes * 2 * spec_.depth, 256), true);
@@ -313,6 +324,7 @@ void Net::build_bf16() {
         tp.n_store = n;
         tp.x = act_x_.as<__nv_bfloat16>();
         tp.t = act_t_.as<__nv_bfloat16>();
+        tp.xt = act_xt_.as<__nv_bfloat16>();
         tp.stride = c_pad_;
         tp.b_slots = tower8_pick_b_slots(n);
         int cols = 32;

@@ -120,7 +120,7 @@ private:
     int tower_layers_ = 0;
     Tower8Maps tower_maps_{};
     Tower8Params tower_params_{};
-    DeviceBuffer d_tower_layers_, w_tower_;
+    DeviceBuffer d_tower_layers_, w_tower_, act_xt_;
 };
 
 // thread-local error plumbing for the C ABI

@@ -109,8 +109,9 @@ struct TowerLayerDev {
     const float* bias;
 };
 struct Tower8Maps {
-    CUtensorMap a[3];
-    CUtensorMap w[2];
+    CUtensorMap a[3];    // loads: encoded planes, X, T   -- (c, x, board, y) order, box (64, 8, 4, 8), SWIZZLE_128B
+    CUtensorMap w[2];    // loads: first-layer weights, concatenated block weights -- box (64, n)
+    CUtensorMap out[2];  // stores: X, T                  -- (c, x, board, y) order, box (c_pad, 8, 4, 1), no swizzle
 };
 struct Tower8Params {
     int num_layers;
@@ -120,13 +121,14 @@ struct Tower8Params {
     int n, n_store;
     __nv_bfloat16* x;
     __nv_bfloat16* t;
+    __nv_bfloat16* xt;  // channel-major copy of the residual stream: [unit][128 channels][256 positions]
     int stride;  // elements per row of X / T
     int b_slots, tmem_cols;
     unsigned long long* timeline;
     int debug;  // development aid (KZB_DEBUG): 1 = skip A loads, 2 = skip B loads, 4 = skip epilogue memory traffic
 };
 void launch_tower8(const Tower8Maps& maps, const Tower8Params& p, int grid, cudaStream_t s);
-size_t tower8_smem_bytes(int n, int b_slots);
+size_t tower8_smem_bytes(int w_slots);
 int tower8_pick_b_slots(int n);
 int tower8_max_local_units();
 void tower8_prepare();
