@@ -285,7 +285,7 @@ void Net::build_bf16() {
         auto omap = [&](DeviceBuffer& buf) {  // TMA store of one rank of a 4-board unit: [4 boards][8 x][c_pad]
             uint64_t dims[4] = {uint64_t(c_pad_), 8, uint64_t(rows_alloc_ / 64), 8};
             uint64_t strides[3] = {uint64_t(c_pad_) * 2, uint64_t(c_pad_) * 2 * 64, uint64_t(c_pad_) * 2 * 8};
-            uint32_t box[4] = {uint32_t(c_pad_), 8, 4, 1};
+            uint32_t box[4] = {32, 8, 4, 1};  // one epilogue warp's 32 channels
             return make_tmap(buf.ptr, 4, dims, strides, box, false);
         };
         tower_maps_.out[0] = omap(act_x_);

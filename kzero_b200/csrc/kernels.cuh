@@ -111,7 +111,7 @@ struct TowerLayerDev {
 struct Tower8Maps {
     CUtensorMap a[3];    // loads: encoded planes, X, T   -- (c, x, board, y) order, box (64, 8, 4, 8), SWIZZLE_128B
     CUtensorMap w[2];    // loads: first-layer weights, concatenated block weights -- box (64, n)
-    CUtensorMap out[2];  // stores: X, T                  -- (c, x, board, y) order, box (c_pad, 8, 4, 1), no swizzle
+    CUtensorMap out[2];  // stores: X, T                  -- (c, x, board, y) order, box (32, 8, 4, 1), no swizzle
 };
 struct Tower8Params {
     int num_layers;

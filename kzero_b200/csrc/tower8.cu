@@ -18,13 +18,15 @@
 //   * accumulator: TMEM lane = output channel, column n = rank*32 + board*8 + file.  2 buffers x 256 columns.
 //
 // Epilogue (warps 2..5, thread = one output channel): tcgen05.ld 32 columns (= one rank of the 4 boards) ->
-//   +bias -> relu -> +residual -> bf16 -> transposed through a shared-memory staging tile -> TMA store (NHWC rows).
+//   +bias -> relu -> +residual -> bf16 -> transposed through a per-warp shared-memory staging tile -> TMA store
+//   (NHWC rows, 32 channels x one rank of the 4 boards per store).
 //   The reference block is x + relu(bn(conv(...))): relu BEFORE the add (python/lib/model/post_act.py:218-228).
-//   The residual stream is additionally kept channel-major (XT[unit][channel][256 positions], bf16, bit-identical
-//   to X) so that the thread owning a channel reads / writes its residual with contiguous 32-byte accesses.
+//   The residual stream is additionally kept channel-major (XT[unit][rank][half][channel][16 positions], bf16,
+//   bit-identical to X) so that the thread owning a channel reads / writes its residual with 32-byte accesses that
+//   are 1 KiB-contiguous across the warp.
 // Cross-layer dependency: after the unit's TMA stores have completed the epilogue arrives on ready[unit]; the
 //   producer waits on it before it lets the TMA engine read those rows for the next layer.
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2..5 epilogue.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2..9 epilogue.
 #include "kernels.cuh"
 #include "tc_common.cuh"
 
@@ -33,7 +35,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kBoards = 4;
 constexpr int kAtom = 1024;
 constexpr int kRankBytes = kBoards * kAtom;   // one rank of 4 boards, 64 channels
@@ -42,7 +44,7 @@ constexpr int kXSlots = 3;
 constexpr int kXStride = kXBox + kRankBytes;  // slot + the zero rank that follows it
 constexpr int kXRegion = kRankBytes + kXSlots * kXStride;
 constexpr int kWBytes = 128 * 128;            // weight tile: 128 out-channels x 64 k, 16 KiB
-constexpr int kStageBytes = 32 * 256;         // output staging: one rank (32 positions) x 128 ch bf16
+constexpr int kStageBytes = 8 * 2 * 32 * 64;  // output staging: 8 epilogue warps x 2 buffers x [32 positions][32 ch] bf16
 constexpr int kMaxLocalUnits = 16;
 
 struct SmemT {
@@ -58,7 +60,7 @@ __device__ __forceinline__ SmemT carve_t(uint8_t* base, int w_slots) {
     s.x = base;
     s.w = base + kXRegion;
     s.stage = s.w + size_t(w_slots) * kWBytes;
-    uint8_t* p = s.stage + 2 * kStageBytes;
+    uint8_t* p = s.stage + kStageBytes;
     s.x_full = reinterpret_cast<uint64_t*>(p);
     s.x_empty = s.x_full + kXSlots;
     s.w_full = s.x_empty + kXSlots;
@@ -110,9 +112,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&sm.tmem_full[i], 1);
-            mbar_init(&sm.tmem_empty[i], 4);
+            mbar_init(&sm.tmem_empty[i], 8);
         }
-        for (int i = 0; i < kMaxLocalUnits; i++) mbar_init(&sm.ready[i], 1);
+        for (int i = 0; i < kMaxLocalUnits; i++) mbar_init(&sm.ready[i], 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -244,40 +246,47 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
+        // Eight warps, two per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31): warp (q, half)
+        // owns output channels 32q..32q+31 and ranks 4*half..4*half+3 of the unit.  Warps are independent of each
+        // other: own staging buffers, own TMA stores (box = 32 channels x one rank of the 4 boards), own arrivals.
+        // Two epilogue warps per scheduler hide each other's ALU / TMEM / shared-memory latencies.
         const int quarter = warp % 4;
-        const int et = threadIdx.x - 64;     // 0..127
+        const int half = (warp - 2) / 4;
         const int c = quarter * 32 + lane;   // output channel = TMEM lane of this thread
-        const bool c_ok = c < p.n_store;
-        const int row_pitch = p.stride * 2;  // bytes per staged position (all channels of the row)
-        const bool live = !(p.debug & 4);
+        const bool warp_ok = quarter * 32 < p.n_store;  // narrow nets: upper warps have no channels
+        const bool live = !(p.debug & 4) && warp_ok;
+        uint8_t* const wstage = sm.stage + (warp - 2) * (2 * 32 * 64);  // 2 buffers x [32 positions][32 ch] bf16
         int item = 0;
-        uint32_t chunk = 0;
         for (int L = 0; L < p.num_layers; L++) {
             const TowerLayerDev ld = p.layers[L];
-            const float bias = c_ok ? ld.bias[c] : 0.0f;
+            const float bias = warp_ok ? ld.bias[c] : 0.0f;
             const bool relu = c < ld.relu_n;
             const bool to_x = ld.out_buf == 1;
+            const bool has_res = ld.has_res != 0;
             const CUtensorMap* omap = &maps.out[to_x ? 0 : 1];
             int ul = 0;
             for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, item++, ul++) {
                 const int buf = item & 1;
-                __nv_bfloat16* xt = p.xt + (size_t(unit) * 128 + c) * 256;  // this channel's 256 positions
+                // channel-major residual copy, laid out so that one warp-wide 32-byte access is 1 KiB contiguous:
+                // XT[unit][rank][16-position half][channel][16 positions]
+                __nv_bfloat16* xt = p.xt + size_t(unit) * (128 * 256) + size_t(c) * 16;
                 uint32_t res[16];
-                if (ld.has_res && c_ok && live) {
-                    ldg256(xt, res);
-                    ldg256(xt + 16, res + 8);
+                if (has_res && live) {
+                    ldg256(xt + ((4 * half) * 2 + 0) * 2048, res);
+                    ldg256(xt + ((4 * half) * 2 + 1) * 2048, res + 8);
                 }
                 mbar_wait(&sm.tmem_full[buf], (item >> 1) & 1);
                 tc_fence_after();
                 if (warp == 2 && lane == 0) KZB_STAMP(item, 3);
                 const uint32_t taddr = tmem_base + uint32_t(buf) * 256u + (uint32_t(quarter * 32) << 16);
 
-                for (int y = 0; y < 8; y++, chunk++) {
+#pragma unroll 1
+                for (int yy = 0; yy < 4; yy++) {
+                    const int y = 4 * half + yy;
                     uint32_t r[32];
                     tmem_ld32(taddr + y * 32, r);
                     tmem_ld_wait();
-                    uint8_t* stage = sm.stage + (chunk & 1) * kStageBytes;
                     uint32_t packed[16];
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
@@ -287,47 +296,48 @@ __global__ void __launch_bounds__(kThreads, 1)
                             f0 = f0 < 0.0f ? 0.0f : f0;  // NaN stays NaN, like torch/ONNX Relu
                             f1 = f1 < 0.0f ? 0.0f : f1;
                         }
-                        if (ld.has_res) {
+                        if (has_res) {
                             f0 += bf16_lo(res[j]);
                             f1 += bf16_hi(res[j]);
                         }
                         packed[j] = pack_bf16(f0, f1);
                     }
-                    // next rank's residual while this one is being written out
-                    if (ld.has_res && c_ok && live && y < 7) {
-                        ldg256(xt + (y + 1) * 32, res);
-                        ldg256(xt + (y + 1) * 32 + 16, res + 8);
+                    if (has_res && live && yy < 3) {  // next rank's residual
+                        ldg256(xt + ((y + 1) * 2 + 0) * 2048, res);
+                        ldg256(xt + ((y + 1) * 2 + 1) * 2048, res + 8);
                     }
-                    if (c_ok && live) {
-                        // transposed staging tile [position j][channel]: 32 lanes write 64 contiguous bytes per j
-                        uint8_t* sp = stage + c * 2;
+                    // staging buffer (yy & 1) was last read by the store of chunk yy-2: allow only the store of
+                    // chunk yy-1 to be still reading
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    uint8_t* stage = wstage + (yy & 1) * (32 * 64);
+                    if (live) {
+                        // transposed tile [position j][32 channels]: the 32 lanes write 64 contiguous bytes per j
+                        uint8_t* sp = stage + lane * 2;
 #pragma unroll
                         for (int j = 0; j < 16; j++) {
-                            *reinterpret_cast<uint16_t*>(sp + (2 * j) * row_pitch) = uint16_t(packed[j] & 0xffffu);
-                            *reinterpret_cast<uint16_t*>(sp + (2 * j + 1) * row_pitch) = uint16_t(packed[j] >> 16);
+                            *reinterpret_cast<uint16_t*>(sp + (2 * j) * 64) = uint16_t(packed[j] & 0xffffu);
+                            *reinterpret_cast<uint16_t*>(sp + (2 * j + 1) * 64) = uint16_t(packed[j] >> 16);
                         }
                         if (to_x) {  // channel-major copy of the residual stream
-                            stg256(xt + y * 32, packed);
-                            stg256(xt + y * 32 + 16, packed + 8);
+                            stg256(xt + (y * 2 + 0) * 2048, packed);
+                            stg256(xt + (y * 2 + 1) * 2048, packed + 8);
                         }
                     }
-                    // the staging buffer written two chunks from now must no longer be read by the store issued
-                    // for the previous chunk: wait for it BEFORE the barrier that releases the writers
-                    if (et == 0) tma_store_wait_read0();
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (et == 0 && live) {
-                        tma_store_4d(omap, stage, 0, 0, unit * kBoards, y);
+                    __syncwarp();
+                    if (lane == 0 && live) {
+                        tma_store_4d(omap, stage, quarter * 32, 0, unit * kBoards, y);
                         tma_store_commit();
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.tmem_empty[buf]);
-                if (et == 0) {
-                    tma_store_wait_all();  // this unit's rows are in global memory (async proxy, like the loads)
+                if (lane == 0) {
+                    mbar_arrive(&sm.tmem_empty[buf]);
+                    tma_store_wait_all();  // this warp's rows of the unit are in global memory (async proxy, like the loads)
                     mbar_arrive(&sm.ready[ul]);
-                    KZB_STAMP(item, 4);
+                    if (warp == 2) KZB_STAMP(item, 4);
                 }
             }
         }
@@ -345,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 }  // namespace
 
 size_t tower8_smem_bytes(int w_slots) {
-    return 1024 + size_t(kXRegion) + size_t(w_slots) * kWBytes + 2 * kStageBytes + (2 * kXSlots + 2 * w_slots + 4 + kMaxLocalUnits) * 8 + 16;
+    return 1024 + size_t(kXRegion) + size_t(w_slots) * kWBytes + kStageBytes + (2 * kXSlots + 2 * w_slots + 4 + kMaxLocalUnits) * 8 + 16;
 }
 
 int tower8_pick_b_slots(int /*n*/) {
