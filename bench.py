@@ -61,52 +61,86 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region: an NVML polling thread (a 50-step chess run
+    lasts tens of milliseconds, far below nvidia-smi's -lms resolution), nvidia-smi as the fallback."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+               "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, device: int):
         self.device = device
-        self.rows = []
-        self.proc = None
+        self.samples = []  # (sm_mhz, power_w, reasons bitmask)
+        self.sm_max = None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.source = None
+
+    def _handle(self):
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.device).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:  # noqa: BLE001
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = self.device
+            if visible:
+                try:
+                    index = int(visible.split(",")[self.device])
+                except ValueError:
+                    pass
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            nv, h = self._handle()
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            def poll():
+                while not self.stop_flag.is_set():
+                    try:
+                        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                        pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        self.samples.append((sm, pw, rs))
+                    except Exception:  # noqa: BLE001
+                        pass
+                    time.sleep(0.002)
+
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.source = None
+
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw", "--format=csv,noheader,nounits",
+                                  "-i", str(self.device)], capture_output=True, text=True, timeout=20).stdout.strip().split(",")
+            return float(out[0]), float(out[1]), float(out[2])
+        except Exception:  # noqa: BLE001
+            return None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                smax.append(float(r[2]))
-                power.append(float(r[3]))
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except (ValueError, IndexError):
-                continue
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            one = self._smi_once()
+            if one is None:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source available"]}
+            return {"sm_mhz": one[0], "sm_max_mhz": one[1], "reasons": [], "samples": 1, "power_w_max": one[2],
+                    "source": "nvidia-smi (single query right after the timed region)"}
+        sm = [s[0] for s in self.samples]
+        power = [s[1] for s in self.samples]
         busy = [s for s, pw in zip(sm, power) if pw >= 0.5 * max(power)] or sm
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": float(max(power))}
+        mask = 0
+        for s in self.samples:
+            mask |= s[2]
+        reasons = sorted(name for name, bit in self.REASONS.items() if mask & bit)
+        return {"sm_mhz": float(np.median(busy)), "sm_min_mhz": float(min(busy)), "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(sm), "power_w_max": float(max(power)), "source": "nvml, polled every ~2 ms during the timed regions"}
 
 
 def cpu_restatement_rate(cfg, onnx_bytes, spec, seconds_target: float, threads: int):
@@ -171,8 +205,8 @@ def run_reference(args, cfg, spec, onnx_bytes):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="chess", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -279,10 +313,12 @@ def main():
             "gpu_launches": int(net.launches_per_eval() * args.steps),
             "launches_per_step": int(net.launches_per_eval()),
             "tflops_whole_step": float(info.flops_per_position) * batch * args.steps / dev_s / 1e12,
+            # the tower kernel is timed alone (one ~0.45 ms launch between L2 flushes, the GPU idles in between), so the
+            # denominator is the BURST cuBLAS figure; the sustained-loop figure is reported beside it
             "roofline": {"bound": "tensor", "kernel": "tower8_kernel" if "tower8" in share else "conv_tc_kernel",
-                         "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops_sustained"], "frac_of_burst_peak": achieved / peaks["tflops_burst"],
-                         "peak_source": peaks["source"] + " (bf16_tflops_sustained)", "traffic": traffic,
+                         "achieved": achieved, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["tflops_burst"], "frac_of_sustained_peak": achieved / peaks["tflops_sustained"],
+                         "peak_source": peaks["source"] + " (bf16_tflops, burst: kernel timed in isolation)", "traffic": traffic,
                          "launches_per_step": tower_launches, "avg_launch_ms": tower_s * 1e3 / max(tower_launches, 1),
                          "algorithmic_flops_per_launch": tower_flops / max(tower_launches, 1)},
             "step_breakdown_ms": share,
