@@ -143,47 +143,61 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": float(max(power)), "source": "nvml, polled every ~2 ms during the timed regions"}
 
 
-def cpu_restatement_rate(cfg, onnx_bytes, spec, seconds_target: float, threads: int):
-    """positions/s of the oracle (expand planes -> ONNX graph in f32 -> decode_output) on `threads` host threads."""
-    import oracle
-    from oracle.graph_exec import OnnxOracle
+class CpuRestatement:
+    """The oracle (expand planes -> ONNX graph in f32 -> decode_output) as a timed CPU implementation of the path."""
 
-    oracle.set_threads(threads)
-    net = OnnxOracle(onnx_bytes)
+    def __init__(self, onnx_bytes, spec, threads: int):
+        import oracle
+        from oracle.graph_exec import OnnxOracle
 
-    def run(n, seed):
+        self.oracle = oracle
+        self.spec = spec
+        oracle.set_threads(threads)
+        self.net = OnnxOracle(onnx_bytes)
+
+    def run(self, n: int, seed: int) -> float:
+        """seconds for one pass over n synthetic positions"""
+        spec = self.spec
         bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, n, seed=seed)
         t0 = time.perf_counter()
-        planes = oracle.expand_planes(bits, scalars, (spec.bool_channels, spec.board_size, spec.board_size),
-                                      spec.scalar_channels)
-        s, p = net.run(planes)
-        oracle.decode_output(s, p, mv_idx, mv_off)
+        planes = self.oracle.expand_planes(bits, scalars, (spec.bool_channels, spec.board_size, spec.board_size),
+                                           spec.scalar_channels)
+        s, p = self.net.run(planes)
+        self.oracle.decode_output(s, p, mv_idx, mv_off)
         return time.perf_counter() - t0
 
-    probe_n = max(2, min(cfg["batch"], threads))
-    dt = run(probe_n, 100)
-    n = int(max(probe_n, min(cfg["batch"], seconds_target / max(dt / probe_n, 1e-9))))
-    dt = run(n, 101)
+    def sample_size(self, batch: int, seconds_target: float, threads: int) -> int:
+        probe_n = max(2, min(batch, threads))
+        self.run(probe_n, 99)  # first pass pays thread start-up and page faults
+        dt = self.run(probe_n, 100)
+        return int(max(probe_n, min(batch, seconds_target / max(dt / probe_n, 1e-9))))
+
+
+def cpu_restatement_rate(cfg, onnx_bytes, spec, seconds_target: float, threads: int):
+    """positions/s of the oracle on `threads` host threads over a bounded sample of the workload."""
+    cpu = CpuRestatement(onnx_bytes, spec, threads)
+    n = cpu.sample_size(cfg["batch"], seconds_target, threads)
+    dt = cpu.run(n, 101)
     return n / dt, n, dt
 
 
 def run_reference(args, cfg, spec, onnx_bytes):
-    """--impl reference: the reference's CPU implementation of the path (restated; see module docstring)."""
+    """--impl reference: the reference's CPU implementation of the path (restated; see module docstring).
+    Every step is a bounded sample of the workload sized so that the whole run ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    rates = []
-    sample = 0
     total = args.steps + args.warmup
-    per_step_seconds = max(2.0, min(20.0, 120.0 / total))
-    t_steps = []
+    per_step_seconds = max(0.25, min(20.0, 150.0 / total))
+    cpu = CpuRestatement(onnx_bytes, spec, threads)
+    sample = cpu.sample_size(cfg["batch"], per_step_seconds, threads)
+    rates, t_steps = [], []
     for i in range(total):
-        rate, n, dt = cpu_restatement_rate(cfg, onnx_bytes, spec, per_step_seconds, threads)
+        dt = cpu.run(sample, 200 + i)
         if i >= args.warmup:
-            rates.append(rate)
+            rates.append(sample / dt)
             t_steps.append(dt)
-            sample = n
     value = float(np.mean(rates))
     desc = (f"{sample} positions per step of the same workload (bounded sample; rate is per position so it "
             f"extrapolates linearly to batch {cfg['batch']})")
@@ -222,29 +236,24 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
 
+    from kzero_b200 import replicas
     from kzero_b200.network import B200Network, PRECISION_BF16, mapper_for
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = replicas.context_from_env()
+    rank, world, local_rank = ctx.rank, ctx.world, ctx.local_rank
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    dist = replicas.init_process_group(ctx, "nccl", torch.device("cuda", local_rank))
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        replicas.barrier(ctx, torch.cuda.synchronize)
 
     batch = cfg["batch"]
     net = B200Network(mapper_for(spec), onnx_bytes, batch, device=local_rank, precision=PRECISION_BF16)
     info = net.info()
-    inputs = [netgen.synthetic_positions(spec, batch, seed=1000 * rank + i) for i in range(N_INPUT_SETS)]
+    inputs = [netgen.synthetic_positions(spec, batch, seed=replicas.game_seed(ctx, i)) for i in range(N_INPUT_SETS)]
 
     # ---- device-resident throughput ("value"): K steps, each timed with CUDA events on the net's stream,
     #      L2 flushed (256 MiB memset) before every step outside the timed region
@@ -281,10 +290,7 @@ def main():
     clocks = sampler.stop()
 
     dev_s = float(step_ms.sum()) * 1e-3
-    times = torch.tensor([dev_s, e2e_s, wall_value], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_s, e2e_s, wall_value = (float(v) for v in times.tolist())
+    dev_s, e2e_s, wall_value = replicas.max_over_ranks(ctx, [dev_s, e2e_s, wall_value], device="cuda")
 
     if rank == 0:
         peaks = measured_peaks()
@@ -301,13 +307,13 @@ def main():
         if tpath.exists() and args.config == "chess":
             traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
         line = {
-            "metric": "NN positions/sec", "value": world * batch * args.steps / dev_s, "unit": "positions/s",
+            "metric": "NN positions/sec", "value": replicas.job_throughput(ctx, batch, args.steps, dev_s), "unit": "positions/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "batch_per_gpu": batch, "parallelism": f"replicas x{world} (sharded by game, no collective)",
+            "config": {"workload": cfg["workload"], "batch_per_gpu": batch, **replicas.parallelism_note(ctx),
                        "l2": "flushed before every timed step (256 MiB memset, untimed)", "conv_mode": int(info.conv_mode),
                        "flops_per_position": float(info.flops_per_position)},
-            "e2e": {"value": world * batch * args.steps / e2e_s, "unit": "positions/s", "h2d_bytes_per_step": h2d,
+            "e2e": {"value": replicas.job_throughput(ctx, batch, args.steps, e2e_s), "unit": "positions/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
                     "inputs": f"{N_INPUT_SETS} distinct synthetic batches rotated, host numpy buffers"},
             "gpu_launches": int(net.launches_per_eval() * args.steps),
@@ -333,7 +339,7 @@ def main():
                                               "interpreter with C/OpenMP conv loops + plane expansion + decode_output)"}
         print(json.dumps(line), flush=True)
     net.close()
-    if world > 1:
+    if dist is not None:
         dist.destroy_process_group()
 
 
