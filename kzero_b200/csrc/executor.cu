@@ -128,6 +128,8 @@ Net::Net(int device, const void* onnx, size_t len, int max_batch, int precision)
     upload(d_fc2_b_, spec_.fc2.b);
     if (spec_.has_extra) upload(d_extra_w_, spec_.extra_fc.w);
     upload(d_policy_src_, spec_.policy_src);
+    static_assert(sizeof(NetSpec::AttEntry) == sizeof(AttEntryDev), "AttEntry layout");
+    upload(d_att_entries_, spec_.att_entries);
 
     d_nchw_.alloc(size_t(max_batch_) * spec_.cin * area * 4, false);
     d_out_scalars_.alloc(size_t(max_batch_) * 5 * 4, false);
@@ -160,6 +162,33 @@ static ConvParams merged_small_conv(const NetSpec& s) {
     return m;
 }
 
+// the attention head's 1x1 convs (post_act.py:120-121) in launches of <= 256 output channels (UMMA N limit), each
+// writing its channel range of the concatenated feature matrix E[rows][att_stride]
+struct AttChunk {
+    std::string name;
+    ConvParams conv;
+    int out_off;
+};
+static std::vector<AttChunk> att_chunks(const NetSpec& s) {
+    std::vector<AttChunk> out;
+    for (size_t k = 0; k < s.att_convs.size(); k++) {
+        const ConvParams& c = s.att_convs[k];
+        for (int c0 = 0; c0 < c.cout; c0 += 256) {
+            AttChunk ch;
+            ch.name = "att_conv" + std::to_string(k) + "_" + std::to_string(c0 / 256);
+            ch.conv.cin = c.cin;
+            ch.conv.ksize = c.ksize;
+            ch.conv.cout = std::min(256, c.cout - c0);
+            const size_t per = size_t(c.cin) * c.ksize * c.ksize;
+            ch.conv.w.assign(c.w.begin() + size_t(c0) * per, c.w.begin() + size_t(c0 + ch.conv.cout) * per);
+            ch.conv.b.assign(c.b.begin() + c0, c.b.begin() + c0 + ch.conv.cout);
+            ch.out_off = s.att_chan_base[k] + c0;
+            out.push_back(std::move(ch));
+        }
+    }
+    return out;
+}
+
 void Net::build_bf16() {
     act_bf16_ = true;
     const int W = spec_.board_w, H = spec_.board_h, C = spec_.channels;
@@ -188,9 +217,11 @@ void Net::build_bf16() {
     act_h1_.alloc(size_t(rows_alloc_) * cp_pad_ * 2);
     act_s1_.alloc(size_t(rows_alloc_) * s1_stride_ * 4);
     act_pm_.alloc(size_t(rows_alloc_) * pm_stride_ * 4);
+    att_stride_ = spec_.has_attention ? spec_.att_chan_base.back() : 0;
+    act_att_.alloc(size_t(rows_alloc_) * att_stride_ * 4);
 
     auto add = [&](const std::string& name, const ConvParams& c, DeviceBuffer& in, int in_stride, const DeviceBuffer* res,
-                   DeviceBuffer& out, int out_stride, bool out_f32, int n, int relu_n) {
+                   DeviceBuffer& out, int out_stride, bool out_f32, int n, int relu_n, int out_off = 0) {
         auto st = std::make_unique<ConvStep>();
         st->name = name;
         st->taps = c.ksize * c.ksize;
@@ -245,7 +276,7 @@ void Net::build_bf16() {
         p.relu_n = relu_n;
         p.res = res ? res->as<__nv_bfloat16>() : nullptr;
         p.res_stride = c_pad_;
-        p.out = out.ptr;
+        p.out = static_cast<uint8_t*>(out.ptr) + size_t(out_off) * (out_f32 ? 4 : 2);
         p.out_stride = out_stride;
         p.out_f32 = out_f32 ? 1 : 0;
         p.n_store = n;
@@ -261,9 +292,15 @@ void Net::build_bf16() {
         add("block" + std::to_string(d) + "_conv1", spec_.blocks[2 * d], act_x_, c_pad_, nullptr, act_t_, c_pad_, false, c_pad_, c_pad_);
         add("block" + std::to_string(d) + "_conv2", spec_.blocks[2 * d + 1], act_t_, c_pad_, &act_x_, act_x_, c_pad_, false, c_pad_, c_pad_);
     }
-    add("policy_conv1", spec_.policy_conv1, act_x_, c_pad_, nullptr, act_h1_, cp_pad_, false, cp_pad_, cp_pad_);
-    add("scalar_conv", merged_small_conv(spec_), act_x_, c_pad_, nullptr, act_s1_, s1_stride_, true, 16, spec_.scalar_conv.cout);
-    add("policy_conv2", spec_.policy_conv2, act_h1_, cp_pad_, nullptr, act_pm_, pm_stride_, true, pm_stride_, 0);
+    if (spec_.has_attention) {
+        add("scalar_conv", merged_small_conv(spec_), act_x_, c_pad_, nullptr, act_s1_, s1_stride_, true, 16, spec_.scalar_conv.cout);
+        for (const AttChunk& ch : att_chunks(spec_))
+            add(ch.name, ch.conv, act_x_, c_pad_, nullptr, act_att_, att_stride_, true, round_up(ch.conv.cout, 16), 0, ch.out_off);
+    } else {
+        add("policy_conv1", spec_.policy_conv1, act_x_, c_pad_, nullptr, act_h1_, cp_pad_, false, cp_pad_, cp_pad_);
+        add("scalar_conv", merged_small_conv(spec_), act_x_, c_pad_, nullptr, act_s1_, s1_stride_, true, 16, spec_.scalar_conv.cout);
+        add("policy_conv2", spec_.policy_conv2, act_h1_, cp_pad_, nullptr, act_pm_, pm_stride_, true, pm_stride_, 0);
+    }
 
     // whole-tower persistent kernel: all 2*depth+1 conv3x3 layers in one launch (tower8.cu)
     const char* no_t8 = std::getenv("KZB_NO_TOWER8");
@@ -358,8 +395,11 @@ void Net::build_f32() {
     act_s1_.alloc(size_t(rows_alloc_) * s1_stride_ * 4);
     act_pm_.alloc(size_t(rows_alloc_) * pm_stride_ * 4);
 
+    att_stride_ = spec_.has_attention ? spec_.att_chan_base.back() : 0;
+    act_att_.alloc(size_t(rows_alloc_) * att_stride_ * 4);
+
     auto add = [&](const std::string& name, const ConvParams& c, DeviceBuffer& in, int in_stride, const DeviceBuffer* res,
-                   DeviceBuffer& out, int out_stride, int relu_n) {
+                   DeviceBuffer& out, int out_stride, int relu_n, int out_off = 0) {
         auto st = std::make_unique<ConvStep>();
         st->name = name;
         st->taps = c.ksize * c.ksize;
@@ -377,7 +417,7 @@ void Net::build_f32() {
         p.bias = st->bias.as<float>();
         p.res = res ? res->as<float>() : nullptr;
         p.res_stride = c_pad_;
-        p.out = out.as<float>();
+        p.out = out.as<float>() + out_off;
         p.out_stride = out_stride;
         p.cin = c.cin;
         p.cout = c.cout;
@@ -391,9 +431,14 @@ void Net::build_f32() {
         add("block" + std::to_string(d) + "_conv1", spec_.blocks[2 * d], act_x_, c_pad_, nullptr, act_t_, c_pad_, C);
         add("block" + std::to_string(d) + "_conv2", spec_.blocks[2 * d + 1], act_t_, c_pad_, &act_x_, act_x_, c_pad_, C);
     }
-    add("policy_conv1", spec_.policy_conv1, act_x_, c_pad_, nullptr, act_h1_, cp_pad_, spec_.policy_conv1.cout);
-    add("scalar_conv", merged_small_conv(spec_), act_x_, c_pad_, nullptr, act_s1_, s1_stride_, spec_.scalar_conv.cout);
-    add("policy_conv2", spec_.policy_conv2, act_h1_, cp_pad_, nullptr, act_pm_, pm_stride_, 0);
+    if (spec_.has_attention) {
+        add("scalar_conv", merged_small_conv(spec_), act_x_, c_pad_, nullptr, act_s1_, s1_stride_, spec_.scalar_conv.cout);
+        for (const AttChunk& ch : att_chunks(spec_)) add(ch.name, ch.conv, act_x_, c_pad_, nullptr, act_att_, att_stride_, 0, ch.out_off);
+    } else {
+        add("policy_conv1", spec_.policy_conv1, act_x_, c_pad_, nullptr, act_h1_, cp_pad_, spec_.policy_conv1.cout);
+        add("scalar_conv", merged_small_conv(spec_), act_x_, c_pad_, nullptr, act_s1_, s1_stride_, spec_.scalar_conv.cout);
+        add("policy_conv2", spec_.policy_conv2, act_h1_, cp_pad_, nullptr, act_pm_, pm_stride_, 0);
+    }
 }
 
 void Net::bind_mapper(int scalar_count, int bool_channels, int h, int w, int policy_len) {
@@ -541,8 +586,13 @@ void Net::run_tail(int batch, bool packed, const StepHook& hook) {
     p.hs = spec_.fc1.out;
     p.extra_w = spec_.has_extra ? d_extra_w_.as<float>() : nullptr;
     p.extra_b = spec_.has_extra ? spec_.extra_fc.b[0] : 0.0f;
-    p.policy_src = d_policy_src_.as<int32_t>();
+    p.policy_src = spec_.has_attention ? nullptr : d_policy_src_.as<int32_t>();
     p.policy_len = spec_.policy_len;
+    p.att = act_att_.as<float>();
+    p.att_stride = att_stride_;
+    p.att_q = spec_.att_q;
+    p.att_div = spec_.att_div;
+    p.att_entries = spec_.has_attention ? d_att_entries_.as<AttEntryDev>() : nullptr;
     p.out_scalars = d_out_scalars_.as<float>();
     p.out_logits = d_out_logits_.as<float>();
     if (packed) {

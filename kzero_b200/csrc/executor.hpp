@@ -103,8 +103,9 @@ private:
     bool act_bf16_ = true;
 
     DeviceBuffer d_bits_, d_scalars_, d_mv_idx_, d_mv_off_, d_nchw_;
-    DeviceBuffer act_in_, act_x_, act_t_, act_h1_, act_s1_, act_pm_;
-    DeviceBuffer d_fc1_t_, d_fc1_b_, d_fc2_w_, d_fc2_b_, d_extra_w_, d_policy_src_;
+    DeviceBuffer act_in_, act_x_, act_t_, act_h1_, act_s1_, act_pm_, act_att_;
+    int att_stride_ = 0;
+    DeviceBuffer d_fc1_t_, d_fc1_b_, d_fc2_w_, d_fc2_b_, d_extra_w_, d_policy_src_, d_att_entries_;
     DeviceBuffer d_out_scalars_, d_out_logits_, d_out_values_, d_out_probs_, d_err_;
     DeviceBuffer d_flush_, d_timeline_;
     std::string timeline_step_;

@@ -3,7 +3,8 @@
 // Replaces, for this path:
 //   - the scalar head's Flatten/Gemm/Relu/Gemm steps (python/lib/model/post_act.py:15-19), which the
 //     reference executes as separate cuBLAS launches,
-//   - the policy Flatten/Gather/Concat plumbing (post_act.py:76-88, 102-112),
+//   - the policy Flatten/Gather/Concat plumbing (post_act.py:76-88, 102-112) and the attention head's
+//     slice / reshape / bmm / scale / Gather chain (post_act.py:130-141), evaluated only for the requested indices,
 //   - and, in packed mode, the CPU-side decode_output (rust/kz-core/src/network/common.rs:16-100):
 //     value = tanh(s0), wdl = softmax(s1..3), moves_left = s4, policy = softmax over the LEGAL moves only
 //     (gathered by the host-supplied move_to_index list), so only n_legal probabilities per position cross
@@ -94,6 +95,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) heads_tail_kernel(HeadsTa
     }
 
     auto logit = [&](int i) -> float {
+        if (p.att_entries) {  // attention head: q_from(from square) . q_to(to square / under-promotion slot) / sqrt(Q)
+            const AttEntryDev e = p.att_entries[i];
+            const float* a = p.att + size_t(p.lay.row(b, e.a_sq)) * p.att_stride + e.a_chan;
+            const float* c = p.att + size_t(p.lay.row(b, e.b_sq)) * p.att_stride + e.b_chan;
+            float acc = 0.0f;
+            for (int q = 0; q < p.att_q; q++) acc = fmaf(a[q * e.a_stride], c[q * e.b_stride], acc);
+            return acc / p.att_div;
+        }
         int src = p.policy_src[i];
         if (src >= 0) return p.pm[size_t(p.lay.row(b, src % area)) * p.pm_stride + src / area];
         return src == -1 ? 0.0f : extra;

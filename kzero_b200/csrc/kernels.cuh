@@ -134,6 +134,9 @@ int tower8_max_local_units();
 void tower8_prepare();
 
 // ---------------------------------------------------------------------------------------------- K3
+struct AttEntryDev {  // same layout as NetSpec::AttEntry
+    int32_t a_chan, a_stride, a_sq, b_chan, b_stride, b_sq;
+};
 struct HeadsTailParams {
     int batch;
     RowLayout lay;
@@ -148,8 +151,13 @@ struct HeadsTailParams {
     int hs;
     const float* extra_w;  // [A] or null
     float extra_b;
-    const int32_t* policy_src;  // [P]
+    const int32_t* policy_src;  // [P]; null for the attention head
     int policy_len;
+    // attention policy head (post_act.py:115-141): logit[i] = dot_q(E[a.sq][a.chan + q*a.stride], E[b.sq][b.chan + q*b.stride]) / att_div
+    const float* att;  // [rows][att_stride]: concatenated outputs of the head's 1x1 convs
+    int att_stride, att_q;
+    float att_div;
+    const AttEntryDev* att_entries;  // [P] or null
     // planes mode (twin of CudaExecutor::evaluate, network/cudnn.rs:73)
     float* out_scalars;  // [batch][5] raw
     float* out_logits;   // [batch][P]

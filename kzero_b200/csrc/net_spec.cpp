@@ -1,5 +1,6 @@
 #include "net_spec.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <map>
 #include <stdexcept>
@@ -325,7 +326,346 @@ struct Matcher {
             return out;
         }
         fail("unsupported op in policy head: " + op +
-             " (supported: conv policy heads of post_act.py:54-112; the attention head is not built yet)");
+             " (supported: the conv policy heads of post_act.py:54-112 and the attention head :115-141)");
+    }
+
+    // ------------------------------------------------------------------------------------------------
+    // Attention policy head (post_act.py:115-141).  The exporter turns its slicing / reshaping into a long
+    // chain of Slice / Shape / Concat / Reshape / Transpose / Gather / Unsqueeze nodes.
+    // Instead of matching that chain node by node, the head's index plumbing is EVALUATED symbolically at
+    // batch size 1 on integer tensors of element ids: id = (src << 32) | (channel * A + square), src 0 = the
+    // tower output, src k+1 = output of the k-th 1x1 head conv.  Pure index ops just shuffle ids, so at the
+    // MatMul both operands say exactly which conv outputs are multiplied.
+    struct Sym {
+        std::vector<int64_t> shape;
+        std::vector<int64_t> v;
+        bool elem = false;
+        int64_t numel() const {
+            int64_t n = 1;
+            for (auto d : shape) n *= d;
+            return n;
+        }
+    };
+    std::map<std::string, Sym> sym_memo;
+
+    static std::vector<int64_t> strides_of(const std::vector<int64_t>& shape) {
+        std::vector<int64_t> st(shape.size(), 1);
+        for (int i = int(shape.size()) - 2; i >= 0; i--) st[i] = st[i + 1] * shape[i + 1];
+        return st;
+    }
+
+    std::vector<int64_t> sym_ints(const std::string& name, const char* what) {
+        const Sym& t = sym_eval(name);
+        if (t.elem) fail(std::string(what) + " must be an integer tensor");
+        return t.v;
+    }
+
+    const Sym& sym_eval(const std::string& name, int guard = 0) {
+        auto memo = sym_memo.find(name);
+        if (memo != sym_memo.end()) return memo->second;
+        if (guard > 64) fail("policy head too deep");
+        Sym out;
+        const int area = spec.area();
+        if (name == tower_out) {
+            out.shape = {1, spec.channels, spec.board_h, spec.board_w};
+            out.elem = true;
+            out.v.resize(size_t(spec.channels) * area);
+            for (size_t i = 0; i < out.v.size(); i++) out.v[i] = int64_t(i);
+            return sym_memo[name] = std::move(out);
+        }
+        if (const OnnxTensor* c = constant(name)) {
+            if (c->dtype == 1) fail("unexpected float constant '" + name + "' in the policy head's index plumbing");
+            out.shape = c->dims;
+            out.v = c->i64;
+            return sym_memo[name] = std::move(out);
+        }
+        const OnnxNode* n = prod(name);
+        if (!n) fail("policy output depends on non-node value '" + name + "'");
+        const std::string& op = n->op;
+        auto in = [&](size_t i) -> const Sym& { return sym_eval(n->inputs.at(i), guard + 1); };
+        auto norm_axis = [&](int64_t ax, size_t rank) {
+            if (ax < 0) ax += int64_t(rank);
+            if (ax < 0 || ax >= int64_t(rank)) fail(op + " axis out of range");
+            return size_t(ax);
+        };
+        if (op == "Identity") {
+            out = in(0);
+        } else if (op == "Shape") {
+            const Sym& x = in(0);
+            out.shape = {int64_t(x.shape.size())};
+            out.v = x.shape;
+        } else if (op == "Conv") {
+            const Sym& x = in(0);
+            if (!x.elem || x.shape.size() != 4 || x.shape[0] != 1 || x.shape[1] != spec.channels)
+                fail("attention head conv must read (a spatial slice of) the tower output");
+            const int64_t hw = x.shape[2] * x.shape[3];
+            std::vector<int64_t> sq(size_t(hw), 0);
+            for (int64_t c = 0; c < spec.channels; c++)
+                for (int64_t i = 0; i < hw; i++) {
+                    int64_t id = x.v[size_t(c * hw + i)];
+                    if ((id >> 32) != 0 || (id & 0xffffffff) / area != c) fail("attention head conv input permutes tower channels");
+                    int64_t s = (id & 0xffffffff) % area;
+                    if (c == 0) sq[size_t(i)] = s;
+                    else if (sq[size_t(i)] != s) fail("attention head conv input mixes squares");
+                }
+            ConvParams cp = read_conv(*n, 1);
+            if (cp.cin != spec.channels) fail("head conv input channels mismatch");
+            fold_preceding_bn(cp);
+            const int64_t k = int64_t(spec.att_convs.size());
+            out.shape = {1, cp.cout, x.shape[2], x.shape[3]};
+            out.elem = true;
+            out.v.resize(size_t(cp.cout * hw));
+            for (int64_t co = 0; co < cp.cout; co++)
+                for (int64_t i = 0; i < hw; i++) out.v[size_t(co * hw + i)] = ((k + 1) << 32) | (co * area + sq[size_t(i)]);
+            spec.att_convs.push_back(std::move(cp));
+        } else if (op == "Slice") {
+            const Sym& x = in(0);
+            std::vector<int64_t> starts, ends, axes, steps;
+            if (n->inputs.size() >= 3) {  // opset >= 10: tensors
+                starts = sym_ints(n->inputs[1], "Slice starts");
+                ends = sym_ints(n->inputs[2], "Slice ends");
+                if (n->inputs.size() > 3 && !n->inputs[3].empty()) axes = sym_ints(n->inputs[3], "Slice axes");
+                if (n->inputs.size() > 4 && !n->inputs[4].empty()) steps = sym_ints(n->inputs[4], "Slice steps");
+            } else {
+                starts = n->attr_ints("starts");
+                ends = n->attr_ints("ends");
+                axes = n->attr_ints("axes");
+            }
+            if (axes.empty())
+                for (size_t i = 0; i < starts.size(); i++) axes.push_back(int64_t(i));
+            if (steps.empty()) steps.assign(starts.size(), 1);
+            if (starts.size() != ends.size() || starts.size() != axes.size() || starts.size() != steps.size()) fail("malformed Slice");
+            std::vector<int64_t> lo(x.shape.size(), 0), cnt = x.shape;
+            for (size_t i = 0; i < axes.size(); i++) {
+                size_t ax = norm_axis(axes[i], x.shape.size());
+                if (steps[i] != 1) fail("Slice step != 1 is not supported");
+                int64_t d = x.shape[ax], s0 = starts[i], e0 = ends[i];
+                if (s0 < 0) s0 += d;
+                if (e0 < 0) e0 += d;
+                s0 = std::min(std::max<int64_t>(s0, 0), d);
+                e0 = std::min(std::max<int64_t>(e0, 0), d);
+                lo[ax] = s0;
+                cnt[ax] = std::max<int64_t>(e0 - s0, 0);
+            }
+            out.shape = cnt;
+            out.elem = x.elem;
+            out.v.resize(size_t(out.numel()));
+            auto xs = strides_of(x.shape), os = strides_of(out.shape);
+            for (int64_t f = 0; f < out.numel(); f++) {
+                int64_t src = 0, r = f;
+                for (size_t d = 0; d < out.shape.size(); d++) {
+                    int64_t i = r / os[d];
+                    r %= os[d];
+                    src += (i + lo[d]) * xs[d];
+                }
+                out.v[size_t(f)] = x.v[size_t(src)];
+            }
+        } else if (op == "Concat") {
+            const Sym& first = in(0);
+            size_t ax = norm_axis(n->attr_i("axis", 0), first.shape.size());
+            out.shape = first.shape;
+            out.elem = first.elem;
+            out.shape[ax] = 0;
+            std::vector<const Sym*> parts;
+            for (size_t i = 0; i < n->inputs.size(); i++) {
+                const Sym& p = in(i);
+                if (p.shape.size() != first.shape.size() || p.elem != first.elem) fail("Concat of mismatched tensors");
+                out.shape[ax] += p.shape[ax];
+                parts.push_back(&p);
+            }
+            int64_t outer = 1, inner = 1;
+            for (size_t d = 0; d < ax; d++) outer *= first.shape[d];
+            for (size_t d = ax + 1; d < first.shape.size(); d++) inner *= first.shape[d];
+            for (int64_t o = 0; o < outer; o++)
+                for (const Sym* p : parts) {
+                    int64_t len = p->shape[ax] * inner;
+                    out.v.insert(out.v.end(), p->v.begin() + o * len, p->v.begin() + (o + 1) * len);
+                }
+        } else if (op == "Reshape" || op == "Flatten" || op == "Unsqueeze" || op == "Squeeze") {
+            const Sym& x = in(0);
+            out = x;
+            if (op == "Reshape") {
+                std::vector<int64_t> target = sym_ints(n->inputs.at(1), "Reshape shape");
+                int64_t known = 1, infer = -1;
+                for (size_t i = 0; i < target.size(); i++) {
+                    if (target[i] == 0) {
+                        if (i >= x.shape.size()) fail("Reshape 0 beyond input rank");
+                        target[i] = x.shape[i];
+                    }
+                    if (target[i] == -1) {
+                        if (infer >= 0) fail("Reshape with two -1");
+                        infer = int64_t(i);
+                    } else {
+                        known *= target[i];
+                    }
+                }
+                if (infer >= 0) {
+                    if (known == 0 || x.numel() % known) fail("Reshape cannot infer -1");
+                    target[size_t(infer)] = x.numel() / known;
+                }
+                out.shape = target;
+            } else if (op == "Flatten") {
+                size_t ax = size_t(n->attr_i("axis", 1));
+                if (ax > x.shape.size()) fail("Flatten axis out of range");
+                int64_t a0 = 1, a1 = 1;
+                for (size_t d = 0; d < x.shape.size(); d++) (d < ax ? a0 : a1) *= x.shape[d];
+                out.shape = {a0, a1};
+            } else if (op == "Unsqueeze") {
+                std::vector<int64_t> axes = n->attr_ints("axes");
+                if (axes.empty() && n->inputs.size() > 1) axes = sym_ints(n->inputs[1], "Unsqueeze axes");
+                std::vector<int64_t> shp = x.shape;
+                std::sort(axes.begin(), axes.end());
+                for (auto a : axes) {
+                    if (a < 0) a += int64_t(shp.size()) + 1;
+                    if (a < 0 || a > int64_t(shp.size())) fail("Unsqueeze axis out of range");
+                    shp.insert(shp.begin() + a, 1);
+                }
+                out.shape = shp;
+            } else {
+                std::vector<int64_t> axes = n->attr_ints("axes");
+                std::vector<int64_t> shp;
+                for (size_t d = 0; d < x.shape.size(); d++) {
+                    bool drop = axes.empty() ? x.shape[d] == 1 : false;
+                    for (auto a : axes)
+                        if (norm_axis(a, x.shape.size()) == d) drop = true;
+                    if (drop && x.shape[d] != 1) fail("Squeeze of a non-unit dimension");
+                    if (!drop) shp.push_back(x.shape[d]);
+                }
+                out.shape = shp;
+            }
+            if (out.numel() != x.numel()) fail(op + " changes the element count");
+        } else if (op == "Transpose") {
+            const Sym& x = in(0);
+            std::vector<int64_t> perm = n->attr_ints("perm");
+            if (perm.empty())
+                for (size_t d = x.shape.size(); d-- > 0;) perm.push_back(int64_t(d));
+            if (perm.size() != x.shape.size()) fail("Transpose perm rank mismatch");
+            out.elem = x.elem;
+            for (auto p : perm) out.shape.push_back(x.shape.at(size_t(p)));
+            out.v.resize(x.v.size());
+            auto xs = strides_of(x.shape), os = strides_of(out.shape);
+            for (int64_t f = 0; f < out.numel(); f++) {
+                int64_t src = 0, r = f;
+                for (size_t d = 0; d < out.shape.size(); d++) {
+                    src += (r / os[d]) * xs[size_t(perm[d])];
+                    r %= os[d];
+                }
+                out.v[size_t(f)] = x.v[size_t(src)];
+            }
+        } else if (op == "Gather") {
+            const Sym& x = in(0);
+            const Sym& idx = in(1);
+            if (idx.elem) fail("Gather indices must be integers");
+            size_t ax = norm_axis(n->attr_i("axis", 0), x.shape.size());
+            out.elem = x.elem;
+            int64_t outer = 1, inner = 1;
+            for (size_t d = 0; d < ax; d++) {
+                outer *= x.shape[d];
+                out.shape.push_back(x.shape[d]);
+            }
+            for (auto d : idx.shape) out.shape.push_back(d);
+            for (size_t d = ax + 1; d < x.shape.size(); d++) {
+                inner *= x.shape[d];
+                out.shape.push_back(x.shape[d]);
+            }
+            const int64_t dim = x.shape[ax];
+            for (int64_t o = 0; o < outer; o++)
+                for (int64_t j : idx.v) {
+                    if (j < 0) j += dim;
+                    if (j < 0 || j >= dim) fail("Gather index out of range");
+                    auto b = x.v.begin() + (o * dim + j) * inner;
+                    out.v.insert(out.v.end(), b, b + inner);
+                }
+        } else {
+            fail("unsupported op in the attention policy head: " + op);
+        }
+        return sym_memo[name] = std::move(out);
+    }
+
+    // one MatMul operand row/column -> (channel0, channel stride per q, square) inside the concatenated conv outputs
+    NetSpec::AttOperand att_operand(const std::vector<int64_t>& ids) const {
+        const int area = spec.area();
+        NetSpec::AttOperand o{0, 0, 0};
+        int64_t src0 = -1, chan0 = 0, sq0 = 0;
+        for (size_t q = 0; q < ids.size(); q++) {
+            int64_t src = ids[q] >> 32, rest = ids[q] & 0xffffffff;
+            int64_t chan = rest / area, sq = rest % area;
+            if (src < 1) fail("attention MatMul operand is not a head conv output");
+            if (q == 0) {
+                src0 = src;
+                chan0 = chan;
+                sq0 = sq;
+            } else {
+                if (src != src0 || sq != sq0) fail("attention MatMul operand mixes convs or squares along the query axis");
+                if (q == 1) o.chan_stride = int32_t(chan - chan0);
+                if (chan != chan0 + int64_t(q) * o.chan_stride) fail("attention MatMul operand is not affine in the query index");
+            }
+        }
+        o.chan = int32_t(spec.att_chan_base[size_t(src0 - 1)] + chan0);
+        o.sq = int32_t(sq0);
+        return o;
+    }
+
+    // policy = [Gather(const, axis 1)] o Flatten o [Div|Mul scalar] o MatMul(X, Y); returns false if there is no MatMul
+    bool match_attention_head(const std::string& policy_out) {
+        std::string cur = policy_out;
+        const OnnxTensor* gather_idx = nullptr;
+        double div = 1.0;
+        const OnnxNode* mm = nullptr;
+        for (int guard = 0; guard < 16 && !mm; guard++) {
+            const OnnxNode* n = prod(cur);
+            if (!n) return false;
+            if (n->op == "MatMul") {
+                mm = n;
+            } else if (n->op == "Identity" || (n->op == "Flatten" && n->attr_i("axis", 1) == 1)) {
+                cur = n->inputs.at(0);
+            } else if (n->op == "Gather" && !gather_idx && n->attr_i("axis", 0) == 1) {
+                gather_idx = constant(n->inputs.at(1));
+                if (!gather_idx || gather_idx->dtype == 1) return false;
+                cur = n->inputs.at(0);
+            } else if (n->op == "Div" || n->op == "Mul") {
+                const OnnxTensor* c = constant(n->inputs.at(1));
+                if (!c || c->dtype != 1 || c->f32.size() != 1) return false;
+                div = n->op == "Div" ? div * double(c->f32[0]) : div / double(c->f32[0]);
+                cur = n->inputs.at(0);
+            } else {
+                return false;
+            }
+        }
+        if (!mm) return false;
+        const Sym x = sym_eval(mm->inputs.at(0));
+        const Sym y = sym_eval(mm->inputs.at(1));
+        if (!x.elem || !y.elem || x.shape.size() != 3 || y.shape.size() != 3 || x.shape[0] != 1 || y.shape[0] != 1 ||
+            x.shape[2] != y.shape[1])
+            fail("attention MatMul operands must be [BATCH, M, Q] x [BATCH, Q, N]");
+        const int64_t M = x.shape[1], Q = x.shape[2], N = y.shape[2];
+        spec.att_chan_base.assign(1, 0);
+        for (auto& c : spec.att_convs) spec.att_chan_base.push_back(spec.att_chan_base.back() + (c.cout + 15) / 16 * 16);
+        std::vector<NetSpec::AttOperand> rows, cols;
+        rows.resize(size_t(M));
+        cols.resize(size_t(N));
+        std::vector<int64_t> ids(size_t(Q), 0);
+        for (int64_t i = 0; i < M; i++) {
+            for (int64_t q = 0; q < Q; q++) ids[size_t(q)] = x.v[size_t(i * Q + q)];
+            rows[size_t(i)] = att_operand(ids);
+        }
+        for (int64_t j = 0; j < N; j++) {
+            for (int64_t q = 0; q < Q; q++) ids[size_t(q)] = y.v[size_t(q * N + j)];
+            cols[size_t(j)] = att_operand(ids);
+        }
+        const int64_t count = gather_idx ? int64_t(gather_idx->i64.size()) : M * N;
+        spec.att_entries.resize(size_t(count));
+        for (int64_t p = 0; p < count; p++) {
+            int64_t f = gather_idx ? gather_idx->i64[size_t(p)] : p;
+            if (f < 0) f += M * N;
+            if (f < 0 || f >= M * N) fail("policy Gather index out of range");
+            spec.att_entries[size_t(p)] = NetSpec::AttEntry{rows[size_t(f / N)], cols[size_t(f % N)]};
+        }
+        spec.has_attention = true;
+        spec.att_q = int(Q);
+        spec.att_div = float(div);
+        spec.policy_len = int(count);
+        return true;
     }
 
     void match_heads() {
@@ -334,9 +674,11 @@ struct Matcher {
         if (g.outputs.size() != 2)
             fail("Wrong number of outputs, expected (scalars, policy), got " + std::to_string(g.outputs.size()));
         match_scalar_head(g.outputs[0].name);
-        spec.policy_src = provenance(g.outputs[1].name);
-        spec.policy_len = int(spec.policy_src.size());
-        if (spec.policy_conv2.w.empty()) fail("policy head has no conv map");
+        if (!match_attention_head(g.outputs[1].name)) {
+            spec.policy_src = provenance(g.outputs[1].name);
+            spec.policy_len = int(spec.policy_src.size());
+            if (spec.policy_conv2.w.empty()) fail("policy head has no conv map");
+        }
         for (size_t i = 1; i < g.outputs[1].dims.size(); i++) spec.policy_shape.push_back(g.outputs[1].dims[i]);
     }
 };
@@ -347,6 +689,11 @@ double NetSpec::flops_per_position() const {
     double a = area();
     double f = 2.0 * a * 9 * cin * channels + double(depth) * 2 * (2.0 * a * 9 * channels * channels);
     f += 2.0 * a * channels * (scalar_conv.cout + policy_conv1.cout) + 2.0 * a * policy_conv1.cout * policy_conv2.cout;
+    if (has_attention) {
+        // conv_bulk on every square, conv_under on one rank (post_act.py:131-132), then the [A, Q] x [Q, N] product
+        for (auto& c : att_convs) f += 2.0 * channels * c.cout * (c.cout == 3 * att_q ? board_w : a);
+        f += 2.0 * a * att_q * (a + 3.0 * board_w);
+    }
     f += 2.0 * fc1.in * fc1.out + 2.0 * fc2.in * fc2.out;
     if (has_extra) f += 2.0 * a * channels + 2.0 * extra_fc.in * extra_fc.out;
     return f;

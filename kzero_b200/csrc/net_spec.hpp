@@ -7,6 +7,7 @@
 //   tower   :201-228   x0 = conv3x3(in)+b ; D x [ x <- x + relu(bn(conv3x3(relu(bn(conv3x3(x)))))) ] ; t = bn(x)
 //   scalars :10-23     conv1x1(t)->relu->flatten->fc->relu->fc(5)
 //   policy  :54-112    conv1x1(t)->relu->conv1x1(Pc) then Flatten [+ Gather(const) | ++zeros | ++(conv1x1(t,1)->flatten->fc)]
+//   policy  :115-141   attention head: conv1x1 "bulk"/"under" -> slices/reshapes -> bmm(q_from^T, q_to)/sqrt(Q) -> Gather(const)
 // BN folding: a = gamma/sqrt(var+eps), b = beta - a*mean;
 //   conv followed by BN:   W' = a (.) W,  bias' = a (.) bias + b
 //   BN followed by 1x1 conv (final BN into each head conv): W' = W diag(a), bias' = bias + W b   (exact, no padding)
@@ -51,6 +52,22 @@ struct NetSpec {
     bool has_extra = false;
     ConvParams extra_conv;  // 1x1 C->1, final BN folded in (no relu)
     FcParams extra_fc;      // A -> E
+
+    // attention policy head (post_act.py:115-141): logit[i] = (sum_q E[a.sq][a.chan + q*a.chan_stride] *
+    // E[b.sq][b.chan + q*b.chan_stride]) / att_div, where E[sq][chan] is the concatenation (channel offsets
+    // att_chan_base, each conv padded to a multiple of 16 channels) of the 1x1 convs in att_convs over the tower output.
+    struct AttOperand {
+        int32_t chan, chan_stride, sq;
+    };
+    struct AttEntry {
+        AttOperand a, b;
+    };
+    bool has_attention = false;
+    int att_q = 0;
+    float att_div = 1.0f;
+    std::vector<ConvParams> att_convs;  // final BN folded in, no relu
+    std::vector<int> att_chan_base;     // [att_convs.size() + 1]
+    std::vector<AttEntry> att_entries;  // [policy_len]
 
     int policy_len = 0;
     // policy_src[i] >= 0: pc * A + sq into policy_conv2's output (channel-major, as Flatten sees NCHW)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"libkzb200.so does not export {name}"
 
 
-@pytest.mark.parametrize("name", [n for n in NET_NAMES if "att" not in n])
+@pytest.mark.parametrize("name", NET_NAMES)
 def test_inspect_recognises_reference_exports(name):
     onnx_bytes, x, _, policy = load_net_fixture(name)
     info = inspect_onnx(onnx_bytes)
@@ -54,10 +54,25 @@ def test_inspect_accepts_unfolded_bn():
     assert info.depth == 3 and info.channels == 16
 
 
-def test_inspect_rejects_attention_head_with_message():
-    onnx_bytes, *_ = load_net_fixture("chess_att_2x32")
-    with pytest.raises(KzbError, match="policy head"):
-        inspect_onnx(onnx_bytes)
+def test_inspect_attention_head_flops_and_size():
+    """The attention policy head (post_act.py:115-141) with Q = channels, as supervised_main_alpha.py:76 builds it:
+    conv_bulk C->2Q on 64 squares, conv_under C->3Q on one rank, [64,Q]x[Q,88] product."""
+    c = q = 128
+    info = inspect_onnx(netgen.build_onnx(netgen.game_spec("chess-att"), 2, c, query_channels=q))
+    assert info.policy_len == 1880
+    tower = 2 * 64 * 9 * 21 * c + 2 * 2 * (2 * 64 * 9 * c * c)
+    scalar = 2 * 64 * c * 4 + 2 * 256 * 32 + 2 * 32 * 5
+    att = 2 * 64 * c * 2 * q + 2 * 8 * c * 3 * q + 2 * 64 * 88 * q
+    assert info.flops_per_position == pytest.approx(tower + scalar + att, rel=1e-9)
+
+
+def test_inspect_rejects_unknown_policy_head_with_message():
+    """A graph whose policy output is not one of the reference's heads must fail with a message, not mis-evaluate."""
+    onnx_bytes, *_ = load_net_fixture("chess_conv_2x32")
+    broken = onnx_bytes.replace(b"Gather", b"Gathex")  # same length: the policy head's last op becomes unknown
+    assert broken != onnx_bytes
+    with pytest.raises(KzbError, match="policy head|unsupported"):
+        inspect_onnx(broken)
 
 
 def test_inspect_rejects_garbage():

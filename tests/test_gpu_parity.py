@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 FP32_TOL = 1e-4
 BF16_POLICY_TOL = 2e-2
 
-FIXTURE_GAMES = {"ataxx7_2x32": "ataxx-7", "chess_conv_2x32": "chess", "go9_2x32": "go-9",
+FIXTURE_GAMES = {"ataxx7_2x32": "ataxx-7", "chess_conv_2x32": "chess", "chess_att_2x32": "chess-att", "go9_2x32": "go-9",
                  "ataxx5_scripted_1x16": "ataxx-5"}
 
 
@@ -157,6 +157,23 @@ def test_bf16_packed_vs_oracle(game, depth, ch, n, variant, monkeypatch):
     agree = np.sign(s[clear, 0]) == np.sign(ref_s[clear, 0])
     assert agree.all(), f"value sign agreement {agree.mean():.4f}"
     _check_packed(values, probs, ref_values, ref_probs, mv_off, 5e-2, 1e-2)
+
+
+@pytest.mark.parametrize("precision,tol_logit,tol_v,tol_p", [(PRECISION_FP32, FP32_TOL, FP32_TOL, FP32_TOL),
+                                                              (PRECISION_BF16, BF16_POLICY_TOL, 5e-2, 1e-2)])
+@pytest.mark.parametrize("depth,ch,q,n", [(2, 32, 32, 19), (3, 128, 128, 70)])
+def test_attention_head_vs_oracle(depth, ch, q, n, precision, tol_logit, tol_v, tol_p):
+    """AttentionPolicyHead (post_act.py:115-141), incl. Q = channels = 128 as supervised_main_alpha.py:76 builds it
+    (conv_under has 384 output channels -> two launches)."""
+    spec = netgen.game_spec("chess-att")
+    onnx_bytes = netgen.build_onnx(spec, depth, ch, seed=21, query_channels=q)
+    bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, n, seed=22)
+    ref_s, ref_p, ref_values, ref_probs = _oracle_packed(spec, onnx_bytes, bits, scalars, mv_idx, mv_off)
+    with B200Network(mapper_for(spec), onnx_bytes, n, precision=precision) as net:
+        values, probs = net.evaluate_packed(bits, scalars, mv_idx, mv_off)
+        s, p = net.evaluate_planes(_oracle_planes(spec, bits, scalars))
+    assert np.abs(p - ref_p).max() <= tol_logit, np.abs(p - ref_p).max()
+    _check_packed(values, probs, ref_values, ref_probs, mv_off, tol_v, tol_p)
 
 
 # ------------------------------------------------------------------------------------------- contract edges
