@@ -287,10 +287,35 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+
+    # ---- informational: the same call from TWO executor threads with one network instance each, the reference's
+    #      `gpu_threads_per_device = 2` topology (rust/kz-selfplay/src/server/server_alphazero.rs:89-121): one thread's
+    #      host work and PCIe copies overlap the other's kernels.  Not the headline: the reference's own settings use
+    #      one executor thread per device (python/main/loop_main_alpha.py:25).
+    net2 = B200Network(mapper_for(spec), onnx_bytes, batch, device=local_rank, precision=PRECISION_BF16)
+    for i in range(3):
+        net2.evaluate_packed(*inputs[i % N_INPUT_SETS])
+
+    def executor_thread(n, offset, count):
+        for i in range(count):
+            n.evaluate_packed(*inputs[(i + offset) % N_INPUT_SETS])
+
+    half = (args.steps + 1) // 2
+    threads = [threading.Thread(target=executor_thread, args=(n, k, half)) for k, n in enumerate((net, net2))]
+    barrier()
+    t0 = time.perf_counter()
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    e2e2_s = time.perf_counter() - t0
+    barrier()
+    net2.close()
     clocks = sampler.stop()
 
     dev_s = float(step_ms.sum()) * 1e-3
-    dev_s, e2e_s, wall_value = replicas.max_over_ranks(ctx, [dev_s, e2e_s, wall_value], device="cuda")
+    dev_s, e2e_s, wall_value, e2e2_s = replicas.max_over_ranks(ctx, [dev_s, e2e_s, wall_value, e2e2_s], device="cuda")
 
     if rank == 0:
         peaks = measured_peaks()
@@ -316,6 +341,10 @@ def main():
             "e2e": {"value": replicas.job_throughput(ctx, batch, args.steps, e2e_s), "unit": "positions/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
                     "inputs": f"{N_INPUT_SETS} distinct synthetic batches rotated, host numpy buffers"},
+            "e2e_two_executor_threads": {"value": replicas.job_throughput(ctx, batch, 2 * half, e2e2_s), "unit": "positions/s",
+                                         "ms_per_step": e2e2_s / (2 * half) * 1e3,
+                                         "note": "informational: 2 executor threads x 1 network instance each per GPU "
+                                                 "(the reference's gpu_threads_per_device = 2 topology)"},
             "gpu_launches": int(net.launches_per_eval() * args.steps),
             "launches_per_step": int(net.launches_per_eval()),
             "tflops_whole_step": float(info.flops_per_position) * batch * args.steps / dev_s / 1e12,

@@ -1,5 +1,6 @@
 #include "executor.hpp"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -79,7 +80,8 @@ void PinnedBuffer::alloc(size_t n) {
     ptr = nullptr;
     bytes = n;
     if (n == 0) return;
-    CK(cudaMallocHost(&ptr, n));
+    // mapped + portable: kernels of any device in this process may write results straight into it
+    CK(cudaHostAlloc(&ptr, n, cudaHostAllocMapped | cudaHostAllocPortable));
 }
 
 template <typename T>
@@ -112,6 +114,8 @@ Net::Net(int device, const void* onnx, size_t len, int max_batch, int precision)
         throw std::runtime_error("more than 256 channels is not supported");
 
     CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    if (const char* tr = std::getenv("KZB_TRACE"))
+        if (tr[0] == '1') trace_ = new double[5]();
     if (precision_ == 1)
         build_bf16();
     else
@@ -138,6 +142,10 @@ Net::Net(int device, const void* onnx, size_t len, int max_batch, int precision)
 }
 
 Net::~Net() {
+    if (trace_ && trace_[4] > 0)  // KZB_TRACE=1: mean host-side microseconds per kzb_eval_packed phase
+        std::fprintf(stderr, "[kzb trace] calls %.0f: stage+H2D enqueue %.1f us, launches+D2H enqueue %.1f us, sync wait %.1f us, copy out %.1f us\n",
+                     trace_[4], trace_[0] / trace_[4], trace_[1] / trace_[4], trace_[2] / trace_[4], trace_[3] / trace_[4]);
+    delete[] trace_;
     cudaSetDevice(device_);
     if (stream_) {
         cudaStreamSynchronize(stream_);
@@ -199,7 +207,8 @@ void Net::build_bf16() {
     else
         lay_ = RowLayout{W, H, W + 1, (W + 1) * (H + 1)};
     const int boards_per_tile = mode_ == 1 ? 128 / (W * H) : 0;
-    const int boards_alloc = mode_ == 1 ? round_up(max_batch_, 4) : max_batch_;
+    // 8x8: whole 4-board units; the cluster-pair tower kernel pads the batch to an even number of units
+    const int boards_alloc = mode_ == 1 ? round_up(max_batch_, 8) : max_batch_;
     const char* no_tc8 = std::getenv("KZB_NO_CONV8");
     const bool allow_tc8 = mode_ == 1 && !(no_tc8 && no_tc8[0] == '1');
     conv_tc_prepare();
@@ -304,7 +313,7 @@ void Net::build_bf16() {
 
     // whole-tower persistent kernel: all 2*depth+1 conv3x3 layers in one launch (tower8.cu)
     const char* no_t8 = std::getenv("KZB_NO_TOWER8");
-    const int units_max = (max_batch_ + 3) / 4;
+    const int units_max = ((max_batch_ + 3) / 4 + 1) & ~1;
     if (allow_tc8 && c_pad_ <= 128 && !(no_t8 && no_t8[0] == '1') &&
         (units_max + num_sms_ - 1) / num_sms_ <= tower8_max_local_units()) {
         tower8_prepare();
@@ -328,7 +337,15 @@ void Net::build_bf16() {
         tower_maps_.out[0] = omap(act_x_);
         tower_maps_.out[1] = omap(act_t_);
         act_xt_.alloc(size_t(rows_alloc_ / 256 + 1) * 128 * 256 * 2);
-        tower_maps_.w[0] = convs_[0]->tmap_b;
+        const char* cl_env = std::getenv("KZB_TOWER_CLUSTER");
+        const int cluster = (cl_env && cl_env[0] == '1') ? 1 : 2;
+        {
+            ConvStep& f = *convs_[0];
+            uint64_t dims[2] = {uint64_t(9 * cin_pad_), uint64_t(n)};
+            uint64_t strides[1] = {uint64_t(9 * cin_pad_) * 2};
+            uint32_t box[2] = {64, uint32_t(n / cluster)};
+            tower_maps_.w[0] = make_tmap(f.w_bf16.ptr, 2, dims, strides, box);
+        }
         const size_t layer_w_bytes = size_t(n) * 9 * c_pad_ * 2;
         w_tower_.alloc(std::max<size_t>(layer_w_bytes * 2 * spec_.depth, 256), true);
         for (int i = 0; i < 2 * spec_.depth; i++)
@@ -336,7 +353,7 @@ void Net::build_bf16() {
         {
             uint64_t dims[2] = {uint64_t(9 * c_pad_), uint64_t(std::max(1, 2 * spec_.depth) * n)};
             uint64_t strides[1] = {uint64_t(9 * c_pad_) * 2};
-            uint32_t box[2] = {64, uint32_t(n)};
+            uint32_t box[2] = {64, uint32_t(n / cluster)};
             tower_maps_.w[1] = make_tmap(w_tower_.ptr, 2, dims, strides, box);
         }
         std::vector<TowerLayerDev> layers(tower_layers_);
@@ -364,6 +381,7 @@ void Net::build_bf16() {
         tp.xt = act_xt_.as<__nv_bfloat16>();
         tp.stride = c_pad_;
         tp.b_slots = tower8_pick_b_slots(n);
+        tp.cluster = cluster;
         int cols = 32;
         while (cols < 4 * n) cols *= 2;
         tp.tmem_cols = cols;
@@ -532,6 +550,7 @@ void Net::run_network(int batch, const StepHook& hook) {
     if (use_tower8_) {
         Tower8Params tp = tower_params_;
         tp.num_units = (batch + 3) / 4;
+        if (tp.cluster == 2) tp.num_units = (tp.num_units + 1) & ~1;  // rows of the padding unit exist (boards_alloc) and are never read back
         tp.valid_rows = batch * 64;
         if (timeline_step_ == "tower8") tp.timeline = d_timeline_.as<unsigned long long>();
         launch_tower8(tower_maps_, tp, num_sms_, stream_);
@@ -570,7 +589,7 @@ void Net::run_network(int batch, const StepHook& hook) {
     }
 }
 
-void Net::run_tail(int batch, bool packed, const StepHook& hook) {
+void Net::run_tail(int batch, bool packed, const StepHook& hook, bool to_host) {
     HeadsTailParams p{};
     p.batch = batch;
     p.lay = lay_;
@@ -599,9 +618,12 @@ void Net::run_tail(int batch, bool packed, const StepHook& hook) {
         InBlock ib = in_block(max_batch_, scalar_count_, bits_stride_);
         p.mv_off = d_mv_off_.as<uint32_t>();
         p.mv_idx = reinterpret_cast<const uint32_t*>(d_mv_off_.as<uint8_t>() + ib.off_idx);
-        p.err_flag = d_err_.as<int>();
-        p.out_values = reinterpret_cast<float*>(d_err_.as<uint8_t>() + 16);
-        p.out_probs = reinterpret_cast<float*>(d_err_.as<uint8_t>() + 16 + align16(size_t(max_batch_) * 5 * 4));
+        // results either stay in HBM (staged timing) or are written straight into the pinned, device-mapped host block
+        // (kzb_eval_packed: no separate D2H copies, the posted PCIe writes overlap the kernel)
+        uint8_t* out = to_host ? h_out_.as<uint8_t>() : d_err_.as<uint8_t>();
+        p.err_flag = reinterpret_cast<int*>(out);
+        p.out_values = reinterpret_cast<float*>(out + 16);
+        p.out_probs = reinterpret_cast<float*>(out + 16 + align16(size_t(max_batch_) * 5 * 4));
     }
     launch_heads_tail(p, packed, stream_);
     if (hook) hook("heads_tail");
@@ -627,26 +649,37 @@ void Net::eval_packed(const uint8_t* bits, const float* scalars, int batch, cons
     check_batch(batch);
     require_mapper();
     if (batch == 0) return;
+    using clk = std::chrono::steady_clock;
+    const bool trace = trace_ != nullptr;
+    clk::time_point t0, t1, t2, t3, t4;
+    if (trace) t0 = clk::now();
     CK(cudaSetDevice(device_));
     upload_packed(bits, scalars, batch, mv_idx, mv_off);
-    CK(cudaMemsetAsync(d_err_.ptr, 0, 16, stream_));
+    if (trace) t1 = clk::now();
+    *h_out_.as<volatile int>() = 0;  // error word; the tail kernel only ever writes non-zero into it
     run_encode(batch, nullptr);
     run_network(batch, nullptr);
-    run_tail(batch, true, nullptr);
+    run_tail(batch, true, nullptr, /*to_host=*/true);
     const size_t probs_off = 16 + align16(size_t(max_batch_) * 5 * 4);
-    // values are right behind the error word; probabilities start at a fixed offset: two spans, one stream
-    CK(cudaMemcpyAsync(h_out_.ptr, d_err_.ptr, 16 + size_t(batch) * 5 * 4, cudaMemcpyDeviceToHost, stream_));
-    if (staged_moves_)
-        CK(cudaMemcpyAsync(h_out_.as<uint8_t>() + probs_off, d_err_.as<uint8_t>() + probs_off, staged_moves_ * 4,
-                           cudaMemcpyDeviceToHost, stream_));
+    if (trace) t2 = clk::now();
     CK(cudaStreamSynchronize(stream_));
     CK(cudaGetLastError());
+    if (trace) t3 = clk::now();
     int err = *h_out_.as<int>();
     if (err != 0)
         throw std::runtime_error("Softmax input sum must be strictly positive (board " + std::to_string(err - 1) +
                                  "): the network produced NaN/inf logits");
     std::memcpy(out_values, h_out_.as<uint8_t>() + 16, size_t(batch) * 5 * 4);
     if (staged_moves_) std::memcpy(out_policy, h_out_.as<uint8_t>() + probs_off, staged_moves_ * 4);
+    if (trace) {
+        t4 = clk::now();
+        auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        trace_[0] += us(t0, t1);
+        trace_[1] += us(t1, t2);
+        trace_[2] += us(t2, t3);
+        trace_[3] += us(t3, t4);
+        trace_[4] += 1;
+    }
 }
 
 void Net::encode_planes(const uint8_t* bits, const float* scalars, int batch, float* out_nchw) {

@@ -87,7 +87,7 @@ private:
     void upload_packed(const uint8_t* bits, const float* scalars, int batch, const uint32_t* mv_idx, const uint32_t* mv_off);
     void run_encode(int batch, const StepHook& hook);
     void run_network(int batch, const StepHook& hook);
-    void run_tail(int batch, bool packed, const StepHook& hook);
+    void run_tail(int batch, bool packed, const StepHook& hook, bool to_host = false);
     void flush_l2();
 
     int device_, max_batch_, precision_;
@@ -111,6 +111,7 @@ private:
     std::string timeline_step_;
     PinnedBuffer h_in_, h_out_;
     size_t mv_cap_ = 0;
+    double* trace_ = nullptr;  // KZB_TRACE=1: accumulated host-side phase times of eval_packed
     int staged_batch_ = 0;
     size_t staged_moves_ = 0;
 

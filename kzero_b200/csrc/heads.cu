@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) heads_tail_kernel(HeadsTa
         float mx = fmaxf(sc[1], fmaxf(sc[2], sc[3]));
         float e0 = expf(sc[1] - mx), e1 = expf(sc[2] - mx), e2 = expf(sc[3] - mx);
         float sum = (e0 + e1) + e2;
-        if (!(sum > 0.0f)) atomicCAS(p.err_flag, 0, 1 + b);
+        if (!(sum > 0.0f)) *reinterpret_cast<volatile int*>(p.err_flag) = 1 + b;
         ov[1] = e0 / sum;
         ov[2] = e1 / sum;
         ov[3] = e2 / sum;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) heads_tail_kernel(HeadsTa
         }
         sum = warp_sum(sum);
         if (!(sum > 0.0f)) {  // NaN logits: the reference panics here (common.rs:110)
-            if (lane == 0) atomicCAS(p.err_flag, 0, 1 + b);
+            if (lane == 0) *reinterpret_cast<volatile int*>(p.err_flag) = 1 + b;
         }
 #pragma unroll
         for (int k = 0; k < kRegMoves; k++) {
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) heads_tail_kernel(HeadsTa
     }
     sum = warp_sum(sum);
     if (!(sum > 0.0f)) {
-        if (lane == 0) atomicCAS(p.err_flag, 0, 1 + b);
+        if (lane == 0) *reinterpret_cast<volatile int*>(p.err_flag) = 1 + b;
     }
     for (int j = lane; j < n; j += 32) p.out_probs[o0 + j] /= sum;
 }

@@ -110,7 +110,7 @@ struct TowerLayerDev {
 };
 struct Tower8Maps {
     CUtensorMap a[3];    // loads: encoded planes, X, T   -- (c, x, board, y) order, box (64, 8, 4, 8), SWIZZLE_128B
-    CUtensorMap w[2];    // loads: first-layer weights, concatenated block weights -- box (64, n)
+    CUtensorMap w[2];    // loads: first-layer weights, concatenated block weights -- box (64, n / cluster)
     CUtensorMap out[2];  // stores: X, T                  -- (c, x, board, y) order, box (32, 8, 4, 1), no swizzle
 };
 struct Tower8Params {
@@ -124,6 +124,7 @@ struct Tower8Params {
     __nv_bfloat16* xt;  // channel-major copy of the residual stream: [unit][128 channels][256 positions]
     int stride;  // elements per row of X / T
     int b_slots, tmem_cols;
+    int cluster;  // 1: every CTA streams its own weight tiles; 2: CTA pairs, each loads half of every tile and multicasts it
     unsigned long long* timeline;
     int debug;  // development aid (KZB_DEBUG): 1 = skip A loads, 2 = skip B loads, 4 = skip epilogue memory traffic
 };
@@ -166,7 +167,7 @@ struct HeadsTailParams {
     const uint32_t* mv_off;  // [batch+1]
     float* out_values;       // [batch][5]: tanh(v), softmax(wdl), moves_left
     float* out_probs;        // CSR-aligned with mv_idx
-    int* err_flag;           // set to 1+board when a softmax sum is not > 0 (common.rs:110)
+    int* err_flag;           // set to 1+board (any failing board) when a softmax sum is not > 0 (common.rs:110); may be host memory
 };
 void launch_heads_tail(const HeadsTailParams& p, bool packed, cudaStream_t s);
 

@@ -35,7 +35,10 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiWarps = 8;                   // 2 per TMEM lane quarter (16 measured no faster: the epilogue is bound by L2 traffic, not by latency)
+constexpr int kChunks = 32 / kEpiWarps;        // ranks (32-position chunks) per epilogue warp and unit
+constexpr int kStageBufs = kEpiWarps == 8 ? 2 : 1;
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, the rest epilogue
 constexpr int kBoards = 4;
 constexpr int kAtom = 1024;
 constexpr int kRankBytes = kBoards * kAtom;   // one rank of 4 boards, 64 channels
@@ -44,7 +47,7 @@ constexpr int kXSlots = 3;
 constexpr int kXStride = kXBox + kRankBytes;  // slot + the zero rank that follows it
 constexpr int kXRegion = kRankBytes + kXSlots * kXStride;
 constexpr int kWBytes = 128 * 128;            // weight tile: 128 out-channels x 64 k, 16 KiB
-constexpr int kStageBytes = 8 * 2 * 32 * 64;  // output staging: 8 epilogue warps x 2 buffers x [32 positions][32 ch] bf16
+constexpr int kStageBytes = kEpiWarps * kStageBufs * 32 * 64;  // output staging: per warp [32 positions][32 ch] bf16 tiles
 constexpr int kMaxLocalUnits = 16;
 
 struct SmemT {
@@ -85,6 +88,10 @@ __device__ __forceinline__ void stg256(void* ptr, const uint32_t* r) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// CL = CTAs per cluster.  CL = 2: the two CTAs of a pair walk the same (layer, item) sequence on different boards and
+// share every weight tile: each loads half of it (n/2 output channels) and TMA-multicasts it into both CTAs' rings, which
+// halves the weight traffic out of L2 (the kernel is otherwise pinned by L2->SM bandwidth, profiles/).
+template <int CL>
 __global__ void __launch_bounds__(kThreads, 1)
     tower8_kernel(const __grid_constant__ Tower8Maps maps, const Tower8Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -108,13 +115,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         for (int i = 0; i < p.b_slots; i++) {
             mbar_init(&sm.w_full[i], 1);
-            mbar_init(&sm.w_empty[i], 1);
+            mbar_init(&sm.w_empty[i], CL);  // released by the MMA warps of every CTA the tile was multicast to
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&sm.tmem_full[i], 1);
-            mbar_init(&sm.tmem_empty[i], 8);
+            mbar_init(&sm.tmem_empty[i], kEpiWarps);
         }
-        for (int i = 0; i < kMaxLocalUnits; i++) mbar_init(&sm.ready[i], 8);
+        for (int i = 0; i < kMaxLocalUnits; i++) mbar_init(&sm.ready[i], kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -132,8 +139,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros -> visible to UMMA reads
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast / committed to them
     tc_fence_after();
     const uint32_t tmem_base = *sm.tmem_ptr;
+    const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t kMask = uint16_t((1u << CL) - 1);
     if (tl && threadIdx.x == 0) tl[1] = clock64();
 
     if (warp == 0) {
@@ -173,8 +183,15 @@ __global__ void __launch_bounds__(kThreads, 1)
                                     mbar_arrive(&sm.w_full[w_slot]);
                                 } else {
                                     mbar_expect_tx(&sm.w_full[w_slot], w_bytes);
-                                    tma_load_2d(wmap, &sm.w_full[w_slot], sm.w + size_t(w_slot) * kWBytes,
-                                                tap * ld.cin_pad + kb * 64, ld.w_row0);
+                                    if (CL == 1) {
+                                        tma_load_2d(wmap, &sm.w_full[w_slot], sm.w + size_t(w_slot) * kWBytes,
+                                                    tap * ld.cin_pad + kb * 64, ld.w_row0);
+                                    } else {  // my n/CL rows of the tile, into every CTA of the cluster
+                                        const int rows = p.n / CL;
+                                        tma_load_2d_multicast(wmap, &sm.w_full[w_slot],
+                                                              sm.w + size_t(w_slot) * kWBytes + size_t(cta_rank) * rows * 128,
+                                                              tap * ld.cin_pad + kb * 64, ld.w_row0 + int(cta_rank) * rows, kMask);
+                                    }
                                 }
                                 if (++w_slot == p.b_slots) {
                                     w_slot = 0;
@@ -222,7 +239,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                                     umma_bf16(tmem_d, desc_hi | uint64_t(w_lo + 2 * k), desc_hi | uint64_t(x_t + 2 * k), idesc,
                                               (!first || k != 0) ? 1u : 0u);
                                 }
-                                umma_commit(&sm.w_empty[w_slot]);
+                                if (CL == 1) umma_commit(&sm.w_empty[w_slot]);
+                                else umma_commit_multicast(&sm.w_empty[w_slot], kMask);
                                 if (dy == 1) umma_commit(&sm.x_empty[x_slot]);
                             }
                             __syncwarp();
@@ -252,11 +270,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         // other: own staging buffers, own TMA stores (box = 32 channels x one rank of the 4 boards), own arrivals.
         // Two epilogue warps per scheduler hide each other's ALU / TMEM / shared-memory latencies.
         const int quarter = warp % 4;
-        const int half = (warp - 2) / 4;
+        const int part = (warp - 2) / 4;     // which kChunks ranks of the unit
         const int c = quarter * 32 + lane;   // output channel = TMEM lane of this thread
         const bool warp_ok = quarter * 32 < p.n_store;  // narrow nets: upper warps have no channels
         const bool live = !(p.debug & 4) && warp_ok;
-        uint8_t* const wstage = sm.stage + (warp - 2) * (2 * 32 * 64);  // 2 buffers x [32 positions][32 ch] bf16
+        uint8_t* const wstage = sm.stage + (warp - 2) * (kStageBufs * 32 * 64);
         int item = 0;
         for (int L = 0; L < p.num_layers; L++) {
             const TowerLayerDev ld = p.layers[L];
@@ -273,8 +291,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                 __nv_bfloat16* xt = p.xt + size_t(unit) * (128 * 256) + size_t(c) * 16;
                 uint32_t res[16];
                 if (has_res && live) {
-                    ldg256(xt + ((4 * half) * 2 + 0) * 2048, res);
-                    ldg256(xt + ((4 * half) * 2 + 1) * 2048, res + 8);
+                    ldg256(xt + ((kChunks * part) * 2 + 0) * 2048, res);
+                    ldg256(xt + ((kChunks * part) * 2 + 1) * 2048, res + 8);
                 }
                 mbar_wait(&sm.tmem_full[buf], (item >> 1) & 1);
                 tc_fence_after();
@@ -282,8 +300,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                 const uint32_t taddr = tmem_base + uint32_t(buf) * 256u + (uint32_t(quarter * 32) << 16);
 
 #pragma unroll 1
-                for (int yy = 0; yy < 4; yy++) {
-                    const int y = 4 * half + yy;
+                for (int yy = 0; yy < kChunks; yy++) {
+                    const int y = kChunks * part + yy;
                     uint32_t r[32];
                     tmem_ld32(taddr + y * 32, r);
                     tmem_ld_wait();
@@ -302,15 +320,18 @@ __global__ void __launch_bounds__(kThreads, 1)
                         }
                         packed[j] = pack_bf16(f0, f1);
                     }
-                    if (has_res && live && yy < 3) {  // next rank's residual
+                    if (has_res && live && yy < kChunks - 1) {  // next rank's residual
                         ldg256(xt + ((y + 1) * 2 + 0) * 2048, res);
                         ldg256(xt + ((y + 1) * 2 + 1) * 2048, res + 8);
                     }
                     // staging buffer (yy & 1) was last read by the store of chunk yy-2: allow only the store of
                     // chunk yy-1 to be still reading
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    if (lane == 0) {
+                        if (kStageBufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
                     __syncwarp();
-                    uint8_t* stage = wstage + (yy & 1) * (32 * 64);
+                    uint8_t* stage = wstage + (yy & (kStageBufs - 1)) * (32 * 64);
                     if (live) {
                         // transposed tile [position j][32 channels]: the 32 lanes write 64 contiguous bytes per j
                         uint8_t* sp = stage + lane * 2;
@@ -345,6 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or signal its barriers
     if (tl && threadIdx.x == 0) tl[2] = clock64();
     if (warp == 1) {
         tc_fence_after();
@@ -366,11 +388,33 @@ int tower8_pick_b_slots(int /*n*/) {
 
 int tower8_max_local_units() { return kMaxLocalUnits; }
 
-void tower8_prepare() { cudaFuncSetAttribute(tower8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }
+void tower8_prepare() {
+    cudaFuncSetAttribute(tower8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tower8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
 
+// cluster == 2 requires an even p.num_units (the executor pads the batch with one all-zero unit): then the two CTAs of a
+// pair (blockIdx 2c, 2c+1; units blockIdx + k * gridDim) always own the same number of units and stay in lockstep on the
+// shared weight ring.
 void launch_tower8(const Tower8Maps& maps, const Tower8Params& p, int grid, cudaStream_t s) {
     if (p.num_units <= 0 || p.num_layers <= 0) return;
-    tower8_kernel<<<std::min(grid, p.num_units), kThreads, tower8_smem_bytes(p.b_slots), s>>>(maps, p);
+    if (p.cluster == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(unsigned(std::min(grid & ~1, p.num_units)));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = tower8_smem_bytes(p.b_slots);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, tower8_kernel<2>, maps, p);
+    } else {
+        tower8_kernel<1><<<std::min(grid, p.num_units), kThreads, tower8_smem_bytes(p.b_slots), s>>>(maps, p);
+    }
 }
 
 }  // namespace kzb

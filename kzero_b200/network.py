@@ -74,6 +74,13 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+def _arr(a, dtype) -> np.ndarray:
+    """`a` itself when it already is a C-contiguous array of `dtype` (the hot call stays copy-free), else a converted copy."""
+    if type(a) is np.ndarray and a.dtype == dtype and a.flags.c_contiguous:
+        return a
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
 def device_count() -> int:
     return int(_abi.lib().kzb_device_count())
 
@@ -103,6 +110,7 @@ class B200Network:
             self.close()
             raise
         self._max_batch_size = int(max_batch_size)
+        self._bits_bytes = mapper.bits_bytes()
 
     # -- lifetime ---------------------------------------------------------------------------------
     def close(self) -> None:
@@ -155,17 +163,20 @@ class B200Network:
     # -- array forms of the same call ---------------------------------------------------------------
     def evaluate_packed(self, bits: np.ndarray, scalars: np.ndarray, mv_idx: np.ndarray, mv_off: np.ndarray):
         """kzb_eval_packed: -> (values [n,5], probs [mv_off[-1]])."""
-        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        bits = _arr(bits, np.uint8)
         n = bits.shape[0]
-        assert bits.reshape(n, -1).shape[1] == self.mapper.bits_bytes()
-        scalars = np.ascontiguousarray(scalars, dtype=np.float32).reshape(n, self.mapper.input_scalar_count)
-        mv_idx = np.ascontiguousarray(mv_idx, dtype=np.uint32)
-        mv_off = np.ascontiguousarray(mv_off, dtype=np.uint32)
+        assert bits.size == n * self._bits_bytes
+        scalars = _arr(scalars, np.float32)
+        assert scalars.size == n * self.mapper.input_scalar_count
+        mv_idx = _arr(mv_idx, np.uint32)
+        mv_off = _arr(mv_off, np.uint32)
         assert mv_off.shape[0] == n + 1
         values = np.empty((n, 5), dtype=np.float32)
         probs = np.empty((int(mv_off[-1]),), dtype=np.float32)
-        _abi.check(self._lib.kzb_eval_packed(self._handle, _ptr(bits), _ptr(scalars), n, _ptr(mv_idx), _ptr(mv_off),
-                                             _ptr(values), _ptr(probs)))
+        rc = self._lib.kzb_eval_packed(self._handle, bits.ctypes.data, scalars.ctypes.data, n, mv_idx.ctypes.data,
+                                       mv_off.ctypes.data, values.ctypes.data, probs.ctypes.data)
+        if rc != 0:
+            _abi.check(rc)
         return values, probs
 
     def evaluate_planes(self, nchw: np.ndarray):

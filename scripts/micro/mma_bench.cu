@@ -52,7 +52,7 @@ int main() {
     unsigned long long* d; cudaMalloc(&d, 148 * 16);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     const int iters = 4096;
-    for (int grid : {148}) for (int m : {128}) for (int n : {128, 256}) for (int ce : {0, 4, 8, 16, 32, 128}) {
+    for (int grid : {148}) for (int m : {128}) for (int n : {64, 128, 192, 256}) for (int ce : {0, 4, 16}) {
         bench<<<grid, 128, 60 * 1024>>>(m, n, iters, ce, d);
         cudaError_t e = cudaDeviceSynchronize();
         unsigned long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
