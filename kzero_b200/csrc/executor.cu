@@ -301,6 +301,7 @@ void Net::build_bf16() {
         add("block" + std::to_string(d) + "_conv1", spec_.blocks[2 * d], act_x_, c_pad_, nullptr, act_t_, c_pad_, false, c_pad_, c_pad_);
         add("block" + std::to_string(d) + "_conv2", spec_.blocks[2 * d + 1], act_t_, c_pad_, &act_x_, act_x_, c_pad_, false, c_pad_, c_pad_);
     }
+    head_first_ = convs_.size();
     if (spec_.has_attention) {
         add("scalar_conv", merged_small_conv(spec_), act_x_, c_pad_, nullptr, act_s1_, s1_stride_, true, 16, spec_.scalar_conv.cout);
         for (const AttChunk& ch : att_chunks(spec_))
@@ -309,6 +310,38 @@ void Net::build_bf16() {
         add("policy_conv1", spec_.policy_conv1, act_x_, c_pad_, nullptr, act_h1_, cp_pad_, false, cp_pad_, cp_pad_);
         add("scalar_conv", merged_small_conv(spec_), act_x_, c_pad_, nullptr, act_s1_, s1_stride_, true, 16, spec_.scalar_conv.cout);
         add("policy_conv2", spec_.policy_conv2, act_h1_, cp_pad_, nullptr, act_pm_, pm_stride_, true, pm_stride_, 0);
+    }
+
+    // fused heads kernel: policy conv1 -> relu -> conv2, scalar conv -> relu -> fc -> relu -> fc, masked softmax (heads8.cu)
+    const char* no_h8 = std::getenv("KZB_NO_HEADS8");
+    if (mode_ == 1 && !spec_.has_attention && !spec_.has_extra && !(no_h8 && no_h8[0] == '1')) {
+        Heads8Params hp{};
+        hp.kblocks = c_pad_ / 64;
+        hp.n1 = cp_pad_;
+        hp.n2 = pm_stride_;
+        hp.pc = spec_.policy_conv2.cout;
+        hp.hc = spec_.scalar_conv.cout;
+        hp.hs = spec_.fc1.out;
+        bool src_ok = true;
+        for (int32_t v : spec_.policy_src) src_ok = src_ok && v >= kPolicySrcZero;
+        if (src_ok && heads8_supported(hp)) {
+            heads8_prepare();
+            ConvStep& c1 = *convs_[head_first_];
+            ConvStep& cs = *convs_[head_first_ + 1];
+            ConvStep& c2 = *convs_[head_first_ + 2];
+            hp.b1 = c1.bias.as<float>();
+            hp.bs = cs.bias.as<float>();
+            hp.b2 = c2.bias.as<float>();
+            heads_maps_.w1 = c1.tmap_b;
+            heads_maps_.ws = cs.tmap_b;
+            heads_maps_.w2 = c2.tmap_b;
+            uint64_t dims[2] = {uint64_t(c_pad_), uint64_t(rows_alloc_)};
+            uint64_t strides[1] = {uint64_t(c_pad_) * 2};
+            uint32_t box[2] = {64, 128};
+            heads_maps_.x = make_tmap(act_x_.ptr, 2, dims, strides, box);
+            heads_params_ = hp;
+            use_heads8_ = true;
+        }
     }
 
     // whole-tower persistent kernel: all 2*depth+1 conv3x3 layers in one launch (tower8.cu)
@@ -557,7 +590,8 @@ void Net::run_network(int batch, const StepHook& hook) {
         if (hook) hook("tower8");
         first_step = size_t(tower_layers_);
     }
-    for (size_t si = first_step; si < convs_.size(); si++) {
+    const size_t last_step = (use_heads8_ && precision_ == 1) ? head_first_ : convs_.size();
+    for (size_t si = first_step; si < last_step; si++) {
         auto& st = convs_[si];
         if (precision_ == 1) {
             ConvTcParams p = st->tc;
@@ -590,6 +624,32 @@ void Net::run_network(int batch, const StepHook& hook) {
 }
 
 void Net::run_tail(int batch, bool packed, const StepHook& hook, bool to_host) {
+    if (use_heads8_ && precision_ == 1) {
+        Heads8Params p = heads_params_;
+        p.num_tiles = (batch + 1) / 2;
+        p.batch = batch;
+        p.fc1_t = d_fc1_t_.as<float>();
+        p.fc1_b = d_fc1_b_.as<float>();
+        p.fc2_w = d_fc2_w_.as<float>();
+        p.fc2_b = d_fc2_b_.as<float>();
+        p.policy_src = d_policy_src_.as<int32_t>();
+        p.policy_len = spec_.policy_len;
+        p.packed = packed ? 1 : 0;
+        p.out_scalars = d_out_scalars_.as<float>();
+        p.out_logits = d_out_logits_.as<float>();
+        if (packed) {
+            InBlock ib = in_block(max_batch_, scalar_count_, bits_stride_);
+            p.mv_off = d_mv_off_.as<uint32_t>();
+            p.mv_idx = reinterpret_cast<const uint32_t*>(d_mv_off_.as<uint8_t>() + ib.off_idx);
+            uint8_t* out = to_host ? h_out_.as<uint8_t>() : d_err_.as<uint8_t>();
+            p.err_flag = reinterpret_cast<int*>(out);
+            p.out_values = reinterpret_cast<float*>(out + 16);
+            p.out_probs = reinterpret_cast<float*>(out + 16 + align16(size_t(max_batch_) * 5 * 4));
+        }
+        launch_heads8(heads_maps_, p, num_sms_, stream_);
+        if (hook) hook("heads8");
+        return;
+    }
     HeadsTailParams p{};
     p.batch = batch;
     p.lay = lay_;

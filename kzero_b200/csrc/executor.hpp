@@ -70,7 +70,11 @@ public:
     void stage_packed(const uint8_t* bits, const float* scalars, int batch, const uint32_t* mv_idx, const uint32_t* mv_off);
     void time_staged(int iters, bool flush_l2, float* ms_out);
     void profile_staged(bool flush_l2, std::vector<std::string>& names, std::vector<float>& ms);
-    int launches_per_eval() const { return int(convs_.size()) + 2 - (use_tower8_ ? tower_layers_ - 1 : 0); }
+    int launches_per_eval() const {
+        int n = int(convs_.size()) + 2 - (use_tower8_ ? tower_layers_ - 1 : 0);
+        if (use_heads8_) n -= int(convs_.size() - head_first_);  // head convs + tail become one launch
+        return n;
+    }
 
     const NetSpec& spec() const { return spec_; }
     int device() const { return device_; }
@@ -116,6 +120,12 @@ private:
     size_t staged_moves_ = 0;
 
     std::vector<std::unique_ptr<ConvStep>> convs_;
+
+    // fused heads kernel (8x8 boards, conv policy head): replaces the three head conv steps and the tail kernel
+    bool use_heads8_ = false;
+    size_t head_first_ = 0;  // index of the first head conv step in convs_
+    Heads8Maps heads_maps_{};
+    Heads8Params heads_params_{};
 
     // whole-tower persistent kernel (8x8 boards): covers convs_[0 .. tower_layers_)
     bool use_tower8_ = false;

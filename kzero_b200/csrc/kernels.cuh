@@ -171,4 +171,39 @@ struct HeadsTailParams {
 };
 void launch_heads_tail(const HeadsTailParams& p, bool packed, cudaStream_t s);
 
+// ---------------------------------------------------------------------------------------------- K1' + K3 fused (heads8.cu)
+struct Heads8Maps {
+    CUtensorMap x;   // tower output rows [rows][c_pad] bf16, box (64, 128), SWIZZLE_128B
+    CUtensorMap w1;  // policy conv1 [n1][c_pad], box (64, n1)
+    CUtensorMap w2;  // policy conv2 [n2][n1],    box (64, n2)
+    CUtensorMap ws;  // scalar conv  [16][c_pad], box (64, 16)
+};
+struct Heads8Params {
+    int num_tiles;  // 128-row tiles = pairs of 8x8 boards
+    int batch;
+    int kblocks;    // c_pad / 64
+    int n1, n2;     // padded output channels of policy conv1 (multiple of 64) / conv2 (multiple of 16)
+    int pc;         // real output channels of policy conv2
+    int hc, hs;     // scalar head: conv channels, hidden size (<= 32)
+    const float *b1, *b2, *bs;  // [n1], [n2], [16]
+    const float* fc1_t;         // [hc*64][hs]
+    const float* fc1_b;         // [hs]
+    const float* fc2_w;         // [5][hs]
+    const float* fc2_b;         // [5]
+    const int32_t* policy_src;  // [P]: pc*64 + sq, or -1 for a constant-zero logit
+    int policy_len;
+    int packed;
+    const uint32_t* mv_idx;
+    const uint32_t* mv_off;
+    float* out_values;
+    float* out_probs;
+    int* err_flag;
+    float* out_scalars;
+    float* out_logits;
+};
+size_t heads8_smem_bytes(const Heads8Params& p);
+bool heads8_supported(const Heads8Params& p);
+void heads8_prepare();
+void launch_heads8(const Heads8Maps& maps, const Heads8Params& p, int grid, cudaStream_t s);
+
 }  // namespace kzb
