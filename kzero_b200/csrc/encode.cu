@@ -117,7 +117,57 @@ __global__ void nchw_to_rows_kernel(const float* __restrict__ in, int batch, int
     }
 }
 
+// k-chunk-major input for the second-generation 8x8 tower (tower8k.cu): out[kc][board][square][8 channels] bf16.
+// One CTA per board, thread = (kc, square), one 16-byte store each; 64 consecutive threads write 1 KiB contiguous.
+template <bool PACKED>
+__global__ void encode_kc_kernel(EncodeParams p, const float* __restrict__ nchw, int channels, int kc_total, int boards_total) {
+    extern __shared__ uint8_t smem[];
+    float* s_scalars = reinterpret_cast<float*>(smem);
+    uint8_t* s_bits = smem + ((p.scalar_count * 4 + 15) / 16) * 16;
+    const int b = blockIdx.x;
+    if (PACKED) {
+        for (int i = threadIdx.x; i < p.scalar_count; i += blockDim.x) s_scalars[i] = p.scalars[size_t(b) * p.scalar_count + i];
+        for (int i = threadIdx.x; i < p.bits_stride; i += blockDim.x) s_bits[i] = p.bits[size_t(b) * p.bits_stride + i];
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < kc_total * 64; t += blockDim.x) {
+        const int kc = t >> 6, sq = t & 63;
+        Vec8<__nv_bfloat16> out;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int c = kc * 8 + j;
+            float f = 0.0f;
+            if (PACKED) {
+                if (c < p.scalar_count) {
+                    f = s_scalars[c];  // mod.rs:54-56
+                } else if (c < p.scalar_count + p.bool_channels) {
+                    const int i = (c - p.scalar_count) * 64 + sq;  // mod.rs:57-59, bit_buffer.rs:73-75
+                    f = float((s_bits[i >> 3] >> (i & 7)) & 1);
+                }
+            } else if (c < channels) {
+                f = nchw[(size_t(b) * channels + c) * 64 + sq];
+            }
+            out.set(j, f);
+        }
+        out.store(p.out, (size_t(kc) * boards_total + b) * 64 + sq);
+    }
+}
+
 }  // namespace
+
+void launch_encode_kc(const EncodeParams& p, int kc_total, int boards_total, cudaStream_t s) {
+    if (p.batch <= 0) return;
+    size_t smem = ((p.scalar_count * 4 + 15) / 16) * 16 + p.bits_stride;
+    encode_kc_kernel<true><<<p.batch, std::min(kc_total * 64, 512), smem, s>>>(p, nullptr, 0, kc_total, boards_total);
+}
+
+void launch_nchw_to_kc(const float* in, int batch, int channels, int kc_total, int boards_total, void* out, cudaStream_t s) {
+    if (batch <= 0) return;
+    EncodeParams p{};
+    p.batch = batch;
+    p.out = out;
+    encode_kc_kernel<false><<<batch, std::min(kc_total * 64, 512), 0, s>>>(p, in, channels, kc_total, boards_total);
+}
 
 void launch_encode_nhwc(const EncodeParams& p, bool out_bf16, cudaStream_t s) {
     if (p.batch <= 0) return;

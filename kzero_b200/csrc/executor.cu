@@ -402,6 +402,10 @@ void Net::build_bf16() {
             l.has_res = conv2 ? 1 : 0;
             l.out_buf = (first || conv2) ? 1 : 2;
             l.bias = convs_[i]->bias.as<float>();
+            // second-generation kernel: a narrow single-k-block first layer only stages / multiplies the chunks that exist
+            l.ksteps = (first && l.kblocks == 1) ? std::max(1, (spec_.cin + 15) / 16) : 4;
+            l.kchunks = 2 * l.ksteps;
+            l.out_rowmajor = (i == tower_layers_ - 1) ? 1 : 0;
         }
         upload(d_tower_layers_, layers);
         Tower8Params& tp = tower_params_;
@@ -418,6 +422,37 @@ void Net::build_bf16() {
         int cols = 32;
         while (cols < 4 * n) cols *= 2;
         tp.tmem_cols = cols;
+        // second generation (tower8k.cu): k-chunk-major activations, one staged copy per k-block
+        const char* v1 = std::getenv("KZB_TOWER_V1");
+        if (!(v1 && v1[0] == '1')) {
+            tower8k_prepare();
+            const uint64_t boards_total = uint64_t(rows_alloc_ / 64);
+            act_ink_.alloc(size_t(cin_pad_ / 8) * boards_total * 1024);
+            act_xk_.alloc(size_t(c_pad_ / 8) * boards_total * 1024);
+            act_tk_.alloc(size_t(c_pad_ / 8) * boards_total * 1024);
+            auto kload = [&](DeviceBuffer& buf, int kc_total) {  // (x*8+c8, board, y, kc)
+                uint64_t dims[4] = {64, boards_total, 8, uint64_t(kc_total)};
+                uint64_t strides[3] = {1024, 128, boards_total * 1024};
+                uint32_t box[4] = {72, 4, 8, 1};  // 72 > 64: the engine zero-fills the pad row of every 8-position group
+                return make_tmap(buf.ptr, 4, dims, strides, box, false);
+            };
+            auto kstore = [&](DeviceBuffer& buf, int kc_total) {  // (x*8+c8, kc, board, y)
+                uint64_t dims[4] = {64, uint64_t(kc_total), boards_total, 8};
+                uint64_t strides[3] = {boards_total * 1024, 1024, 128};
+                uint32_t box[4] = {80, 4, 4, 1};  // staging rows are 160 bytes (bank spreading); elements 64..79 are clipped
+                return make_tmap(buf.ptr, 4, dims, strides, box, false);
+            };
+            tower_kmaps_.a[0] = kload(act_ink_, cin_pad_ / 8);
+            tower_kmaps_.a[1] = kload(act_xk_, c_pad_ / 8);
+            tower_kmaps_.a[2] = kload(act_tk_, c_pad_ / 8);
+            tower_kmaps_.out[0] = kstore(act_xk_, c_pad_ / 8);
+            tower_kmaps_.out[1] = kstore(act_tk_, c_pad_ / 8);
+            tower_kmaps_.out[2] = omap(act_x_);
+            tower_kmaps_.w[0] = tower_maps_.w[0];
+            tower_kmaps_.w[1] = tower_maps_.w[1];
+            tower_k_b_slots_ = tower8k_pick_b_slots();
+            use_tower8k_ = true;
+        }
         tp.timeline = nullptr;
         const char* dbg = std::getenv("KZB_DEBUG");
         tp.debug = dbg ? std::atoi(dbg) : 0;
@@ -574,7 +609,12 @@ void Net::run_encode(int batch, const StepHook& hook) {
     p.lay = lay_;
     p.c_pad = cin_pad_;
     p.out = act_in_.ptr;
-    launch_encode_nhwc(p, act_bf16_, stream_);
+    if (use_tower8k_) {
+        p.out = act_ink_.ptr;
+        launch_encode_kc(p, cin_pad_ / 8, rows_alloc_ / 64, stream_);
+    } else {
+        launch_encode_nhwc(p, act_bf16_, stream_);
+    }
     if (hook) hook("encode");
 }
 
@@ -586,7 +626,12 @@ void Net::run_network(int batch, const StepHook& hook) {
         if (tp.cluster == 2) tp.num_units = (tp.num_units + 1) & ~1;  // rows of the padding unit exist (boards_alloc) and are never read back
         tp.valid_rows = batch * 64;
         if (timeline_step_ == "tower8") tp.timeline = d_timeline_.as<unsigned long long>();
-        launch_tower8(tower_maps_, tp, num_sms_, stream_);
+        if (use_tower8k_) {
+            tp.b_slots = tower_k_b_slots_;
+            launch_tower8k(tower_kmaps_, tp, num_sms_, stream_);
+        } else {
+            launch_tower8(tower_maps_, tp, num_sms_, stream_);
+        }
         if (hook) hook("tower8");
         first_step = size_t(tower_layers_);
     }
@@ -646,6 +691,7 @@ void Net::run_tail(int batch, bool packed, const StepHook& hook, bool to_host) {
             p.out_values = reinterpret_cast<float*>(out + 16);
             p.out_probs = reinterpret_cast<float*>(out + 16 + align16(size_t(max_batch_) * 5 * 4));
         }
+        p.timeline = timeline_step_ == "heads8" ? d_timeline_.as<unsigned long long>() : nullptr;
         launch_heads8(heads_maps_, p, num_sms_, stream_);
         if (hook) hook("heads8");
         return;
@@ -695,7 +741,10 @@ void Net::eval_planes(const float* nchw, int batch, float* out_scalars, float* o
     CK(cudaSetDevice(device_));
     const int area = spec_.area();
     CK(cudaMemcpyAsync(d_nchw_.ptr, nchw, size_t(batch) * spec_.cin * area * 4, cudaMemcpyHostToDevice, stream_));
-    launch_nchw_to_rows(d_nchw_.as<float>(), batch, spec_.cin, lay_, cin_pad_, act_in_.ptr, act_bf16_, stream_);
+    if (use_tower8k_)
+        launch_nchw_to_kc(d_nchw_.as<float>(), batch, spec_.cin, cin_pad_ / 8, rows_alloc_ / 64, act_ink_.ptr, stream_);
+    else
+        launch_nchw_to_rows(d_nchw_.as<float>(), batch, spec_.cin, lay_, cin_pad_, act_in_.ptr, act_bf16_, stream_);
     run_network(batch, nullptr);
     run_tail(batch, false, nullptr);
     CK(cudaMemcpyAsync(out_scalars, d_out_scalars_.ptr, size_t(batch) * 5 * 4, cudaMemcpyDeviceToHost, stream_));

@@ -133,6 +133,11 @@ private:
     Tower8Maps tower_maps_{};
     Tower8Params tower_params_{};
     DeviceBuffer d_tower_layers_, w_tower_, act_xt_;
+    // second generation (tower8k.cu): k-chunk-major activation tensors A[kc][board][y][x][8]
+    bool use_tower8k_ = false;
+    Tower8kMaps tower_kmaps_{};
+    int tower_k_b_slots_ = 0;
+    DeviceBuffer act_ink_, act_xk_, act_tk_;
 };
 
 // thread-local error plumbing for the C ABI

@@ -98,6 +98,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     const SmemH sm = carve_h(smem, p);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int kb = p.kblocks, kb2 = p.n1 / 64;
+    // development aid: stamps [0] kernel start, [1] setup done, [2] end; per tile t (8 + 8t + k):
+    //   k=0 d1_full seen, 1 epi1 done, 2 d2_full seen, 3 epi2 done (after barrier), 4 tail done, 5 MMA1 issued, 6 MMA2 issued
+    unsigned long long* tl = p.timeline ? p.timeline + size_t(blockIdx.x) * 1024 : nullptr;
+#define KZB_HSTAMP(t, k) do { if (tl && (t) < 100 && lane == 0) tl[8 + (t) * 8 + (k)] = clock64(); } while (0)
+    if (tl && threadIdx.x == 0) tl[0] = clock64();
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.x)) : "memory");
@@ -124,6 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *sm.tmem_ptr;
+    if (tl && threadIdx.x == 0) tl[1] = clock64();
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -181,6 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 umma_commit(&sm.x_empty[stage]);
                 umma_commit(sm.d1_full);
             }
+            KZB_HSTAMP(local, 5);
             __syncwarp();
             if (++stage == kXStages) {
                 stage = 0;
@@ -200,6 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 }
                 umma_commit(sm.d2_full);
             }
+            KZB_HSTAMP(local, 6);
             __syncwarp();
         }
     } else {
@@ -216,8 +224,10 @@ __global__ void __launch_bounds__(kThreads, 1)
             const uint32_t par = uint32_t(local) & 1;
             // every warp is done reading L / S of the previous tile before H / S are overwritten
             epi_bar();
+            if (warp == 2 && local > 0) KZB_HSTAMP(local - 1, 4);
             mbar_wait(sm.d1_full, par);
             tc_fence_after();
+            if (warp == 2) KZB_HSTAMP(local, 0);
             // ---- epi1: scalar conv -> S, policy conv1 -> H
             {
                 uint32_t r[16];
@@ -254,10 +264,12 @@ __global__ void __launch_bounds__(kThreads, 1)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // H (generic proxy) -> UMMA reads
             tc_fence_before();
             mbar_arrive(sm.h_full);
+            if (warp == 2) KZB_HSTAMP(local, 1);
 
             // ---- epi2: policy conv2 -> fp32 logits L[board][pc*64 + sq]
             mbar_wait(sm.d2_full, par);
             tc_fence_after();
+            if (warp == 2) KZB_HSTAMP(local, 2);
             for (int c0 = 0; c0 < p.n2; c0 += 16) {
                 uint32_t r[16];
                 tmem_ld16(lane_addr + kD2Col + c0, r);
@@ -269,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             tc_fence_before();
             mbar_arrive(sm.d2_free);
             epi_bar();  // L and S complete
+            if (warp == 2) KZB_HSTAMP(local, 3);
 
             // ---- tail: two warps per board; the even one runs the scalar head, both split the policy work
             const int b = tile * 2 + (quarter >> 1);
@@ -382,6 +395,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     tc_fence_before();
     __syncthreads();
+    if (tl && threadIdx.x == 0) tl[2] = clock64();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");

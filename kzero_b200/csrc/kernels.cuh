@@ -107,6 +107,10 @@ struct TowerLayerDev {
     int has_res;  // add X (same rows) after the relu
     int out_buf;  // 1 = X, 2 = T
     const float* bias;
+    // second-generation kernel (tower8k.cu)
+    int kchunks;       // 8-channel chunks staged per k-block (8, fewer for a narrow first layer)
+    int ksteps;        // K=16 MMA steps per k-block and tap (kchunks / 2)
+    int out_rowmajor;  // last layer: store [position][C] rows (what the head kernels read) instead of k-chunk-major
 };
 struct Tower8Maps {
     CUtensorMap a[3];    // loads: encoded planes, X, T   -- (c, x, board, y) order, box (64, 8, 4, 8), SWIZZLE_128B
@@ -129,6 +133,22 @@ struct Tower8Params {
     int debug;  // development aid (KZB_DEBUG): 1 = skip A loads, 2 = skip B loads, 4 = skip epilogue memory traffic
 };
 void launch_tower8(const Tower8Maps& maps, const Tower8Params& p, int grid, cudaStream_t s);
+
+// second generation (tower8k.cu): k-chunk-major activations A[kc][board][y][x][8], every tap = a descriptor offset
+struct Tower8kMaps {
+    CUtensorMap a[3];    // loads: encoded planes, X, T -- dims (x*8+c8: 64, board, y: 8, kc), box (72, 4, 8, 1), no swizzle
+    CUtensorMap w[2];    // loads: first-layer weights, concatenated block weights -- box (64, n / cluster), SWIZZLE_128B
+    CUtensorMap out[3];  // stores: X, T k-chunk-major -- dims (64, kc, board, y), box (80, 4, 4, 1); [2] = X row-major (c, x, board, y), box (32, 8, 4, 1)
+};
+void launch_tower8k(const Tower8kMaps& maps, const Tower8Params& p, int grid, cudaStream_t s);
+size_t tower8k_smem_bytes(int w_slots);
+int tower8k_pick_b_slots();
+int tower8k_max_local_units();
+void tower8k_prepare();
+
+// K2 / layout twins for the k-chunk-major tower input: out[kc][boards_total][64 squares][8 channels] bf16
+void launch_encode_kc(const EncodeParams& p, int kc_total, int boards_total, cudaStream_t s);
+void launch_nchw_to_kc(const float* in, int batch, int channels, int kc_total, int boards_total, void* out, cudaStream_t s);
 size_t tower8_smem_bytes(int w_slots);
 int tower8_pick_b_slots(int n);
 int tower8_max_local_units();
@@ -200,6 +220,7 @@ struct Heads8Params {
     int* err_flag;
     float* out_scalars;
     float* out_logits;
+    unsigned long long* timeline;  // development aid (KZB_TIMELINE=heads8): per-CTA clock64() stamps
 };
 size_t heads8_smem_bytes(const Heads8Params& p);
 bool heads8_supported(const Heads8Params& p);

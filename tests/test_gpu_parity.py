@@ -128,12 +128,12 @@ def test_fp32_packed_vs_oracle(game, depth, ch, n):
     _check_packed(values, probs, ref_values, ref_probs, mv_off, FP32_TOL, FP32_TOL)
 
 
-@pytest.mark.parametrize("variant", ["default", "no_heads8", "no_tower8", "no_conv8", "linear"])
+@pytest.mark.parametrize("variant", ["default", "tower_v1", "no_heads8", "no_tower8", "no_conv8", "linear"])
 @pytest.mark.parametrize("game,depth,ch,n", [("ataxx-7", 8, 64, 256), ("chess", 16, 128, 64), ("go-9", 4, 64, 40),
                                               ("chess", 2, 32, 7), ("chess", 3, 64, 130)])
 def test_bf16_packed_vs_oracle(game, depth, ch, n, variant, monkeypatch):
-    """The tensor-core path in all its forms: whole-tower persistent kernel + fused heads kernel (tower8.cu, heads8.cu,
-    default for 8x8 boards), the same tower with per-op head convs + tail kernel (KZB_NO_HEADS8=1),
+    """The tensor-core path in all its forms: whole-tower persistent kernel + fused heads kernel (tower8k.cu, heads8.cu,
+    default for 8x8 boards), the first-generation tower kernel (tower8.cu, KZB_TOWER_V1=1), the same tower with per-op head convs + tail kernel (KZB_NO_HEADS8=1),
     per-layer 8x8 specialisation (conv_tc8.cu, KZB_NO_TOWER8=1), generic 4-D TMA box per tap (KZB_NO_CONV8=1),
     padded-row 2-D TMA (every other board size / KZB_FORCE_LINEAR=1)."""
     if variant != "default" and game != "chess":
@@ -142,6 +142,7 @@ def test_bf16_packed_vs_oracle(game, depth, ch, n, variant, monkeypatch):
     monkeypatch.setenv("KZB_FORCE_LINEAR", force_linear)
     monkeypatch.setenv("KZB_NO_CONV8", "1" if variant == "no_conv8" else "0")
     monkeypatch.setenv("KZB_NO_TOWER8", "1" if variant == "no_tower8" else "0")
+    monkeypatch.setenv("KZB_TOWER_V1", "1" if variant == "tower_v1" else "0")
     monkeypatch.setenv("KZB_NO_HEADS8", "1" if variant in ("no_heads8", "no_conv8") else "0")
     spec = netgen.game_spec(game)
     onnx_bytes = netgen.build_onnx(spec, depth, ch, seed=9)
