@@ -109,6 +109,81 @@ int kzb_profile_staged(kzb_net* net, int flush_l2, char* names_out, size_t names
 /* Number of kernel launches one kzb_eval_packed call issues. */
 int kzb_launches_per_eval(const kzb_net* net);
 
+/* ---- self-play driver ("next" row N1; BASELINE.json configs[3]) ---------------------------------
+ * The producer side of the hot path: generator threads running concurrent AlphaZero tree searches and executor
+ * threads batching their requests into the evaluator above.  Replaces, for measurement purposes, what
+ * `selfplay_server_main` spawns per device (rust/kz-selfplay/src/server/server_alphazero.rs:32-124):
+ * `generator_alphazero_main` (generator_alphazero.rs:23-260) + `batched_executor_loop` (executor.rs:27-146), with the
+ * search of rust/kz-core/src/zero/{step,node,tree}.rs.  No TCP control plane, no game files. */
+
+#define KZB_GAME_SYNTH_CHESS 0 /* chess-shaped synthetic game: 13x8x8 bools + 8 scalars, 1880-move policy, 20..45 legal moves */
+#define KZB_GAME_ATAXX7 1      /* 7x7 ataxx, AtaxxStdMapper encoding (rust/kz-core/src/mapping/ataxx.rs)                      */
+
+/* Field for field the reference's settings: StartupSettings (rust/kz-selfplay/src/server/protocol.rs:11-40:
+ * cpu_threads_per_device, gpu_threads_per_device, gpu_batch_size, search_batch_size) and Settings (protocol.rs:58-110). */
+typedef struct kzb_selfplay_config {
+    int32_t game;
+    int32_t visits;            /* full_iterations: root visits per move                                             */
+    int32_t search_batch;      /* search_batch_size: requests gathered per tree per round (virtual loss)            */
+    int32_t gpu_batch;         /* gpu_batch_size: max positions per evaluator call                                  */
+    int32_t cpu_threads;       /* cpu_threads_per_device: generator threads                                         */
+    int32_t gpu_threads;       /* gpu_threads_per_device: executor threads, one network instance each               */
+    int32_t concurrent_games;  /* 0 = the reference's ceil((gpu_threads + 1) * gpu_batch / search_batch)             */
+    int32_t max_game_length;
+    int32_t cache_size;        /* per-game LRU evaluation cache                                                     */
+    int32_t zero_temp_move_count;
+    int32_t max_moves;         /* stop after this many played moves (0 = run for duration_s)                        */
+    float duration_s;
+    float temperature;         /* move selection temperature                                                        */
+    float dirichlet_alpha, dirichlet_eps;
+    float policy_temperature_root, policy_temperature_child; /* search_policy_temperature_*                        */
+    float exploration_weight, moves_left_weight, moves_left_clip, moves_left_sharpness; /* UctWeights              */
+    float fpu_root;
+    int32_t fpu_root_relative; /* FpuMode: 0 fixed, 1 relative                                                      */
+    float fpu_child;
+    int32_t fpu_child_relative;
+    float virtual_loss;        /* search_virtual_loss_weight                                                        */
+    int32_t q_mode_wdl;        /* QMode: 0 value head, 1 wdl head with draw_score                                   */
+    float draw_score;
+    uint64_t seed;
+} kzb_selfplay_config;
+
+/* The counters of the reference's collector line `evals/s: real / cached / potential` (collector.rs:172-191). */
+typedef struct kzb_selfplay_stats {
+    double seconds;
+    uint64_t real_evals;      /* positions evaluated by the network                                                 */
+    uint64_t cached_evals;    /* requests served from the per-game LRU caches                                       */
+    uint64_t potential_evals; /* batches * gpu_batch                                                                */
+    uint64_t batches;
+    uint64_t max_batch;
+    uint64_t games_finished, moves_played;
+    uint64_t root_visits;     /* sum of root visits of the finished searches                                        */
+    uint64_t concurrent_games;
+} kzb_selfplay_stats;
+
+/* The reference's typical production settings (python/main/loop_main_alpha.py:24-52, UctWeights::default). */
+void kzb_selfplay_default_config(kzb_selfplay_config* config);
+
+/* Run self-play on `device` with the network in `onnx_bytes` until duration_s / max_moves; MCTS nodes/sec =
+ * (real_evals + cached_evals) / seconds, NN positions/sec = real_evals / seconds. */
+int kzb_selfplay_run(int device, const void* onnx_bytes, size_t onnx_len, int precision, const kzb_selfplay_config* config,
+                     kzb_selfplay_stats* stats);
+
+/* Host-only (no GPU): one tree search of `config->visits` visits from the position `plies` random moves into game
+ * `game_seed`, gathered in rounds of `config->search_batch` (virtual loss) and answered by a deterministic stand-in
+ * network (eval_kind 0: uniform, the reference's DummyNetwork, network/dummy.rs:44-60; 1: hashed pseudo-random).
+ * Exists so that the search (zero_step_gather / zero_step_apply / uct) can be checked against the oracle's restatement. */
+typedef struct kzb_mcts_trace_out {
+    int32_t capacity;       /* in: length of the three arrays below                                                 */
+    int32_t n_children;     /* out: root children = available moves, in available_moves order                       */
+    uint64_t* child_visits; /* complete_visits per root child                                                       */
+    uint32_t* child_moves;  /* the child's move (= its policy index in the bundled games)                           */
+    float* child_policy;    /* net_policy per root child                                                            */
+    float root_values[5];   /* Tree::values(): value, win, draw, loss, moves_left from the root player's view       */
+    uint64_t root_visits, tree_nodes, evals;
+} kzb_mcts_trace_out;
+int kzb_mcts_trace(const kzb_selfplay_config* config, uint64_t game_seed, int plies, int eval_kind, kzb_mcts_trace_out* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,36 @@ class NetInfo(ctypes.Structure):
                 ("conv_mode", ctypes.c_int32), ("flops_per_position", ctypes.c_double)]
 
 
+class SelfplayConfig(ctypes.Structure):
+    """kzb_selfplay_config (include/kzb200.h)."""
+    _fields_ = [("game", ctypes.c_int32), ("visits", ctypes.c_int32), ("search_batch", ctypes.c_int32), ("gpu_batch", ctypes.c_int32),
+                ("cpu_threads", ctypes.c_int32), ("gpu_threads", ctypes.c_int32), ("concurrent_games", ctypes.c_int32),
+                ("max_game_length", ctypes.c_int32), ("cache_size", ctypes.c_int32), ("zero_temp_move_count", ctypes.c_int32),
+                ("max_moves", ctypes.c_int32), ("duration_s", ctypes.c_float), ("temperature", ctypes.c_float),
+                ("dirichlet_alpha", ctypes.c_float), ("dirichlet_eps", ctypes.c_float),
+                ("policy_temperature_root", ctypes.c_float), ("policy_temperature_child", ctypes.c_float),
+                ("exploration_weight", ctypes.c_float), ("moves_left_weight", ctypes.c_float), ("moves_left_clip", ctypes.c_float),
+                ("moves_left_sharpness", ctypes.c_float), ("fpu_root", ctypes.c_float), ("fpu_root_relative", ctypes.c_int32),
+                ("fpu_child", ctypes.c_float), ("fpu_child_relative", ctypes.c_int32), ("virtual_loss", ctypes.c_float),
+                ("q_mode_wdl", ctypes.c_int32), ("draw_score", ctypes.c_float), ("seed", ctypes.c_uint64)]
+
+
+class SelfplayStats(ctypes.Structure):
+    """kzb_selfplay_stats (include/kzb200.h)."""
+    _fields_ = [("seconds", ctypes.c_double), ("real_evals", ctypes.c_uint64), ("cached_evals", ctypes.c_uint64),
+                ("potential_evals", ctypes.c_uint64), ("batches", ctypes.c_uint64), ("max_batch", ctypes.c_uint64),
+                ("games_finished", ctypes.c_uint64), ("moves_played", ctypes.c_uint64), ("root_visits", ctypes.c_uint64),
+                ("concurrent_games", ctypes.c_uint64)]
+
+
+class MctsTraceOut(ctypes.Structure):
+    """kzb_mcts_trace_out (include/kzb200.h)."""
+    _fields_ = [("capacity", ctypes.c_int32), ("n_children", ctypes.c_int32), ("child_visits", ctypes.POINTER(ctypes.c_uint64)),
+                ("child_moves", ctypes.POINTER(ctypes.c_uint32)), ("child_policy", ctypes.POINTER(ctypes.c_float)),
+                ("root_values", ctypes.c_float * 5), ("root_visits", ctypes.c_uint64), ("tree_nodes", ctypes.c_uint64),
+                ("evals", ctypes.c_uint64)]
+
+
 # every symbol include/kzb200.h declares: name -> (restype, argtypes)
 _vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
 SYMBOLS = {
@@ -32,6 +62,9 @@ SYMBOLS = {
     "kzb_time_staged": (_i, [_vp, _i, _i, _vp]),
     "kzb_profile_staged": (_i, [_vp, _i, _vp, _sz, _vp, _i, ctypes.POINTER(_i)]),
     "kzb_launches_per_eval": (_i, [_vp]),
+    "kzb_selfplay_default_config": (None, [ctypes.POINTER(SelfplayConfig)]),
+    "kzb_selfplay_run": (_i, [_i, _vp, _sz, _i, ctypes.POINTER(SelfplayConfig), ctypes.POINTER(SelfplayStats)]),
+    "kzb_mcts_trace": (_i, [ctypes.POINTER(SelfplayConfig), ctypes.c_uint64, _i, _i, ctypes.POINTER(MctsTraceOut)]),
 }
 
 

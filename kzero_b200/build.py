@@ -19,7 +19,7 @@ OBJ = PKG / "_obj"
 LIB = PKG / "libkzb200.so"
 
 SOURCES = ["onnx_reader.cpp", "net_spec.cpp", "api.cpp", "executor.cu", "encode.cu", "conv_fp32.cu", "conv_tc.cu", "conv_tc8.cu", "tower8.cu",
-           "tower8k.cu", "heads.cu", "heads8.cu"]
+           "tower8k.cu", "heads.cu", "heads8.cu", "selfplay/selfplay.cpp"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unknown-pragmas", "-Xptxas", "-v"]
@@ -33,7 +33,7 @@ def _nvcc() -> str:
 
 
 def _newest_dep() -> float:
-    deps = list(CSRC.glob("*")) + [PKG.parent / "include" / "kzb200.h", Path(__file__)]
+    deps = [p for p in CSRC.rglob("*") if p.is_file()] + [PKG.parent / "include" / "kzb200.h", Path(__file__)]
     return max(p.stat().st_mtime for p in deps)
 
 
@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
 
     def compile_one(src: str):
-        obj = OBJ / (src + ".o")
+        obj = OBJ / (src.replace("/", "_") + ".o")
         cmd = [nvcc, *NVCC_FLAGS, "-x", "cu", "-c", str(CSRC / src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r

@@ -1,0 +1,506 @@
+// Self-play driver: generator threads running many concurrent MCTS games + executor threads that batch their
+// evaluation requests into the B200 evaluator (BASELINE.json configs[3]).
+//
+// Restates the structure of the reference's self-play server for the AlphaZero path:
+//   executor  : batched_executor_loop, rust/kz-selfplay/src/server/executor.rs:27-146 -- collect jobs until the batch is
+//               full or RunCondition::JobCount(gpu_batch / search_batch) jobs are queued (:240-253), evaluate, scatter
+//               the results back to the jobs in order (:278-301)
+//   generator : generate_simulation / build_tree / apply_eval, rust/kz-selfplay/src/server/generator_alphazero.rs:70-260 --
+//               per move: gather up to search_batch requests (virtual loss), serve LRU-cache hits immediately, send the
+//               rest as one job, apply the answers (policy temperature, Dirichlet noise at the root), until the root has
+//               `visits` visits; then pick a move (MoveSelector) and start a new tree
+//   topology  : cpu_threads generator threads and gpu_threads executor instances per device, concurrent_games =
+//               ceil((gpu_threads + 1) * gpu_batch / search_batch), rust/kz-selfplay/src/server/server_alphazero.rs:47-121
+// Differences that are deliberate: generator threads are plain threads that round-robin their games instead of async
+// tasks; boards are ENCODED ON THE GENERATOR THREADS into the packed (bits, scalars, legal-index) record, so the
+// executor thread only concatenates records and calls the evaluator (the reference encodes f32 planes on the executor
+// thread, network/cudnn.rs:62-64); no game records are written (row N2).
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <list>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <unordered_map>
+
+#include "../../../include/kzb200.h"
+#include "../executor.hpp"
+#include "games.hpp"
+#include "mcts.hpp"
+
+#define KZB_API extern "C" __attribute__((visibility("default")))
+
+namespace kzb {
+namespace selfplay {
+namespace {
+
+struct Eval {
+    ValuesPov values;
+    std::vector<float> policy;
+};
+
+// per-game LRU cache of evaluations keyed by the board hash (generator_alphazero.rs:68,77-79)
+class LruCache {
+public:
+    explicit LruCache(size_t cap) : cap_(cap) {}
+    const Eval* get(uint64_t key) {
+        auto it = map_.find(key);
+        if (it == map_.end()) return nullptr;
+        order_.splice(order_.begin(), order_, it->second);
+        return &it->second->second;
+    }
+    void put(uint64_t key, const Eval& e) {
+        if (cap_ == 0) return;
+        auto it = map_.find(key);
+        if (it != map_.end()) {
+            it->second->second = e;
+            order_.splice(order_.begin(), order_, it->second);
+            return;
+        }
+        order_.emplace_front(key, e);
+        map_[key] = order_.begin();
+        if (map_.size() > cap_) {
+            map_.erase(order_.back().first);
+            order_.pop_back();
+        }
+    }
+    void clear() {
+        map_.clear();
+        order_.clear();
+    }
+
+private:
+    size_t cap_;
+    std::list<std::pair<uint64_t, Eval>> order_;
+    std::unordered_map<uint64_t, std::list<std::pair<uint64_t, Eval>>::iterator> map_;
+};
+
+SearchSettings search_settings(const kzb_selfplay_config& c) {
+    SearchSettings s;
+    s.weights = {c.exploration_weight, c.moves_left_weight, c.moves_left_clip, c.moves_left_sharpness};
+    s.q_mode = {c.q_mode_wdl != 0, c.draw_score};
+    s.fpu_root = {c.fpu_root_relative != 0, c.fpu_root};
+    s.fpu_child = {c.fpu_child_relative != 0, c.fpu_child};
+    s.virtual_loss = c.virtual_loss;
+    return s;
+}
+
+// one evaluation job = the requests of one gather round of one game, already encoded (job_channel.rs:9-22)
+struct Job {
+    int n = 0;
+    std::vector<uint8_t> bits;
+    std::vector<float> scalars;
+    std::vector<uint32_t> mv_idx, mv_off;  // local CSR, mv_off[0] = 0
+    std::vector<float> values, probs;      // filled by the executor
+    std::atomic<int> done{0};
+    int owner = 0;  // generator thread to wake
+};
+
+struct Shared {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Job*> queue;
+    size_t queued_positions = 0;
+    std::atomic<bool> stop{false};
+    std::string error;
+    // per generator thread wake-up
+    std::vector<std::unique_ptr<std::mutex>> gen_mu;
+    std::vector<std::unique_ptr<std::condition_variable>> gen_cv;
+    // statistics (collector.rs:172-191: real / cached evals)
+    std::atomic<uint64_t> real_evals{0}, cached_evals{0}, batches{0}, games{0}, moves{0}, root_visits{0}, max_batch_seen{0},
+        potential_evals{0};
+};
+
+template <typename Game>
+struct Slot {
+    Game board;
+    std::unique_ptr<Tree<Game>> tree;
+    LruCache cache;
+    Rng rng;
+    uint32_t move_count = 0;
+    uint64_t next_seed;
+    bool waiting = false;
+    std::vector<Request<Game>> requests;
+    Job job;
+    Slot(uint64_t seed, size_t cache_size) : board(Game::start(seed)), cache(cache_size), rng(seed ^ 0x5EEDull), next_seed(seed + 0x1000) {
+        tree = std::make_unique<Tree<Game>>(board);
+    }
+};
+
+template <typename Game>
+void apply_eval(Slot<Game>& slot, const Request<Game>& req, Eval eval, const kzb_selfplay_config& c) {
+    // generator_alphazero.rs:217-245
+    const float temperature = req.node == 0 ? c.policy_temperature_root : c.policy_temperature_child;
+    policy_softmax_temperature_in_place(eval.policy.data(), eval.policy.size(), temperature);
+    if (req.node == 0) add_dirichlet_noise(eval.policy.data(), eval.policy.size(), c.dirichlet_alpha, c.dirichlet_eps, slot.rng);
+    zero_step_apply(*slot.tree, req.node, req.board.next_player(), eval.values, eval.policy.data(), eval.policy.size());
+}
+
+template <typename Game>
+void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Shared& sh, const kzb_selfplay_config& c) {
+    const SearchSettings settings = search_settings(c);
+    const GameShape shape = Game::shape();
+    const int bits_bytes = shape.bits_bytes();
+    std::vector<uint32_t> scratch;
+    try {
+        while (!sh.stop.load(std::memory_order_relaxed)) {
+            bool progressed = false;
+            for (auto& sp : slots) {
+                Slot<Game>& slot = *sp;
+                if (slot.waiting) {
+                    if (!slot.job.done.load(std::memory_order_acquire)) continue;
+                    // answers are back: cache + apply in request order (generator_alphazero.rs:206-210)
+                    for (int i = 0; i < slot.job.n; i++) {
+                        Eval e;
+                        const float* v = slot.job.values.data() + size_t(i) * 5;
+                        e.values = {v[0], v[1], v[2], v[3], v[4]};
+                        e.policy.assign(slot.job.probs.begin() + slot.job.mv_off[i], slot.job.probs.begin() + slot.job.mv_off[i + 1]);
+                        slot.cache.put(slot.requests[size_t(i)].board.hash(), e);
+                        apply_eval(slot, slot.requests[size_t(i)], std::move(e), c);
+                    }
+                    slot.waiting = false;
+                }
+                progressed = true;
+                Tree<Game>& tree = *slot.tree;
+                if (tree.root_visits() >= uint64_t(c.visits)) {
+                    // pick and play a move (generator_alphazero.rs:108-130)
+                    std::vector<float> policy;
+                    tree.policy(policy);
+                    const size_t pick = select_move(policy.data(), policy.size(), slot.move_count, c.temperature, uint32_t(c.zero_temp_move_count), slot.rng);
+                    const uint32_t mv = tree.nodes[size_t(tree.nodes[0].child_start) + pick].last_move;
+                    sh.root_visits.fetch_add(tree.root_visits(), std::memory_order_relaxed);
+                    sh.moves.fetch_add(1, std::memory_order_relaxed);
+                    slot.board.play(mv);
+                    slot.move_count++;
+                    if (slot.board.done() || slot.move_count >= uint32_t(c.max_game_length)) {
+                        sh.games.fetch_add(1, std::memory_order_relaxed);
+                        slot.board = Game::start(slot.next_seed++);
+                        slot.move_count = 0;
+                        slot.cache.clear();  // a new cache for every game (generator_alphazero.rs:77-79)
+                    }
+                    slot.tree = std::make_unique<Tree<Game>>(slot.board);
+                    continue;
+                }
+                // collect a batch of requests (generator_alphazero.rs:165-201)
+                slot.requests.clear();
+                int terminal_gathers = 0;
+                uint64_t cached = 0;
+                while (int(slot.requests.size()) < c.search_batch && terminal_gathers < c.search_batch) {
+                    Request<Game> req;
+                    if (zero_step_gather(tree, settings, slot.rng, req, scratch)) {
+                        if (const Eval* hit = slot.cache.get(req.board.hash())) {
+                            cached++;
+                            apply_eval(slot, req, *hit, c);
+                        } else {
+                            slot.requests.push_back(std::move(req));
+                        }
+                    } else {
+                        terminal_gathers++;
+                    }
+                }
+                if (cached) sh.cached_evals.fetch_add(cached, std::memory_order_relaxed);
+                if (slot.requests.empty()) continue;
+                // encode the requests into one job
+                Job& job = slot.job;
+                job.n = int(slot.requests.size());
+                job.owner = tid;
+                job.bits.resize(size_t(job.n) * bits_bytes);
+                job.scalars.resize(size_t(job.n) * shape.scalar_count);
+                job.mv_off.assign(1, 0);
+                job.mv_idx.clear();
+                for (int i = 0; i < job.n; i++) {
+                    const Game& b = slot.requests[size_t(i)].board;
+                    b.encode(job.bits.data() + size_t(i) * bits_bytes, job.scalars.data() + size_t(i) * shape.scalar_count);
+                    b.moves(scratch);
+                    for (uint32_t mv : scratch) job.mv_idx.push_back(b.move_to_index(mv));
+                    job.mv_off.push_back(uint32_t(job.mv_idx.size()));
+                }
+                job.values.resize(size_t(job.n) * 5);
+                job.probs.resize(job.mv_idx.size());
+                job.done.store(0, std::memory_order_relaxed);
+                slot.waiting = true;
+                {
+                    std::lock_guard<std::mutex> lk(sh.mu);
+                    sh.queue.push_back(&job);
+                    sh.queued_positions += size_t(job.n);
+                }
+                sh.cv.notify_one();
+            }
+            if (!progressed) {
+                std::unique_lock<std::mutex> lk(*sh.gen_mu[size_t(tid)]);
+                sh.gen_cv[size_t(tid)]->wait_for(lk, std::chrono::microseconds(100));
+            }
+        }
+    } catch (const std::exception& e) {
+        std::lock_guard<std::mutex> lk(sh.mu);
+        if (sh.error.empty()) sh.error = std::string("generator thread: ") + e.what();
+        sh.stop.store(true);
+        sh.cv.notify_all();
+    }
+}
+
+void executor_main(Net& net, Shared& sh, const kzb_selfplay_config& c, const GameShape shape) {
+    const size_t job_count = size_t(std::max(1, c.gpu_batch / std::max(1, c.search_batch)));  // RunCondition::JobCount
+    const int bits_bytes = shape.bits_bytes();
+    std::vector<uint8_t> bits(size_t(c.gpu_batch) * bits_bytes);
+    std::vector<float> scalars(size_t(c.gpu_batch) * shape.scalar_count), values(size_t(c.gpu_batch) * 5), probs;
+    std::vector<uint32_t> mv_idx, mv_off;
+    std::vector<Job*> jobs;
+    try {
+        while (true) {
+            jobs.clear();
+            size_t n = 0;
+            {
+                std::unique_lock<std::mutex> lk(sh.mu);
+                // executor.rs:240-253 should_eval: a full batch, or JobCount jobs queued; plus a short timeout so that the
+                // last few games of a run (fewer than JobCount producers left) still get answers
+                sh.cv.wait_for(lk, std::chrono::microseconds(200), [&] {
+                    return sh.stop.load() || sh.queued_positions >= size_t(c.gpu_batch) || sh.queue.size() >= job_count;
+                });
+                if (sh.stop.load()) return;
+                while (!sh.queue.empty() && n + size_t(sh.queue.front()->n) <= size_t(c.gpu_batch)) {
+                    Job* j = sh.queue.front();
+                    sh.queue.pop_front();
+                    sh.queued_positions -= size_t(j->n);
+                    n += size_t(j->n);
+                    jobs.push_back(j);
+                }
+            }
+            if (jobs.empty()) continue;
+            mv_off.assign(1, 0);
+            mv_idx.clear();
+            size_t row = 0;
+            for (Job* j : jobs) {
+                std::memcpy(bits.data() + row * bits_bytes, j->bits.data(), j->bits.size());
+                std::memcpy(scalars.data() + row * shape.scalar_count, j->scalars.data(), j->scalars.size() * 4);
+                const uint32_t base = uint32_t(mv_idx.size());
+                mv_idx.insert(mv_idx.end(), j->mv_idx.begin(), j->mv_idx.end());
+                for (int i = 1; i <= j->n; i++) mv_off.push_back(base + j->mv_off[size_t(i)]);
+                row += size_t(j->n);
+            }
+            probs.resize(std::max<size_t>(mv_idx.size(), 1));
+            net.eval_packed(bits.data(), scalars.data(), int(n), mv_idx.data(), mv_off.data(), values.data(), probs.data());
+            row = 0;
+            for (Job* j : jobs) {
+                std::memcpy(j->values.data(), values.data() + row * 5, size_t(j->n) * 5 * 4);
+                const uint32_t base = mv_off[row];
+                std::memcpy(j->probs.data(), probs.data() + base, j->probs.size() * 4);
+                row += size_t(j->n);
+                const int owner = j->owner;
+                j->done.store(1, std::memory_order_release);
+                sh.gen_cv[size_t(owner)]->notify_one();
+            }
+            sh.real_evals.fetch_add(n, std::memory_order_relaxed);
+            sh.potential_evals.fetch_add(uint64_t(c.gpu_batch), std::memory_order_relaxed);
+            sh.batches.fetch_add(1, std::memory_order_relaxed);
+            uint64_t prev = sh.max_batch_seen.load();
+            while (prev < n && !sh.max_batch_seen.compare_exchange_weak(prev, n)) {
+            }
+        }
+    } catch (const std::exception& e) {
+        std::lock_guard<std::mutex> lk(sh.mu);
+        if (sh.error.empty()) sh.error = std::string("executor thread: ") + e.what();
+        sh.stop.store(true);
+        sh.cv.notify_all();
+    }
+}
+
+template <typename Game>
+void run_selfplay(int device, const void* onnx, size_t len, int precision, const kzb_selfplay_config& c, kzb_selfplay_stats& out) {
+    const GameShape shape = Game::shape();
+    if (c.visits < 1 || c.search_batch < 1 || c.gpu_batch < c.search_batch || c.cpu_threads < 1 || c.gpu_threads < 1)
+        throw std::runtime_error("selfplay config: need visits >= 1, 1 <= search_batch <= gpu_batch, cpu_threads >= 1, gpu_threads >= 1");
+    std::vector<std::unique_ptr<Net>> nets;
+    for (int i = 0; i < c.gpu_threads; i++) {
+        nets.push_back(std::make_unique<Net>(device, onnx, len, c.gpu_batch, precision));
+        nets.back()->bind_mapper(shape.scalar_count, shape.bool_channels, shape.board, shape.board, shape.policy_len);
+    }
+    // server_alphazero.rs:47: concurrent_games = ceil((gpu_threads + 1) * gpu_batch / search_batch)
+    int games = c.concurrent_games > 0 ? c.concurrent_games : ((c.gpu_threads + 1) * c.gpu_batch + c.search_batch - 1) / c.search_batch;
+    Shared sh;
+    std::vector<std::vector<std::unique_ptr<Slot<Game>>>> per_thread(size_t(c.cpu_threads));
+    for (int g = 0; g < games; g++)
+        per_thread[size_t(g % c.cpu_threads)].push_back(std::make_unique<Slot<Game>>(c.seed * 1000003ull + uint64_t(g) * 7919ull + 1, size_t(c.cache_size)));
+    for (int t = 0; t < c.cpu_threads; t++) {
+        sh.gen_mu.push_back(std::make_unique<std::mutex>());
+        sh.gen_cv.push_back(std::make_unique<std::condition_variable>());
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> threads;
+    for (int i = 0; i < c.gpu_threads; i++) threads.emplace_back([&, i] { executor_main(*nets[size_t(i)], sh, c, shape); });
+    for (int t = 0; t < c.cpu_threads; t++) threads.emplace_back([&, t] { generator_main<Game>(t, per_thread[size_t(t)], sh, c); });
+    while (!sh.stop.load()) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(2));
+        const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (el >= c.duration_s || (c.max_moves > 0 && sh.moves.load() >= uint64_t(c.max_moves))) sh.stop.store(true);
+    }
+    sh.cv.notify_all();
+    for (auto& cv : sh.gen_cv) cv->notify_all();
+    for (auto& t : threads) t.join();
+    const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!sh.error.empty()) throw std::runtime_error(sh.error);
+    out.seconds = seconds;
+    out.real_evals = sh.real_evals.load();
+    out.cached_evals = sh.cached_evals.load();
+    out.potential_evals = sh.potential_evals.load();
+    out.batches = sh.batches.load();
+    out.games_finished = sh.games.load();
+    out.moves_played = sh.moves.load();
+    out.root_visits = sh.root_visits.load();
+    out.max_batch = sh.max_batch_seen.load();
+    out.concurrent_games = uint64_t(games);
+}
+
+// deterministic stand-in network for the host-only search trace (the twin lives in oracle/mcts_oracle.py)
+template <typename Game>
+Eval pseudo_eval(const Game& b, int kind, std::vector<uint32_t>& scratch) {
+    b.moves(scratch);
+    const size_t n = scratch.size();
+    Eval e;
+    e.policy.resize(n);
+    if (kind == 0) {  // DummyNetwork: uniform wdl and policy (rust/kz-core/src/network/dummy.rs:44-60)
+        for (auto& p : e.policy) p = 1.0f / float(n);
+        e.values = {0.0f, 1.0f / 3.0f, 1.0f / 3.0f, 1.0f / 3.0f, 0.0f};
+        return e;
+    }
+    const uint64_t h = b.hash();
+    float sum = 0.0f;
+    for (size_t i = 0; i < n; i++) {
+        e.policy[i] = float((splitmix64(h + i + 1) >> 40) % 1000 + 1);
+        sum += e.policy[i];
+    }
+    for (auto& p : e.policy) p /= sum;
+    const float v = float(int((splitmix64(h ^ 0xABCDull) >> 40) % 2001) - 1000) / 1000.0f;
+    e.values.value = v;
+    e.values.win = (1.0f + v) * 0.5f * 0.8f;
+    e.values.loss = (1.0f - v) * 0.5f * 0.8f;
+    e.values.draw = 0.2f;
+    e.values.moves_left = float((h >> 50) % 50);
+    return e;
+}
+
+template <typename Game>
+void trace_search(const kzb_selfplay_config& c, uint64_t game_seed, int plies, int eval_kind, kzb_mcts_trace_out& out) {
+    const SearchSettings settings = search_settings(c);
+    Game board = Game::start(game_seed);
+    Rng rng(c.seed);
+    std::vector<uint32_t> scratch;
+    for (int i = 0; i < plies && !board.done(); i++) {  // walk into the game a little so that the root is not special
+        board.moves(scratch);
+        board.play(scratch[rng.gen_range(uint32_t(scratch.size()))]);
+    }
+    if (board.done()) throw std::runtime_error("trace: the game ended before the requested ply");
+    Tree<Game> tree(board);
+    std::vector<Request<Game>> requests;
+    uint64_t evals = 0;
+    while (tree.root_visits() < uint64_t(c.visits)) {  // build_tree, generator_alphazero.rs:151-215 without the cache
+        requests.clear();
+        int terminal = 0;
+        while (int(requests.size()) < c.search_batch && terminal < c.search_batch) {
+            Request<Game> req;
+            if (zero_step_gather(tree, settings, rng, req, scratch)) requests.push_back(std::move(req));
+            else terminal++;
+        }
+        for (auto& req : requests) {
+            Eval e = pseudo_eval(req.board, eval_kind, scratch);
+            const float t = req.node == 0 ? c.policy_temperature_root : c.policy_temperature_child;
+            policy_softmax_temperature_in_place(e.policy.data(), e.policy.size(), t);
+            zero_step_apply(tree, req.node, req.board.next_player(), e.values, e.policy.data(), e.policy.size());
+            evals++;
+        }
+    }
+    const Node& root = tree.nodes[0];
+    if (root.child_count > out.capacity) throw std::runtime_error("trace: child capacity too small");
+    out.n_children = root.child_count;
+    for (int i = 0; i < root.child_count; i++) {
+        const Node& ch = tree.nodes[size_t(root.child_start + i)];
+        out.child_visits[i] = ch.complete_visits;
+        out.child_moves[i] = ch.last_move;
+        out.child_policy[i] = ch.net_policy;
+    }
+    const ValuesPov v = pov(root.values(), board.next_player());
+    out.root_values[0] = v.value;
+    out.root_values[1] = v.win;
+    out.root_values[2] = v.draw;
+    out.root_values[3] = v.loss;
+    out.root_values[4] = v.moves_left;
+    out.root_visits = root.complete_visits;
+    out.tree_nodes = tree.nodes.size();
+    out.evals = evals;
+}
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        set_last_error("");
+        return 0;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return 1;
+    }
+}
+
+}  // namespace
+}  // namespace selfplay
+}  // namespace kzb
+
+KZB_API void kzb_selfplay_default_config(kzb_selfplay_config* c) {
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+    // python/main/loop_main_alpha.py:24-52 and UctWeights::default (node.rs:66-75)
+    c->game = KZB_GAME_SYNTH_CHESS;
+    c->visits = 800;
+    c->search_batch = 16;
+    c->gpu_batch = 1024;
+    c->cpu_threads = 4;
+    c->gpu_threads = 1;
+    c->concurrent_games = 0;
+    c->max_game_length = 400;
+    c->cache_size = 800;
+    c->zero_temp_move_count = 30;
+    c->max_moves = 0;
+    c->duration_s = 5.0f;
+    c->temperature = 1.0f;
+    c->dirichlet_alpha = 0.03f;
+    c->dirichlet_eps = 0.25f;
+    c->policy_temperature_root = 1.4f;
+    c->policy_temperature_child = 1.0f;
+    c->exploration_weight = 2.0f;
+    c->moves_left_weight = 0.03f;
+    c->moves_left_clip = 20.0f;
+    c->moves_left_sharpness = 0.5f;
+    c->fpu_root = 0.1f;
+    c->fpu_root_relative = 0;
+    c->fpu_child = 0.0f;
+    c->fpu_child_relative = 1;
+    c->virtual_loss = 1.0f;
+    c->q_mode_wdl = 1;
+    c->draw_score = 0.0f;
+    c->seed = 0;
+}
+
+KZB_API int kzb_selfplay_run(int device, const void* onnx_bytes, size_t onnx_len, int precision, const kzb_selfplay_config* config,
+                             kzb_selfplay_stats* stats) {
+    using namespace kzb::selfplay;
+    return guarded([&] {
+        if (!onnx_bytes || !config || !stats) throw std::runtime_error("onnx_bytes, config and stats must not be NULL");
+        std::memset(stats, 0, sizeof(*stats));
+        if (config->game == KZB_GAME_SYNTH_CHESS) run_selfplay<SynthChess>(device, onnx_bytes, onnx_len, precision, *config, *stats);
+        else if (config->game == KZB_GAME_ATAXX7) run_selfplay<Ataxx>(device, onnx_bytes, onnx_len, precision, *config, *stats);
+        else throw std::runtime_error("unknown game");
+    });
+}
+
+KZB_API int kzb_mcts_trace(const kzb_selfplay_config* config, uint64_t game_seed, int plies, int eval_kind, kzb_mcts_trace_out* out) {
+    using namespace kzb::selfplay;
+    return guarded([&] {
+        if (!config || !out || !out->child_visits || !out->child_moves || !out->child_policy) throw std::runtime_error("config / out must not be NULL");
+        if (config->game == KZB_GAME_SYNTH_CHESS) trace_search<SynthChess>(*config, game_seed, plies, eval_kind, *out);
+        else if (config->game == KZB_GAME_ATAXX7) trace_search<Ataxx>(*config, game_seed, plies, eval_kind, *out);
+        else throw std::runtime_error("unknown game");
+    });
+}

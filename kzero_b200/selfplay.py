@@ -1,0 +1,94 @@
+"""Python host mirror of the self-play driver in libkzb200.so (include/kzb200.h, `kzb_selfplay_*`, `kzb_mcts_trace`).
+
+Mirrors what the reference's self-play server runs per device (rust/kz-selfplay/src/server/server_alphazero.rs:32-124):
+generator threads (generator_alphazero.rs:23-260) feeding executor threads (executor.rs:27-146); settings named like
+the reference's `StartupSettings` / `Settings` (protocol.rs:11-110, python/lib/selfplay_client.py).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _abi
+from ._abi import SelfplayConfig, SelfplayStats
+
+GAME_SYNTH_CHESS = 0
+GAME_ATAXX7 = 1
+
+
+def default_config(**overrides) -> SelfplayConfig:
+    """The reference's production settings (python/main/loop_main_alpha.py:24-52), with keyword overrides."""
+    cfg = SelfplayConfig()
+    _abi.lib().kzb_selfplay_default_config(ctypes.byref(cfg))
+    names = {f[0] for f in SelfplayConfig._fields_}
+    for k, v in overrides.items():
+        if k not in names:
+            raise KeyError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+@dataclass
+class SelfplayResult:
+    seconds: float
+    real_evals: int
+    cached_evals: int
+    potential_evals: int
+    batches: int
+    max_batch: int
+    games_finished: int
+    moves_played: int
+    root_visits: int
+    concurrent_games: int
+
+    @property
+    def nn_positions_per_s(self) -> float:  # "real evals/s" of collector.rs:172-191
+        return self.real_evals / self.seconds
+
+    @property
+    def mcts_nodes_per_s(self) -> float:  # real + cached evals per second
+        return (self.real_evals + self.cached_evals) / self.seconds
+
+    @property
+    def mean_batch(self) -> float:
+        return self.real_evals / max(self.batches, 1)
+
+    @property
+    def cache_hit_rate(self) -> float:
+        return self.cached_evals / max(self.real_evals + self.cached_evals, 1)
+
+
+def run(onnx_bytes: bytes, config: SelfplayConfig, device: int = 0, precision: int = 1) -> SelfplayResult:
+    stats = SelfplayStats()
+    _abi.check(_abi.lib().kzb_selfplay_run(device, onnx_bytes, len(onnx_bytes), precision, ctypes.byref(config), ctypes.byref(stats)))
+    return SelfplayResult(**{f[0]: getattr(stats, f[0]) for f in SelfplayStats._fields_})
+
+
+@dataclass
+class TraceResult:
+    child_visits: np.ndarray
+    child_moves: np.ndarray
+    child_policy: np.ndarray
+    root_values: np.ndarray
+    root_visits: int
+    tree_nodes: int
+    evals: int
+
+
+def mcts_trace(config: SelfplayConfig, game_seed: int, plies: int, eval_kind: int, capacity: int = 4096) -> TraceResult:
+    """Host-only search trace (no GPU): see kzb_mcts_trace in include/kzb200.h."""
+    visits = np.zeros(capacity, np.uint64)
+    moves = np.zeros(capacity, np.uint32)
+    policy = np.zeros(capacity, np.float32)
+    out = _abi.MctsTraceOut()
+    out.capacity = capacity
+    out.child_visits = visits.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+    out.child_moves = moves.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+    out.child_policy = policy.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    _abi.check(_abi.lib().kzb_mcts_trace(ctypes.byref(config), game_seed, plies, eval_kind, ctypes.byref(out)))
+    n = out.n_children
+    return TraceResult(visits[:n].copy(), moves[:n].copy(), policy[:n].copy(), np.array(list(out.root_values), np.float32),
+                       int(out.root_visits), int(out.tree_nodes), int(out.evals))

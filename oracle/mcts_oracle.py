@@ -1,0 +1,296 @@
+"""CPU restatement of the reference's AlphaZero tree search -- ORACLE / TEST INFRASTRUCTURE ONLY.
+
+Checks the C++ search behind `kzb_mcts_trace` / `kzb_selfplay_run` (kzero_b200/csrc/selfplay/mcts.hpp).  Restates, in
+plain Python with float32 arithmetic in the same operation order:
+  zero_step_gather / zero_step_apply / tree_propagate_values    rust/kz-core/src/zero/step.rs:61-188
+  Node::uct, Uct::total, UctWeights::default                     rust/kz-core/src/zero/node.rs:66-98,163-206
+  Tree::uct_context, Tree::policy, Tree::values                  rust/kz-core/src/zero/tree.rs:49-66,95-141
+  ZeroValuesAbs::{pov, from_outcome, parent}                     rust/kz-core/src/zero/values.rs:21-68
+  choose_max_by_key                                              rust/kz-util/src/sequence.rs:11-41
+  build_tree's gather-batch / apply loop (no cache, no noise)    rust/kz-selfplay/src/server/generator_alphazero.rs:151-215
+
+Parity pinning: the reference's own tests for this code only assert that a search terminates (rust/kz-core/tests/tree.rs:16-68)
+-- there are no golden trees, so "parity unpinned" applies to the SEARCH oracle: it is an independent second
+implementation of the cited lines, not a copy of reference outputs.  The random generator (xorshift64*), the synthetic
+chess-shaped game and the stand-in networks are this repo's own and are implemented twice (here and in C++).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+F = np.float32
+M64 = (1 << 64) - 1
+
+
+def splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M64
+    return x ^ (x >> 31)
+
+
+class Rng:
+    """xorshift64*, the twin of kzb::selfplay::Rng."""
+
+    def __init__(self, seed: int):
+        self.s = (seed * 0x9E3779B97F4A7C15 + 0xD1B54A32D192ED03) & M64
+        if self.s == 0:
+            self.s = 0x2545F4914F6CDD1D
+
+    def next_u64(self) -> int:
+        s = self.s
+        s ^= s >> 12
+        s = (s ^ (s << 25)) & M64
+        s ^= s >> 27
+        self.s = s
+        return (s * 0x2545F4914F6CDD1D) & M64
+
+    def gen_range(self, n: int) -> int:
+        return (self.next_u64() >> 32) % n
+
+
+class SynthChess:
+    """Twin of kzb::selfplay::SynthChess (kzero_b200/csrc/selfplay/games.hpp)."""
+
+    def __init__(self, h: int, ply: int, max_len: int):
+        self.h, self.ply, self.max_len = h, ply, max_len
+
+    @staticmethod
+    def start(seed: int) -> "SynthChess":
+        return SynthChess(splitmix64(seed ^ 0xC4E55), 0, 60 + splitmix64(seed) % 61)
+
+    def clone(self):
+        return SynthChess(self.h, self.ply, self.max_len)
+
+    def hash(self) -> int:
+        return self.h ^ ((self.ply << 56) & M64)
+
+    def next_player(self) -> int:
+        return self.ply & 1
+
+    def done(self) -> bool:
+        return self.ply >= self.max_len or (self.ply > 10 and (self.h & 127) == 0)
+
+    def outcome(self) -> int:
+        return self.h % 3 - 1
+
+    def moves(self) -> List[int]:
+        n = 20 + (self.h >> 3) % 26
+        a = 3 + 10 * ((self.h >> 8) & 3)
+        b = (self.h >> 16) % 1880
+        return [(b + j * a) % 1880 for j in range(n)]
+
+    def play(self, mv: int) -> None:
+        self.h = splitmix64(self.h ^ ((mv * 0x9E3779B97F4A7C15) & M64))
+        self.ply += 1
+
+
+def pseudo_eval(board, kind: int):
+    """-> (values_pov [value, win, draw, loss, moves_left] f32, policy f32); twin of pseudo_eval in selfplay.cpp."""
+    n = len(board.moves())
+    if kind == 0:  # DummyNetwork, rust/kz-core/src/network/dummy.rs:44-60
+        third = F(1.0) / F(3.0)
+        return np.array([0, third, third, third, 0], F), np.full(n, F(1.0) / F(n), F)
+    h = board.hash()
+    raw = np.array([(splitmix64((h + i + 1) & M64) >> 40) % 1000 + 1 for i in range(n)], F)
+    total = F(0)
+    for r in raw:
+        total = F(total + r)
+    v = F(F(int((splitmix64(h ^ 0xABCD) >> 40) % 2001) - 1000) / F(1000.0))
+    win = F(F(F(F(1.0) + v) * F(0.5)) * F(0.8))
+    loss = F(F(F(F(1.0) - v) * F(0.5)) * F(0.8))
+    return np.array([v, win, F(0.2), loss, F((h >> 50) % 50)], F), (raw / total).astype(F)
+
+
+@dataclass
+class Settings:
+    exploration_weight: float = 2.0
+    moves_left_weight: float = 0.03
+    moves_left_clip: float = 20.0
+    moves_left_sharpness: float = 0.5
+    q_mode_wdl: bool = True
+    draw_score: float = 0.0
+    fpu_root: float = 0.1
+    fpu_root_relative: bool = False
+    fpu_child: float = 0.0
+    fpu_child_relative: bool = True
+    virtual_loss: float = 1.0
+    policy_temperature_root: float = 1.0
+    policy_temperature_child: float = 1.0
+
+
+@dataclass
+class Node:
+    parent: int = -1
+    last_move: int = 0
+    children: Optional[range] = None
+    complete_visits: int = 0
+    virtual_visits: int = 0
+    sum_values: np.ndarray = field(default_factory=lambda: np.zeros(5, F))  # abs: value, win_a, draw, win_b, moves_left
+    net_values: Optional[np.ndarray] = None
+    net_policy: np.float32 = F(np.nan)
+
+    def total_visits(self) -> int:
+        return self.complete_visits + self.virtual_visits
+
+    def values(self) -> np.ndarray:
+        return (self.sum_values / F(self.complete_visits)).astype(F)
+
+
+def pov(v: np.ndarray, player: int) -> np.ndarray:  # values.rs:21-40 (its own inverse)
+    return v if player == 0 else np.array([-v[0], v[3], v[2], v[1], v[4]], F)
+
+
+def q_select(s: Settings, v: np.ndarray) -> np.float32:  # step.rs:237-242
+    return F(F(v[1] + F(F(s.draw_score) * v[2])) - v[3]) if s.q_mode_wdl else v[0]
+
+
+class Tree:
+    def __init__(self, root_board):
+        assert not root_board.done()
+        self.root_board = root_board
+        self.nodes: List[Node] = [Node()]
+
+    def uct_context(self, idx: int):
+        n = self.nodes[idx]
+        mass = F(0)
+        for c in n.children:
+            if self.nodes[c].total_visits() > 0:
+                mass = F(mass + self.nodes[c].net_policy)
+        return n.total_visits(), n.values(), mass
+
+    def uct_total(self, child: Node, ctx, fpu_relative: bool, fpu_value: float, s: Settings, player: int) -> np.float32:
+        parent_total, parent_values, mass = ctx
+        if fpu_relative:
+            fpu = F(q_select(s, pov(parent_values, player)) - F(F(fpu_value) * np.sqrt(mass)))
+        else:
+            fpu = F(fpu_value)
+        vl = F(s.virtual_loss)
+        tvv = F(F(child.complete_visits) + F(vl * F(child.virtual_visits)))
+        if tvv == 0:
+            q = fpu
+        else:
+            total_value = q_select(s, pov(child.sum_values, player))
+            q = F(F(total_value - F(vl * F(child.virtual_visits))) / tvv)
+        u = F(F(child.net_policy * np.sqrt(F(parent_total - 1))) / F(1 + child.total_visits()))
+        m = F(0) if child.complete_visits == 0 else F(child.values()[4] - F(parent_values[4] - F(1.0)))
+        m_unit = F(0)
+        if s.moves_left_weight != 0.0:
+            clip = F(s.moves_left_clip)
+            m_clipped = min(max(m, F(-clip)), clip)
+            m_unit = min(max(F(F(F(s.moves_left_sharpness) * m_clipped) * F(-q)), F(-1.0)), F(1.0))
+        return F(F(q + F(F(s.exploration_weight) * u)) + F(F(s.moves_left_weight) * m_unit))
+
+    def propagate(self, idx: int, values: np.ndarray) -> None:  # step.rs:171-188
+        cur = idx
+        values = values.copy()
+        while True:
+            n = self.nodes[cur]
+            assert n.virtual_visits > 0
+            n.complete_visits += 1
+            n.virtual_visits -= 1
+            n.sum_values = (n.sum_values + values).astype(F)
+            if n.parent < 0:
+                break
+            cur = n.parent
+            values[4] = F(values[4] + F(1.0))
+
+
+def zero_step_gather(tree: Tree, s: Settings, rng: Rng):
+    """-> (node index, board) of the reached un-evaluated node, or None after propagating a terminal outcome."""
+    cur = 0
+    board = tree.root_board.clone()
+    while True:
+        tree.nodes[cur].virtual_visits += 1
+        if board.done():
+            o = board.outcome()
+            tree.propagate(cur, np.array([o, 1.0 if o > 0 else 0.0, 1.0 if o == 0 else 0.0, 1.0 if o < 0 else 0.0, 0.0], F))
+            return None
+        n = tree.nodes[cur]
+        if n.children is None:
+            mvs = board.moves()
+            p = F(F(1.0) / F(len(mvs)))
+            start = len(tree.nodes)
+            for mv in mvs:
+                tree.nodes.append(Node(parent=cur, last_move=mv, net_policy=p))
+            n.children = range(start, start + len(mvs))
+            n.net_values = None
+            return cur, board
+        player = board.next_player()
+        selected, ties, best = -1, 0, None
+        if n.complete_visits == 0:
+            for c in n.children:
+                v = tree.nodes[c].total_visits()
+                if selected < 0 or v < best:
+                    selected, best, ties = c, v, 1
+                elif v == best:
+                    ties += 1
+                    if rng.gen_range(ties) == 0:
+                        selected = c
+        else:
+            rel, val = (s.fpu_root_relative, s.fpu_root) if cur == 0 else (s.fpu_child_relative, s.fpu_child)
+            ctx = tree.uct_context(cur)
+            for c in n.children:
+                u = tree.uct_total(tree.nodes[c], ctx, rel, val, s, player)
+                assert not np.isnan(u)
+                if selected < 0 or u > best:
+                    selected, best, ties = c, u, 1
+                elif u == best:
+                    ties += 1
+                    if rng.gen_range(ties) == 0:
+                        selected = c
+        cur = selected
+        board.play(tree.nodes[cur].last_move)
+
+
+def zero_step_apply(tree: Tree, idx: int, next_player: int, values_pov: np.ndarray, policy: np.ndarray) -> None:
+    n = tree.nodes[idx]
+    assert n.net_values is None
+    abs_values = pov(values_pov, next_player)
+    n.net_values = abs_values
+    tree.propagate(idx, abs_values)
+    assert n.children is not None and len(n.children) == len(policy)
+    for c, p in zip(n.children, policy):
+        tree.nodes[c].net_policy = F(p)
+
+
+def search(game_seed: int, plies: int, rng_seed: int, visits: int, search_batch: int, eval_kind: int, s: Settings):
+    """The twin of trace_search in selfplay.cpp: -> dict(child_visits, child_moves, child_policy, root_values, ...)."""
+    board = SynthChess.start(game_seed)
+    rng = Rng(rng_seed)
+    for _ in range(plies):
+        if board.done():
+            break
+        mvs = board.moves()
+        board.play(mvs[rng.gen_range(len(mvs))])
+    tree = Tree(board)
+    evals = 0
+    while tree.nodes[0].complete_visits < visits:
+        requests, terminal = [], 0
+        while len(requests) < search_batch and terminal < search_batch:
+            r = zero_step_gather(tree, s, rng)
+            if r is None:
+                terminal += 1
+            else:
+                requests.append(r)
+        for idx, b in requests:
+            values, policy = pseudo_eval(b, eval_kind)
+            t = s.policy_temperature_root if idx == 0 else s.policy_temperature_child
+            if t != 1.0:
+                policy = np.power(policy, F(1.0 / t)).astype(F)
+                total = F(0)
+                for p in policy:
+                    total = F(total + p)
+                policy = (policy / total).astype(F)
+            zero_step_apply(tree, idx, b.next_player(), values, policy)
+            evals += 1
+    root = tree.nodes[0]
+    kids = [tree.nodes[c] for c in root.children]
+    return dict(child_visits=np.array([k.complete_visits for k in kids], np.uint64),
+                child_moves=np.array([k.last_move for k in kids], np.uint32),
+                child_policy=np.array([k.net_policy for k in kids], F),
+                root_values=pov(root.values(), board.next_player()), root_visits=root.complete_visits,
+                tree_nodes=len(tree.nodes), evals=evals)

@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Self-play MCTS nodes/sec on B200 (BASELINE.json configs[3] and the second half of its metric).
+
+    python scripts/selfplay_bench.py [--seconds S] [--visits 800] [--cpu-threads T] [--gpu-threads G] [--game chess|ataxx]
+    torchrun --nproc-per-node N scripts/selfplay_bench.py ...      # one replica per GPU, games sharded by replica
+
+Settings default to the reference's production values (python/main/loop_main_alpha.py:24-52: 800 visits, search batch 16,
+virtual loss 1, LRU cache 800, Dirichlet 0.03/0.25, root temperature 1.4); the net is chess 16x128 random-init
+(synthetic, like bench.py).  The game is the chess-SHAPED synthetic game of kzero_b200/csrc/selfplay/games.hpp (no chess
+move generator in this repo), or real 7x7 ataxx with an 8x64 net.  Prints one JSON line on rank 0:
+  nodes/s = (real + cached evals) / s  (the collector's `evals/s: real / cached`, collector.rs:172-191), NN positions/s,
+  mean batch and fill of the evaluator calls.
+"""
+import argparse
+import json
+import os
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from kzero_b200 import netgen, replicas, selfplay  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--game", default="chess", choices=["chess", "ataxx"])
+ap.add_argument("--seconds", type=float, default=10.0)
+ap.add_argument("--visits", type=int, default=800)
+ap.add_argument("--search-batch", type=int, default=16)
+ap.add_argument("--gpu-batch", type=int, default=1024)
+ap.add_argument("--cpu-threads", type=int, default=0, help="0 = host cores / replicas - gpu threads")
+ap.add_argument("--gpu-threads", type=int, default=1)
+ap.add_argument("--concurrent-games", type=int, default=0)
+args = ap.parse_args()
+
+ctx = replicas.context_from_env()
+dist = None
+if ctx.world > 1:
+    import torch
+
+    torch.cuda.set_device(ctx.local_rank)
+    dist = replicas.init_process_group(ctx, "nccl", torch.device("cuda", ctx.local_rank))
+cores = os.cpu_count() or 1
+cpu_threads = args.cpu_threads or max(1, cores // ctx.world - args.gpu_threads)
+if args.game == "chess":
+    spec, depth, channels, game = netgen.game_spec("chess"), 16, 128, selfplay.GAME_SYNTH_CHESS
+else:
+    spec, depth, channels, game = netgen.game_spec("ataxx-7"), 8, 64, selfplay.GAME_ATAXX7
+onnx_bytes = netgen.build_onnx(spec, depth, channels, seed=0)
+cfg = selfplay.default_config(game=game, visits=args.visits, search_batch=args.search_batch, gpu_batch=args.gpu_batch,
+                              cpu_threads=cpu_threads, gpu_threads=args.gpu_threads, concurrent_games=args.concurrent_games,
+                              duration_s=args.seconds, seed=replicas.game_seed(ctx, 0))
+replicas.barrier(ctx)
+r = selfplay.run(onnx_bytes, cfg, device=ctx.local_rank)
+counts = [r.real_evals, r.cached_evals, r.batches, r.moves_played, r.games_finished]
+if dist is not None:
+    import torch
+
+    t = torch.tensor(counts, dtype=torch.float64, device="cuda")
+    dist.all_reduce(t)  # sums over replicas: the games are disjoint
+    counts = [float(v) for v in t.tolist()]
+(seconds,) = replicas.max_over_ranks(ctx, [r.seconds], device="cuda" if dist is not None else "cpu")
+if ctx.is_root:
+    real, cached, batches, moves, games = counts
+    print(json.dumps({
+        "metric": "self-play MCTS nodes/sec", "value": (real + cached) / seconds, "unit": "nodes/s", "n_gpus": ctx.world,
+        "nn_positions_per_s": real / seconds, "cache_hit_rate": cached / max(real + cached, 1),
+        "mean_batch": real / max(batches, 1), "batch_fill": real / max(batches * args.gpu_batch, 1), "max_batch_rank0": r.max_batch,
+        "moves_per_s": moves / seconds, "games_finished": games, "seconds": seconds, "scaling": "weak",
+        "config": {"workload": f"{args.game} self-play, {args.visits} visits, search batch {args.search_batch} with virtual loss, "
+                               f"net {depth}x{channels}, gpu batch {args.gpu_batch}",
+                   "game": "chess-shaped synthetic game (13x8x8 + 8 planes, 1880-move policy, 20-45 legal moves)" if args.game == "chess" else "ataxx 7x7",
+                   "cpu_threads_per_gpu": cpu_threads, "gpu_threads_per_gpu": args.gpu_threads, "concurrent_games_per_gpu": r.concurrent_games,
+                   "host_cores": cores, **replicas.parallelism_note(ctx)},
+        "data": "synthetic"}), flush=True)
+if dist is not None:
+    dist.destroy_process_group()

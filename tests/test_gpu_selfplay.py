@@ -1,0 +1,31 @@
+"""Self-play driver on the GPU: generator threads + executor threads feeding the B200 evaluator with ragged batches."""
+import pytest
+
+from kzero_b200 import netgen, selfplay
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("game,game_name,gpu_threads", [(selfplay.GAME_SYNTH_CHESS, "chess", 1), (selfplay.GAME_ATAXX7, "ataxx-7", 2)])
+def test_selfplay_runs_and_counts_are_consistent(game, game_name, gpu_threads):
+    spec = netgen.game_spec(game_name)
+    onnx_bytes = netgen.build_onnx(spec, 2, 32, seed=31)
+    cfg = selfplay.default_config(game=game, visits=60, search_batch=8, gpu_batch=128, cpu_threads=2, gpu_threads=gpu_threads,
+                                  duration_s=1.5, seed=7)
+    r = selfplay.run(onnx_bytes, cfg)
+    assert r.real_evals > 0 and r.batches > 0 and r.moves_played > 0
+    assert r.max_batch <= 128 and r.mean_batch >= 1
+    assert r.potential_evals == r.batches * 128  # collector.rs:172-191 "potential"
+    # every finished search reached its visit target; each visit is a real eval, a cache hit or a terminal gather
+    assert r.root_visits >= r.moves_played * 60
+    assert r.concurrent_games == (gpu_threads + 1) * 128 // 8  # server_alphazero.rs:47
+    assert r.mcts_nodes_per_s >= r.nn_positions_per_s > 0
+
+
+def test_selfplay_rejects_mismatched_network():
+    from kzero_b200.network import KzbError
+
+    onnx_bytes = netgen.build_onnx(netgen.game_spec("ataxx-7"), 1, 16, seed=32)
+    cfg = selfplay.default_config(game=selfplay.GAME_SYNTH_CHESS, duration_s=0.2)
+    with pytest.raises(KzbError, match="Input shape mismatch"):  # check_graph_shapes, network/common.rs:171-174
+        selfplay.run(onnx_bytes, cfg)
