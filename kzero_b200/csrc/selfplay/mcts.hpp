@@ -85,15 +85,17 @@ struct SearchSettings {
     float virtual_loss = 1.0f;
 };
 
-struct Node {  // node.rs:11-34
+// node.rs:11-34.  One cache line per node: a search touches every child of every node on its path, and with hundreds of
+// concurrent 800-visit trees the nodes do not stay in cache.  (`net_values` is only kept as a flag: the reference stores
+// the network's own values to write them into game records, which this driver does not produce.)
+struct alignas(64) Node {
     int32_t parent = -1;
     uint32_t last_move = 0;
     int32_t child_start = -1, child_count = 0;  // children == None  <=>  child_start < 0
     uint64_t complete_visits = 0, virtual_visits = 0;
     ValuesAbs sum_values;
-    bool has_net_values = false;
-    ValuesAbs net_values;
     float net_policy = NAN;
+    bool has_net_values = false;
     uint64_t total_visits() const { return complete_visits + virtual_visits; }
     ValuesAbs values() const { return sum_values.div(float(complete_visits)); }  // node.rs:126-128
 };
@@ -148,6 +150,45 @@ struct Tree {
         const UctWeights& w = s.weights;
         float m_unit = 0.0f;
         if (w.moves_left_weight != 0.0f) {
+            float m_clipped = std::fmin(std::fmax(m, -w.moves_left_clip), w.moves_left_clip);
+            m_unit = std::fmin(std::fmax(w.moves_left_sharpness * m_clipped * -q, -1.0f), 1.0f);
+        }
+        return q + w.exploration_weight * u + w.moves_left_weight * m_unit;
+    }
+
+    // The per-parent part of uct_total, computed once per selection step instead of once per child (same float
+    // operations in the same order, so the result is bit-identical to uct_total).
+    struct UctParent {
+        float fpu, sqrt_visits, moves_left_m1;
+    };
+    UctParent uct_parent(const UctContext& parent, FpuMode fpu_mode, const SearchSettings& s, int player) const {
+        UctParent u;
+        if (fpu_mode.relative) {
+            float parent_value = s.q_mode.select(pov(parent.values, player));
+            u.fpu = parent_value - fpu_mode.value * std::sqrt(parent.visited_policy_mass);
+        } else {
+            u.fpu = fpu_mode.value;
+        }
+        u.sqrt_visits = std::sqrt(float(parent.total_visits - 1));
+        u.moves_left_m1 = parent.values.moves_left - 1.0f;
+        return u;
+    }
+    float uct_total_fast(const Node& child, const UctParent& up, const SearchSettings& s, int player) const {
+        const float vl = s.virtual_loss;
+        const float total_visits_virtual = float(child.complete_visits) + vl * float(child.virtual_visits);
+        float q;
+        if (total_visits_virtual == 0.0f) {
+            q = up.fpu;
+        } else {
+            float total_value = s.q_mode.select(pov(child.sum_values, player));
+            float total_value_virtual = total_value - vl * float(child.virtual_visits);
+            q = total_value_virtual / total_visits_virtual;
+        }
+        const float u = child.net_policy * up.sqrt_visits / float(1 + child.total_visits());
+        const UctWeights& w = s.weights;
+        float m_unit = 0.0f;
+        if (w.moves_left_weight != 0.0f) {
+            const float m = child.complete_visits == 0 ? 0.0f : child.sum_values.moves_left / float(child.complete_visits) - up.moves_left_m1;
             float m_clipped = std::fmin(std::fmax(m, -w.moves_left_clip), w.moves_left_clip);
             m_unit = std::fmin(std::fmax(w.moves_left_sharpness * m_clipped * -q, -1.0f), 1.0f);
         }
@@ -235,9 +276,11 @@ bool zero_step_gather(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Reque
         } else {
             const FpuMode fpu = cur == 0 ? s.fpu_root : s.fpu_child;
             const UctContext ctx = tree.uct_context(cur);
+            if (ctx.total_visits == 0) throw std::runtime_error("uct is NaN");  // node.rs:171-173
+            const auto up = tree.uct_parent(ctx, fpu, s, player);
             float best = 0.0f;
             for (int c = n.child_start; c < n.child_start + n.child_count; c++) {
-                const float u = tree.uct_total(tree.nodes[c], ctx, fpu, s, player);
+                const float u = tree.uct_total_fast(tree.nodes[c], up, s, player);
                 if (std::isnan(u)) throw std::runtime_error("uct is NaN");  // N32::from_inner panics on NaN
                 if (selected < 0 || u > best) {
                     selected = c;
@@ -261,7 +304,6 @@ void zero_step_apply(Tree<Game>& tree, int node, int next_player, const ValuesPo
     Node& n = tree.nodes[node];
     if (n.has_net_values) throw std::logic_error("Node was already evaluated by the network");
     const ValuesAbs abs = un_pov(values, next_player);
-    n.net_values = abs;
     n.has_net_values = true;
     tree.propagate(node, abs);
     if (n.child_start < 0) throw std::logic_error("Applied node should have initialized children");
