@@ -145,6 +145,8 @@ typedef struct kzb_selfplay_config {
     float virtual_loss;        /* search_virtual_loss_weight                                                        */
     int32_t q_mode_wdl;        /* QMode: 0 value head, 1 wdl head with draw_score                                   */
     float draw_score;
+    int32_t executor_blocking_sync; /* 0: executor threads spin while the GPU works (lowest latency; needs a core each),
+                                       1: they sleep on a blocking event (use when generators and executors share cores) */
     uint64_t seed;
 } kzb_selfplay_config;
 

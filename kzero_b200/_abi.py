@@ -26,7 +26,8 @@ class SelfplayConfig(ctypes.Structure):
                 ("exploration_weight", ctypes.c_float), ("moves_left_weight", ctypes.c_float), ("moves_left_clip", ctypes.c_float),
                 ("moves_left_sharpness", ctypes.c_float), ("fpu_root", ctypes.c_float), ("fpu_root_relative", ctypes.c_int32),
                 ("fpu_child", ctypes.c_float), ("fpu_child_relative", ctypes.c_int32), ("virtual_loss", ctypes.c_float),
-                ("q_mode_wdl", ctypes.c_int32), ("draw_score", ctypes.c_float), ("seed", ctypes.c_uint64)]
+                ("q_mode_wdl", ctypes.c_int32), ("draw_score", ctypes.c_float), ("executor_blocking_sync", ctypes.c_int32),
+                ("seed", ctypes.c_uint64)]
 
 
 class SelfplayStats(ctypes.Structure):

@@ -114,6 +114,7 @@ Net::Net(int device, const void* onnx, size_t len, int max_batch, int precision)
         throw std::runtime_error("more than 256 channels is not supported");
 
     CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    if (const char* bs = std::getenv("KZB_BLOCKING_SYNC")) blocking_sync_ = bs[0] == '1';
     if (const char* tr = std::getenv("KZB_TRACE"))
         if (tr[0] == '1') trace_ = new double[5]();
     if (precision_ == 1)
@@ -147,6 +148,7 @@ Net::~Net() {
                      trace_[4], trace_[0] / trace_[4], trace_[1] / trace_[4], trace_[2] / trace_[4], trace_[3] / trace_[4]);
     delete[] trace_;
     cudaSetDevice(device_);
+    if (done_event_) cudaEventDestroy(done_event_);
     if (stream_) {
         cudaStreamSynchronize(stream_);
         cudaStreamDestroy(stream_);
@@ -771,7 +773,13 @@ void Net::eval_packed(const uint8_t* bits, const float* scalars, int batch, cons
     run_tail(batch, true, nullptr, /*to_host=*/true);
     const size_t probs_off = 16 + align16(size_t(max_batch_) * 5 * 4);
     if (trace) t2 = clk::now();
-    CK(cudaStreamSynchronize(stream_));
+    if (blocking_sync_) {  // the calling thread sleeps while the GPU works (self-play: executor threads share cores with generators)
+        if (!done_event_) CK(cudaEventCreateWithFlags(&done_event_, cudaEventBlockingSync | cudaEventDisableTiming));
+        CK(cudaEventRecord(done_event_, stream_));
+        CK(cudaEventSynchronize(done_event_));
+    } else {
+        CK(cudaStreamSynchronize(stream_));
+    }
     CK(cudaGetLastError());
     if (trace) t3 = clk::now();
     int err = *h_out_.as<int>();

@@ -70,6 +70,8 @@ public:
     void stage_packed(const uint8_t* bits, const float* scalars, int batch, const uint32_t* mv_idx, const uint32_t* mv_off);
     void time_staged(int iters, bool flush_l2, float* ms_out);
     void profile_staged(bool flush_l2, std::vector<std::string>& names, std::vector<float>& ms);
+    // kzb_eval_packed waits for the GPU by spinning (lowest latency, default) or by sleeping on a blocking event
+    void set_blocking_sync(bool on) { blocking_sync_ = on; }
     int launches_per_eval() const {
         int n = int(convs_.size()) + 2 - (use_tower8_ ? tower_layers_ - 1 : 0);
         if (use_heads8_) n -= int(convs_.size() - head_first_);  // head convs + tail become one launch
@@ -115,6 +117,8 @@ private:
     std::string timeline_step_;
     PinnedBuffer h_in_, h_out_;
     size_t mv_cap_ = 0;
+    bool blocking_sync_ = false;
+    cudaEvent_t done_event_ = nullptr;
     double* trace_ = nullptr;  // KZB_TRACE=1: accumulated host-side phase times of eval_packed
     int staged_batch_ = 0;
     size_t staged_moves_ = 0;

@@ -105,6 +105,7 @@ struct Shared {
     std::deque<Job*> queue;
     size_t queued_positions = 0;
     std::atomic<bool> stop{false};
+    size_t job_count = 1;  // RunCondition::JobCount
     std::string error;
     // per generator thread wake-up
     std::vector<std::unique_ptr<std::mutex>> gen_mu;
@@ -125,8 +126,10 @@ struct Slot {
     bool waiting = false;
     std::vector<Request<Game>> requests;
     Job job;
-    Slot(uint64_t seed, size_t cache_size) : board(Game::start(seed)), cache(cache_size), rng(seed ^ 0x5EEDull), next_seed(seed + 0x1000) {
+    Slot(uint64_t seed, size_t cache_size, size_t reserve_nodes)
+        : board(Game::start(seed)), cache(cache_size), rng(seed ^ 0x5EEDull), next_seed(seed + 0x1000) {
         tree = std::make_unique<Tree<Game>>(board);
+        tree->reserve(reserve_nodes);
     }
 };
 
@@ -170,7 +173,7 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                     std::vector<float> policy;
                     tree.policy(policy);
                     const size_t pick = select_move(policy.data(), policy.size(), slot.move_count, c.temperature, uint32_t(c.zero_temp_move_count), slot.rng);
-                    const uint32_t mv = tree.nodes[size_t(tree.nodes[0].child_start) + pick].last_move;
+                    const uint32_t mv = tree.last_move[size_t(tree.child_start[0]) + pick];
                     sh.root_visits.fetch_add(tree.root_visits(), std::memory_order_relaxed);
                     sh.moves.fetch_add(1, std::memory_order_relaxed);
                     slot.board.play(mv);
@@ -182,6 +185,7 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                         slot.cache.clear();  // a new cache for every game (generator_alphazero.rs:77-79)
                     }
                     slot.tree = std::make_unique<Tree<Game>>(slot.board);
+                    slot.tree->reserve(size_t(c.visits) * 48 + 64);
                     continue;
                 }
                 // collect a batch of requests (generator_alphazero.rs:165-201)
@@ -214,20 +218,25 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                 for (int i = 0; i < job.n; i++) {
                     const Game& b = slot.requests[size_t(i)].board;
                     b.encode(job.bits.data() + size_t(i) * bits_bytes, job.scalars.data() + size_t(i) * shape.scalar_count);
-                    b.moves(scratch);
-                    for (uint32_t mv : scratch) job.mv_idx.push_back(b.move_to_index(mv));
+                    // the node's children were created from available_moves() in order (step.rs:89-97): their moves ARE the legal list
+                    const int node = slot.requests[size_t(i)].node;
+                    const size_t c0 = size_t(tree.child_start[size_t(node)]), cn = size_t(tree.child_count[size_t(node)]);
+                    for (size_t k = 0; k < cn; k++) job.mv_idx.push_back(b.move_to_index(tree.last_move[c0 + k]));
                     job.mv_off.push_back(uint32_t(job.mv_idx.size()));
                 }
                 job.values.resize(size_t(job.n) * 5);
                 job.probs.resize(job.mv_idx.size());
                 job.done.store(0, std::memory_order_relaxed);
                 slot.waiting = true;
+                bool wake;
                 {
                     std::lock_guard<std::mutex> lk(sh.mu);
                     sh.queue.push_back(&job);
                     sh.queued_positions += size_t(job.n);
+                    // only wake an executor when its run condition has just become true (executor.rs:240-253)
+                    wake = sh.queued_positions >= size_t(c.gpu_batch) || sh.queue.size() >= sh.job_count;
                 }
-                sh.cv.notify_one();
+                if (wake) sh.cv.notify_one();
             }
             if (!progressed) {
                 std::unique_lock<std::mutex> lk(*sh.gen_mu[size_t(tid)]);
@@ -243,9 +252,10 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
 }
 
 void executor_main(Net& net, Shared& sh, const kzb_selfplay_config& c, const GameShape shape) {
-    const size_t job_count = size_t(std::max(1, c.gpu_batch / std::max(1, c.search_batch)));  // RunCondition::JobCount
+    const size_t job_count = sh.job_count;
     const int bits_bytes = shape.bits_bytes();
     std::vector<uint8_t> bits(size_t(c.gpu_batch) * bits_bytes);
+    std::vector<char> owner_woken(sh.gen_cv.size(), 0);
     std::vector<float> scalars(size_t(c.gpu_batch) * shape.scalar_count), values(size_t(c.gpu_batch) * 5), probs;
     std::vector<uint32_t> mv_idx, mv_off;
     std::vector<Job*> jobs;
@@ -289,10 +299,14 @@ void executor_main(Net& net, Shared& sh, const kzb_selfplay_config& c, const Gam
                 const uint32_t base = mv_off[row];
                 std::memcpy(j->probs.data(), probs.data() + base, j->probs.size() * 4);
                 row += size_t(j->n);
-                const int owner = j->owner;
+                owner_woken[size_t(j->owner)] = 1;
                 j->done.store(1, std::memory_order_release);
-                sh.gen_cv[size_t(owner)]->notify_one();
             }
+            for (size_t o = 0; o < owner_woken.size(); o++)  // one wake-up per generator thread and batch
+                if (owner_woken[o]) {
+                    owner_woken[o] = 0;
+                    sh.gen_cv[o]->notify_one();
+                }
             sh.real_evals.fetch_add(n, std::memory_order_relaxed);
             sh.potential_evals.fetch_add(uint64_t(c.gpu_batch), std::memory_order_relaxed);
             sh.batches.fetch_add(1, std::memory_order_relaxed);
@@ -317,13 +331,15 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
     for (int i = 0; i < c.gpu_threads; i++) {
         nets.push_back(std::make_unique<Net>(device, onnx, len, c.gpu_batch, precision));
         nets.back()->bind_mapper(shape.scalar_count, shape.bool_channels, shape.board, shape.board, shape.policy_len);
+        nets.back()->set_blocking_sync(c.executor_blocking_sync != 0);
     }
     // server_alphazero.rs:47: concurrent_games = ceil((gpu_threads + 1) * gpu_batch / search_batch)
     int games = c.concurrent_games > 0 ? c.concurrent_games : ((c.gpu_threads + 1) * c.gpu_batch + c.search_batch - 1) / c.search_batch;
     Shared sh;
+    sh.job_count = size_t(std::max(1, c.gpu_batch / std::max(1, c.search_batch)));
     std::vector<std::vector<std::unique_ptr<Slot<Game>>>> per_thread(size_t(c.cpu_threads));
     for (int g = 0; g < games; g++)
-        per_thread[size_t(g % c.cpu_threads)].push_back(std::make_unique<Slot<Game>>(c.seed * 1000003ull + uint64_t(g) * 7919ull + 1, size_t(c.cache_size)));
+        per_thread[size_t(g % c.cpu_threads)].push_back(std::make_unique<Slot<Game>>(c.seed * 1000003ull + uint64_t(g) * 7919ull + 1, size_t(c.cache_size), size_t(c.visits) * 48 + 64));
     for (int t = 0; t < c.cpu_threads; t++) {
         sh.gen_mu.push_back(std::make_unique<std::mutex>());
         sh.gen_cv.push_back(std::make_unique<std::condition_variable>());
@@ -394,6 +410,7 @@ void trace_search(const kzb_selfplay_config& c, uint64_t game_seed, int plies, i
     }
     if (board.done()) throw std::runtime_error("trace: the game ended before the requested ply");
     Tree<Game> tree(board);
+    tree.reserve(size_t(c.visits) * 48 + 64);
     std::vector<Request<Game>> requests;
     uint64_t evals = 0;
     while (tree.root_visits() < uint64_t(c.visits)) {  // build_tree, generator_alphazero.rs:151-215 without the cache
@@ -412,23 +429,23 @@ void trace_search(const kzb_selfplay_config& c, uint64_t game_seed, int plies, i
             evals++;
         }
     }
-    const Node& root = tree.nodes[0];
-    if (root.child_count > out.capacity) throw std::runtime_error("trace: child capacity too small");
-    out.n_children = root.child_count;
-    for (int i = 0; i < root.child_count; i++) {
-        const Node& ch = tree.nodes[size_t(root.child_start + i)];
-        out.child_visits[i] = ch.complete_visits;
-        out.child_moves[i] = ch.last_move;
-        out.child_policy[i] = ch.net_policy;
+    const int n_children = tree.child_count[0];
+    if (n_children > out.capacity) throw std::runtime_error("trace: child capacity too small");
+    out.n_children = n_children;
+    for (int i = 0; i < n_children; i++) {
+        const size_t ch = size_t(tree.child_start[0] + i);
+        out.child_visits[i] = tree.complete[ch];
+        out.child_moves[i] = tree.last_move[ch];
+        out.child_policy[i] = tree.net_policy[ch];
     }
-    const ValuesPov v = pov(root.values(), board.next_player());
+    const ValuesPov v = pov(tree.values(0), board.next_player());
     out.root_values[0] = v.value;
     out.root_values[1] = v.win;
     out.root_values[2] = v.draw;
     out.root_values[3] = v.loss;
     out.root_values[4] = v.moves_left;
-    out.root_visits = root.complete_visits;
-    out.tree_nodes = tree.nodes.size();
+    out.root_visits = tree.complete[0];
+    out.tree_nodes = tree.size();
     out.evals = evals;
 }
 
