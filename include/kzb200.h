@@ -147,6 +147,10 @@ typedef struct kzb_selfplay_config {
     float draw_score;
     int32_t executor_blocking_sync; /* 0: executor threads spin while the GPU works (lowest latency; needs a core each),
                                        1: they sleep on a blocking event (use when generators and executors share cores) */
+    int32_t dummy_network;       /* 1: answer every request with uniform wdl / policy instead of evaluating a network -- the
+                                    reference's DummyNetwork / UseDummyNetwork (network/dummy.rs:44-60); needs no GPU      */
+    const char* output_prefix;   /* NULL / "": no records; else finished games are written to <prefix>.bin/.off/.json in the
+                                    reference's format (rust/kz-selfplay/src/binary_output.rs:128-297)                      */
     uint64_t seed;
 } kzb_selfplay_config;
 
@@ -161,6 +165,7 @@ typedef struct kzb_selfplay_stats {
     uint64_t games_finished, moves_played;
     uint64_t root_visits;     /* sum of root visits of the finished searches                                        */
     uint64_t concurrent_games;
+    uint64_t games_written;   /* games in the record files                                                          */
 } kzb_selfplay_stats;
 
 /* The reference's typical production settings (python/main/loop_main_alpha.py:24-52, UctWeights::default). */

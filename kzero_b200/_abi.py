@@ -27,7 +27,7 @@ class SelfplayConfig(ctypes.Structure):
                 ("moves_left_sharpness", ctypes.c_float), ("fpu_root", ctypes.c_float), ("fpu_root_relative", ctypes.c_int32),
                 ("fpu_child", ctypes.c_float), ("fpu_child_relative", ctypes.c_int32), ("virtual_loss", ctypes.c_float),
                 ("q_mode_wdl", ctypes.c_int32), ("draw_score", ctypes.c_float), ("executor_blocking_sync", ctypes.c_int32),
-                ("seed", ctypes.c_uint64)]
+                ("dummy_network", ctypes.c_int32), ("output_prefix", ctypes.c_char_p), ("seed", ctypes.c_uint64)]
 
 
 class SelfplayStats(ctypes.Structure):
@@ -35,7 +35,7 @@ class SelfplayStats(ctypes.Structure):
     _fields_ = [("seconds", ctypes.c_double), ("real_evals", ctypes.c_uint64), ("cached_evals", ctypes.c_uint64),
                 ("potential_evals", ctypes.c_uint64), ("batches", ctypes.c_uint64), ("max_batch", ctypes.c_uint64),
                 ("games_finished", ctypes.c_uint64), ("moves_played", ctypes.c_uint64), ("root_visits", ctypes.c_uint64),
-                ("concurrent_games", ctypes.c_uint64)]
+                ("concurrent_games", ctypes.c_uint64), ("games_written", ctypes.c_uint64)]
 
 
 class MctsTraceOut(ctypes.Structure):

@@ -36,6 +36,7 @@ struct SynthChess {
     uint32_t ply = 0, max_len = 80;
 
     static GameShape shape() { return {13, 8, 8, 1880}; }
+    static const char* name() { return "chess"; }  // the shapes of python/lib/games.py:232-244, so the reference's reader accepts the records
     static SynthChess start(uint64_t seed) {
         SynthChess g;
         g.h = splitmix64(seed ^ 0xC4E55ull);
@@ -98,6 +99,7 @@ struct Ataxx {
     int result = 0;
 
     static GameShape shape() { return {3, 1, 7, 17 * 49 + 1}; }
+    static const char* name() { return "ataxx-7"; }
     static constexpr uint64_t full() { return (1ull << A) - 1; }
     static Ataxx start(uint64_t /*seed*/) {
         Ataxx g;

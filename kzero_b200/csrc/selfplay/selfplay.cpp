@@ -14,7 +14,8 @@
 // Differences that are deliberate: generator threads are plain threads that round-robin their games instead of async
 // tasks; boards are ENCODED ON THE GENERATOR THREADS into the packed (bits, scalars, legal-index) record, so the
 // executor thread only concatenates records and calls the evaluator (the reference encodes f32 planes on the executor
-// thread, network/cudnn.rs:62-64); no game records are written (row N2).
+// thread, network/cudnn.rs:62-64); game records are written by whichever generator thread finishes a game (record_writer.hpp,
+// row N2) instead of a collector thread.
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -30,6 +31,7 @@
 #include "../executor.hpp"
 #include "games.hpp"
 #include "mcts.hpp"
+#include "record_writer.hpp"
 
 #define KZB_API extern "C" __attribute__((visibility("default")))
 
@@ -110,6 +112,9 @@ struct Shared {
     // per generator thread wake-up
     std::vector<std::unique_ptr<std::mutex>> gen_mu;
     std::vector<std::unique_ptr<std::condition_variable>> gen_cv;
+    // finished games go to one writer, the collector's role (collector.rs:59-85)
+    std::mutex writer_mu;
+    std::unique_ptr<RecordWriter> writer;
     // statistics (collector.rs:172-191: real / cached evals)
     std::atomic<uint64_t> real_evals{0}, cached_evals{0}, batches{0}, games{0}, moves{0}, root_visits{0}, max_batch_seen{0},
         potential_evals{0};
@@ -126,6 +131,8 @@ struct Slot {
     bool waiting = false;
     std::vector<Request<Game>> requests;
     Job job;
+    RecordedGame record;   // only filled when records are written
+    Eval root_net_eval;    // the network's own evaluation of the root (generator_alphazero.rs:226-229)
     Slot(uint64_t seed, size_t cache_size, size_t reserve_nodes)
         : board(Game::start(seed)), cache(cache_size), rng(seed ^ 0x5EEDull), next_seed(seed + 0x1000) {
         tree = std::make_unique<Tree<Game>>(board);
@@ -136,10 +143,19 @@ struct Slot {
 template <typename Game>
 void apply_eval(Slot<Game>& slot, const Request<Game>& req, Eval eval, const kzb_selfplay_config& c) {
     // generator_alphazero.rs:217-245
+    if (req.node == 0) slot.root_net_eval = eval;  // before temperature and noise
     const float temperature = req.node == 0 ? c.policy_temperature_root : c.policy_temperature_child;
     policy_softmax_temperature_in_place(eval.policy.data(), eval.policy.size(), temperature);
     if (req.node == 0) add_dirichlet_noise(eval.policy.data(), eval.policy.size(), c.dirichlet_alpha, c.dirichlet_eps, slot.rng);
     zero_step_apply(*slot.tree, req.node, req.board.next_player(), eval.values, eval.policy.data(), eval.policy.size());
+}
+
+template <typename Game>
+void encode_record(const Game& b, const GameShape& shape, RecordedPosition& rp) {
+    rp.bits.assign(size_t(shape.bits_bytes()), 0);
+    rp.scalars.assign(size_t(shape.scalar_count), 0.0f);
+    b.encode(rp.bits.data(), rp.scalars.data());
+    rp.next_player = b.next_player();
 }
 
 template <typename Game>
@@ -176,9 +192,32 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                     const uint32_t mv = tree.last_move[size_t(tree.child_start[0]) + pick];
                     sh.root_visits.fetch_add(tree.root_visits(), std::memory_order_relaxed);
                     sh.moves.fetch_add(1, std::memory_order_relaxed);
+                    if (sh.writer) {  // Position, generator_alphazero.rs:115-123
+                        RecordedPosition rp;
+                        encode_record(slot.board, shape, rp);
+                        const size_t c0 = size_t(tree.child_start[0]), cn = size_t(tree.child_count[0]);
+                        for (size_t k = 0; k < cn; k++) rp.indices.push_back(slot.board.move_to_index(tree.last_move[c0 + k]));
+                        rp.played_index = slot.board.move_to_index(mv);
+                        rp.zero_visits = tree.root_visits();
+                        rp.zero_values = pov(tree.values(0), slot.board.next_player());  // Tree::values, tree.rs:95-98
+                        rp.zero_policy = policy;
+                        rp.net_values = slot.root_net_eval.values;
+                        rp.net_policy = slot.root_net_eval.policy;
+                        slot.record.positions.push_back(std::move(rp));
+                    }
                     slot.board.play(mv);
                     slot.move_count++;
                     if (slot.board.done() || slot.move_count >= uint32_t(c.max_game_length)) {
+                        if (sh.writer) {
+                            encode_record(slot.board, shape, slot.record.final_position);
+                            slot.record.final_done = slot.board.done();
+                            slot.record.outcome = slot.board.done() ? slot.board.outcome() : 0;
+                            {
+                                std::lock_guard<std::mutex> lk(sh.writer_mu);
+                                sh.writer->append(slot.record);
+                            }
+                            slot.record = RecordedGame();
+                        }
                         sh.games.fetch_add(1, std::memory_order_relaxed);
                         slot.board = Game::start(slot.next_seed++);
                         slot.move_count = 0;
@@ -251,7 +290,9 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
     }
 }
 
-void executor_main(Net& net, Shared& sh, const kzb_selfplay_config& c, const GameShape shape) {
+// `net == nullptr`: the reference's DummyNetwork (uniform wdl and policy, rust/kz-core/src/network/dummy.rs:44-60, what the
+// server uses after a UseDummyNetwork command) -- runs the whole driver without a GPU
+void executor_main(Net* net, Shared& sh, const kzb_selfplay_config& c, const GameShape shape) {
     const size_t job_count = sh.job_count;
     const int bits_bytes = shape.bits_bytes();
     std::vector<uint8_t> bits(size_t(c.gpu_batch) * bits_bytes);
@@ -292,7 +333,16 @@ void executor_main(Net& net, Shared& sh, const kzb_selfplay_config& c, const Gam
                 row += size_t(j->n);
             }
             probs.resize(std::max<size_t>(mv_idx.size(), 1));
-            net.eval_packed(bits.data(), scalars.data(), int(n), mv_idx.data(), mv_off.data(), values.data(), probs.data());
+            if (net) {
+                net->eval_packed(bits.data(), scalars.data(), int(n), mv_idx.data(), mv_off.data(), values.data(), probs.data());
+            } else {
+                for (size_t i = 0; i < n; i++) {
+                    const float v[5] = {0.0f, 1.0f / 3.0f, 1.0f / 3.0f, 1.0f / 3.0f, 0.0f};
+                    std::memcpy(values.data() + i * 5, v, sizeof(v));
+                    const uint32_t cnt = mv_off[i + 1] - mv_off[i];
+                    for (uint32_t k = 0; k < cnt; k++) probs[mv_off[i] + k] = 1.0f / float(cnt);
+                }
+            }
             row = 0;
             for (Job* j : jobs) {
                 std::memcpy(j->values.data(), values.data() + row * 5, size_t(j->n) * 5 * 4);
@@ -328,7 +378,7 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
     if (c.visits < 1 || c.search_batch < 1 || c.gpu_batch < c.search_batch || c.cpu_threads < 1 || c.gpu_threads < 1)
         throw std::runtime_error("selfplay config: need visits >= 1, 1 <= search_batch <= gpu_batch, cpu_threads >= 1, gpu_threads >= 1");
     std::vector<std::unique_ptr<Net>> nets;
-    for (int i = 0; i < c.gpu_threads; i++) {
+    for (int i = 0; i < c.gpu_threads && !c.dummy_network; i++) {
         nets.push_back(std::make_unique<Net>(device, onnx, len, c.gpu_batch, precision));
         nets.back()->bind_mapper(shape.scalar_count, shape.bool_channels, shape.board, shape.board, shape.policy_len);
         nets.back()->set_blocking_sync(c.executor_blocking_sync != 0);
@@ -336,6 +386,8 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
     // server_alphazero.rs:47: concurrent_games = ceil((gpu_threads + 1) * gpu_batch / search_batch)
     int games = c.concurrent_games > 0 ? c.concurrent_games : ((c.gpu_threads + 1) * c.gpu_batch + c.search_batch - 1) / c.search_batch;
     Shared sh;
+    if (c.output_prefix && c.output_prefix[0])
+        sh.writer = std::make_unique<RecordWriter>(c.output_prefix, Game::name(), shape.bool_channels, shape.board, shape.scalar_count, shape.policy_len);
     sh.job_count = size_t(std::max(1, c.gpu_batch / std::max(1, c.search_batch)));
     std::vector<std::vector<std::unique_ptr<Slot<Game>>>> per_thread(size_t(c.cpu_threads));
     for (int g = 0; g < games; g++)
@@ -346,7 +398,7 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
     }
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<std::thread> threads;
-    for (int i = 0; i < c.gpu_threads; i++) threads.emplace_back([&, i] { executor_main(*nets[size_t(i)], sh, c, shape); });
+    for (int i = 0; i < c.gpu_threads; i++) threads.emplace_back([&, i] { executor_main(c.dummy_network ? nullptr : nets[size_t(i)].get(), sh, c, shape); });
     for (int t = 0; t < c.cpu_threads; t++) threads.emplace_back([&, t] { generator_main<Game>(t, per_thread[size_t(t)], sh, c); });
     while (!sh.stop.load()) {
         std::this_thread::sleep_for(std::chrono::milliseconds(2));
@@ -357,8 +409,10 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
     for (auto& cv : sh.gen_cv) cv->notify_all();
     for (auto& t : threads) t.join();
     const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (sh.writer) sh.writer->finish();
     if (!sh.error.empty()) throw std::runtime_error(sh.error);
     out.seconds = seconds;
+    out.games_written = sh.writer ? sh.writer->game_count() : 0;
     out.real_evals = sh.real_evals.load();
     out.cached_evals = sh.cached_evals.load();
     out.potential_evals = sh.potential_evals.load();
@@ -504,7 +558,8 @@ KZB_API int kzb_selfplay_run(int device, const void* onnx_bytes, size_t onnx_len
                              kzb_selfplay_stats* stats) {
     using namespace kzb::selfplay;
     return guarded([&] {
-        if (!onnx_bytes || !config || !stats) throw std::runtime_error("onnx_bytes, config and stats must not be NULL");
+        if (!config || !stats) throw std::runtime_error("config and stats must not be NULL");
+        if (!onnx_bytes && !config->dummy_network) throw std::runtime_error("onnx_bytes must not be NULL unless dummy_network is set");
         std::memset(stats, 0, sizeof(*stats));
         if (config->game == KZB_GAME_SYNTH_CHESS) run_selfplay<SynthChess>(device, onnx_bytes, onnx_len, precision, *config, *stats);
         else if (config->game == KZB_GAME_ATAXX7) run_selfplay<Ataxx>(device, onnx_bytes, onnx_len, precision, *config, *stats);

@@ -27,6 +27,8 @@ def default_config(**overrides) -> SelfplayConfig:
     for k, v in overrides.items():
         if k not in names:
             raise KeyError(k)
+        if k == "output_prefix" and isinstance(v, str):
+            v = v.encode()
         setattr(cfg, k, v)
     return cfg
 
@@ -43,6 +45,7 @@ class SelfplayResult:
     moves_played: int
     root_visits: int
     concurrent_games: int
+    games_written: int = 0
 
     @property
     def nn_positions_per_s(self) -> float:  # "real evals/s" of collector.rs:172-191
@@ -61,9 +64,11 @@ class SelfplayResult:
         return self.cached_evals / max(self.real_evals + self.cached_evals, 1)
 
 
-def run(onnx_bytes: bytes, config: SelfplayConfig, device: int = 0, precision: int = 1) -> SelfplayResult:
+def run(onnx_bytes: Optional[bytes], config: SelfplayConfig, device: int = 0, precision: int = 1) -> SelfplayResult:
+    """onnx_bytes may be None when config.dummy_network is set (uniform evaluations, no GPU)."""
     stats = SelfplayStats()
-    _abi.check(_abi.lib().kzb_selfplay_run(device, onnx_bytes, len(onnx_bytes), precision, ctypes.byref(config), ctypes.byref(stats)))
+    _abi.check(_abi.lib().kzb_selfplay_run(device, onnx_bytes, len(onnx_bytes) if onnx_bytes else 0, precision, ctypes.byref(config),
+                                           ctypes.byref(stats)))
     return SelfplayResult(**{f[0]: getattr(stats, f[0]) for f in SelfplayStats._fields_})
 
 

@@ -1,0 +1,121 @@
+"""Self-play record files written by the C++ driver (row N2), read back with the REFERENCE'S OWN loader
+(python/lib/data/file.py, position.py -- imported from /root/reference when present) and with an independent parser of
+the format of rust/kz-selfplay/src/binary_output.rs:128-297.  The driver runs with the DummyNetwork stand-in
+(uniform evaluations, rust/kz-core/src/network/dummy.rs:44-60), so no GPU is needed."""
+import json
+import struct
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from kzero_b200 import selfplay
+
+REFERENCE_PY = Path("/root/reference/python")
+SCALARS = 26
+
+
+def _run(tmp_path, game, **kw):
+    prefix = str(tmp_path / "games_0")
+    cfg = selfplay.default_config(game=game, visits=24, search_batch=4, gpu_batch=32, cpu_threads=2, gpu_threads=1, max_moves=400,
+                                  duration_s=30.0, dummy_network=1, output_prefix=prefix, seed=5, **kw)
+    r = selfplay.run(None, cfg)
+    assert r.games_written > 0 and r.moves_played >= 400
+    return prefix, r
+
+
+def _parse(prefix, bool_count, scalar_count):
+    """Independent reader: -> (meta, list of per-position dicts)."""
+    meta = json.loads(Path(prefix + ".json").read_text())
+    data = Path(prefix + ".bin").read_bytes()
+    off = np.frombuffer(Path(prefix + ".off").read_bytes(), dtype="<u8")
+    n = meta["position_count"]
+    assert off.size == n + meta["game_count"]  # offsets, then one start index per game (binary_output.rs:270)
+    ends = list(off[1:n]) + [len(data)]
+    out = []
+    for start, end in zip(off[:n], ends):
+        rec = data[int(start):int(end)]
+        s = np.frombuffer(rec[:SCALARS * 4], "<f4")
+        pos = SCALARS * 4
+        bits = np.frombuffer(rec[pos:pos + (bool_count + 7) // 8], np.uint8)
+        pos += (bool_count + 7) // 8
+        scal = np.frombuffer(rec[pos:pos + scalar_count * 4], "<f4")
+        pos += scalar_count * 4
+        k = int(s[8])
+        idx = np.frombuffer(rec[pos:pos + 4 * k], "<u4")
+        pos += 4 * k
+        val = np.frombuffer(rec[pos:pos + 4 * k], "<f4")
+        pos += 4 * k
+        assert pos == len(rec)  # every record is consumed to the byte (python/lib/data/taker.py:10-11)
+        out.append(dict(scalars=s, bits=bits, input_scalars=scal, indices=idx, values=val))
+    return meta, out, off[n:]
+
+
+@pytest.mark.parametrize("game,name,bool_shape,scalar_count,policy_len", [
+    (selfplay.GAME_SYNTH_CHESS, "chess", [13, 8, 8], 8, 1880), (selfplay.GAME_ATAXX7, "ataxx-7", [3, 7, 7], 1, 17 * 49 + 1)])
+def test_record_files_are_self_consistent(tmp_path, game, name, bool_shape, scalar_count, policy_len):
+    prefix, r = _run(tmp_path, game)
+    meta, positions, game_starts = _parse(prefix, int(np.prod(bool_shape)), scalar_count)
+    assert meta["game"] == name and meta["input_bool_shape"] == bool_shape and meta["input_scalar_count"] == scalar_count
+    assert meta["policy_shape"] == [policy_len] and meta["game_count"] == r.games_written and len(meta["scalar_names"]) == SCALARS
+    assert meta["includes_terminal_positions"] and meta["includes_game_start_indices"]
+    assert abs(sum(meta["root_wdl"]) - 1) < 1e-6
+    # the checks of python/lib/data/check.py:9-76: games cover all positions, final-position flags, per-game indices
+    pi = 0
+    lengths = []
+    for g in range(meta["game_count"]):
+        assert game_starts[g] == pi
+        length = int(positions[pi]["scalars"][2])
+        lengths.append(length)
+        for k in range(length + 1):
+            s = positions[pi]["scalars"]
+            assert (int(s[0]), int(s[1]), int(s[2])) == (g, k, length)
+            final = k == length
+            assert bool(s[5]) == final
+            if final:
+                assert s[8] == 0 and s[9] == -1 and np.isnan(s[10]) and bool(s[6]) != bool(s[7])
+                assert len(positions[pi]["indices"]) == 0
+            else:
+                p = positions[pi]
+                assert s[3] >= 24 and s[4] == 1 and len(p["indices"]) == int(s[8]) > 0
+                assert abs(float(p["values"].sum()) - 1) < 1e-3 and int(s[9]) in p["indices"].tolist()
+                assert p["indices"].max() < policy_len and len(set(p["indices"].tolist())) == len(p["indices"])
+                assert abs(float(s[12:15].sum()) - 1) < 1e-3 and abs(float(s[17:20].sum()) - 1) < 1e-3 and abs(float(s[22:25].sum()) - 1) < 1e-3
+                assert s[15] == length + 1 - k  # final_moves_left, binary_output.rs:164
+            pi += 1
+    assert pi == meta["position_count"] and max(lengths) == meta["max_game_length"] and min(lengths) == meta["min_game_length"]
+
+
+@pytest.mark.skipif(not REFERENCE_PY.exists(), reason="the reference tree is only present in the build container")
+@pytest.mark.parametrize("game,name", [(selfplay.GAME_SYNTH_CHESS, "chess"), (selfplay.GAME_ATAXX7, "ataxx-7")])
+def test_reference_loader_reads_the_records(tmp_path, game, name):
+    """DataFile.open + Position (python/lib/data/file.py:62-130, position.py:34-103) accept the files and agree with the
+    independent parser on every field they decode."""
+    prefix, r = _run(tmp_path, game)
+    sys.path.insert(0, str(REFERENCE_PY))
+    try:
+        from lib.data.file import DataFile
+        from lib.games import Game
+    finally:
+        sys.path.pop(0)
+    ref_game = Game.find(name)
+    f = DataFile.open(ref_game, prefix)
+    meta, positions, _ = _parse(prefix, int(np.prod(ref_game.input_bool_shape)), ref_game.input_scalar_channels)
+    assert f.info.simulation_count == r.games_written and f.info.position_count == len(positions)
+    assert f.info.includes_final_positions and f.info.includes_simulation_start_indices
+    for pi in list(range(0, len(positions), 7)) + [len(positions) - 1]:
+        p = f.load_position(pi)
+        mine = positions[pi]
+        s = mine["scalars"]
+        assert (p.simulation.index, p.move_index, p.simulation.move_count) == (int(s[0]), int(s[1]), int(s[2]))
+        assert p.zero_visits == int(s[3]) and p.available_mv_count == int(s[8]) and p.played_mv == int(s[9])
+        assert p.is_final == bool(s[5]) and p.is_terminal == bool(s[6])
+        assert np.array_equal(p.policy_indices, mine["indices"].astype(np.int32)) and np.array_equal(p.policy_values, mine["values"])
+        assert np.array_equal(p.input_scalars, mine["input_scalars"])
+        bools = np.unpackbits(mine["bits"], bitorder="little")[:p.input_bools.size].reshape(p.input_bools.shape)
+        assert np.array_equal(p.input_bools, bools)
+        assert p.final_v in (-1.0, 0.0, 1.0) and abs(p.final_wdl.sum() - 1) < 1e-6
+    # the simulations view walks the whole file through the start indices
+    sims = [f.simulations[i] for i in range(len(f.simulations))]
+    assert sum(sim.position_count for sim in sims) == f.info.position_count
