@@ -371,7 +371,7 @@ void Net::build_bf16() {
         };
         tower_maps_.out[0] = omap(act_x_);
         tower_maps_.out[1] = omap(act_t_);
-        act_xt_.alloc(size_t(rows_alloc_ / 256 + 1) * 128 * 256 * 2);
+        act_xt_.alloc(size_t(std::max(rows_alloc_ / 256 + 1, 2 * num_sms_ + 2)) * 128 * 256 * 2);  // one slot per (CTA, local unit)
         const char* cl_env = std::getenv("KZB_TOWER_CLUSTER");
         const int cluster = (cl_env && cl_env[0] == '1') ? 1 : 2;
         {
@@ -432,24 +432,33 @@ void Net::build_bf16() {
             act_ink_.alloc(size_t(cin_pad_ / 8) * boards_total * 1024);
             act_xk_.alloc(size_t(c_pad_ / 8) * boards_total * 1024);
             act_tk_.alloc(size_t(c_pad_ / 8) * boards_total * 1024);
-            auto kload = [&](DeviceBuffer& buf, int kc_total) {  // (x*8+c8, board, y, kc)
+            auto kload = [&](DeviceBuffer& buf, int kc_total, int nb) {  // (x*8+c8, board, y, kc)
                 uint64_t dims[4] = {64, boards_total, 8, uint64_t(kc_total)};
                 uint64_t strides[3] = {1024, 128, boards_total * 1024};
-                uint32_t box[4] = {72, 4, 8, 1};  // 72 > 64: the engine zero-fills the pad row of every 8-position group
+                // 72 > 64: the engine zero-fills the pad row of every 8-position group; 9 > 8: and a zero rank behind the board
+                uint32_t box[4] = {72, uint32_t(nb), 9, 1};
                 return make_tmap(buf.ptr, 4, dims, strides, box, false);
             };
-            auto kstore = [&](DeviceBuffer& buf, int kc_total) {  // (x*8+c8, kc, board, y)
+            auto kstore = [&](DeviceBuffer& buf, int kc_total, int nb) {  // (x*8+c8, kc, board, y)
                 uint64_t dims[4] = {64, uint64_t(kc_total), boards_total, 8};
                 uint64_t strides[3] = {boards_total * 1024, 1024, 128};
-                uint32_t box[4] = {80, 4, 4, 1};  // staging rows are 160 bytes (bank spreading); elements 64..79 are clipped
+                uint32_t box[4] = {80, 4, uint32_t(nb), 1};  // staging rows are 160 bytes (bank spreading); elements 64..79 are clipped
                 return make_tmap(buf.ptr, 4, dims, strides, box, false);
             };
-            tower_kmaps_.a[0] = kload(act_ink_, cin_pad_ / 8);
-            tower_kmaps_.a[1] = kload(act_xk_, c_pad_ / 8);
-            tower_kmaps_.a[2] = kload(act_tk_, c_pad_ / 8);
-            tower_kmaps_.out[0] = kstore(act_xk_, c_pad_ / 8);
-            tower_kmaps_.out[1] = kstore(act_tk_, c_pad_ / 8);
-            tower_kmaps_.out[2] = omap(act_x_);
+            auto rstore = [&](DeviceBuffer& buf, int nb) {  // row-major rows, one rank of an nb-board unit: (c, x, board, y)
+                uint64_t dims[4] = {uint64_t(c_pad_), 8, uint64_t(rows_alloc_ / 64), 8};
+                uint64_t strides[3] = {uint64_t(c_pad_) * 2, uint64_t(c_pad_) * 2 * 64, uint64_t(c_pad_) * 2 * 8};
+                uint32_t box[4] = {32, 8, uint32_t(nb), 1};
+                return make_tmap(buf.ptr, 4, dims, strides, box, false);
+            };
+            for (int nb = 3; nb <= 4; nb++) {
+                tower_kmaps_.a[0][nb - 3] = kload(act_ink_, cin_pad_ / 8, nb);
+                tower_kmaps_.a[1][nb - 3] = kload(act_xk_, c_pad_ / 8, nb);
+                tower_kmaps_.a[2][nb - 3] = kload(act_tk_, c_pad_ / 8, nb);
+                tower_kmaps_.out[0][nb - 3] = kstore(act_xk_, c_pad_ / 8, nb);
+                tower_kmaps_.out[1][nb - 3] = kstore(act_tk_, c_pad_ / 8, nb);
+                tower_kmaps_.out[2][nb - 3] = rstore(act_x_, nb);
+            }
             tower_kmaps_.w[0] = tower_maps_.w[0];
             tower_kmaps_.w[1] = tower_maps_.w[1];
             tower_k_b_slots_ = tower8k_pick_b_slots();
@@ -630,6 +639,16 @@ void Net::run_network(int batch, const StepHook& hook) {
         if (timeline_step_ == "tower8") tp.timeline = d_timeline_.as<unsigned long long>();
         if (use_tower8k_) {
             tp.b_slots = tower_k_b_slots_;
+            // balanced assignment: every CTA owns 6..8 contiguous boards (two units of 4 / 3); otherwise 4-board units
+            const int grid = num_sms_ & ~1;
+            const char* nobal = std::getenv("KZB_NO_BALANCE");
+            tp.balanced = 0;
+            if (!(nobal && nobal[0] == '1') && batch / grid >= 6 && (batch + grid - 1) / grid <= 8) {
+                tp.balanced = 1;
+                tp.bal_grid = grid;
+                tp.bal_base = batch / grid;
+                tp.bal_rem = batch % grid;
+            }
             launch_tower8k(tower_kmaps_, tp, num_sms_, stream_);
         } else {
             launch_tower8(tower_maps_, tp, num_sms_, stream_);

@@ -129,6 +129,8 @@ struct Tower8Params {
     int stride;  // elements per row of X / T
     int b_slots, tmem_cols;
     int cluster;  // 1: every CTA streams its own weight tiles; 2: CTA pairs, each loads half of every tile and multicasts it
+    // tower8k only: balanced board assignment (CTA c owns bal_base + (c < bal_rem) contiguous boards as two units of 4 / 3)
+    int balanced, bal_base, bal_rem, bal_grid;
     unsigned long long* timeline;
     int debug;  // development aid (KZB_DEBUG): 1 = skip A loads, 2 = skip B loads, 4 = skip epilogue memory traffic
 };
@@ -136,9 +138,10 @@ void launch_tower8(const Tower8Maps& maps, const Tower8Params& p, int grid, cuda
 
 // second generation (tower8k.cu): k-chunk-major activations A[kc][board][y][x][8], every tap = a descriptor offset
 struct Tower8kMaps {
-    CUtensorMap a[3];    // loads: encoded planes, X, T -- dims (x*8+c8: 64, board, y: 8, kc), box (72, 4, 8, 1), no swizzle
-    CUtensorMap w[2];    // loads: first-layer weights, concatenated block weights -- box (64, n / cluster), SWIZZLE_128B
-    CUtensorMap out[3];  // stores: X, T k-chunk-major -- dims (64, kc, board, y), box (80, 4, 4, 1); [2] = X row-major (c, x, board, y), box (32, 8, 4, 1)
+    // second index: boards per unit - 3 (units of 3 or 4 boards)
+    CUtensorMap a[3][2];    // loads: encoded planes, X, T -- dims (x*8+c8: 64, board, y: 8, kc), box (72, nb, 9, 1), no swizzle
+    CUtensorMap w[2];       // loads: first-layer weights, concatenated block weights -- box (64, n / cluster), SWIZZLE_128B
+    CUtensorMap out[3][2];  // stores: X, T k-chunk-major -- dims (64, kc, board, y), box (80, 4, nb, 1); [2] = X row-major (c, x, board, y), box (32, 8, nb, 1)
 };
 void launch_tower8k(const Tower8kMaps& maps, const Tower8Params& p, int grid, cudaStream_t s);
 size_t tower8k_smem_bytes(int w_slots);

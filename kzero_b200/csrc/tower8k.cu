@@ -37,9 +37,8 @@ using namespace tc;
 constexpr int kEpiWarps = 8;
 constexpr int kChunks = 32 / kEpiWarps;        // ranks per epilogue warp and unit
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kBoards = 4;
 constexpr int kGroup = 144;                    // 8 positions x 16 B + one zero pad row
-constexpr int kChunkData = 32 * kGroup;        // 4608 B: one k-chunk of a unit = one TMA box
+constexpr int kChunkData = 32 * kGroup;        // 4608 B: the 8 ranks of one k-chunk of a 4-board unit
 constexpr int kLbo = 5248;                     // k-chunk pitch (41 x 128: keeps every TMA destination 128-byte aligned)
 constexpr int kLead = kLbo - kChunkData;       // 640 B zero gap in front of every k-chunk
 constexpr int kHalfBytes = kLead + 8 * kLbo;   // one 64-channel k-block of a unit incl. its gaps: 42,624 B
@@ -87,6 +86,26 @@ __device__ __forceinline__ void stg256(void* ptr, const uint32_t* r) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// Work units.  Legacy scheme: 4-board units, unit u = blockIdx + ul * gridDim.  Balanced scheme (p.balanced): CTA c owns
+// the contiguous boards [c*base + min(c, rem), ...) -- base or base+1 of them, 6..8 -- as two units of 4 or 3 boards, so
+// that every SM carries the same work within one board (1024 boards on 148 SMs: 136 x 7 + 12 x 6 instead of 108 x 8 + 40 x 4).
+// A 3-board unit is an N = 192 MMA (96 cycles, still above the ~94-cycle floor of an M128 MMA).
+struct Unit {
+    int board0, nb;
+};
+__device__ __forceinline__ int local_units(const Tower8Params& p) {
+    if (p.balanced) return 2;
+    return (p.num_units - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+}
+__device__ __forceinline__ Unit unit_of(const Tower8Params& p, int ul) {
+    if (!p.balanced) return {(int(blockIdx.x) + ul * int(gridDim.x)) * 4, 4};
+    const int c = int(blockIdx.x);
+    const int n = p.bal_base + (c < p.bal_rem ? 1 : 0);
+    const int start = c * p.bal_base + min(c, p.bal_rem);
+    const int u0 = (n + 1) / 2;
+    return ul == 0 ? Unit{start, u0} : Unit{start + u0, n - u0};
+}
+
 // SWIZZLE_NONE K-major descriptor, address-independent part: LBO = k-chunk pitch, SBO = group pitch, version 1
 __device__ __forceinline__ uint64_t umma_desc_nosw_hi() {
     return (uint64_t(kLbo >> 4) << 16) | (uint64_t(kGroup >> 4) << 32) | (uint64_t(1) << 46);
@@ -105,9 +124,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (tl && threadIdx.x == 0) tl[0] = clock64();
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < 3; i++) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.a[i])) : "memory");
+        for (int i = 0; i < 6; i++) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.a[i / 2][i % 2])) : "memory");
         for (int i = 0; i < 2; i++) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.w[i])) : "memory");
-        for (int i = 0; i < 3; i++) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.out[i])) : "memory");
+        for (int i = 0; i < 6; i++) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.out[i / 2][i % 2])) : "memory");
         for (int i = 0; i < kXSlots; i++) {
             mbar_init(&sm.x_full[i], 1);
             mbar_init(&sm.x_empty[i], 1);
@@ -146,15 +165,16 @@ __global__ void __launch_bounds__(kThreads, 1)
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             const uint32_t w_bytes = uint32_t(p.n) * 128u;
+            const int n_local = local_units(p);
             int x_slot = 0, w_slot = 0;
             uint32_t x_phase = 0, w_phase = 0;
             int pitem = 0;
             for (int L = 0; L < p.num_layers; L++) {
                 const TowerLayerDev ld = p.layers[L];
-                const CUtensorMap* amap = &maps.a[ld.a_map];
                 const CUtensorMap* wmap = &maps.w[ld.w_map];
-                int ul = 0;
-                for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ul++, pitem++) {
+                for (int ul = 0; ul < n_local; ul++, pitem++) {
+                    const Unit un = unit_of(p, ul);
+                    const CUtensorMap* amap = &maps.a[ld.a_map][un.nb - 3];
                     // rows of this unit written by layer L-1's epilogue must be complete and visible
                     if (L > 0) mbar_wait(&sm.ready[ul], uint32_t(L - 1) & 1);
                     KZB_STAMP(pitem, 5);
@@ -163,10 +183,12 @@ __global__ void __launch_bounds__(kThreads, 1)
                         if (p.debug & 1) {
                             mbar_arrive(&sm.x_full[x_slot]);
                         } else {
-                            mbar_expect_tx(&sm.x_full[x_slot], uint32_t(ld.kchunks) * kChunkData);
+                            // box = (72 elements, nb boards, 9 ranks): rank 8 does not exist, so the engine also writes the zero
+                            // rank that the dy = +1 taps of this chunk and the dy = -1 taps of the next one read
+                            mbar_expect_tx(&sm.x_full[x_slot], uint32_t(ld.kchunks) * uint32_t(9 * un.nb * kGroup));
                             uint8_t* half = sm.x + size_t(x_slot) * kHalfBytes + kLead;
                             for (int c = 0; c < ld.kchunks; c++)
-                                tma_load_4d(amap, &sm.x_full[x_slot], half + size_t(c) * kLbo, 0, unit * kBoards, 0, kb * 8 + c);
+                                tma_load_4d(amap, &sm.x_full[x_slot], half + size_t(c) * kLbo, 0, un.board0, 0, kb * 8 + c);
                         }
                         if (++x_slot == kXSlots) {
                             x_slot = 0;
@@ -201,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         // ------------------------------------------------------------------ MMA issuer
         // The whole warp walks the loops (warp-uniform control flow keeps the address arithmetic on the uniform
         // datapath); lane 0 alone issues tcgen05.mma and the commits that track them.
-        const uint32_t idesc = umma_idesc_bf16(128, 256);
+        const int n_local = local_units(p);
         const uint64_t w_hi = umma_desc_sw128_hi();
         const uint64_t x_hi = umma_desc_nosw_hi();
         int x_slot = 0, w_slot = 0;
@@ -209,7 +231,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         int item = 0;
         for (int L = 0; L < p.num_layers; L++) {
             const int kblocks = p.layers[L].kblocks, ksteps = p.layers[L].ksteps;
-            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, item++) {
+            for (int ul = 0; ul < n_local; ul++, item++) {
+                const int nb = unit_of(p, ul).nb;
+                const uint32_t idesc = umma_idesc_bf16(128, nb * 64);
                 const int buf = item & 1;
                 mbar_wait(&sm.tmem_empty[buf], ((item >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -225,8 +249,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                             mbar_wait(&sm.w_full[w_slot], w_phase);
                             tc_fence_after();
                             const uint32_t w_lo = umma_desc_lo(smem_u32(sm.w + size_t(w_slot) * kWBytes));
-                            // tap (dy, dx): 4 groups per rank, 16 bytes per file -- in 16-byte units
-                            const uint32_t x_t = x_lo + uint32_t(dy * (4 * kGroup / 16) + dx);
+                            // tap (dy, dx): nb groups per rank, 16 bytes per file -- in 16-byte units
+                            const uint32_t x_t = x_lo + uint32_t(dy * (nb * kGroup / 16) + dx);
                             if (lane == 0) {
 #pragma unroll
                                 for (int k = 0; k < 4; k++) {
@@ -268,6 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const bool warp_ok = quarter * 32 < p.n_store;  // narrow nets: upper warps have no channels
         const bool live = !(p.debug & 4) && warp_ok;
         uint8_t* const stage = sm.stage + (warp - 2) * kStageWarp;
+        const int n_local = local_units(p);
         int item = 0;
         for (int L = 0; L < p.num_layers; L++) {
             const TowerLayerDev ld = p.layers[L];
@@ -276,13 +301,14 @@ __global__ void __launch_bounds__(kThreads, 1)
             const bool to_x = ld.out_buf == 1;
             const bool has_res = ld.has_res != 0;
             const bool rowmajor = ld.out_rowmajor != 0;
-            const CUtensorMap* omap = &maps.out[rowmajor ? 2 : (to_x ? 0 : 1)];
-            int ul = 0;
-            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, item++, ul++) {
+            for (int ul = 0; ul < n_local; ul++, item++) {
+                const Unit un = unit_of(p, ul);
+                const int nb = un.nb;
+                const CUtensorMap* omap = &maps.out[rowmajor ? 2 : (to_x ? 0 : 1)][nb - 3];
                 const int buf = item & 1;
                 // channel-major residual copy, laid out so that one warp-wide 32-byte access is 1 KiB contiguous:
-                // XT[unit][rank][16-position half][channel][16 positions]
-                __nv_bfloat16* xt = p.xt + size_t(unit) * (128 * 256) + size_t(c) * 16;
+                // XT[slot][rank][16-position half][channel][16 positions], one slot per (CTA, local unit)
+                __nv_bfloat16* xt = p.xt + size_t(ul * int(gridDim.x) + int(blockIdx.x)) * (128 * 256) + size_t(c) * 16;
                 uint32_t res[16];
                 if (has_res && live) {
                     ldg256(xt + ((kChunks * part) * 2 + 0) * 2048, res);
@@ -297,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 for (int yy = 0; yy < kChunks; yy++) {
                     const int y = kChunks * part + yy;
                     uint32_t r[32];
-                    tmem_ld32(taddr + y * 32, r);
+                    tmem_ld32(taddr + y * (nb * 8), r);  // columns of rank y: nb boards x 8 files (a 3-board unit ignores the last 8)
                     tmem_ld_wait();
                     uint32_t packed[16];
 #pragma unroll
@@ -327,8 +353,10 @@ __global__ void __launch_bounds__(kThreads, 1)
                             uint8_t* sp = stage + lane * 2;
 #pragma unroll
                             for (int j = 0; j < 16; j++) {
-                                *reinterpret_cast<uint16_t*>(sp + (2 * j) * 64) = uint16_t(packed[j] & 0xffffu);
-                                *reinterpret_cast<uint16_t*>(sp + (2 * j + 1) * 64) = uint16_t(packed[j] >> 16);
+                                if ((j >> 2) < nb) {
+                                    *reinterpret_cast<uint16_t*>(sp + (2 * j) * 64) = uint16_t(packed[j] & 0xffffu);
+                                    *reinterpret_cast<uint16_t*>(sp + (2 * j + 1) * 64) = uint16_t(packed[j] >> 16);
+                                }
                             }
                         } else {
                             // [board][kc][80 elements]: position j = board*8 + file -> board*640 + kc*160 + file*16; the 160-byte
@@ -342,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                             for (int j = 0; j < 16; j++) {
                                 const uint32_t other = __shfl_xor_sync(0xffffffffu, packed[j], 1);
                                 const uint32_t word = odd ? __byte_perm(other, packed[j], 0x7632) : __byte_perm(packed[j], other, 0x5410);
-                                *reinterpret_cast<uint32_t*>(sp + ((2 * j) >> 3) * 640 + ((2 * j) & 7) * 16) = word;
+                                if ((j >> 2) < nb) *reinterpret_cast<uint32_t*>(sp + ((2 * j) >> 3) * 640 + ((2 * j) & 7) * 16) = word;
                             }
                         }
                         if (to_x) {  // channel-major copy of the residual stream
@@ -353,8 +381,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0 && live && !(p.debug & 8)) {
-                        if (rowmajor) tma_store_4d(omap, stage, quarter * 32, 0, unit * kBoards, y);   // (c, x, board, y)
-                        else tma_store_4d(omap, stage, 0, quarter * 4, unit * kBoards, y);             // (x*8+c8, kc, board, y)
+                        if (rowmajor) tma_store_4d(omap, stage, quarter * 32, 0, un.board0, y);   // (c, x, board, y)
+                        else tma_store_4d(omap, stage, 0, quarter * 4, un.board0, y);             // (x*8+c8, kc, board, y)
                         tma_store_commit();
                     }
                 }
@@ -404,7 +432,7 @@ void launch_tower8k(const Tower8kMaps& maps, const Tower8Params& p, int grid, cu
     if (p.num_units <= 0 || p.num_layers <= 0) return;
     if (p.cluster == 2) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(unsigned(std::min(grid & ~1, p.num_units)));
+        cfg.gridDim = dim3(unsigned(p.balanced ? p.bal_grid : std::min(grid & ~1, p.num_units)));
         cfg.blockDim = dim3(kThreads);
         cfg.dynamicSmemBytes = tower8k_smem_bytes(p.b_slots);
         cfg.stream = s;
@@ -417,7 +445,7 @@ void launch_tower8k(const Tower8kMaps& maps, const Tower8Params& p, int grid, cu
         cfg.numAttrs = 1;
         cudaLaunchKernelEx(&cfg, tower8k_kernel<2>, maps, p);
     } else {
-        tower8k_kernel<1><<<std::min(grid, p.num_units), kThreads, tower8k_smem_bytes(p.b_slots), s>>>(maps, p);
+        tower8k_kernel<1><<<p.balanced ? p.bal_grid : std::min(grid, p.num_units), kThreads, tower8k_smem_bytes(p.b_slots), s>>>(maps, p);
     }
 }
 

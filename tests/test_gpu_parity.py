@@ -179,6 +179,27 @@ def test_attention_head_vs_oracle(depth, ch, q, n, precision, tol_logit, tol_v, 
     _check_packed(values, probs, ref_values, ref_probs, mv_off, tol_v, tol_p)
 
 
+@pytest.mark.parametrize("n", [887, 888, 1024, 1036, 1184, 1185])
+def test_bf16_balanced_units_match_uniform_units(n, monkeypatch):
+    """tower8k's balanced board assignment (every SM owns 6..8 boards as two units of 4 / 3 boards, batches 888..1184)
+    against the uniform 4-board units (KZB_NO_BALANCE=1): a board's result must not depend on which unit computed it."""
+    spec = netgen.game_spec("chess")
+    onnx_bytes = netgen.build_onnx(spec, 3, 128, seed=41)
+    bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, n, seed=42)
+    monkeypatch.setenv("KZB_NO_BALANCE", "1")
+    with B200Network(mapper_for(spec), onnx_bytes, n) as net:
+        v0, p0 = net.evaluate_packed(bits, scalars, mv_idx, mv_off)
+    monkeypatch.setenv("KZB_NO_BALANCE", "0")
+    with B200Network(mapper_for(spec), onnx_bytes, n) as net:
+        v1, p1 = net.evaluate_packed(bits, scalars, mv_idx, mv_off)
+    assert np.array_equal(v0, v1) and np.array_equal(p0, p1)
+    # and against the oracle on a sample of boards (the tolerance of the bf16 path)
+    pick = np.array([0, 1, n // 2, n - 2, n - 1])
+    planes = _oracle_planes(spec, bits[pick], scalars[pick])
+    ref_s, _ = OnnxOracle(onnx_bytes).run(planes)
+    assert np.abs(np.tanh(ref_s[:, 0]) - v1[pick, 0]).max() <= 5e-2
+
+
 # ------------------------------------------------------------------------------------------- contract edges
 @pytest.mark.parametrize("precision", [PRECISION_FP32, PRECISION_BF16])
 def test_rows_independent_of_batch(precision):
