@@ -146,14 +146,18 @@ class ClockSampler:
 class CpuRestatement:
     """The oracle (expand planes -> ONNX graph in f32 -> decode_output) as a timed CPU implementation of the path."""
 
-    def __init__(self, onnx_bytes, spec, threads: int):
+    def __init__(self, onnx_bytes, spec, threads: int, conv_backend: str = "c"):
         import oracle
         from oracle.graph_exec import OnnxOracle
 
         self.oracle = oracle
         self.spec = spec
         oracle.set_threads(threads)
-        self.net = OnnxOracle(onnx_bytes)
+        if conv_backend == "torch":
+            import torch
+
+            torch.set_num_threads(threads)
+        self.net = OnnxOracle(onnx_bytes, conv_backend=conv_backend)
 
     def run(self, n: int, seed: int) -> float:
         """seconds for one pass over n synthetic positions"""
@@ -173,9 +177,9 @@ class CpuRestatement:
         return int(max(probe_n, min(batch, seconds_target / max(dt / probe_n, 1e-9))))
 
 
-def cpu_restatement_rate(cfg, onnx_bytes, spec, seconds_target: float, threads: int):
+def cpu_restatement_rate(cfg, onnx_bytes, spec, seconds_target: float, threads: int, conv_backend: str = "c"):
     """positions/s of the oracle on `threads` host threads over a bounded sample of the workload."""
-    cpu = CpuRestatement(onnx_bytes, spec, threads)
+    cpu = CpuRestatement(onnx_bytes, spec, threads, conv_backend)
     n = cpu.sample_size(cfg["batch"], seconds_target, threads)
     dt = cpu.run(n, 101)
     return n / dt, n, dt
@@ -350,7 +354,7 @@ def main():
             "tflops_whole_step": float(info.flops_per_position) * batch * args.steps / dev_s / 1e12,
             # the tower kernel is timed alone (one ~0.45 ms launch between L2 flushes, the GPU idles in between), so the
             # denominator is the BURST cuBLAS figure; the sustained-loop figure is reported beside it
-            "roofline": {"bound": "tensor", "kernel": "tower8_kernel" if "tower8" in share else "conv_tc_kernel",
+            "roofline": {"bound": "tensor", "kernel": ("tower8_kernel" if os.environ.get("KZB_TOWER_V1") == "1" else "tower8k_kernel") if "tower8" in share else "conv_tc_kernel",
                          "achieved": achieved, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tflops_burst"], "frac_of_sustained_peak": achieved / peaks["tflops_sustained"],
                          "peak_source": peaks["source"] + " (bf16_tflops, burst: kernel timed in isolation)", "traffic": traffic,
@@ -366,6 +370,10 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "positions/s", "cores": threads, "kind": "port",
                                     "sample": f"{n} positions of the same workload in {dt:.1f} s (oracle/: f32 ONNX graph "
                                               "interpreter with C/OpenMP conv loops + plane expansion + decode_output)"}
+            # informational: the same interpreter with Conv handed to PyTorch's CPU kernels (oneDNN), a much stronger CPU arm
+            rate_t, n_t, dt_t = cpu_restatement_rate(cfg, onnx_bytes, spec, 8.0, threads, "torch")
+            line["cpu_baseline"]["torch_onednn"] = {"value": rate_t, "unit": "positions/s", "cores": threads,
+                                                    "sample": f"{n_t} positions in {dt_t:.1f} s"}
         print(json.dumps(line), flush=True)
     net.close()
     if dist is not None:

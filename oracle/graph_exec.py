@@ -22,7 +22,12 @@ from .onnx_min import Model, load_model
 
 
 class OnnxOracle:
-    def __init__(self, onnx_bytes: bytes):
+    def __init__(self, onnx_bytes: bytes, conv_backend: str = "c"):
+        """conv_backend "c": the straight C/OpenMP loops of kz_oracle.c (the restatement of the reference's naive CPU
+        executor); "torch": the same op-by-op interpreter with Conv / Gemm handed to PyTorch's CPU kernels (oneDNN) --
+        a stronger CPU baseline that bench.py reports beside the port, never used as the parity oracle."""
+        assert conv_backend in ("c", "torch")
+        self.conv_backend = conv_backend
         self.model: Model = load_model(onnx_bytes)
         assert len(self.model.inputs) == 1, "reference nets have exactly one input (network/common.rs:166-168)"
         self.input_name, self.input_shape = self.model.inputs[0]
@@ -39,6 +44,16 @@ class OnnxOracle:
             assert a.get("group", 1) == 1 and list(a.get("strides", [1, 1])) == [1, 1]
             assert list(a.get("dilations", [1, 1])) == [1, 1]
             assert k[0] == k[1] and len(set(pads)) == 1
+            if self.conv_backend == "torch":
+                import warnings
+
+                import torch
+
+                with torch.no_grad(), warnings.catch_warnings():
+                    warnings.simplefilter("ignore")  # read-only numpy views of the initializers are only read
+                    y = torch.nn.functional.conv2d(torch.from_numpy(np.ascontiguousarray(x[0])), torch.from_numpy(np.ascontiguousarray(x[1])),
+                                                   torch.from_numpy(np.ascontiguousarray(x[2])) if len(x) > 2 else None, padding=pads[0])
+                return [y.numpy()]
             return [conv2d(x[0], x[1], x[2] if len(x) > 2 else None, pads[0])]
         if op == "Relu":
             return [np.maximum(x[0], np.float32(0))]
