@@ -132,7 +132,10 @@ typedef struct kzb_selfplay_config {
     int32_t max_game_length;
     int32_t cache_size;        /* per-game LRU evaluation cache                                                     */
     int32_t zero_temp_move_count;
-    int32_t max_moves;         /* stop after this many played moves (0 = run for duration_s)                        */
+    int32_t max_moves;         /* stop after this many played moves (0 = no limit)                                  */
+    int32_t max_games;         /* stop after this many finished games (0 = no limit): one record file = games_per_gen games */
+    int32_t part_iterations;   /* root visits of a non-full search (Settings::part_iterations)                      */
+    float full_search_prob;    /* probability that a move gets the full `visits` (Settings::full_search_prob)       */
     float duration_s;
     float temperature;         /* move selection temperature                                                        */
     float dirichlet_alpha, dirichlet_eps;
@@ -175,6 +178,10 @@ void kzb_selfplay_default_config(kzb_selfplay_config* config);
  * (real_evals + cached_evals) / seconds, NN positions/sec = real_evals / seconds. */
 int kzb_selfplay_run(int device, const void* onnx_bytes, size_t onnx_len, int precision, const kzb_selfplay_config* config,
                      kzb_selfplay_stats* stats);
+
+/* Ask every kzb_selfplay_run in this process to return as soon as possible (the `Stop` command, protocol.rs:37);
+ * callable from any thread.  The flag is cleared when the next run starts. */
+void kzb_selfplay_request_stop(void);
 
 /* Host-only (no GPU): one tree search of `config->visits` visits from the position `plies` random moves into game
  * `game_seed`, gathered in rounds of `config->search_batch` (virtual loss) and answered by a deterministic stand-in

@@ -20,7 +20,8 @@ class SelfplayConfig(ctypes.Structure):
     _fields_ = [("game", ctypes.c_int32), ("visits", ctypes.c_int32), ("search_batch", ctypes.c_int32), ("gpu_batch", ctypes.c_int32),
                 ("cpu_threads", ctypes.c_int32), ("gpu_threads", ctypes.c_int32), ("concurrent_games", ctypes.c_int32),
                 ("max_game_length", ctypes.c_int32), ("cache_size", ctypes.c_int32), ("zero_temp_move_count", ctypes.c_int32),
-                ("max_moves", ctypes.c_int32), ("duration_s", ctypes.c_float), ("temperature", ctypes.c_float),
+                ("max_moves", ctypes.c_int32), ("max_games", ctypes.c_int32), ("part_iterations", ctypes.c_int32),
+                ("full_search_prob", ctypes.c_float), ("duration_s", ctypes.c_float), ("temperature", ctypes.c_float),
                 ("dirichlet_alpha", ctypes.c_float), ("dirichlet_eps", ctypes.c_float),
                 ("policy_temperature_root", ctypes.c_float), ("policy_temperature_child", ctypes.c_float),
                 ("exploration_weight", ctypes.c_float), ("moves_left_weight", ctypes.c_float), ("moves_left_clip", ctypes.c_float),
@@ -65,6 +66,7 @@ SYMBOLS = {
     "kzb_launches_per_eval": (_i, [_vp]),
     "kzb_selfplay_default_config": (None, [ctypes.POINTER(SelfplayConfig)]),
     "kzb_selfplay_run": (_i, [_i, _vp, _sz, _i, ctypes.POINTER(SelfplayConfig), ctypes.POINTER(SelfplayStats)]),
+    "kzb_selfplay_request_stop": (None, []),
     "kzb_mcts_trace": (_i, [ctypes.POINTER(SelfplayConfig), ctypes.c_uint64, _i, _i, ctypes.POINTER(MctsTraceOut)]),
 }
 

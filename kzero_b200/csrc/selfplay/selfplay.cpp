@@ -39,6 +39,8 @@ namespace kzb {
 namespace selfplay {
 namespace {
 
+std::atomic<bool> g_stop_requested{false};
+
 struct Eval {
     ValuesPov values;
     std::vector<float> policy;
@@ -127,6 +129,8 @@ struct Slot {
     LruCache cache;
     Rng rng;
     uint32_t move_count = 0;
+    uint64_t target_visits = 0;  // 0: not drawn yet for this move
+    bool is_full_search = true;
     uint64_t next_seed;
     bool waiting = false;
     std::vector<Request<Game>> requests;
@@ -184,7 +188,11 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                 }
                 progressed = true;
                 Tree<Game>& tree = *slot.tree;
-                if (tree.root_visits() >= uint64_t(c.visits)) {
+                if (slot.target_visits == 0) {  // generator_alphazero.rs:88-94
+                    slot.is_full_search = c.full_search_prob >= 1.0f || slot.rng.gen_bool(c.full_search_prob);
+                    slot.target_visits = uint64_t(slot.is_full_search ? c.visits : std::max(1, c.part_iterations));
+                }
+                if (tree.root_visits() >= slot.target_visits) {
                     // pick and play a move (generator_alphazero.rs:108-130)
                     std::vector<float> policy;
                     tree.policy(policy);
@@ -198,6 +206,7 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                         const size_t c0 = size_t(tree.child_start[0]), cn = size_t(tree.child_count[0]);
                         for (size_t k = 0; k < cn; k++) rp.indices.push_back(slot.board.move_to_index(tree.last_move[c0 + k]));
                         rp.played_index = slot.board.move_to_index(mv);
+                        rp.is_full_search = slot.is_full_search;
                         rp.zero_visits = tree.root_visits();
                         rp.zero_values = pov(tree.values(0), slot.board.next_player());  // Tree::values, tree.rs:95-98
                         rp.zero_policy = policy;
@@ -207,6 +216,7 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                     }
                     slot.board.play(mv);
                     slot.move_count++;
+                    slot.target_visits = 0;
                     if (slot.board.done() || slot.move_count >= uint32_t(c.max_game_length)) {
                         if (sh.writer) {
                             encode_record(slot.board, shape, slot.record.final_position);
@@ -396,6 +406,7 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
         sh.gen_mu.push_back(std::make_unique<std::mutex>());
         sh.gen_cv.push_back(std::make_unique<std::condition_variable>());
     }
+    g_stop_requested.store(false);
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<std::thread> threads;
     for (int i = 0; i < c.gpu_threads; i++) threads.emplace_back([&, i] { executor_main(c.dummy_network ? nullptr : nets[size_t(i)].get(), sh, c, shape); });
@@ -403,7 +414,9 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
     while (!sh.stop.load()) {
         std::this_thread::sleep_for(std::chrono::milliseconds(2));
         const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        if (el >= c.duration_s || (c.max_moves > 0 && sh.moves.load() >= uint64_t(c.max_moves))) sh.stop.store(true);
+        if (el >= c.duration_s || (c.max_moves > 0 && sh.moves.load() >= uint64_t(c.max_moves)) ||
+            (c.max_games > 0 && sh.games.load() >= uint64_t(c.max_games)) || g_stop_requested.load())
+            sh.stop.store(true);
     }
     sh.cv.notify_all();
     for (auto& cv : sh.gen_cv) cv->notify_all();
@@ -534,6 +547,9 @@ KZB_API void kzb_selfplay_default_config(kzb_selfplay_config* c) {
     c->cache_size = 800;
     c->zero_temp_move_count = 30;
     c->max_moves = 0;
+    c->max_games = 0;
+    c->part_iterations = 20;
+    c->full_search_prob = 1.0f;
     c->duration_s = 5.0f;
     c->temperature = 1.0f;
     c->dirichlet_alpha = 0.03f;
@@ -566,6 +582,8 @@ KZB_API int kzb_selfplay_run(int device, const void* onnx_bytes, size_t onnx_len
         else throw std::runtime_error("unknown game");
     });
 }
+
+KZB_API void kzb_selfplay_request_stop(void) { kzb::selfplay::g_stop_requested.store(true); }
 
 KZB_API int kzb_mcts_trace(const kzb_selfplay_config* config, uint64_t game_seed, int plies, int eval_kind, kzb_mcts_trace_out* out) {
     using namespace kzb::selfplay;

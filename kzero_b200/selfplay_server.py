@@ -1,0 +1,183 @@
+"""Self-play server speaking the reference's TCP / JSON control protocol ("next" row N3), so that the
+UNMODIFIED Python training loop (python/lib/loop.py via python/lib/selfplay_client.py:93-132) can drive the B200 driver.
+
+    python -m kzero_b200.selfplay_server [--port 63105] [--device 0]
+
+Mirrors `selfplay_server_main` (rust/kz-selfplay/src/server/server.rs:45-101): bind 127.0.0.1:<port>, accept ONE client,
+read one `StartupSettings` line, then
+  commander  (commander.rs:13-61)   NewSettings / NewNetwork(path) / WaitForNewNetwork / UseDummyNetwork / Stop
+  collector  (collector.rs:15-116)  `{"FinishedFile": {"index": gen}}` after every `games_per_gen` games written to
+                                    `<output_folder>/games_<gen>.{bin,off,json}`, `"Stopped"` at the end
+Messages are one JSON value per line, externally tagged like serde's enums (protocol.rs:30-84).
+
+Differences that are deliberate (documented in DESIGN.md): a generation is one `kzb_selfplay_run` call, so a new network
+or new settings take effect at the next generation boundary (the reference hot-swaps inside a generation) and games still
+running at the boundary are dropped instead of carried over; `eval_random_symmetries`, `start_pos`, `top_moves`,
+`saved_state_channels` and `gpu_batch_size_root` are accepted and ignored (muzero-only or above the boundary); `chess`
+is served by the chess-SHAPED synthetic game (no chess move generator in this repo), `ataxx-7` by the real rules.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import socket
+import threading
+from pathlib import Path
+from typing import Optional
+
+from . import _abi, selfplay
+
+DEFAULT_PORT = 63105  # server.rs:38
+
+
+def parse_fpu(text: str):
+    """FpuMode::from_str, rust/kz-core/src/zero/step.rs:212-226: "fixed+0.1" / "relative-0.2" -> (relative, value)."""
+    for prefix, relative in (("fixed", 0), ("relative", 1)):
+        if text.startswith(prefix):
+            return relative, float(text[len(prefix):])
+    raise ValueError(f"invalid fpu mode {text!r}")
+
+
+def parse_q_mode(text: str):
+    """QMode::from_str, step.rs:255-271: "value" | "wdl" | "wdl+0.0" -> (wdl, draw_score)."""
+    if text == "value":
+        return 0, 0.0
+    if text.startswith("wdl"):
+        rest = text[3:]
+        return 1, float(rest) if rest else 0.0
+    raise ValueError(f"invalid q mode {text!r}")
+
+
+def game_id(name: str) -> int:
+    """Game::parse + the per-game dispatch of server.rs:103-199, for the games this driver bundles."""
+    if name == "chess":
+        return selfplay.GAME_SYNTH_CHESS
+    if name in ("ataxx", "ataxx-7"):
+        return selfplay.GAME_ATAXX7
+    raise ValueError(f"game {name!r} is not available in this driver (chess-shaped synthetic game and ataxx-7 are)")
+
+
+def config_from(startup: dict, settings: dict, seed: int) -> _abi.SelfplayConfig:
+    """StartupSettings (protocol.rs:11-28) + Settings (protocol.rs:86-112) -> kzb_selfplay_config."""
+    w = settings.get("weights") or {}
+    fpu_root_rel, fpu_root = parse_fpu(settings["search_fpu_root"])
+    fpu_child_rel, fpu_child = parse_fpu(settings["search_fpu_child"])
+    q_wdl, draw_score = parse_q_mode(settings["q_mode"])
+    kw = dict(
+        game=game_id(startup["game"]), visits=int(settings["full_iterations"]), part_iterations=int(settings["part_iterations"]),
+        full_search_prob=float(settings["full_search_prob"]), search_batch=int(startup["search_batch_size"]),
+        gpu_batch=int(startup["gpu_batch_size"]), cpu_threads=int(startup["cpu_threads_per_device"]),
+        gpu_threads=int(startup["gpu_threads_per_device"]),
+        max_game_length=int(settings["max_game_length"]) if settings.get("max_game_length") is not None else 2 ** 31 - 1,
+        cache_size=int(settings["cache_size"]), zero_temp_move_count=int(settings["zero_temp_move_count"]),
+        temperature=float(settings["temperature"]), dirichlet_alpha=float(settings["dirichlet_alpha"]),
+        dirichlet_eps=float(settings["dirichlet_eps"]), policy_temperature_root=float(settings["search_policy_temperature_root"]),
+        policy_temperature_child=float(settings["search_policy_temperature_child"]), fpu_root=fpu_root, fpu_root_relative=fpu_root_rel,
+        fpu_child=fpu_child, fpu_child_relative=fpu_child_rel, virtual_loss=float(settings["search_virtual_loss_weight"]),
+        q_mode_wdl=q_wdl, draw_score=draw_score, max_games=int(startup["games_per_gen"]), duration_s=1e9, seed=seed)
+    for name in ("exploration_weight", "moves_left_weight", "moves_left_clip", "moves_left_sharpness"):
+        if w.get(name) is not None:  # Weights::to_uct, protocol.rs:122-132: None -> UctWeights::default
+            kw[name] = float(w[name])
+    return selfplay.default_config(**kw)
+
+
+class SelfplayServer:
+    def __init__(self, port: int = DEFAULT_PORT, device: int = 0):
+        self.port, self.device = port, device
+        self.lock = threading.Condition()
+        self.settings: Optional[dict] = None
+        self.network = None  # None: wait (WaitForNewNetwork); "dummy"; or ONNX bytes
+        self.stop = False
+        self.listener = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        self.listener.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        self.listener.bind(("127.0.0.1", port))  # server.rs:58
+        self.listener.listen(1)
+        self.port = self.listener.getsockname()[1]
+
+    # -- commander.rs:13-61 -----------------------------------------------------------------------
+    def _commander(self, reader):
+        for line in reader:
+            line = line.strip()
+            if not line:
+                continue
+            cmd = json.loads(line)
+            with self.lock:
+                if cmd == "Stop":
+                    self.stop = True
+                    _abi.lib().kzb_selfplay_request_stop()
+                elif cmd == "WaitForNewNetwork":
+                    self.network = None
+                elif cmd == "UseDummyNetwork":
+                    self.network = "dummy"
+                elif isinstance(cmd, dict) and "NewSettings" in cmd:
+                    self.settings = cmd["NewSettings"]
+                elif isinstance(cmd, dict) and "NewNetwork" in cmd:
+                    self.network = Path(cmd["NewNetwork"]).read_bytes()  # load_graph, server_alphazero.rs:126-128
+                elif isinstance(cmd, dict) and "StartupSettings" in cmd:
+                    raise RuntimeError("Already received startup settings")  # commander.rs:30
+                else:
+                    raise ValueError(f"unknown command {cmd!r}")
+                self.lock.notify_all()
+                if self.stop:
+                    return
+        with self.lock:  # client went away
+            self.stop = True
+            _abi.lib().kzb_selfplay_request_stop()
+            self.lock.notify_all()
+
+    # -- server.rs:45-101 + collector.rs:15-116 --------------------------------------------------------
+    def serve(self):
+        conn, _ = self.listener.accept()
+        reader = conn.makefile("r")
+        first = json.loads(reader.readline())
+        startup = first["StartupSettings"]  # server.rs:64
+        if startup.get("muzero"):
+            raise ValueError("MuZero is not working in the reference either (Readme.md:73) and is not built here")
+        os.makedirs(startup["output_folder"], exist_ok=True)
+        threading.Thread(target=self._commander, args=(reader,), daemon=True).start()
+
+        def send(message):
+            conn.sendall((json.dumps(message) + "\n").encode())
+
+        gen = int(startup["first_gen"])
+        try:
+            while True:
+                with self.lock:
+                    while not self.stop and (self.settings is None or self.network is None):
+                        self.lock.wait()
+                    if self.stop:
+                        break
+                    settings, network = dict(self.settings), self.network
+                cfg = config_from(startup, settings, seed=gen)
+                cfg.output_prefix = str(Path(startup["output_folder"]) / f"games_{gen}").encode()
+                if network == "dummy":
+                    cfg.dummy_network = 1
+                    result = selfplay.run(None, cfg, device=self.device)
+                else:
+                    result = selfplay.run(network, cfg, device=self.device)
+                if self.stop:
+                    break
+                print(f"generation {gen}: {result.games_written} games, {result.moves_played} moves, "
+                      f"{result.mcts_nodes_per_s:,.0f} nodes/s, {result.nn_positions_per_s:,.0f} NN positions/s", flush=True)
+                send({"FinishedFile": {"index": gen}})  # ServerUpdate::FinishedFile, protocol.rs:80-84
+                gen += 1
+        finally:
+            try:
+                send("Stopped")
+            except OSError:
+                pass
+            conn.close()
+            self.listener.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--port", type=int, default=DEFAULT_PORT)
+    ap.add_argument("--device", type=int, default=0)
+    args = ap.parse_args()
+    SelfplayServer(args.port, args.device).serve()
+
+
+if __name__ == "__main__":
+    main()

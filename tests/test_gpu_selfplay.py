@@ -29,3 +29,30 @@ def test_selfplay_rejects_mismatched_network():
     cfg = selfplay.default_config(game=selfplay.GAME_SYNTH_CHESS, duration_s=0.2)
     with pytest.raises(KzbError, match="Input shape mismatch"):  # check_graph_shapes, network/common.rs:171-174
         selfplay.run(onnx_bytes, cfg)
+
+
+def test_server_hot_path_with_a_real_network(tmp_path):
+    """N3 end to end on the GPU: StartupSettings -> NewSettings -> NewNetwork(path) -> FinishedFile -> Stop."""
+    import json
+    import socket
+    import threading
+
+    from kzero_b200 import selfplay_server
+    from test_selfplay_server import SETTINGS, STARTUP
+
+    onnx_path = tmp_path / "net.onnx"
+    onnx_path.write_bytes(netgen.build_onnx(netgen.game_spec("ataxx-7"), 2, 32, seed=33))
+    server = selfplay_server.SelfplayServer(port=0)
+    thread = threading.Thread(target=server.serve, daemon=True)
+    thread.start()
+    s = socket.create_connection(("127.0.0.1", server.port))
+    f = s.makefile("r")
+    for m in ({"StartupSettings": dict(STARTUP, output_folder=str(tmp_path), first_gen=0)}, {"NewSettings": SETTINGS},
+              {"NewNetwork": str(onnx_path)}):
+        s.sendall((json.dumps(m) + "\n").encode())
+    assert json.loads(f.readline()) == {"FinishedFile": {"index": 0}}
+    s.sendall(b'"Stop"\n')
+    assert [json.loads(line) for line in f][-1] == "Stopped"
+    thread.join(timeout=60)
+    meta = json.loads((tmp_path / "games_0.json").read_text())
+    assert meta["game_count"] >= 6 and meta["position_count"] > meta["game_count"]

@@ -1,0 +1,92 @@
+"""The TCP / JSON control protocol (row N3) exercised with the REFERENCE'S OWN client class
+(python/lib/selfplay_client.py, imported from /root/reference when present): StartupSettings, NewSettings,
+UseDummyNetwork, two FinishedFile notifications, Stop -- and the files the run leaves behind are read back with the
+reference's DataFile loader.  DummyNetwork evaluations: no GPU needed."""
+import json
+import socket
+import sys
+import threading
+from pathlib import Path
+
+import pytest
+
+from kzero_b200 import selfplay_server
+
+REFERENCE_PY = Path("/root/reference/python")
+
+STARTUP = dict(game="ataxx-7", muzero=False, start_pos="default", first_gen=3, output_folder=None, games_per_gen=6,
+               cpu_threads_per_device=2, gpu_threads_per_device=1, gpu_batch_size=32, gpu_batch_size_root=0, search_batch_size=4,
+               saved_state_channels=0, eval_random_symmetries=True)
+SETTINGS = dict(max_game_length=60, weights=dict(exploration_weight=None, moves_left_weight=None, moves_left_clip=None,
+                                                 moves_left_sharpness=None),
+                q_mode="wdl+0.0", temperature=1.0, zero_temp_move_count=30, dirichlet_alpha=0.2, dirichlet_eps=0.25,
+                search_policy_temperature_root=1.4, search_policy_temperature_child=1.0, search_fpu_root="fixed+0.1",
+                search_fpu_child="relative+0", search_virtual_loss_weight=1.0, full_search_prob=0.5, full_iterations=24,
+                part_iterations=6, top_moves=100, cache_size=100)
+
+
+def test_mode_strings_parse_like_the_reference():
+    assert selfplay_server.parse_fpu("fixed+0.1") == (0, 0.1) and selfplay_server.parse_fpu("relative-0.25") == (1, -0.25)
+    assert selfplay_server.parse_q_mode("value") == (0, 0.0) and selfplay_server.parse_q_mode("wdl") == (1, 0.0)
+    assert selfplay_server.parse_q_mode("wdl-0.5") == (1, -0.5)  # step.rs:282-303 round trips
+    with pytest.raises(ValueError):
+        selfplay_server.parse_fpu("nonsense")
+
+
+def _serve():
+    server = selfplay_server.SelfplayServer(port=0)
+    t = threading.Thread(target=server.serve, daemon=True)
+    t.start()
+    return server, t
+
+
+def test_protocol_with_raw_socket(tmp_path):
+    server, thread = _serve()
+    s = socket.create_connection(("127.0.0.1", server.port))
+    f = s.makefile("r")
+
+    def send(m):
+        s.sendall((json.dumps(m) + "\n").encode())
+
+    send({"StartupSettings": dict(STARTUP, output_folder=str(tmp_path))})
+    send({"NewSettings": SETTINGS})
+    send("UseDummyNetwork")
+    assert json.loads(f.readline()) == {"FinishedFile": {"index": 3}}
+    assert json.loads(f.readline()) == {"FinishedFile": {"index": 4}}
+    send("Stop")
+    lines = [json.loads(line) for line in f]
+    assert lines[-1] == "Stopped"
+    thread.join(timeout=30)
+    assert not thread.is_alive()
+    for gen in (3, 4):
+        meta = json.loads((tmp_path / f"games_{gen}.json").read_text())
+        assert meta["game"] == "ataxx-7" and meta["game_count"] >= 6 and meta["max_game_length"] <= 60
+
+
+@pytest.mark.skipif(not REFERENCE_PY.exists(), reason="the reference tree is only present in the build container")
+def test_reference_client_drives_the_server(tmp_path):
+    sys.path.insert(0, str(REFERENCE_PY))
+    try:
+        from lib.data.file import DataFile
+        from lib.games import Game
+        from lib.selfplay_client import SelfplayClient, SelfplaySettings, StartupSettings, UctWeights
+    finally:
+        sys.path.pop(0)
+    server, thread = _serve()
+    client = SelfplayClient(server.port)
+    client.send_startup_settings(StartupSettings(**dict(STARTUP, output_folder=str(tmp_path), first_gen=0)))
+    client.send_new_settings(SelfplaySettings(**dict(SETTINGS, weights=UctWeights.default())))
+    client.send_dummy_network()
+    assert client.wait_for_file() == 0
+    assert client.wait_for_file() == 1
+    client.send_stop()
+    with pytest.raises(RuntimeError, match="stopped"):
+        while True:
+            client.wait_for_file()
+    thread.join(timeout=30)
+    f = DataFile.open(Game.find("ataxx-7"), str(tmp_path / "games_0"))
+    assert f.info.simulation_count >= 6
+    positions = [f.load_position(i) for i in range(f.info.position_count)]
+    # full_search_prob = 0.5: both kinds of searches were recorded, with their visit targets (generator_alphazero.rs:88-94)
+    kinds = {(p.is_full_search, p.zero_visits >= 24) for p in positions if not p.is_final}
+    assert (True, True) in kinds and any(not full for full, _ in kinds)
