@@ -89,6 +89,19 @@ int kzb_eval_planes(kzb_net* net, const float* nchw_in, int batch, float* out_sc
 int kzb_eval_packed(kzb_net* net, const uint8_t* bits, const float* scalars, int batch, const uint32_t* mv_idx,
                     const uint32_t* mv_off, float* out_values, float* out_policy);
 
+/* Board symmetries on the GPU ("next" row N4; replaces RandomSymmetryNetwork's host-side work, network/symmetry.rs:41-67,
+ * 126-148: `board.map(sym)` before the evaluation and `unmap_eval` after it).  The tables are supplied by the caller and are
+ * game-agnostic here:
+ *   square_src [n_sym][H*W]      plane square sq of the MAPPED board is square square_src[s][sq] of the original board
+ *   policy_map [n_sym][policy_len]  policy index of map_move(sym, mv) for the move with index i (for ataxx: the `map_mv`
+ *                                rows of python/lib/mapping/ataxx_symmetry.json)
+ * kzb_eval_packed_sym takes the ORIGINAL boards' records and legal-move indices plus one symmetry id per board; the input
+ * planes are transformed while they are expanded and every legal index is looked up through policy_map before the
+ * masked softmax, so the result is what RandomSymmetryNetwork returns for that choice of symmetries. */
+int kzb_net_set_symmetries(kzb_net* net, int n_sym, const int32_t* square_src, const int32_t* policy_map);
+int kzb_eval_packed_sym(kzb_net* net, const uint8_t* bits, const float* scalars, const uint8_t* sym, int batch,
+                        const uint32_t* mv_idx, const uint32_t* mv_off, float* out_values, float* out_policy);
+
 /* K2 alone, for bit-exact parity checks: twin of InputMapper::encode_input_full (mapping/mod.rs:40-63),
  * out_nchw [batch, scalar_count + bool_channels, H, W] f32, produced on the GPU. */
 int kzb_encode_planes(kzb_net* net, const uint8_t* bits, const float* scalars, int batch, float* out_nchw);

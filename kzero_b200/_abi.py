@@ -60,6 +60,8 @@ SYMBOLS = {
     "kzb_eval_planes": (_i, [_vp, _vp, _i, _vp, _vp]),
     "kzb_eval_packed": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "kzb_encode_planes": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "kzb_net_set_symmetries": (_i, [_vp, _i, _vp, _vp]),
+    "kzb_eval_packed_sym": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "kzb_stage_packed": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "kzb_time_staged": (_i, [_vp, _i, _i, _vp]),
     "kzb_profile_staged": (_i, [_vp, _i, _vp, _sz, _vp, _i, ctypes.POINTER(_i)]),

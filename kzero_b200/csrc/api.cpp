@@ -134,6 +134,31 @@ KZB_API int kzb_eval_packed(kzb_net* net, const uint8_t* bits, const float* scal
     });
 }
 
+KZB_API int kzb_net_set_symmetries(kzb_net* net, int n_sym, const int32_t* square_src, const int32_t* policy_map) {
+    return guarded([&] {
+        need(net, "net");
+        need(square_src, "square_src");
+        need(policy_map, "policy_map");
+        net->impl.set_symmetries(n_sym, square_src, policy_map);
+    });
+}
+
+KZB_API int kzb_eval_packed_sym(kzb_net* net, const uint8_t* bits, const float* scalars, const uint8_t* sym, int batch,
+                                const uint32_t* mv_idx, const uint32_t* mv_off, float* out_values, float* out_policy) {
+    return guarded([&] {
+        need(net, "net");
+        need(bits, "bits");
+        need(sym, "sym");
+        need(mv_off, "mv_off");
+        need(out_values, "out_values");
+        if (batch > 0 && mv_off[batch] > 0) {
+            need(mv_idx, "mv_idx");
+            need(out_policy, "out_policy");
+        }
+        net->impl.eval_packed(bits, scalars, batch, mv_idx, mv_off, out_values, out_policy, sym);
+    });
+}
+
 KZB_API int kzb_encode_planes(kzb_net* net, const uint8_t* bits, const float* scalars, int batch, float* out_nchw) {
     return guarded([&] {
         need(net, "net");

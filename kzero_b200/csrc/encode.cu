@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(kEncodeThreads) encode_nhwc_kernel(EncodeParam
     __syncthreads();
 
     const int W = p.lay.W, H = p.lay.H, area = W * H;
+    const int32_t* sym_row = p.sym ? p.square_src + size_t(p.sym[b]) * area : nullptr;
     const int groups = p.c_pad / 8;
     const int vecs = p.lay.board_pitch * groups;
     const size_t vec_base = size_t(b) * p.lay.board_pitch * groups;
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(kEncodeThreads) encode_nhwc_kernel(EncodeParam
         int y = r / p.lay.rank_pitch, x = r % p.lay.rank_pitch;
         bool on_board = x < W && y < H;
         int sq = y * W + x;
+        const int src_sq = (sym_row && on_board) ? sym_row[sq] : sq;
         Vec8<T> out;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(kEncodeThreads) encode_nhwc_kernel(EncodeParam
                 if (c < p.scalar_count) {
                     f = s_scalars[c];  // mod.rs:54-56: each scalar broadcast over the plane
                 } else if (c < p.scalar_count + p.bool_channels) {
-                    int i = (c - p.scalar_count) * area + sq;  // mod.rs:57-59, bit_buffer.rs:73-75
+                    int i = (c - p.scalar_count) * area + src_sq;  // mod.rs:57-59, bit_buffer.rs:73-75
                     f = float((s_bits[i >> 3] >> (i & 7)) & 1);
                 }
             }
@@ -130,8 +132,10 @@ __global__ void encode_kc_kernel(EncodeParams p, const float* __restrict__ nchw,
         for (int i = threadIdx.x; i < p.bits_stride; i += blockDim.x) s_bits[i] = p.bits[size_t(b) * p.bits_stride + i];
         __syncthreads();
     }
+    const int32_t* sym_row = (PACKED && p.sym) ? p.square_src + size_t(p.sym[b]) * 64 : nullptr;
     for (int t = threadIdx.x; t < kc_total * 64; t += blockDim.x) {
         const int kc = t >> 6, sq = t & 63;
+        const int src_sq = sym_row ? sym_row[sq] : sq;
         Vec8<__nv_bfloat16> out;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -141,7 +145,7 @@ __global__ void encode_kc_kernel(EncodeParams p, const float* __restrict__ nchw,
                 if (c < p.scalar_count) {
                     f = s_scalars[c];  // mod.rs:54-56
                 } else if (c < p.scalar_count + p.bool_channels) {
-                    const int i = (c - p.scalar_count) * 64 + sq;  // mod.rs:57-59, bit_buffer.rs:73-75
+                    const int i = (c - p.scalar_count) * 64 + src_sq;  // mod.rs:57-59, bit_buffer.rs:73-75
                     f = float((s_bits[i >> 3] >> (i & 7)) & 1);
                 }
             } else if (c < channels) {

@@ -610,7 +610,9 @@ void Net::upload_packed(const uint8_t* bits, const float* scalars, int batch, co
 
 void Net::run_encode(int batch, const StepHook& hook) {
     InBlock ib = in_block(max_batch_, scalar_count_, bits_stride_);
-    EncodeParams p;
+    EncodeParams p{};
+    p.sym = cur_sym_;
+    p.square_src = d_sym_square_.as<int32_t>();
     p.bits = d_mv_off_.as<uint8_t>() + ib.off_bits;
     p.scalars = reinterpret_cast<const float*>(d_mv_off_.as<uint8_t>() + ib.off_scalars);
     p.batch = batch;
@@ -707,6 +709,8 @@ void Net::run_tail(int batch, bool packed, const StepHook& hook, bool to_host) {
             InBlock ib = in_block(max_batch_, scalar_count_, bits_stride_);
             p.mv_off = d_mv_off_.as<uint32_t>();
             p.mv_idx = reinterpret_cast<const uint32_t*>(d_mv_off_.as<uint8_t>() + ib.off_idx);
+            p.sym = cur_sym_;
+            p.policy_map = d_sym_policy_.as<int32_t>();
             uint8_t* out = to_host ? h_out_.as<uint8_t>() : d_err_.as<uint8_t>();
             p.err_flag = reinterpret_cast<int*>(out);
             p.out_values = reinterpret_cast<float*>(out + 16);
@@ -745,6 +749,8 @@ void Net::run_tail(int batch, bool packed, const StepHook& hook, bool to_host) {
         InBlock ib = in_block(max_batch_, scalar_count_, bits_stride_);
         p.mv_off = d_mv_off_.as<uint32_t>();
         p.mv_idx = reinterpret_cast<const uint32_t*>(d_mv_off_.as<uint8_t>() + ib.off_idx);
+        p.sym = cur_sym_;
+        p.policy_map = d_sym_policy_.as<int32_t>();
         // results either stay in HBM (staged timing) or are written straight into the pinned, device-mapped host block
         // (kzb_eval_packed: no separate D2H copies, the posted PCIe writes overlap the kernel)
         uint8_t* out = to_host ? h_out_.as<uint8_t>() : d_err_.as<uint8_t>();
@@ -774,11 +780,42 @@ void Net::eval_planes(const float* nchw, int batch, float* out_scalars, float* o
     CK(cudaGetLastError());
 }
 
+void Net::set_symmetries(int n_sym, const int32_t* square_src, const int32_t* policy_map) {
+    require_mapper();
+    if (n_sym < 1 || n_sym > 255) throw std::runtime_error("symmetry count must be in 1..255");
+    const int area = spec_.area(), plen = spec_.policy_len;
+    for (int i = 0; i < n_sym * area; i++)
+        if (square_src[i] < 0 || square_src[i] >= area) throw std::runtime_error("symmetry square table entry out of range");
+    for (int i = 0; i < n_sym * plen; i++)
+        if (policy_map[i] < -1 || policy_map[i] >= plen)  // -1: this index is not a move (the reference's tables use it, too)
+            throw std::runtime_error("symmetry policy table entry out of range");
+    CK(cudaSetDevice(device_));
+    upload(d_sym_square_, std::vector<int32_t>(square_src, square_src + size_t(n_sym) * area));
+    upload(d_sym_policy_, std::vector<int32_t>(policy_map, policy_map + size_t(n_sym) * plen));
+    d_sym_.alloc(size_t(max_batch_), true);
+    h_sym_.alloc(size_t(max_batch_));
+    n_sym_ = n_sym;
+}
+
 void Net::eval_packed(const uint8_t* bits, const float* scalars, int batch, const uint32_t* mv_idx, const uint32_t* mv_off,
-                      float* out_values, float* out_policy) {
+                      float* out_values, float* out_policy, const uint8_t* sym) {
     check_batch(batch);
     require_mapper();
     if (batch == 0) return;
+    cur_sym_ = nullptr;
+    if (sym) {
+        if (n_sym_ == 0) throw std::runtime_error("kzb_net_set_symmetries must be called before an evaluation with symmetries");
+        for (int i = 0; i < batch; i++)
+            if (sym[i] >= n_sym_) throw std::runtime_error("symmetry index out of range");
+        CK(cudaSetDevice(device_));
+        std::memcpy(h_sym_.ptr, sym, size_t(batch));
+        CK(cudaMemcpyAsync(d_sym_.ptr, h_sym_.ptr, size_t(batch), cudaMemcpyHostToDevice, stream_));
+        cur_sym_ = d_sym_.as<uint8_t>();
+    }
+    struct ClearSym {  // the staged / planes paths never apply a symmetry
+        const uint8_t*& ref;
+        ~ClearSym() { ref = nullptr; }
+    } clear_sym{cur_sym_};
     using clk = std::chrono::steady_clock;
     const bool trace = trace_ != nullptr;
     clk::time_point t0, t1, t2, t3, t4;

@@ -65,7 +65,8 @@ public:
     void bind_mapper(int scalar_count, int bool_channels, int h, int w, int policy_len);
     void eval_planes(const float* nchw, int batch, float* out_scalars, float* out_logits);
     void eval_packed(const uint8_t* bits, const float* scalars, int batch, const uint32_t* mv_idx, const uint32_t* mv_off,
-                     float* out_values, float* out_policy);
+                     float* out_values, float* out_policy, const uint8_t* sym = nullptr);
+    void set_symmetries(int n_sym, const int32_t* square_src, const int32_t* policy_map);
     void encode_planes(const uint8_t* bits, const float* scalars, int batch, float* out_nchw);
     void stage_packed(const uint8_t* bits, const float* scalars, int batch, const uint32_t* mv_idx, const uint32_t* mv_off);
     void time_staged(int iters, bool flush_l2, float* ms_out);
@@ -118,6 +119,10 @@ private:
     PinnedBuffer h_in_, h_out_;
     size_t mv_cap_ = 0;
     bool blocking_sync_ = false;
+    int n_sym_ = 0;
+    const uint8_t* cur_sym_ = nullptr;  // device pointer while an evaluation with symmetries is in flight
+    DeviceBuffer d_sym_square_, d_sym_policy_, d_sym_;
+    PinnedBuffer h_sym_;
     cudaEvent_t done_event_ = nullptr;
     double* trace_ = nullptr;  // KZB_TRACE=1: accumulated host-side phase times of eval_packed
     int staged_batch_ = 0;

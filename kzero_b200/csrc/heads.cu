@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) heads_tail_kernel(HeadsTa
     const uint32_t o0 = p.mv_off[b], o1 = p.mv_off[b + 1];
     const int n = int(o1 - o0);
     if (n <= 0) return;  // terminal board: empty policy (common.rs:77)
+    const int32_t* pmap = p.sym ? p.policy_map + size_t(p.sym[b]) * p.policy_len : nullptr;
     constexpr int kRegMoves = 12;  // up to 384 legal moves stay in registers (chess <= 218, go-19 <= 362)
     if (n <= 32 * kRegMoves) {
         float l[kRegMoves];
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) heads_tail_kernel(HeadsTa
             l[k] = -INFINITY;
             if (j < n) {
                 uint32_t idx = p.mv_idx[o0 + j];
+                if (pmap && idx < uint32_t(p.policy_len)) idx = uint32_t(pmap[idx]);
                 l[k] = idx < uint32_t(p.policy_len) ? logit(int(idx)) : NAN;
                 mx = fmaxf(mx, l[k]);
             }
@@ -169,6 +171,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) heads_tail_kernel(HeadsTa
     float mx = -INFINITY;
     for (int j = lane; j < n; j += 32) {
         uint32_t idx = p.mv_idx[o0 + j];
+        if (pmap && idx < uint32_t(p.policy_len)) idx = uint32_t(pmap[idx]);
         float l = idx < uint32_t(p.policy_len) ? logit(int(idx)) : NAN;
         p.out_probs[o0 + j] = l;  // stage the gathered logit; each lane re-reads only its own entries
         mx = fmaxf(mx, l);

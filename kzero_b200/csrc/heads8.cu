@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             const uint32_t o0 = p.mv_off[b], o1 = p.mv_off[b + 1];
             const int n = int(o1 - o0);
             if (n <= 0) continue;  // terminal board: empty policy (common.rs:77)
+            const int32_t* pmap = p.sym ? p.policy_map + size_t(p.sym[b]) * p.policy_len : nullptr;
             constexpr int kRegMoves = 8;  // up to 256 legal moves in registers (chess <= 218)
             if (n <= 32 * kRegMoves) {
                 float l[kRegMoves];
@@ -349,7 +350,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const int j = lane + 32 * k;
                     l[k] = -INFINITY;
                     if (j < n) {
-                        const uint32_t idx = p.mv_idx[o0 + j];
+                        uint32_t idx = p.mv_idx[o0 + j];
+                        if (pmap && idx < uint32_t(p.policy_len)) idx = uint32_t(pmap[idx]);
                         l[k] = idx < uint32_t(p.policy_len) ? logit(int(idx)) : NAN;
                         mx = fmaxf(mx, l[k]);
                     }
@@ -374,19 +376,22 @@ __global__ void __launch_bounds__(kThreads, 1)
             } else {
                 float mx = -INFINITY;
                 for (int j = lane; j < n; j += 32) {
-                    const uint32_t idx = p.mv_idx[o0 + j];
+                    uint32_t idx = p.mv_idx[o0 + j];
+                        if (pmap && idx < uint32_t(p.policy_len)) idx = uint32_t(pmap[idx]);
                     mx = fmaxf(mx, idx < uint32_t(p.policy_len) ? logit(int(idx)) : NAN);
                 }
                 mx = warp_max(mx);
                 float sum = 0.0f;
                 for (int j = lane; j < n; j += 32) {
-                    const uint32_t idx = p.mv_idx[o0 + j];
+                    uint32_t idx = p.mv_idx[o0 + j];
+                        if (pmap && idx < uint32_t(p.policy_len)) idx = uint32_t(pmap[idx]);
                     sum += expf((idx < uint32_t(p.policy_len) ? logit(int(idx)) : NAN) - mx);
                 }
                 sum = warp_sum(sum);
                 if (!(sum > 0.0f) && lane == 0) *reinterpret_cast<volatile int*>(p.err_flag) = 1 + b;
                 for (int j = lane; j < n; j += 32) {
-                    const uint32_t idx = p.mv_idx[o0 + j];
+                    uint32_t idx = p.mv_idx[o0 + j];
+                        if (pmap && idx < uint32_t(p.policy_len)) idx = uint32_t(pmap[idx]);
                     p.out_probs[o0 + j] = expf((idx < uint32_t(p.policy_len) ? logit(int(idx)) : NAN) - mx) / sum;
                 }
             }

@@ -33,6 +33,10 @@ struct EncodeParams {
     RowLayout lay;
     int c_pad;  // channels per row in the output (>= scalar_count + bool_channels, multiple of 8)
     void* out;  // [batch*board_pitch][c_pad] bf16 or f32
+    // optional board symmetry (RandomSymmetryNetwork on the GPU, network/symmetry.rs:41-67): plane square sq of board b is
+    // read from square square_src[sym[b]*A + sq] of the record; null = identity
+    const uint8_t* sym;
+    const int32_t* square_src;
 };
 void launch_encode_nhwc(const EncodeParams& p, bool out_bf16, cudaStream_t s);
 // exact twin of InputMapper::encode_input_full (mapping/mod.rs:40-63): out [batch][Cs+Cb][H*W] f32
@@ -188,6 +192,9 @@ struct HeadsTailParams {
     // packed mode (fused decode_output, network/common.rs:16-100)
     const uint32_t* mv_idx;
     const uint32_t* mv_off;  // [batch+1]
+    // optional symmetry: legal index i of board b is looked up at policy_map[sym[b]*P + i] (unmap_eval, symmetry.rs:126-148)
+    const uint8_t* sym;
+    const int32_t* policy_map;
     float* out_values;       // [batch][5]: tanh(v), softmax(wdl), moves_left
     float* out_probs;        // CSR-aligned with mv_idx
     int* err_flag;           // set to 1+board (any failing board) when a softmax sum is not > 0 (common.rs:110); may be host memory
@@ -218,6 +225,8 @@ struct Heads8Params {
     int packed;
     const uint32_t* mv_idx;
     const uint32_t* mv_off;
+    const uint8_t* sym;         // optional symmetry, as in HeadsTailParams
+    const int32_t* policy_map;
     float* out_values;
     float* out_probs;
     int* err_flag;

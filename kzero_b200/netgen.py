@@ -146,6 +146,9 @@ def game_spec(name: str) -> GameSpec:
         return GameSpec("chess", 8, 13, 8, 1880, 73, "chess_conv")
     if name == "chess-att":
         return GameSpec("chess", 8, 13, 8, 1880, 73, "chess_att")
+    if name.startswith("chess-hist-"):  # ChessHistoryMapper, rust/kz-core/src/mapping/chess.rs:25-40
+        n = int(name.split("-")[2])
+        return GameSpec(name, 8, 1 + 12 * (n + 1), 7 + (n + 1), 1880, 73, "chess_conv")
     if name.startswith("ataxx-"):  # games.py:144-159, ataxx.rs:21,94-104
         s = int(name.split("-")[1])
         return GameSpec(name, s, 3, 1, 17 * s * s + 1, 17, "ataxx")
@@ -207,7 +210,7 @@ def build_onnx(game: GameSpec, depth: int, channels: int, seed: int = 0, scalar_
 
     # tower: post_act.py:201-228
     w0, b0 = _conv_params(rng, c, game.input_channels, 3)
-    if game.name == "chess":
+    if game.name == "chess":  # (not chess-hist: its scalar order differs)
         # the two raw-count scalar planes (repetitions 0..2, halfmove clock 0..99, chess.rs:158-160) would
         # dominate a random-init net; a trained net has learned weights ~1/range for them, so scale likewise
         w0[:, 6] *= np.float32(1 / 2)
@@ -322,6 +325,22 @@ def synthetic_positions(game: GameSpec, n: int, seed: int = 0, min_moves: int = 
         scalars[:, 2:6] = rng.integers(0, 2, size=(n, 4))
         scalars[:, 6] = rng.integers(0, 3, n)
         scalars[:, 7] = rng.integers(0, 100, n)
+        lo, hi = 20, 45
+    elif game.name.startswith("chess-hist"):  # chess.rs:42-95: en passant plane, then 12 piece planes per board
+        boards = (cb - 1) // 12
+        ep = rng.random(n) < 0.05
+        planes[np.nonzero(ep)[0], 0, 40 + rng.integers(0, 8, size=int(ep.sum()))] = 1
+        for h in range(boards):
+            occ = rng.random((n, a))
+            piece = rng.integers(0, 12, size=(n, a))
+            for p in range(12):
+                planes[:, 1 + 12 * h + p, :] = (occ < 0.35) & (piece == p)
+        stm = rng.integers(0, 2, n)
+        scalars[:, 0] = stm
+        scalars[:, 1] = 1 - stm
+        scalars[:, 2:6] = rng.integers(0, 2, size=(n, 4))
+        scalars[:, 6] = rng.integers(0, 100, n) / np.float32(100)  # scaled like a trained net would see it
+        scalars[:, 7:] = 1 + rng.integers(0, 3, size=(n, boards))  # 1 + repetitions (0 would be a padded board)
         lo, hi = 20, 45
     elif game.name.startswith("ataxx"):
         cell = rng.choice(4, size=(n, a), p=[0.3, 0.3, 0.05, 0.35])

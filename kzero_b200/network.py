@@ -179,6 +179,29 @@ class B200Network:
             _abi.check(rc)
         return values, probs
 
+    def set_symmetries(self, square_src: np.ndarray, policy_map: np.ndarray) -> None:
+        """kzb_net_set_symmetries: square_src [n_sym, H*W], policy_map [n_sym, policy_len] (see include/kzb200.h)."""
+        square_src = np.ascontiguousarray(square_src, dtype=np.int32)
+        policy_map = np.ascontiguousarray(policy_map, dtype=np.int32)
+        assert square_src.shape[0] == policy_map.shape[0] and policy_map.shape[1] == self.mapper.policy_len()
+        _abi.check(self._lib.kzb_net_set_symmetries(self._handle, square_src.shape[0], _ptr(square_src), _ptr(policy_map)))
+
+    def evaluate_packed_sym(self, bits, scalars, sym, mv_idx, mv_off):
+        """kzb_eval_packed_sym: like evaluate_packed, every board evaluated under its symmetry sym[i] (RandomSymmetryNetwork
+        on the GPU, network/symmetry.rs:41-67)."""
+        bits = _arr(bits, np.uint8)
+        n = bits.shape[0]
+        scalars = _arr(scalars, np.float32)
+        sym = _arr(sym, np.uint8)
+        mv_idx = _arr(mv_idx, np.uint32)
+        mv_off = _arr(mv_off, np.uint32)
+        assert sym.shape == (n,) and mv_off.shape[0] == n + 1
+        values = np.empty((n, 5), dtype=np.float32)
+        probs = np.empty((int(mv_off[-1]),), dtype=np.float32)
+        _abi.check(self._lib.kzb_eval_packed_sym(self._handle, _ptr(bits), _ptr(scalars), _ptr(sym), n, _ptr(mv_idx), _ptr(mv_off),
+                                                 _ptr(values), _ptr(probs)))
+        return values, probs
+
     def evaluate_planes(self, nchw: np.ndarray):
         """kzb_eval_planes, the twin of CudaExecutor::evaluate: -> (scalars [n,5] raw, policy logits [n,P])."""
         nchw = np.ascontiguousarray(nchw, dtype=np.float32)

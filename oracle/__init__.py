@@ -116,6 +116,7 @@ def decode_output(scalars: np.ndarray, policy_logits: np.ndarray, mv_idx: np.nda
     mv_idx = np.ascontiguousarray(mv_idx, dtype=np.uint32)
     mv_off = np.ascontiguousarray(mv_off, dtype=np.uint32)
     assert mv_off.shape[0] == b + 1
+    assert mv_idx.size == 0 or int(mv_idx.max()) < policy_logits.shape[1], "policy index out of range"
     out_v = np.empty((b, 5), dtype=np.float32)
     out_p = np.empty((int(mv_off[-1]),), dtype=np.float32)
     rc = lib().kzo_decode_output(_p(scalars), _p(policy_logits), b, policy_logits.shape[1], _p(mv_idx), _p(mv_off),

@@ -200,6 +200,95 @@ def test_bf16_balanced_units_match_uniform_units(n, monkeypatch):
     assert np.abs(np.tanh(ref_s[:, 0]) - v1[pick, 0]).max() <= 5e-2
 
 
+def test_chess_history_mapper_shapes():
+    """ChessHistoryMapper (rust/kz-core/src/mapping/chess.rs:25-95, row N4): (7 + N + 1) scalars and 1 + 12 (N + 1) bool
+    planes go through the same encode / tower / heads path; planes bit-exact, fp32 within 1e-4, bf16 within 2e-2."""
+    spec = netgen.game_spec("chess-hist-2")
+    assert (spec.scalar_channels, spec.bool_channels) == (10, 37)
+    onnx_bytes = netgen.build_onnx(spec, 2, 64, seed=51)
+    bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, 40, seed=52)
+    ref_s, ref_p, ref_values, ref_probs = _oracle_packed(spec, onnx_bytes, bits, scalars, mv_idx, mv_off)
+    with B200Network(mapper_for(spec), onnx_bytes, 40, precision=PRECISION_FP32) as net:
+        planes = net.encode_planes(bits, scalars)
+        values, probs = net.evaluate_packed(bits, scalars, mv_idx, mv_off)
+    assert np.array_equal(planes.view(np.uint32), _oracle_planes(spec, bits, scalars).view(np.uint32))
+    _check_packed(values, probs, ref_values, ref_probs, mv_off, FP32_TOL, FP32_TOL)
+    with B200Network(mapper_for(spec), onnx_bytes, 40, precision=PRECISION_BF16) as net:
+        values, probs = net.evaluate_packed(bits, scalars, mv_idx, mv_off)
+        s, p = net.evaluate_planes(_oracle_planes(spec, bits, scalars))
+    assert np.abs(p - ref_p).max() <= BF16_POLICY_TOL
+    _check_packed(values, probs, ref_values, ref_probs, mv_off, 5e-2, 1e-2)
+
+
+def _ataxx7_symmetry_tables():
+    """From the reference's golden table (tests/golden/ataxx7_symmetry.json <- python/lib/mapping/ataxx_symmetry.json):
+    square_src as AtaxxSymmetry.map_bools moves planes (python/lib/games.py:115-131), policy_map = map_mv."""
+    import json
+
+    rows = json.loads((GOLDEN / "ataxx7_symmetry.json").read_text())
+    square_src, policy_map = [], []
+    for r in rows:
+        idx = np.arange(49).reshape(1, 7, 7)
+        if r["transpose"]:
+            idx = np.transpose(idx, (0, 2, 1))
+        if r["flip_x"]:
+            idx = idx[:, :, ::-1]
+        if r["flip_y"]:
+            idx = idx[:, ::-1, :]
+        square_src.append(idx.reshape(-1))
+        policy_map.append(np.array(r["map_mv"]))
+    return np.stack(square_src), np.stack(policy_map), rows
+
+
+@pytest.mark.parametrize("precision,tol_v,tol_p", [(PRECISION_FP32, FP32_TOL, FP32_TOL), (PRECISION_BF16, 5e-2, 1e-2)])
+def test_symmetries_on_the_gpu_match_mapping_on_the_host(precision, tol_v, tol_p):
+    """Row N4: kzb_eval_packed_sym == what RandomSymmetryNetwork computes (network/symmetry.rs:41-67,126-148): evaluate
+    the MAPPED board, read every original move's probability at the mapped move.  Host side of the comparison: planes
+    transformed with the reference's own flags, indices mapped with the reference's own map_mv table, then the oracle."""
+    spec = netgen.game_spec("ataxx-7")
+    onnx_bytes = netgen.build_onnx(spec, 2, 32, seed=53)
+    n = 48
+    bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, n, seed=54)
+    square_src, policy_map, rows = _ataxx7_symmetry_tables()
+    # legal lists only hold indices that are moves (python/lib/mapping/ataxx_valid.txt); the others map to -1
+    valid = np.nonzero((policy_map >= 0).all(axis=0))[0].astype(np.uint32)
+    assert len(valid) > 400 and (policy_map[:, valid] >= 0).all()
+    rng = np.random.default_rng(55)
+    for i in range(n):
+        k = int(mv_off[i + 1] - mv_off[i])
+        mv_idx[mv_off[i]:mv_off[i + 1]] = rng.choice(valid, size=k, replace=False)
+    sym = (np.arange(n) % 8).astype(np.uint8)
+    planes = _oracle_planes(spec, bits, scalars)  # [n, 1 + 3, 7, 7]
+    mapped = planes.copy()
+    mapped_idx = mv_idx.copy()
+    for i in range(n):
+        r = rows[sym[i]]
+        b = planes[i, 1:]
+        if r["transpose"]:
+            b = np.transpose(b, (0, 2, 1))
+        if r["flip_x"]:
+            b = b[:, :, ::-1]
+        if r["flip_y"]:
+            b = b[:, ::-1, :]
+        mapped[i, 1:] = b
+        sl = slice(int(mv_off[i]), int(mv_off[i + 1]))
+        mapped_idx[sl] = policy_map[sym[i]][mv_idx[sl]]
+    s, p = OnnxOracle(onnx_bytes).run(mapped)
+    ref_values, ref_probs = oracle.decode_output(s, p, mapped_idx, mv_off)
+    with B200Network(mapper_for(spec), onnx_bytes, n, precision=precision) as net:
+        net.set_symmetries(square_src, policy_map)
+        values, probs = net.evaluate_packed_sym(bits, scalars, sym, mv_idx, mv_off)
+        plain_v, plain_p = net.evaluate_packed(bits, scalars, mv_idx, mv_off)  # a later plain call is not affected
+        ident_v, ident_p = net.evaluate_packed_sym(bits, scalars, np.zeros(n, np.uint8), mv_idx, mv_off)
+        with pytest.raises(KzbError, match="symmetry index"):
+            net.evaluate_packed_sym(bits, scalars, np.full(n, 8, np.uint8), mv_idx, mv_off)
+    _check_packed(values, probs, ref_values, ref_probs, mv_off, tol_v, tol_p)
+    assert not (rows[0]["transpose"] or rows[0]["flip_x"] or rows[0]["flip_y"])  # symmetry 0 is the identity ...
+    assert np.array_equal(policy_map[0][valid], valid)                            # ... on everything that is a move
+    assert np.array_equal(ident_v, plain_v) and np.array_equal(ident_p, plain_p)
+    assert not np.allclose(plain_p, probs, atol=1e-3)  # the symmetries did change the evaluations of a random net
+
+
 # ------------------------------------------------------------------------------------------- contract edges
 @pytest.mark.parametrize("precision", [PRECISION_FP32, PRECISION_BF16])
 def test_rows_independent_of_batch(precision):
