@@ -132,24 +132,30 @@ __global__ void encode_kc_kernel(EncodeParams p, const float* __restrict__ nchw,
         for (int i = threadIdx.x; i < p.bits_stride; i += blockDim.x) s_bits[i] = p.bits[size_t(b) * p.bits_stride + i];
         __syncthreads();
     }
-    const int32_t* sym_row = (PACKED && p.sym) ? p.square_src + size_t(p.sym[b]) * 64 : nullptr;
+    const int rec_area = p.rec_w * p.rec_h;
+    const int32_t* sym_row = (PACKED && p.sym) ? p.square_src + size_t(p.sym[b]) * rec_area : nullptr;
     for (int t = threadIdx.x; t < kc_total * 64; t += blockDim.x) {
         const int kc = t >> 6, sq = t & 63;
-        const int src_sq = sym_row ? sym_row[sq] : sq;
+        // the record's board sits top-left in the 8x8 grid; squares outside it stay zero
+        const int y = sq >> 3, x = sq & 7;
+        const bool on_board = x < p.rec_w && y < p.rec_h;
+        const int rec_sq = y * p.rec_w + x;
+        const int src_sq = (sym_row && on_board) ? sym_row[rec_sq] : rec_sq;
         Vec8<__nv_bfloat16> out;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int c = kc * 8 + j;
             float f = 0.0f;
-            if (PACKED) {
+            if (!on_board) {
+            } else if (PACKED) {
                 if (c < p.scalar_count) {
                     f = s_scalars[c];  // mod.rs:54-56
                 } else if (c < p.scalar_count + p.bool_channels) {
-                    const int i = (c - p.scalar_count) * 64 + src_sq;  // mod.rs:57-59, bit_buffer.rs:73-75
+                    const int i = (c - p.scalar_count) * rec_area + src_sq;  // mod.rs:57-59, bit_buffer.rs:73-75
                     f = float((s_bits[i >> 3] >> (i & 7)) & 1);
                 }
             } else if (c < channels) {
-                f = nchw[(size_t(b) * channels + c) * 64 + sq];
+                f = nchw[(size_t(b) * channels + c) * rec_area + rec_sq];
             }
             out.set(j, f);
         }
@@ -165,11 +171,14 @@ void launch_encode_kc(const EncodeParams& p, int kc_total, int boards_total, cud
     encode_kc_kernel<true><<<p.batch, std::min(kc_total * 64, 512), smem, s>>>(p, nullptr, 0, kc_total, boards_total);
 }
 
-void launch_nchw_to_kc(const float* in, int batch, int channels, int kc_total, int boards_total, void* out, cudaStream_t s) {
+void launch_nchw_to_kc(const float* in, int batch, int channels, int rec_w, int rec_h, int kc_total, int boards_total, void* out,
+                       cudaStream_t s) {
     if (batch <= 0) return;
     EncodeParams p{};
     p.batch = batch;
     p.out = out;
+    p.rec_w = rec_w;
+    p.rec_h = rec_h;
     encode_kc_kernel<false><<<batch, std::min(kc_total * 64, 512), 0, s>>>(p, in, channels, kc_total, boards_total);
 }
 

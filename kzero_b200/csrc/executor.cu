@@ -122,12 +122,30 @@ Net::Net(int device, const void* onnx, size_t len, int max_batch, int precision)
     else
         build_f32();
 
-    // tail parameters (shared by both precisions)
+    if (embed8_ && !use_tower8k_) throw std::logic_error("internal: small board embedded in 8x8 without the masking tower kernel");
+
+    // tail parameters (shared by both precisions).  When a small board is embedded in the 8x8 grid (embed8_), the flatten
+    // order (channel, y, x) of the scalar head's fc1 and the policy provenance table are re-indexed to 8x8 squares; squares
+    // outside the board get zero weights / are never referenced.
     const int area = spec_.area(), hs = spec_.fc1.out, hc = spec_.scalar_conv.cout;
-    std::vector<float> fc1_t(size_t(hc) * area * hs);
+    const int bw = spec_.board_w;
+    auto sq8 = [&](int sq) { return embed8_ ? (sq / bw) * 8 + sq % bw : sq; };
+    const int area_k = embed8_ ? 64 : area;
+    std::vector<float> fc1_t(size_t(hc) * area_k * hs, 0.0f);
     for (int j = 0; j < hs; j++)
-        for (int i = 0; i < hc * area; i++) fc1_t[size_t(i) * hs + j] = spec_.fc1.w[size_t(j) * hc * area + i];
+        for (int c = 0; c < hc; c++)
+            for (int sq = 0; sq < area; sq++)
+                fc1_t[(size_t(c) * area_k + sq8(sq)) * hs + j] = spec_.fc1.w[size_t(j) * hc * area + size_t(c) * area + sq];
     upload(d_fc1_t_, fc1_t);
+    if (embed8_) {
+        for (auto& v : spec_.policy_src)
+            if (v >= 0) v = (v / area) * 64 + sq8(v % area);
+        if (spec_.has_extra) {
+            std::vector<float> ew(64, 0.0f);
+            for (int sq = 0; sq < area; sq++) ew[size_t(sq8(sq))] = spec_.extra_fc.w[size_t(sq)];
+            spec_.extra_fc.w = ew;
+        }
+    }
     upload(d_fc1_b_, spec_.fc1.b);
     upload(d_fc2_w_, spec_.fc2.w);
     upload(d_fc2_b_, spec_.fc2.b);
@@ -201,8 +219,19 @@ static std::vector<AttChunk> att_chunks(const NetSpec& s) {
 
 void Net::build_bf16() {
     act_bf16_ = true;
-    const int W = spec_.board_w, H = spec_.board_h, C = spec_.channels;
+    const int C = spec_.channels;
     const char* force = std::getenv("KZB_FORCE_LINEAR");
+    // Boards smaller than 8x8 (ataxx 2..7, ttt) are embedded top-left in an 8x8 grid and run on the 8x8 whole-tower kernel:
+    // the squares outside the board are forced to zero after every layer (tower8k's epilogue mask), so they act as the
+    // convolution's zero padding.  Only when that kernel will really be used -- the per-layer kernels have no such mask.
+    {
+        auto off = [](const char* name) { const char* v = std::getenv(name); return v && v[0] == '1'; };
+        const bool small = spec_.board_w <= 8 && spec_.board_h <= 8 && (spec_.board_w < 8 || spec_.board_h < 8);
+        const int units = (((max_batch_ + 3) / 4 + 1) & ~1);
+        embed8_ = small && !off("KZB_FORCE_LINEAR") && !off("KZB_NO_CONV8") && !off("KZB_NO_TOWER8") && !off("KZB_TOWER_V1") &&
+                  !off("KZB_NO_EMBED8") && round_up(C, 64) <= 128 && (units + num_sms_ - 1) / num_sms_ <= tower8k_max_local_units();
+    }
+    const int W = embed8_ ? 8 : spec_.board_w, H = embed8_ ? 8 : spec_.board_h;  // the board as the kernels see it
     mode_ = (W == 8 && H == 8 && !(force && force[0] == '1')) ? 1 : 0;
     if (mode_ == 1)
         lay_ = RowLayout{W, H, W, W * H};
@@ -421,6 +450,8 @@ void Net::build_bf16() {
         tp.stride = c_pad_;
         tp.b_slots = tower8_pick_b_slots(n);
         tp.cluster = cluster;
+        tp.board_w = spec_.board_w;
+        tp.board_h = spec_.board_h;
         int cols = 32;
         while (cols < 4 * n) cols *= 2;
         tp.tmem_cols = cols;
@@ -611,6 +642,8 @@ void Net::upload_packed(const uint8_t* bits, const float* scalars, int batch, co
 void Net::run_encode(int batch, const StepHook& hook) {
     InBlock ib = in_block(max_batch_, scalar_count_, bits_stride_);
     EncodeParams p{};
+    p.rec_w = spec_.board_w;
+    p.rec_h = spec_.board_h;
     p.sym = cur_sym_;
     p.square_src = d_sym_square_.as<int32_t>();
     p.bits = d_mv_off_.as<uint8_t>() + ib.off_bits;
@@ -769,7 +802,8 @@ void Net::eval_planes(const float* nchw, int batch, float* out_scalars, float* o
     const int area = spec_.area();
     CK(cudaMemcpyAsync(d_nchw_.ptr, nchw, size_t(batch) * spec_.cin * area * 4, cudaMemcpyHostToDevice, stream_));
     if (use_tower8k_)
-        launch_nchw_to_kc(d_nchw_.as<float>(), batch, spec_.cin, cin_pad_ / 8, rows_alloc_ / 64, act_ink_.ptr, stream_);
+        launch_nchw_to_kc(d_nchw_.as<float>(), batch, spec_.cin, spec_.board_w, spec_.board_h, cin_pad_ / 8, rows_alloc_ / 64, act_ink_.ptr,
+                          stream_);
     else
         launch_nchw_to_rows(d_nchw_.as<float>(), batch, spec_.cin, lay_, cin_pad_, act_in_.ptr, act_bf16_, stream_);
     run_network(batch, nullptr);

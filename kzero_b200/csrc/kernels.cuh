@@ -37,6 +37,8 @@ struct EncodeParams {
     // read from square square_src[sym[b]*A + sq] of the record; null = identity
     const uint8_t* sym;
     const int32_t* square_src;
+    // k-chunk-major output only: the record's own board (<= 8x8), embedded top-left in the 8x8 grid the tower works on
+    int rec_w, rec_h;
 };
 void launch_encode_nhwc(const EncodeParams& p, bool out_bf16, cudaStream_t s);
 // exact twin of InputMapper::encode_input_full (mapping/mod.rs:40-63): out [batch][Cs+Cb][H*W] f32
@@ -133,6 +135,9 @@ struct Tower8Params {
     int stride;  // elements per row of X / T
     int b_slots, tmem_cols;
     int cluster;  // 1: every CTA streams its own weight tiles; 2: CTA pairs, each loads half of every tile and multicasts it
+    // tower8k only: the real board inside the 8x8 grid (ataxx 7x7, ...): outputs on squares outside it are forced to zero after
+    // every layer, so that they keep acting as the convolution's zero padding
+    int board_w, board_h;
     // tower8k only: balanced board assignment (CTA c owns bal_base + (c < bal_rem) contiguous boards as two units of 4 / 3)
     int balanced, bal_base, bal_rem, bal_grid;
     unsigned long long* timeline;
@@ -155,7 +160,8 @@ void tower8k_prepare();
 
 // K2 / layout twins for the k-chunk-major tower input: out[kc][boards_total][64 squares][8 channels] bf16
 void launch_encode_kc(const EncodeParams& p, int kc_total, int boards_total, cudaStream_t s);
-void launch_nchw_to_kc(const float* in, int batch, int channels, int kc_total, int boards_total, void* out, cudaStream_t s);
+void launch_nchw_to_kc(const float* in, int batch, int channels, int rec_w, int rec_h, int kc_total, int boards_total, void* out,
+                       cudaStream_t s);
 size_t tower8_smem_bytes(int w_slots);
 int tower8_pick_b_slots(int n);
 int tower8_max_local_units();

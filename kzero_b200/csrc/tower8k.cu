@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                     tmem_ld32(taddr + y * (nb * 8), r);  // columns of rank y: nb boards x 8 files (a 3-board unit ignores the last 8)
                     tmem_ld_wait();
                     uint32_t packed[16];
+                    const bool rank_ok = y < p.board_h;  // boards smaller than 8x8: squares outside stay zero (padding)
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         float f0 = __uint_as_float(r[2 * j]) + bias;
@@ -338,6 +339,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                             f0 += bf16_lo(res[j]);
                             f1 += bf16_hi(res[j]);
                         }
+                        if (!rank_ok || ((2 * j) & 7) >= p.board_w) f0 = 0.0f;
+                        if (!rank_ok || ((2 * j + 1) & 7) >= p.board_w) f1 = 0.0f;
                         packed[j] = pack_bf16(f0, f1);
                     }
                     if (has_res && live && yy < kChunks - 1) {  // next rank's residual
