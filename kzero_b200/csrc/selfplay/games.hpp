@@ -112,16 +112,34 @@ struct Ataxx {
     bool done() const { return finished; }
     int outcome() const { return result; }
 
+    // neighbourhood masks per tile (Chebyshev distance <= 1 / <= 2), built once
+    struct Masks {
+        uint64_t r1[A], r2[A];
+        Masks() {
+            for (int i = 0; i < A; i++) {
+                r1[i] = r2[i] = 0;
+                const int x = i % S, y = i / S;
+                for (int dy = -2; dy <= 2; dy++)
+                    for (int dx = -2; dx <= 2; dx++) {
+                        const int xx = x + dx, yy = y + dy;
+                        if (xx < 0 || xx >= S || yy < 0 || yy >= S) continue;
+                        r2[i] |= 1ull << (yy * S + xx);
+                        if (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1) r1[i] |= 1ull << (yy * S + xx);
+                    }
+            }
+        }
+    };
+    static const Masks& masks() {
+        static const Masks m;
+        return m;
+    }
     static uint64_t ring(uint64_t m, int r) {  // all tiles at Chebyshev distance <= r of any tile in m
+        const Masks& k = masks();
         uint64_t out = 0;
-        for (int i = 0; i < A; i++) {
-            if (!((m >> i) & 1)) continue;
-            const int x = i % S, y = i / S;
-            for (int dy = -r; dy <= r; dy++)
-                for (int dx = -r; dx <= r; dx++) {
-                    const int xx = x + dx, yy = y + dy;
-                    if (xx >= 0 && xx < S && yy >= 0 && yy < S) out |= 1ull << (yy * S + xx);
-                }
+        while (m) {
+            const int i = __builtin_ctzll(m);
+            m &= m - 1;
+            out |= r == 1 ? k.r1[i] : k.r2[i];
         }
         return out;
     }
