@@ -130,7 +130,7 @@ def test_fp32_packed_vs_oracle(game, depth, ch, n):
 
 @pytest.mark.parametrize("variant", ["default", "tower_v1", "no_heads8", "no_tower8", "no_conv8", "linear", "no_embed8"])
 @pytest.mark.parametrize("game,depth,ch,n", [("ataxx-7", 8, 64, 256), ("chess", 16, 128, 64), ("go-9", 4, 64, 40),
-                                              ("chess", 2, 32, 7), ("chess", 3, 64, 130)])
+                                              ("chess", 2, 32, 7), ("chess", 3, 64, 130), ("chess", 2, 256, 12)])
 def test_bf16_packed_vs_oracle(game, depth, ch, n, variant, monkeypatch):
     """The tensor-core path in all its forms: whole-tower persistent kernel + fused heads kernel (tower8k.cu, heads8.cu,
     default for 8x8 boards), the first-generation tower kernel (tower8.cu, KZB_TOWER_V1=1), the same tower with per-op head convs + tail kernel (KZB_NO_HEADS8=1),
