@@ -233,10 +233,13 @@ __global__ void __launch_bounds__(kThreads, 1)
                 uint32_t r[16];
                 tmem_ld16(lane_addr + kDsCol, r);
                 tmem_ld_wait();
+                float bias[16];
+#pragma unroll
+                for (int c = 0; c < 16; c++) bias[c] = sm.bs[c];
 #pragma unroll
                 for (int c = 0; c < 16; c++) {
                     if (c < p.hc) {
-                        float f = __uint_as_float(r[c]) + sm.bs[c];
+                        float f = __uint_as_float(r[c]) + bias[c];
                         sm.s[tb * n_in + c * 64 + sq] = f < 0.0f ? 0.0f : f;
                     }
                 }
@@ -244,6 +247,9 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int c0 = 0; c0 < p.n1; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(lane_addr + kD1Col + c0, r);
+                float bias[32];  // loaded before any store of this chunk (see epi2)
+#pragma unroll
+                for (int j = 0; j < 32; j++) bias[j] = sm.b1[c0 + j];
                 tmem_ld_wait();
                 uint8_t* hrow = sm.hl + size_t(c0 >> 6) * kTile + row * 128;
 #pragma unroll
@@ -251,8 +257,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                     uint32_t pk[4];
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        float f0 = __uint_as_float(r[g * 8 + 2 * j]) + sm.b1[c0 + g * 8 + 2 * j];
-                        float f1 = __uint_as_float(r[g * 8 + 2 * j + 1]) + sm.b1[c0 + g * 8 + 2 * j + 1];
+                        float f0 = __uint_as_float(r[g * 8 + 2 * j]) + bias[g * 8 + 2 * j];
+                        float f1 = __uint_as_float(r[g * 8 + 2 * j + 1]) + bias[g * 8 + 2 * j + 1];
                         f0 = f0 < 0.0f ? 0.0f : f0;
                         f1 = f1 < 0.0f ? 0.0f : f1;
                         pk[j] = pack_bf16(f0, f1);
@@ -274,9 +280,15 @@ __global__ void __launch_bounds__(kThreads, 1)
                 uint32_t r[16];
                 tmem_ld16(lane_addr + kD2Col + c0, r);
                 tmem_ld_wait();
+                // biases first, then the stores: the compiler cannot move a shared-memory load across a shared-memory store
+                // that may alias it, and with one warp per scheduler a load -> add -> store chain per element costs ~60 cycles
+                float bias[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) bias[j] = sm.b2[c0 + j];
+                float* lrow = L + size_t(tb * p.pc + c0) * 64 + sq;
 #pragma unroll
                 for (int j = 0; j < 16; j++)
-                    if (c0 + j < p.pc) L[(tb * p.pc + c0 + j) * 64 + sq] = __uint_as_float(r[j]) + sm.b2[c0 + j];
+                    if (c0 + j < p.pc) lrow[j * 64] = __uint_as_float(r[j]) + bias[j];
             }
             tc_fence_before();
             mbar_arrive(sm.d2_free);
