@@ -115,6 +115,7 @@ Net::Net(int device, const void* onnx, size_t len, int max_batch, int precision)
 
     CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     if (const char* bs = std::getenv("KZB_BLOCKING_SYNC")) blocking_sync_ = bs[0] == '1';
+    if (const char* ng = std::getenv("KZB_NO_GRAPH")) use_graph_ = ng[0] != '1';
     if (const char* tr = std::getenv("KZB_TRACE"))
         if (tr[0] == '1') trace_ = new double[5]();
     if (precision_ == 1)
@@ -167,6 +168,7 @@ Net::~Net() {
     delete[] trace_;
     cudaSetDevice(device_);
     if (done_event_) cudaEventDestroy(done_event_);
+    if (full_batch_graph_) cudaGraphExecDestroy(full_batch_graph_);
     if (stream_) {
         cudaStreamSynchronize(stream_);
         cudaStreamDestroy(stream_);
@@ -858,9 +860,35 @@ void Net::eval_packed(const uint8_t* bits, const float* scalars, int batch, cons
     upload_packed(bits, scalars, batch, mv_idx, mv_off);
     if (trace) t1 = clk::now();
     *h_out_.as<volatile int>() = 0;  // error word; the tail kernel only ever writes non-zero into it
-    run_encode(batch, nullptr);
-    run_network(batch, nullptr);
-    run_tail(batch, true, nullptr, /*to_host=*/true);
+    // The kernel sequence of a FULL batch without symmetries is captured once into a CUDA graph and replayed: one launch call
+    // instead of one per kernel (self-play batches are full 99 % of the time).  Every other shape takes the direct path.
+    const bool graphable = use_graph_ && batch == max_batch_ && cur_sym_ == nullptr;
+    if (graphable && full_batch_graph_) {
+        CK(cudaGraphLaunch(full_batch_graph_, stream_));
+    } else if (graphable) {
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        run_encode(batch, nullptr);
+        run_network(batch, nullptr);
+        run_tail(batch, true, nullptr, /*to_host=*/true);
+        CK(cudaStreamEndCapture(stream_, &graph));
+        cudaError_t ge = cudaGraphInstantiate(&full_batch_graph_, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ge != cudaSuccess) {  // fall back to direct launches for good
+            cudaGetLastError();
+            full_batch_graph_ = nullptr;
+            use_graph_ = false;
+            run_encode(batch, nullptr);
+            run_network(batch, nullptr);
+            run_tail(batch, true, nullptr, /*to_host=*/true);
+        } else {
+            CK(cudaGraphLaunch(full_batch_graph_, stream_));
+        }
+    } else {
+        run_encode(batch, nullptr);
+        run_network(batch, nullptr);
+        run_tail(batch, true, nullptr, /*to_host=*/true);
+    }
     const size_t probs_off = 16 + align16(size_t(max_batch_) * 5 * 4);
     if (trace) t2 = clk::now();
     if (blocking_sync_) {  // the calling thread sleeps while the GPU works (self-play: executor threads share cores with generators)

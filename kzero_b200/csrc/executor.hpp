@@ -120,6 +120,8 @@ private:
     PinnedBuffer h_in_, h_out_;
     size_t mv_cap_ = 0;
     bool blocking_sync_ = false;
+    bool use_graph_ = true;                         // replay a captured graph for full batches (KZB_NO_GRAPH=1 disables)
+    cudaGraphExec_t full_batch_graph_ = nullptr;
     int n_sym_ = 0;
     const uint8_t* cur_sym_ = nullptr;  // device pointer while an evaluation with symmetries is in flight
     DeviceBuffer d_sym_square_, d_sym_policy_, d_sym_;
