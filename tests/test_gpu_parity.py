@@ -353,6 +353,22 @@ def test_errors_match_reference_panics():
         B200Network(wrong, onnx_bytes, 8)
 
 
+@pytest.mark.parametrize("game", ["chess", "ataxx-7", "go-9"])
+def test_bf16_nan_inputs_are_reported_not_emitted(game):
+    """The tensor-core paths (whole-tower + fused heads for chess / ataxx, per-layer for go) must surface NaN logits as an
+    error like the reference's softmax assert (common.rs:110), never as NaN probabilities."""
+    spec = netgen.game_spec(game)
+    onnx_bytes = netgen.build_onnx(spec, 2, 64, seed=61)
+    bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, 9, seed=62)
+    bad = scalars.copy()
+    bad[4, 0] = np.nan
+    with B200Network(mapper_for(spec), onnx_bytes, 16, precision=PRECISION_BF16) as net:
+        with pytest.raises(KzbError, match="strictly positive"):
+            net.evaluate_packed(bits, bad, mv_idx, mv_off)
+        v, p = net.evaluate_packed(bits, scalars, mv_idx, mv_off)  # the handle stays usable
+        assert np.isfinite(v).all() and np.isfinite(p).all()
+
+
 def test_concurrent_instances_match(tmp_path):
     """Pattern of rust/kz-misc/src/bin/test_concurrent.rs:32-145: several executors on one device, each in
     its own thread, must keep reproducing the same outputs."""
