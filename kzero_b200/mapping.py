@@ -8,7 +8,7 @@ Restated from:
   generate_all_flat_moves_pov   rust/kz-core/src/mapping/chess.rs:439-481  (1880 POV moves)
   ClassifiedPovMove::from_move / to_channel   chess.rs:305-357             (73-channel conv index)
   flat_to_att                   rust/kz-misc/src/bin/write_chess_mapping.rs:50-66
-Square index = rank*8 + file, A1 = 0.  tests/test_mapping.py checks these tables against the Gather
+Square index = rank*8 + file, A1 = 0.  tests/test_netgen.py checks these tables against the Gather
 constants inside the golden ONNX fixtures exported from the reference (tests/golden/).
 """
 from __future__ import annotations
