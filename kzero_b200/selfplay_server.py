@@ -14,7 +14,9 @@ Differences that are deliberate (documented in DESIGN.md): a generation is one `
 or new settings take effect at the next generation boundary (the reference hot-swaps inside a generation) and games still
 running at the boundary are dropped instead of carried over; `eval_random_symmetries`, `start_pos`, `top_moves`,
 `saved_state_channels` and `gpu_batch_size_root` are accepted and ignored (muzero-only or above the boundary); `chess`
-is served by the chess-SHAPED synthetic game (no chess move generator in this repo), `ataxx-7` by the real rules.
+is served by the chess-SHAPED synthetic game (no chess move generator in this repo), `ataxx-7` by the real rules; one
+server process drives ONE device (the reference takes several `--device` flags, server.rs:49-51) -- start one process per
+GPU on different ports, the games are independent.
 """
 from __future__ import annotations
 
