@@ -164,7 +164,9 @@ typedef struct kzb_selfplay_config {
     int32_t executor_blocking_sync; /* 0: executor threads spin while the GPU works (lowest latency; needs a core each),
                                        1: they sleep on a blocking event (use when generators and executors share cores) */
     int32_t dummy_network;       /* 1: answer every request with uniform wdl / policy instead of evaluating a network -- the
-                                    reference's DummyNetwork / UseDummyNetwork (network/dummy.rs:44-60); needs no GPU      */
+                                    reference's DummyNetwork / UseDummyNetwork (network/dummy.rs:44-60); needs no GPU.
+                                    2: a deterministic pseudo-network (sharp policies and values hashed from the encoded
+                                    record) for host-side profiling and tests, also without a GPU                      */
     const char* output_prefix;   /* NULL / "": no records; else finished games are written to <prefix>.bin/.off/.json in the
                                     reference's format (rust/kz-selfplay/src/binary_output.rs:128-297)                      */
     uint64_t seed;

@@ -13,6 +13,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -88,151 +89,202 @@ struct SearchSettings {
     float virtual_loss = 1.0f;
 };
 
-// Node storage (node.rs:11-34) is a structure of arrays indexed by node id: the children of a node have consecutive
-// ids, so a selection step reads a handful of contiguous float / u32 slices instead of one 64..88-byte struct per
-// child, and the UCT scan over them vectorises (AVX2, 8 children per step; same IEEE operations in the same order as
-// the scalar code, so trees stay bit-identical to the oracle's).  `net_values` is only kept as a flag: the reference
-// stores the network's own values to write them into game records, which this driver does not produce.
+// Node storage.  The reference keeps one 64..88-byte Node per child (node.rs:11-34), and most of them are never visited:
+// a node's children are created together (step.rs:89-97) but a search of V visits touches only about V of them.  So the
+// tree is split in two:
+//   child slots   one per created child, ids consecutive per parent (id 0 = the root): last_move, net_policy and `stat`,
+//                 the index of the child's entry in the visited pool, 0 while it has never been visited
+//   visited pool  one 64-byte (one cache line) entry per node that has been visited at least once: the visit counters,
+//                 the value sums and the links; entry 0 is an all-zero sentinel that stands for every unvisited child
+// A selection step therefore reads the children's policy and stat slices plus one line per VISITED child, instead of
+// seven separate statistics slices, and the pool (about 64 KB for an 800-visit search) stays cache resident while a
+// generator thread rotates over dozens of trees.  Unvisited children all share q = fpu, so their uct is one multiply-add
+// chain over the policy slice; visited children go through the same scalar formula as before.  The IEEE operations
+// and their order are those of the reference's Node::uct, so trees stay bit-identical to the oracle's.
 struct UctContext {  // node.rs:55-64
     uint64_t total_visits;
     ValuesAbs values;
     float visited_policy_mass;
 };
 
+struct alignas(64) Visited {
+    uint32_t complete = 0, virt = 0;                          // complete_visits, virtual_visits
+    float value = 0, win_a = 0, draw = 0, win_b = 0, ml = 0;  // sum_values (abs)
+    int32_t parent = -1;                                      // pool index of the parent, -1 for the root
+    int32_t child_start = -1, child_count = 0;                // child slots; children == None  <=>  child_start < 0
+    int32_t slot = 0;                                         // this node's own child slot
+    uint8_t has_net_values = 0;
+};
+
 namespace detail {
 struct UctParent {  // the per-parent part of Node::uct, computed once per selection step
     float fpu, sqrt_visits, moves_left_m1;
 };
-struct UctArrays {
-    const uint32_t *complete, *virt;
-    const float *value, *win_a, *draw, *win_b, *ml, *policy;
-};
-// node.rs:163-206 + Uct::total :87-98 for child i (scalar reference form)
-inline float uct_one(const UctArrays& a, int i, const UctParent& up, const SearchSettings& s, int player) {
+// node.rs:163-206 + Uct::total :87-98 for one child
+inline float uct_one(const Visited& v, float policy, const UctParent& up, const SearchSettings& s, int player) {
     const float vl = s.virtual_loss;
-    const float cv = float(a.complete[i]), vv = float(a.virt[i]);
+    const float cv = float(v.complete), vv = float(v.virt);
     const float tvv = cv + vl * vv;
     float q;
     if (tvv == 0.0f) {
         q = up.fpu;
     } else {
         float total_value;
-        if (s.q_mode.wdl) total_value = player == 0 ? a.win_a[i] + s.q_mode.draw_score * a.draw[i] - a.win_b[i]
-                                                    : a.win_b[i] + s.q_mode.draw_score * a.draw[i] - a.win_a[i];
-        else total_value = player == 0 ? a.value[i] : -a.value[i];
+        if (s.q_mode.wdl) total_value = player == 0 ? v.win_a + s.q_mode.draw_score * v.draw - v.win_b
+                                                    : v.win_b + s.q_mode.draw_score * v.draw - v.win_a;
+        else total_value = player == 0 ? v.value : -v.value;
         q = (total_value - vl * vv) / tvv;
     }
-    const float u = a.policy[i] * up.sqrt_visits / float(1u + a.complete[i] + a.virt[i]);
+    const float u = policy * up.sqrt_visits / float(1u + v.complete + v.virt);
     const UctWeights& w = s.weights;
     float m_unit = 0.0f;
     if (w.moves_left_weight != 0.0f) {
-        const float m = a.complete[i] == 0 ? 0.0f : a.ml[i] / cv - up.moves_left_m1;
+        const float m = v.complete == 0 ? 0.0f : v.ml / cv - up.moves_left_m1;
         const float m_clipped = std::fmin(std::fmax(m, -w.moves_left_clip), w.moves_left_clip);
         m_unit = std::fmin(std::fmax(w.moves_left_sharpness * m_clipped * -q, -1.0f), 1.0f);
     }
     return q + w.exploration_weight * u + w.moves_left_weight * m_unit;
 }
 #if defined(__x86_64__)
-__attribute__((target("avx2"))) inline void uct_many_avx2(const UctArrays& a, int n, const UctParent& up, const SearchSettings& s,
-                                                          int player, float* out) {
+// The same formula for 8 visited children at a time: the first 32 bytes of their pool entries (complete, virt, value,
+// win_a, draw, win_b, ml, parent) are loaded as one row each and transposed into columns.  Same IEEE operations in the
+// same order as uct_one.  `idx` / `policy` are padded to a multiple of 8 (index 0 = the sentinel).
+__attribute__((target("avx2"))) inline void uct_visited_avx2(const Visited* pool, const int32_t* idx, const float* policy, int k,
+                                                             const UctParent& up, const SearchSettings& s, int player, float* out) {
     const __m256 vl = _mm256_set1_ps(s.virtual_loss), fpu = _mm256_set1_ps(up.fpu), sq = _mm256_set1_ps(up.sqrt_visits);
     const __m256 mlm1 = _mm256_set1_ps(up.moves_left_m1), ds = _mm256_set1_ps(s.q_mode.draw_score), zero = _mm256_setzero_ps();
     const UctWeights& w = s.weights;
     const __m256 ew = _mm256_set1_ps(w.exploration_weight), mw = _mm256_set1_ps(w.moves_left_weight);
     const __m256 clip = _mm256_set1_ps(w.moves_left_clip), nclip = _mm256_set1_ps(-w.moves_left_clip), sharp = _mm256_set1_ps(w.moves_left_sharpness);
     const __m256 one = _mm256_set1_ps(1.0f), none = _mm256_set1_ps(-1.0f);
-    const float* own = player == 0 ? a.win_a : a.win_b;
-    const float* opp = player == 0 ? a.win_b : a.win_a;
-    int i = 0;
-    for (; i + 8 <= n; i += 8) {
-        const __m256i cvi = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(a.complete + i));
-        const __m256i vvi = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(a.virt + i));
+    for (int g = 0; g < k; g += 8) {
+        __m256 r[8];
+        for (int j = 0; j < 8; j++) r[j] = _mm256_load_ps(reinterpret_cast<const float*>(pool + idx[g + j]));
+        // 8x8 transpose
+        const __m256 t0 = _mm256_unpacklo_ps(r[0], r[1]), t1 = _mm256_unpackhi_ps(r[0], r[1]);
+        const __m256 t2 = _mm256_unpacklo_ps(r[2], r[3]), t3 = _mm256_unpackhi_ps(r[2], r[3]);
+        const __m256 t4 = _mm256_unpacklo_ps(r[4], r[5]), t5 = _mm256_unpackhi_ps(r[4], r[5]);
+        const __m256 t6 = _mm256_unpacklo_ps(r[6], r[7]), t7 = _mm256_unpackhi_ps(r[6], r[7]);
+        const __m256 u0 = _mm256_shuffle_ps(t0, t2, 0x44), u1 = _mm256_shuffle_ps(t0, t2, 0xEE);
+        const __m256 u2 = _mm256_shuffle_ps(t1, t3, 0x44), u3 = _mm256_shuffle_ps(t1, t3, 0xEE);
+        const __m256 u4 = _mm256_shuffle_ps(t4, t6, 0x44), u5 = _mm256_shuffle_ps(t4, t6, 0xEE);
+        const __m256 u6 = _mm256_shuffle_ps(t5, t7, 0x44), u7 = _mm256_shuffle_ps(t5, t7, 0xEE);
+        const __m256i cvi = _mm256_castps_si256(_mm256_permute2f128_ps(u0, u4, 0x20));  // complete
+        const __m256i vvi = _mm256_castps_si256(_mm256_permute2f128_ps(u1, u5, 0x20));  // virt
+        const __m256 value = _mm256_permute2f128_ps(u2, u6, 0x20), win_a = _mm256_permute2f128_ps(u3, u7, 0x20);
+        const __m256 draw = _mm256_permute2f128_ps(u0, u4, 0x31), win_b = _mm256_permute2f128_ps(u1, u5, 0x31);
+        const __m256 ml = _mm256_permute2f128_ps(u2, u6, 0x31);
         const __m256 cv = _mm256_cvtepi32_ps(cvi), vv = _mm256_cvtepi32_ps(vvi);
         const __m256 vlvv = _mm256_mul_ps(vl, vv);
         const __m256 tvv = _mm256_add_ps(cv, vlvv);
         __m256 total_value;
         if (s.q_mode.wdl) {
-            total_value = _mm256_sub_ps(_mm256_add_ps(_mm256_loadu_ps(own + i), _mm256_mul_ps(ds, _mm256_loadu_ps(a.draw + i))), _mm256_loadu_ps(opp + i));
+            const __m256 own = player == 0 ? win_a : win_b, opp = player == 0 ? win_b : win_a;
+            total_value = _mm256_sub_ps(_mm256_add_ps(own, _mm256_mul_ps(ds, draw)), opp);
         } else {
-            total_value = _mm256_loadu_ps(a.value + i);
+            total_value = value;
             if (player != 0) total_value = _mm256_sub_ps(zero, total_value);  // -x == 0 - x except for the sign of zero, which no later step sees
         }
         __m256 q = _mm256_div_ps(_mm256_sub_ps(total_value, vlvv), tvv);
         q = _mm256_blendv_ps(q, fpu, _mm256_cmp_ps(tvv, zero, _CMP_EQ_OQ));
         const __m256 denom = _mm256_cvtepi32_ps(_mm256_add_epi32(_mm256_add_epi32(cvi, vvi), _mm256_set1_epi32(1)));
-        const __m256 u = _mm256_div_ps(_mm256_mul_ps(_mm256_loadu_ps(a.policy + i), sq), denom);
+        const __m256 u = _mm256_div_ps(_mm256_mul_ps(_mm256_loadu_ps(policy + g), sq), denom);
         __m256 total = _mm256_add_ps(q, _mm256_mul_ps(ew, u));
         if (w.moves_left_weight != 0.0f) {
-            __m256 m = _mm256_sub_ps(_mm256_div_ps(_mm256_loadu_ps(a.ml + i), cv), mlm1);
+            __m256 m = _mm256_sub_ps(_mm256_div_ps(ml, cv), mlm1);
             m = _mm256_blendv_ps(m, zero, _mm256_castsi256_ps(_mm256_cmpeq_epi32(cvi, _mm256_setzero_si256())));
             const __m256 m_clipped = _mm256_min_ps(_mm256_max_ps(m, nclip), clip);
             const __m256 m_unit = _mm256_min_ps(_mm256_max_ps(_mm256_mul_ps(_mm256_mul_ps(sharp, m_clipped), _mm256_sub_ps(zero, q)), none), one);
             total = _mm256_add_ps(total, _mm256_mul_ps(mw, m_unit));
         }
-        _mm256_storeu_ps(out + i, total);
+        _mm256_storeu_ps(out + g, total);
     }
-    for (; i < n; i++) out[i] = uct_one(a, i, up, s, player);
 }
 #endif
-inline void uct_many(const UctArrays& a, int n, const UctParent& up, const SearchSettings& s, int player, float* out) {
+// uct of children that have never been visited: the formula above with zero counters, where q and the moves-left term
+// are per-parent constants.  `x / 1.0f` is exact, so it is dropped.
+#define KZB_UCT_UNVISITED_BODY                                                      \
+    for (int i = 0; i < n; i++) out[i] = (q + ew * (policy[i] * sq)) + ml_term;
+inline void uct_unvisited_generic(const float* policy, int n, float q, float ew, float sq, float ml_term, float* out) { KZB_UCT_UNVISITED_BODY }
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) inline void uct_unvisited_avx2(const float* policy, int n, float q, float ew, float sq, float ml_term,
+                                                               float* __restrict__ out) { KZB_UCT_UNVISITED_BODY }
+#endif
+#undef KZB_UCT_UNVISITED_BODY
+inline void uct_unvisited(const float* policy, int n, const UctParent& up, const SearchSettings& s, float* out) {
+    const float q = up.fpu;
+    const UctWeights& w = s.weights;
+    float m_unit = 0.0f;
+    if (w.moves_left_weight != 0.0f) {
+        const float m_clipped = std::fmin(std::fmax(0.0f, -w.moves_left_clip), w.moves_left_clip);
+        m_unit = std::fmin(std::fmax(w.moves_left_sharpness * m_clipped * -q, -1.0f), 1.0f);
+    }
+    const float ml_term = w.moves_left_weight * m_unit;
 #if defined(__x86_64__)
     static const bool have_avx2 = __builtin_cpu_supports("avx2");
-    if (have_avx2) return uct_many_avx2(a, n, up, s, player, out);
+    if (have_avx2) return uct_unvisited_avx2(policy, n, q, w.exploration_weight, up.sqrt_visits, ml_term, out);
 #endif
-    for (int i = 0; i < n; i++) out[i] = uct_one(a, i, up, s, player);
+    uct_unvisited_generic(policy, n, q, w.exploration_weight, up.sqrt_visits, ml_term, out);
 }
 }  // namespace detail
 
 template <typename Game>
 struct Tree {
     Game root_board;
-    // structure
-    std::vector<int32_t> parent, child_start, child_count;  // children == None  <=>  child_start < 0
+    // child slots
     std::vector<uint32_t> last_move;
-    std::vector<uint8_t> has_net_values;
-    // statistics
-    std::vector<uint32_t> complete, virt;                       // complete_visits, virtual_visits
-    std::vector<float> s_value, s_win_a, s_draw, s_win_b, s_ml;  // sum_values (abs)
     std::vector<float> net_policy;
-    std::vector<float> uct_scratch;
+    std::vector<int32_t> stat;
+    // visited pool; [0] is the sentinel, [1] the root
+    std::vector<Visited> pool;
+    std::vector<float> uct_scratch, vis_policy, vis_out;
+    std::vector<int32_t> vis_idx, vis_pos;
+    static constexpr int kRoot = 1;  // pool index of the root
 
     explicit Tree(const Game& root) : root_board(root) {  // tree.rs:31-39
         if (root.done()) throw std::runtime_error("Cannot build tree for done board");
-        push_node(-1, 0, NAN);
+        last_move.push_back(0), net_policy.push_back(NAN), stat.push_back(kRoot);
+        pool.resize(2);
     }
-    size_t size() const { return parent.size(); }
-    void reserve(size_t n) {
-        parent.reserve(n), child_start.reserve(n), child_count.reserve(n), last_move.reserve(n), has_net_values.reserve(n);
-        complete.reserve(n), virt.reserve(n), s_value.reserve(n), s_win_a.reserve(n), s_draw.reserve(n), s_win_b.reserve(n);
-        s_ml.reserve(n), net_policy.reserve(n);
+    size_t size() const { return last_move.size(); }  // nodes in the reference's sense: the root and every created child
+    void reserve(size_t slots, size_t visited) {
+        last_move.reserve(slots), net_policy.reserve(slots), stat.reserve(slots);
+        pool.reserve(visited + 2);
     }
-    int push_node(int par, uint32_t mv, float p) {  // Node::new, node.rs:104-118
-        parent.push_back(par), child_start.push_back(-1), child_count.push_back(0), last_move.push_back(mv), has_net_values.push_back(0);
-        complete.push_back(0), virt.push_back(0);
-        s_value.push_back(0), s_win_a.push_back(0), s_draw.push_back(0), s_win_b.push_back(0), s_ml.push_back(0), net_policy.push_back(p);
-        return int(parent.size()) - 1;
-    }
-    // all children of `par` at once (step.rs:89-97): one resize per array instead of a push_back per node and field
-    int push_children(int par, const std::vector<uint32_t>& moves, float p) {
-        const size_t start = parent.size(), n = moves.size(), end = start + n;
-        parent.resize(end, par), child_start.resize(end, -1), child_count.resize(end, 0), has_net_values.resize(end, 0);
-        complete.resize(end, 0), virt.resize(end, 0);
-        s_value.resize(end, 0.0f), s_win_a.resize(end, 0.0f), s_draw.resize(end, 0.0f), s_win_b.resize(end, 0.0f), s_ml.resize(end, 0.0f);
-        net_policy.resize(end, p);
+    // all children of a node at once (step.rs:89-97), with a uniform prior
+    int push_children(const std::vector<uint32_t>& moves, float p) {
+        const size_t start = last_move.size(), end = start + moves.size();
+        net_policy.resize(end, p), stat.resize(end, 0);
         last_move.insert(last_move.end(), moves.begin(), moves.end());
         return int(start);
     }
-    uint64_t root_visits() const { return complete[0]; }
-    uint64_t total_visits(int n) const { return uint64_t(complete[size_t(n)]) + virt[size_t(n)]; }
-    ValuesAbs sum_values(int n) const { return {s_value[size_t(n)], s_win_a[size_t(n)], s_draw[size_t(n)], s_win_b[size_t(n)], s_ml[size_t(n)]}; }
-    ValuesAbs values(int n) const { return sum_values(n).div(float(complete[size_t(n)])); }  // node.rs:126-128
+    int visit_child(int parent, int slot) {  // the pool entry of a child slot, created on its first visit
+        int v = stat[size_t(slot)];
+        if (v == 0) {
+            v = int(pool.size());
+            pool.emplace_back();
+            pool.back().parent = parent;
+            pool.back().slot = slot;
+            stat[size_t(slot)] = v;
+        }
+        return v;
+    }
+    const Visited& root() const { return pool[kRoot]; }
+    uint64_t root_visits() const { return pool[kRoot].complete; }
+    uint32_t child_visits(int slot) const { return pool[size_t(stat[size_t(slot)])].complete; }  // 0 through the sentinel
+    static ValuesAbs sum_values(const Visited& v) { return {v.value, v.win_a, v.draw, v.win_b, v.ml}; }
+    static ValuesAbs values(const Visited& v) { return sum_values(v).div(float(v.complete)); }  // node.rs:126-128
+    ValuesAbs root_values() const { return values(pool[kRoot]); }
 
     UctContext uct_context(int node) const {  // tree.rs:49-66, node.rs:153-161
+        const Visited& pn = pool[size_t(node)];
         float mass = 0.0f;
-        const int c0 = child_start[size_t(node)], c1 = c0 + child_count[size_t(node)];
-        for (int c = c0; c < c1; c++)
-            if (complete[size_t(c)] + virt[size_t(c)] > 0) mass += net_policy[size_t(c)];
-        return {total_visits(node), values(node), mass};
+        const int c0 = pn.child_start, c1 = c0 + pn.child_count;
+        for (int c = c0; c < c1; c++) {
+            const int v = stat[size_t(c)];
+            if (v != 0 && pool[size_t(v)].complete + pool[size_t(v)].virt > 0) mass += net_policy[size_t(c)];
+        }
+        return {uint64_t(pn.complete) + pn.virt, values(pn), mass};
     }
 
     detail::UctParent uct_parent(const UctContext& par, FpuMode fpu_mode, const SearchSettings& s, int player) const {
@@ -247,90 +299,113 @@ struct Tree {
         u.moves_left_m1 = par.values.moves_left - 1.0f;
         return u;
     }
-    detail::UctArrays arrays(int first_child) const {
-        const size_t o = size_t(first_child);
-        return {complete.data() + o, virt.data() + o, s_value.data() + o, s_win_a.data() + o, s_draw.data() + o, s_win_b.data() + o,
-                s_ml.data() + o, net_policy.data() + o};
-    }
 
     void propagate(int node, ValuesAbs v) {  // step.rs:171-188
         int cur = node;
         while (true) {
-            const size_t i = size_t(cur);
-            if (virt[i] == 0) throw std::logic_error("propagate: node has no virtual visit");
-            complete[i] += 1;
-            virt[i] -= 1;
-            s_value[i] += v.value, s_win_a[i] += v.win_a, s_draw[i] += v.draw, s_win_b[i] += v.win_b, s_ml[i] += v.moves_left;
-            if (parent[i] < 0) break;
-            cur = parent[i];
+            Visited& n = pool[size_t(cur)];
+            if (n.virt == 0) throw std::logic_error("propagate: node has no virtual visit");
+            n.complete += 1;
+            n.virt -= 1;
+            n.value += v.value, n.win_a += v.win_a, n.draw += v.draw, n.win_b += v.win_b, n.ml += v.moves_left;
+            if (n.parent < 0) break;
+            cur = n.parent;
             v = v.parent();
         }
     }
 
     // tree.rs:132-141: visit distribution over the root's children
     void policy(std::vector<float>& out) const {
-        out.resize(size_t(child_count[0]));
-        const float denom = std::fmax(float(complete[0]) - 1.0f, 0.0f);
-        for (int i = 0; i < child_count[0]; i++) out[size_t(i)] = float(complete[size_t(child_start[0] + i)]) / denom;
+        const Visited& r = pool[kRoot];
+        out.resize(size_t(r.child_count));
+        const float denom = std::fmax(float(r.complete) - 1.0f, 0.0f);
+        for (int i = 0; i < r.child_count; i++) out[size_t(i)] = float(child_visits(r.child_start + i)) / denom;
     }
 };
 
 template <typename Game>
 struct Request {
-    int node = -1;
+    int node = -1;  // pool index of the node to evaluate
     Game board;
+    bool is_root() const { return node == Tree<Game>::kRoot; }
 };
 
 // step.rs:61-135.  Returns true and fills `req` when an un-evaluated node was reached; false when a terminal node
 // was reached (its outcome has been propagated).
 template <typename Game>
 bool zero_step_gather(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Request<Game>& req, std::vector<uint32_t>& scratch) {
-    int cur = 0;
+    int cur = Tree<Game>::kRoot;
     Game board = tree.root_board;
     while (true) {
-        tree.virt[size_t(cur)] += 1;
+        tree.pool[size_t(cur)].virt += 1;
         if (board.done()) {
             tree.propagate(cur, ValuesAbs::from_outcome(board.outcome(), 0.0f));
             return false;
         }
-        if (tree.child_start[size_t(cur)] < 0) {
+        if (tree.pool[size_t(cur)].child_start < 0) {
             // initialise the children with a uniform policy, step.rs:84-103
             board.moves(scratch);
             const float p = 1.0f / float(scratch.size());
-            const int start = tree.push_children(cur, scratch, p);
-            tree.child_start[size_t(cur)] = start;
-            tree.child_count[size_t(cur)] = int(scratch.size());
-            tree.has_net_values[size_t(cur)] = 0;
+            const int start = tree.push_children(scratch, p);
+            Visited& n = tree.pool[size_t(cur)];
+            n.child_start = start;
+            n.child_count = int(scratch.size());
+            n.has_net_values = 0;
             req.node = cur;
             req.board = board;
             return true;
         }
-        const int c0 = tree.child_start[size_t(cur)], n = tree.child_count[size_t(cur)];
+        const Visited& pn = tree.pool[size_t(cur)];
+        const int c0 = pn.child_start, n = pn.child_count;
+        const int32_t* stat = tree.stat.data() + c0;
         const int player = board.next_player();
         int selected = -1;
         uint32_t ties = 0;
-        if (tree.complete[size_t(cur)] == 0) {
+        if (pn.complete == 0) {
             // a random least-visited child, step.rs:112-114 (choose_max_by_key over Reverse(total_visits))
             uint64_t best = 0;
-            for (int c = c0; c < c0 + n; c++) {
-                const uint64_t v = tree.total_visits(c);
+            for (int i = 0; i < n; i++) {
+                const Visited& ch = tree.pool[size_t(stat[i])];
+                const uint64_t v = uint64_t(ch.complete) + ch.virt;
                 if (selected < 0 || v < best) {
-                    selected = c;
+                    selected = c0 + i;
                     best = v;
                     ties = 1;
                 } else if (v == best) {
                     ties++;
-                    if (rng.gen_range(ties) == 0) selected = c;
+                    if (rng.gen_range(ties) == 0) selected = c0 + i;
                 }
             }
         } else {
-            const FpuMode fpu = cur == 0 ? s.fpu_root : s.fpu_child;
-            const UctContext ctx = tree.uct_context(cur);
+            const FpuMode fpu = cur == Tree<Game>::kRoot ? s.fpu_root : s.fpu_child;
+            // one pass over the stat slice: the visited children (for the vector evaluation below) and, in child
+            // order, the policy mass of those with visits (uct_context, tree.rs:49-66)
+            const float* policy = tree.net_policy.data() + c0;
+            if (tree.uct_scratch.size() < size_t(n) + 8) tree.uct_scratch.resize(size_t(n) + 8), tree.vis_policy.resize(size_t(n) + 8), tree.vis_out.resize(size_t(n) + 8), tree.vis_idx.resize(size_t(n) + 8), tree.vis_pos.resize(size_t(n) + 8);
+            int k = 0;
+            float mass = 0.0f;
+            for (int i = 0; i < n; i++) {
+                const int v = stat[i];
+                if (v == 0) continue;
+                tree.vis_idx[size_t(k)] = v, tree.vis_pos[size_t(k)] = i, tree.vis_policy[size_t(k)] = policy[i];
+                k++;
+                if (tree.pool[size_t(v)].complete + tree.pool[size_t(v)].virt > 0) mass += policy[i];
+            }
+            const UctContext ctx{uint64_t(pn.complete) + pn.virt, Tree<Game>::values(pn), mass};
             if (ctx.total_visits == 0) throw std::runtime_error("uct is NaN");  // node.rs:171-173
             const detail::UctParent up = tree.uct_parent(ctx, fpu, s, player);
-            if (tree.uct_scratch.size() < size_t(n)) tree.uct_scratch.resize(size_t(n));
             float* u = tree.uct_scratch.data();
-            detail::uct_many(tree.arrays(c0), n, up, s, player, u);
+            detail::uct_unvisited(policy, n, up, s, u);
+#if defined(__x86_64__)
+            static const bool have_avx2 = __builtin_cpu_supports("avx2");
+            if (have_avx2 && k > 2) {
+                for (int j = k; j < ((k + 7) & ~7); j++) tree.vis_idx[size_t(j)] = 0, tree.vis_policy[size_t(j)] = 0.0f;
+                detail::uct_visited_avx2(tree.pool.data(), tree.vis_idx.data(), tree.vis_policy.data(), k, up, s, player, tree.vis_out.data());
+                for (int j = 0; j < k; j++) u[tree.vis_pos[size_t(j)]] = tree.vis_out[size_t(j)];
+            } else
+#endif
+                for (int j = 0; j < k; j++)
+                    u[tree.vis_pos[size_t(j)]] = detail::uct_one(tree.pool[size_t(tree.vis_idx[size_t(j)])], tree.vis_policy[size_t(j)], up, s, player);
             float best = 0.0f;
             for (int i = 0; i < n; i++) {  // choose_max_by_key with random tie break, kz-util/src/sequence.rs:11-41
                 if (std::isnan(u[i])) throw std::runtime_error("uct is NaN");  // N32::from_inner panics on NaN
@@ -345,21 +420,21 @@ bool zero_step_gather(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Reque
             }
         }
         if (selected < 0) throw std::logic_error("Board is not done, this node should have a child");
-        cur = selected;
-        board.play(tree.last_move[size_t(cur)]);
+        board.play(tree.last_move[size_t(selected)]);
+        cur = tree.visit_child(cur, selected);
     }
 }
 
 // step.rs:140-167.  `policy` has one entry per child, in available_moves order.
 template <typename Game>
 void zero_step_apply(Tree<Game>& tree, int node, int next_player, const ValuesPov& values, const float* policy, size_t n_policy) {
-    const size_t i = size_t(node);
-    if (tree.has_net_values[i]) throw std::logic_error("Node was already evaluated by the network");
-    tree.has_net_values[i] = 1;
+    Visited& n = tree.pool[size_t(node)];
+    if (n.has_net_values) throw std::logic_error("Node was already evaluated by the network");
+    n.has_net_values = 1;
+    if (n.child_start < 0) throw std::logic_error("Applied node should have initialized children");
+    if (size_t(n.child_count) != n_policy) throw std::logic_error("Wrong children length");
+    std::memcpy(tree.net_policy.data() + n.child_start, policy, n_policy * sizeof(float));
     tree.propagate(node, un_pov(values, next_player));
-    if (tree.child_start[i] < 0) throw std::logic_error("Applied node should have initialized children");
-    if (size_t(tree.child_count[i]) != n_policy) throw std::logic_error("Wrong children length");
-    for (int c = 0; c < tree.child_count[i]; c++) tree.net_policy[size_t(tree.child_start[i] + c)] = policy[c];
 }
 
 // rust/kz-core/src/network/common.rs:133-163

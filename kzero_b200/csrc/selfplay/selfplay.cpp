@@ -19,6 +19,8 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <list>
@@ -26,6 +28,9 @@
 #include <mutex>
 #include <thread>
 #include <unordered_map>
+#if defined(__x86_64__)
+#include <x86intrin.h>
+#endif
 
 #include "../../../include/kzb200.h"
 #include "../executor.hpp"
@@ -41,45 +46,117 @@ namespace {
 
 std::atomic<bool> g_stop_requested{false};
 
+// KZB_SP_PROFILE=1: per-section cycle counts of the generator threads, printed when a run ends (host tuning aid)
+enum Section { kSecApply, kSecMove, kSecGather, kSecEncode, kSecQueue, kSecCount };
+const char* const kSectionNames[kSecCount] = {"apply answers", "pick move / new tree", "gather", "encode job", "enqueue"};
+struct SectionClock {
+    bool on = false;
+    uint64_t cycles[kSecCount] = {}, last = 0;
+    static uint64_t now() {
+#if defined(__x86_64__)
+        return __rdtsc();
+#else
+        return uint64_t(std::chrono::steady_clock::now().time_since_epoch().count());
+#endif
+    }
+    void start() { if (on) last = now(); }
+    void lap(Section s) {
+        if (!on) return;
+        const uint64_t t = now();
+        cycles[s] += t - last;
+        last = t;
+    }
+};
+std::mutex g_profile_mu;
+uint64_t g_profile_cycles[kSecCount];
+
 struct Eval {
     ValuesPov values;
     std::vector<float> policy;
 };
 
-// per-game LRU cache of evaluations keyed by the board hash (generator_alphazero.rs:68,77-79)
+// per-game LRU cache of evaluations keyed by the board hash (generator_alphazero.rs:68,77-79).  Flat storage: entries
+// live in one array, linked into the recency list and into hash chains by index, and keep their policy vector when they
+// are recycled -- a lookup or an insert allocates nothing once the cache is warm.
 class LruCache {
 public:
-    explicit LruCache(size_t cap) : cap_(cap) {}
-    const Eval* get(uint64_t key) {
-        auto it = map_.find(key);
-        if (it == map_.end()) return nullptr;
-        order_.splice(order_.begin(), order_, it->second);
-        return &it->second->second;
+    struct Entry {
+        uint64_t key = 0;
+        int32_t prev = -1, next = -1, chain = -1;
+        ValuesPov values;
+        std::vector<float> policy;
+    };
+    explicit LruCache(size_t cap) : cap_(cap) {
+        size_t buckets = 16;
+        while (buckets < cap * 2) buckets *= 2;
+        mask_ = buckets - 1;
+        if (cap_) heads_.assign(buckets, -1);
+        entries_.reserve(cap_);
     }
-    void put(uint64_t key, const Eval& e) {
-        if (cap_ == 0) return;
-        auto it = map_.find(key);
-        if (it != map_.end()) {
-            it->second->second = e;
-            order_.splice(order_.begin(), order_, it->second);
-            return;
+    const Entry* get(uint64_t key) {
+        if (cap_ == 0) return nullptr;
+        for (int32_t i = heads_[size_t(key) & mask_]; i >= 0; i = entries_[size_t(i)].chain)
+            if (entries_[size_t(i)].key == key) {
+                touch(i);
+                return &entries_[size_t(i)];
+            }
+        return nullptr;
+    }
+    // the entry for `key`, made most recent; the caller fills `values` and `policy`.  nullptr when the cache is disabled.
+    Entry* put(uint64_t key) {
+        if (cap_ == 0) return nullptr;
+        for (int32_t i = heads_[size_t(key) & mask_]; i >= 0; i = entries_[size_t(i)].chain)
+            if (entries_[size_t(i)].key == key) {
+                touch(i);
+                return &entries_[size_t(i)];
+            }
+        int32_t i;
+        if (entries_.size() < cap_) {
+            i = int32_t(entries_.size());
+            entries_.emplace_back();
+        } else {  // recycle the least recently used entry
+            i = tail_;
+            unlink(i);
+            int32_t* link = &heads_[size_t(entries_[size_t(i)].key) & mask_];
+            while (*link != i) link = &entries_[size_t(*link)].chain;
+            *link = entries_[size_t(i)].chain;
         }
-        order_.emplace_front(key, e);
-        map_[key] = order_.begin();
-        if (map_.size() > cap_) {
-            map_.erase(order_.back().first);
-            order_.pop_back();
-        }
+        Entry& e = entries_[size_t(i)];
+        e.key = key;
+        e.chain = heads_[size_t(key) & mask_];
+        heads_[size_t(key) & mask_] = i;
+        push_front(i);
+        return &e;
     }
     void clear() {
-        map_.clear();
-        order_.clear();
+        std::fill(heads_.begin(), heads_.end(), -1);
+        entries_.clear();
+        head_ = tail_ = -1;
     }
 
 private:
-    size_t cap_;
-    std::list<std::pair<uint64_t, Eval>> order_;
-    std::unordered_map<uint64_t, std::list<std::pair<uint64_t, Eval>>::iterator> map_;
+    void unlink(int32_t i) {
+        Entry& e = entries_[size_t(i)];
+        if (e.prev >= 0) entries_[size_t(e.prev)].next = e.next; else head_ = e.next;
+        if (e.next >= 0) entries_[size_t(e.next)].prev = e.prev; else tail_ = e.prev;
+    }
+    void push_front(int32_t i) {
+        Entry& e = entries_[size_t(i)];
+        e.prev = -1;
+        e.next = head_;
+        if (head_ >= 0) entries_[size_t(head_)].prev = i;
+        head_ = i;
+        if (tail_ < 0) tail_ = i;
+    }
+    void touch(int32_t i) {
+        if (head_ == i) return;
+        unlink(i);
+        push_front(i);
+    }
+    size_t cap_, mask_ = 0;
+    int32_t head_ = -1, tail_ = -1;
+    std::vector<int32_t> heads_;
+    std::vector<Entry> entries_;
 };
 
 SearchSettings search_settings(const kzb_selfplay_config& c) {
@@ -137,21 +214,31 @@ struct Slot {
     Job job;
     RecordedGame record;   // only filled when records are written
     Eval root_net_eval;    // the network's own evaluation of the root (generator_alphazero.rs:226-229)
-    Slot(uint64_t seed, size_t cache_size, size_t reserve_nodes)
+    Slot(uint64_t seed, size_t cache_size, size_t visits)
         : board(Game::start(seed)), cache(cache_size), rng(seed ^ 0x5EEDull), next_seed(seed + 0x1000) {
         tree = std::make_unique<Tree<Game>>(board);
-        tree->reserve(reserve_nodes);
+        tree->reserve(visits * 48 + 64, visits * 2 + 64);
     }
 };
 
+// generator_alphazero.rs:217-245.  `policy` is read-only (a slice of the job's answer or a cache entry); the copy that
+// temperature and noise need goes through `tmp`, and only when they actually change something.
 template <typename Game>
-void apply_eval(Slot<Game>& slot, const Request<Game>& req, Eval eval, const kzb_selfplay_config& c) {
-    // generator_alphazero.rs:217-245
-    if (req.node == 0) slot.root_net_eval = eval;  // before temperature and noise
-    const float temperature = req.node == 0 ? c.policy_temperature_root : c.policy_temperature_child;
-    policy_softmax_temperature_in_place(eval.policy.data(), eval.policy.size(), temperature);
-    if (req.node == 0) add_dirichlet_noise(eval.policy.data(), eval.policy.size(), c.dirichlet_alpha, c.dirichlet_eps, slot.rng);
-    zero_step_apply(*slot.tree, req.node, req.board.next_player(), eval.values, eval.policy.data(), eval.policy.size());
+void apply_eval(Slot<Game>& slot, const Request<Game>& req, const ValuesPov& values, const float* policy, size_t n,
+                const kzb_selfplay_config& c, std::vector<float>& tmp) {
+    const bool root = req.is_root();
+    if (root) {  // the network's own answer, before temperature and noise
+        slot.root_net_eval.values = values;
+        slot.root_net_eval.policy.assign(policy, policy + n);
+    }
+    const float temperature = root ? c.policy_temperature_root : c.policy_temperature_child;
+    if (temperature != 1.0f || root) {
+        tmp.assign(policy, policy + n);
+        policy_softmax_temperature_in_place(tmp.data(), n, temperature);
+        if (root) add_dirichlet_noise(tmp.data(), n, c.dirichlet_alpha, c.dirichlet_eps, slot.rng);
+        policy = tmp.data();
+    }
+    zero_step_apply(*slot.tree, req.node, req.board.next_player(), values, policy, n);
 }
 
 template <typename Game>
@@ -168,6 +255,9 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
     const GameShape shape = Game::shape();
     const int bits_bytes = shape.bits_bytes();
     std::vector<uint32_t> scratch;
+    std::vector<float> policy_tmp;
+    SectionClock clock;
+    clock.on = std::getenv("KZB_SP_PROFILE") != nullptr;
     try {
         while (!sh.stop.load(std::memory_order_relaxed)) {
             bool progressed = false;
@@ -175,18 +265,24 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                 Slot<Game>& slot = *sp;
                 if (slot.waiting) {
                     if (!slot.job.done.load(std::memory_order_acquire)) continue;
+                    clock.start();
                     // answers are back: cache + apply in request order (generator_alphazero.rs:206-210)
                     for (int i = 0; i < slot.job.n; i++) {
-                        Eval e;
                         const float* v = slot.job.values.data() + size_t(i) * 5;
-                        e.values = {v[0], v[1], v[2], v[3], v[4]};
-                        e.policy.assign(slot.job.probs.begin() + slot.job.mv_off[i], slot.job.probs.begin() + slot.job.mv_off[i + 1]);
-                        slot.cache.put(slot.requests[size_t(i)].board.hash(), e);
-                        apply_eval(slot, slot.requests[size_t(i)], std::move(e), c);
+                        const ValuesPov values{v[0], v[1], v[2], v[3], v[4]};
+                        const float* probs = slot.job.probs.data() + slot.job.mv_off[size_t(i)];
+                        const size_t count = slot.job.mv_off[size_t(i) + 1] - slot.job.mv_off[size_t(i)];
+                        if (LruCache::Entry* e = slot.cache.put(slot.requests[size_t(i)].board.hash())) {
+                            e->values = values;
+                            e->policy.assign(probs, probs + count);
+                        }
+                        apply_eval(slot, slot.requests[size_t(i)], values, probs, count, c, policy_tmp);
                     }
                     slot.waiting = false;
+                    clock.lap(kSecApply);
                 }
                 progressed = true;
+                clock.start();
                 Tree<Game>& tree = *slot.tree;
                 if (slot.target_visits == 0) {  // generator_alphazero.rs:88-94
                     slot.is_full_search = c.full_search_prob >= 1.0f || slot.rng.gen_bool(c.full_search_prob);
@@ -197,18 +293,18 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                     std::vector<float> policy;
                     tree.policy(policy);
                     const size_t pick = select_move(policy.data(), policy.size(), slot.move_count, c.temperature, uint32_t(c.zero_temp_move_count), slot.rng);
-                    const uint32_t mv = tree.last_move[size_t(tree.child_start[0]) + pick];
+                    const size_t c0 = size_t(tree.root().child_start), cn = size_t(tree.root().child_count);
+                    const uint32_t mv = tree.last_move[c0 + pick];
                     sh.root_visits.fetch_add(tree.root_visits(), std::memory_order_relaxed);
                     sh.moves.fetch_add(1, std::memory_order_relaxed);
                     if (sh.writer) {  // Position, generator_alphazero.rs:115-123
                         RecordedPosition rp;
                         encode_record(slot.board, shape, rp);
-                        const size_t c0 = size_t(tree.child_start[0]), cn = size_t(tree.child_count[0]);
                         for (size_t k = 0; k < cn; k++) rp.indices.push_back(slot.board.move_to_index(tree.last_move[c0 + k]));
                         rp.played_index = slot.board.move_to_index(mv);
                         rp.is_full_search = slot.is_full_search;
                         rp.zero_visits = tree.root_visits();
-                        rp.zero_values = pov(tree.values(0), slot.board.next_player());  // Tree::values, tree.rs:95-98
+                        rp.zero_values = pov(tree.root_values(), slot.board.next_player());  // Tree::values, tree.rs:95-98
                         rp.zero_policy = policy;
                         rp.net_values = slot.root_net_eval.values;
                         rp.net_policy = slot.root_net_eval.policy;
@@ -234,7 +330,8 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                         slot.cache.clear();  // a new cache for every game (generator_alphazero.rs:77-79)
                     }
                     slot.tree = std::make_unique<Tree<Game>>(slot.board);
-                    slot.tree->reserve(size_t(c.visits) * 48 + 64);
+                    slot.tree->reserve(size_t(c.visits) * 48 + 64, size_t(c.visits) * 2 + 64);
+                    clock.lap(kSecMove);
                     continue;
                 }
                 // collect a batch of requests (generator_alphazero.rs:165-201)
@@ -244,9 +341,9 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                 while (int(slot.requests.size()) < c.search_batch && terminal_gathers < c.search_batch) {
                     Request<Game> req;
                     if (zero_step_gather(tree, settings, slot.rng, req, scratch)) {
-                        if (const Eval* hit = slot.cache.get(req.board.hash())) {
+                        if (const LruCache::Entry* hit = slot.cache.get(req.board.hash())) {
                             cached++;
-                            apply_eval(slot, req, *hit, c);
+                            apply_eval(slot, req, hit->values, hit->policy.data(), hit->policy.size(), c, policy_tmp);
                         } else {
                             slot.requests.push_back(std::move(req));
                         }
@@ -255,6 +352,7 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                     }
                 }
                 if (cached) sh.cached_evals.fetch_add(cached, std::memory_order_relaxed);
+                clock.lap(kSecGather);
                 if (slot.requests.empty()) continue;
                 // encode the requests into one job
                 Job& job = slot.job;
@@ -262,21 +360,26 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                 job.owner = tid;
                 job.bits.resize(size_t(job.n) * bits_bytes);
                 job.scalars.resize(size_t(job.n) * shape.scalar_count);
-                job.mv_off.assign(1, 0);
-                job.mv_idx.clear();
+                job.mv_off.resize(size_t(job.n) + 1);
+                job.mv_off[0] = 0;
+                for (int i = 0; i < job.n; i++)
+                    job.mv_off[size_t(i) + 1] = job.mv_off[size_t(i)] + uint32_t(tree.pool[size_t(slot.requests[size_t(i)].node)].child_count);
+                job.mv_idx.resize(job.mv_off[size_t(job.n)]);
                 for (int i = 0; i < job.n; i++) {
                     const Game& b = slot.requests[size_t(i)].board;
                     b.encode(job.bits.data() + size_t(i) * bits_bytes, job.scalars.data() + size_t(i) * shape.scalar_count);
                     // the node's children were created from available_moves() in order (step.rs:89-97): their moves ARE the legal list
                     const int node = slot.requests[size_t(i)].node;
-                    const size_t c0 = size_t(tree.child_start[size_t(node)]), cn = size_t(tree.child_count[size_t(node)]);
-                    for (size_t k = 0; k < cn; k++) job.mv_idx.push_back(b.move_to_index(tree.last_move[c0 + k]));
-                    job.mv_off.push_back(uint32_t(job.mv_idx.size()));
+                    const uint32_t* mv = tree.last_move.data() + size_t(tree.pool[size_t(node)].child_start);
+                    uint32_t* idx = job.mv_idx.data() + job.mv_off[size_t(i)];
+                    const size_t cn = size_t(tree.pool[size_t(node)].child_count);
+                    for (size_t k = 0; k < cn; k++) idx[k] = b.move_to_index(mv[k]);
                 }
                 job.values.resize(size_t(job.n) * 5);
                 job.probs.resize(job.mv_idx.size());
                 job.done.store(0, std::memory_order_relaxed);
                 slot.waiting = true;
+                clock.lap(kSecEncode);
                 bool wake;
                 {
                     std::lock_guard<std::mutex> lk(sh.mu);
@@ -286,6 +389,7 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                     wake = sh.queued_positions >= size_t(c.gpu_batch) || sh.queue.size() >= sh.job_count;
                 }
                 if (wake) sh.cv.notify_one();
+                clock.lap(kSecQueue);
             }
             if (!progressed) {
                 std::unique_lock<std::mutex> lk(*sh.gen_mu[size_t(tid)]);
@@ -297,6 +401,10 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
         if (sh.error.empty()) sh.error = std::string("generator thread: ") + e.what();
         sh.stop.store(true);
         sh.cv.notify_all();
+    }
+    if (clock.on) {
+        std::lock_guard<std::mutex> lk(g_profile_mu);
+        for (int i = 0; i < kSecCount; i++) g_profile_cycles[i] += clock.cycles[i];
     }
 }
 
@@ -347,10 +455,30 @@ void executor_main(Net* net, Shared& sh, const kzb_selfplay_config& c, const Gam
                 net->eval_packed(bits.data(), scalars.data(), int(n), mv_idx.data(), mv_off.data(), values.data(), probs.data());
             } else {
                 for (size_t i = 0; i < n; i++) {
+                    const uint32_t cnt = mv_off[i + 1] - mv_off[i];
+                    float* p = probs.data() + mv_off[i];
+                    if (c.dummy_network == 2) {  // a deterministic pseudo-network: sharp, position-dependent answers
+                        uint64_t h = 0xCBF29CE484222325ull;
+                        for (int k = 0; k < bits_bytes; k += 8) {
+                            uint64_t w = 0;
+                            std::memcpy(&w, bits.data() + i * bits_bytes + k, size_t(std::min(8, bits_bytes - k)));
+                            h = splitmix64(h ^ w);
+                        }
+                        float sum = 0.0f;
+                        for (uint32_t k = 0; k < cnt; k++) {
+                            const float u = float((splitmix64(h + k + 1) >> 40) % 1000 + 1) * 1e-3f;
+                            p[k] = u * u * u * u;
+                            sum += p[k];
+                        }
+                        for (uint32_t k = 0; k < cnt; k++) p[k] /= sum;
+                        const float val = float(int((splitmix64(h ^ 0xABCDull) >> 40) % 2001) - 1000) / 1000.0f;
+                        const float v[5] = {val, (1.0f + val) * 0.4f, 0.2f, (1.0f - val) * 0.4f, float((h >> 50) % 50)};
+                        std::memcpy(values.data() + i * 5, v, sizeof(v));
+                        continue;
+                    }
                     const float v[5] = {0.0f, 1.0f / 3.0f, 1.0f / 3.0f, 1.0f / 3.0f, 0.0f};
                     std::memcpy(values.data() + i * 5, v, sizeof(v));
-                    const uint32_t cnt = mv_off[i + 1] - mv_off[i];
-                    for (uint32_t k = 0; k < cnt; k++) probs[mv_off[i] + k] = 1.0f / float(cnt);
+                    for (uint32_t k = 0; k < cnt; k++) p[k] = 1.0f / float(cnt);
                 }
             }
             row = 0;
@@ -401,12 +529,13 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
     sh.job_count = size_t(std::max(1, c.gpu_batch / std::max(1, c.search_batch)));
     std::vector<std::vector<std::unique_ptr<Slot<Game>>>> per_thread(size_t(c.cpu_threads));
     for (int g = 0; g < games; g++)
-        per_thread[size_t(g % c.cpu_threads)].push_back(std::make_unique<Slot<Game>>(c.seed * 1000003ull + uint64_t(g) * 7919ull + 1, size_t(c.cache_size), size_t(c.visits) * 48 + 64));
+        per_thread[size_t(g % c.cpu_threads)].push_back(std::make_unique<Slot<Game>>(c.seed * 1000003ull + uint64_t(g) * 7919ull + 1, size_t(c.cache_size), size_t(c.visits)));
     for (int t = 0; t < c.cpu_threads; t++) {
         sh.gen_mu.push_back(std::make_unique<std::mutex>());
         sh.gen_cv.push_back(std::make_unique<std::condition_variable>());
     }
     g_stop_requested.store(false);
+    for (auto& v : g_profile_cycles) v = 0;
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<std::thread> threads;
     for (int i = 0; i < c.gpu_threads; i++) threads.emplace_back([&, i] { executor_main(c.dummy_network ? nullptr : nets[size_t(i)].get(), sh, c, shape); });
@@ -423,6 +552,11 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
     for (auto& t : threads) t.join();
     const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (sh.writer) sh.writer->finish();
+    if (std::getenv("KZB_SP_PROFILE")) {
+        const double nodes = double(sh.real_evals.load() + sh.cached_evals.load());
+        for (int i = 0; i < kSecCount; i++)
+            std::fprintf(stderr, "[kzb selfplay] %-22s %8.1f cycles / node\n", kSectionNames[i], double(g_profile_cycles[i]) / std::max(nodes, 1.0));
+    }
     if (!sh.error.empty()) throw std::runtime_error(sh.error);
     out.seconds = seconds;
     out.games_written = sh.writer ? sh.writer->game_count() : 0;
@@ -477,7 +611,7 @@ void trace_search(const kzb_selfplay_config& c, uint64_t game_seed, int plies, i
     }
     if (board.done()) throw std::runtime_error("trace: the game ended before the requested ply");
     Tree<Game> tree(board);
-    tree.reserve(size_t(c.visits) * 48 + 64);
+    tree.reserve(size_t(c.visits) * 48 + 64, size_t(c.visits) * 2 + 64);
     std::vector<Request<Game>> requests;
     uint64_t evals = 0;
     while (tree.root_visits() < uint64_t(c.visits)) {  // build_tree, generator_alphazero.rs:151-215 without the cache
@@ -490,28 +624,28 @@ void trace_search(const kzb_selfplay_config& c, uint64_t game_seed, int plies, i
         }
         for (auto& req : requests) {
             Eval e = pseudo_eval(req.board, eval_kind, scratch);
-            const float t = req.node == 0 ? c.policy_temperature_root : c.policy_temperature_child;
+            const float t = req.is_root() ? c.policy_temperature_root : c.policy_temperature_child;
             policy_softmax_temperature_in_place(e.policy.data(), e.policy.size(), t);
             zero_step_apply(tree, req.node, req.board.next_player(), e.values, e.policy.data(), e.policy.size());
             evals++;
         }
     }
-    const int n_children = tree.child_count[0];
+    const int n_children = tree.root().child_count;
     if (n_children > out.capacity) throw std::runtime_error("trace: child capacity too small");
     out.n_children = n_children;
     for (int i = 0; i < n_children; i++) {
-        const size_t ch = size_t(tree.child_start[0] + i);
-        out.child_visits[i] = tree.complete[ch];
+        const size_t ch = size_t(tree.root().child_start + i);
+        out.child_visits[i] = tree.child_visits(int(ch));
         out.child_moves[i] = tree.last_move[ch];
         out.child_policy[i] = tree.net_policy[ch];
     }
-    const ValuesPov v = pov(tree.values(0), board.next_player());
+    const ValuesPov v = pov(tree.root_values(), board.next_player());
     out.root_values[0] = v.value;
     out.root_values[1] = v.win;
     out.root_values[2] = v.draw;
     out.root_values[3] = v.loss;
     out.root_values[4] = v.moves_left;
-    out.root_visits = tree.complete[0];
+    out.root_visits = tree.root_visits();
     out.tree_nodes = tree.size();
     out.evals = evals;
 }
