@@ -383,13 +383,20 @@ bool zero_step_gather(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Reque
             const float* policy = tree.net_policy.data() + c0;
             if (tree.uct_scratch.size() < size_t(n) + 8) tree.uct_scratch.resize(size_t(n) + 8), tree.vis_policy.resize(size_t(n) + 8), tree.vis_out.resize(size_t(n) + 8), tree.vis_idx.resize(size_t(n) + 8), tree.vis_pos.resize(size_t(n) + 8);
             int k = 0;
+            {
+                int32_t* vis_idx = tree.vis_idx.data();
+                int32_t* vis_pos = tree.vis_pos.data();
+                float* vis_policy = tree.vis_policy.data();
+                for (int i = 0; i < n; i++) {  // branch-free compaction: always write, advance only past visited children
+                    const int v = stat[i];
+                    vis_idx[k] = v, vis_pos[k] = i, vis_policy[k] = policy[i];
+                    k += v != 0;
+                }
+            }
             float mass = 0.0f;
-            for (int i = 0; i < n; i++) {
-                const int v = stat[i];
-                if (v == 0) continue;
-                tree.vis_idx[size_t(k)] = v, tree.vis_pos[size_t(k)] = i, tree.vis_policy[size_t(k)] = policy[i];
-                k++;
-                if (tree.pool[size_t(v)].complete + tree.pool[size_t(v)].virt > 0) mass += policy[i];
+            for (int j = 0; j < k; j++) {
+                const Visited& ch = tree.pool[size_t(tree.vis_idx[size_t(j)])];
+                if (ch.complete + ch.virt > 0) mass += tree.vis_policy[size_t(j)];
             }
             const UctContext ctx{uint64_t(pn.complete) + pn.virt, Tree<Game>::values(pn), mass};
             if (ctx.total_visits == 0) throw std::runtime_error("uct is NaN");  // node.rs:171-173
@@ -406,18 +413,27 @@ bool zero_step_gather(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Reque
 #endif
                 for (int j = 0; j < k; j++)
                     u[tree.vis_pos[size_t(j)]] = detail::uct_one(tree.pool[size_t(tree.vis_idx[size_t(j)])], tree.vis_policy[size_t(j)], up, s, player);
-            float best = 0.0f;
-            for (int i = 0; i < n; i++) {  // choose_max_by_key with random tie break, kz-util/src/sequence.rs:11-41
-                if (std::isnan(u[i])) throw std::runtime_error("uct is NaN");  // N32::from_inner panics on NaN
-                if (selected < 0 || u[i] > best) {
-                    selected = c0 + i;
-                    best = u[i];
-                    ties = 1;
-                } else if (u[i] == best) {
+            // choose_max_by_key with random tie break, kz-util/src/sequence.rs:11-41.  The running maximum is kept with
+            // selects (the "new best" branch is unpredictable); only an exact tie, which is rare, branches.
+            float best = u[0];
+            int arg = 0;
+            bool nan = u[0] != u[0];
+            ties = 1;
+            for (int i = 1; i < n; i++) {
+                const float x = u[i];
+                nan |= x != x;
+                if (__builtin_expect(x == best, 0)) {
                     ties++;
-                    if (rng.gen_range(ties) == 0) selected = c0 + i;
+                    if (rng.gen_range(ties) == 0) arg = i;
+                    continue;
                 }
+                const bool gt = x > best;
+                best = gt ? x : best;
+                arg = gt ? i : arg;
+                ties = gt ? 1u : ties;
             }
+            if (nan) throw std::runtime_error("uct is NaN");  // N32::from_inner panics on NaN
+            selected = c0 + arg;
         }
         if (selected < 0) throw std::logic_error("Board is not done, this node should have a child");
         board.play(tree.last_move[size_t(selected)]);
