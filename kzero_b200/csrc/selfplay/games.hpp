@@ -54,9 +54,14 @@ struct SynthChess {
         return (b + j * a) % 1880;
     }
     void moves(std::vector<uint32_t>& out) const {  // a move IS its policy index
-        const uint32_t n = move_count();
+        const uint32_t n = move_count(), a = 3 + 10 * uint32_t((h >> 8) & 3);
         out.resize(n);
-        for (uint32_t j = 0; j < n; j++) out[j] = index_of(j);
+        uint32_t idx = uint32_t((h >> 16) % 1880);  // index_of(j), stepped instead of recomputed
+        for (uint32_t j = 0; j < n; j++) {
+            out[j] = idx;
+            idx += a;
+            idx -= idx >= 1880 ? 1880 : 0;
+        }
     }
     uint32_t move_to_index(uint32_t mv) const { return mv; }
     void play(uint32_t mv) {
@@ -69,15 +74,11 @@ struct SynthChess {
         uint64_t occupied = 0, s = h;
         for (int piece = 0; piece < 12; piece++) {
             const int count = (piece % 6 == 0) ? 6 : (piece % 6 == 5 ? 1 : 2);
+            s = splitmix64(s);  // one hash per piece type; its 6-bit fields are the squares
             uint64_t bb = 0;
-            for (int k = 0; k < count; k++) {
-                s = splitmix64(s);
-                const uint64_t sq = s & 63;
-                if (!((occupied >> sq) & 1)) {
-                    occupied |= 1ull << sq;
-                    bb |= 1ull << sq;
-                }
-            }
+            for (int k = 0; k < count; k++) bb |= 1ull << ((s >> (6 * k)) & 63);
+            bb &= ~occupied;
+            occupied |= bb;
             std::memcpy(bits + piece * 8, &bb, 8);  // BitBuffer::push_block: little-endian u64, bit_buffer.rs:37-55
         }
         const int stm = next_player();

@@ -226,6 +226,49 @@ inline void uct_unvisited(const float* policy, int n, const UctParent& up, const
 #endif
     uct_unvisited_generic(policy, n, q, w.exploration_weight, up.sqrt_visits, ml_term, out);
 }
+// The scalar rule; `best` / `arg` / `ties` carry the running state so that a caller can skip elements it knows to be
+// smaller than the running best.
+inline void argmax_scan(const float* u, int begin, int end, float& best, int& arg, uint32_t& ties, bool& nan, Rng& rng) {
+    for (int i = begin; i < end; i++) {
+        const float x = u[i];
+        nan |= x != x;
+        if (__builtin_expect(x == best, 0)) {
+            ties++;
+            if (rng.gen_range(ties) == 0) arg = i;
+            continue;
+        }
+        const bool gt = x > best;  // selects, not a branch: "new best" is unpredictable
+        best = gt ? x : best;
+        arg = gt ? i : arg;
+        ties = gt ? 1u : ties;
+    }
+}
+#if defined(__x86_64__)
+// 8 elements at a time: a block with no element >= the running best (and no NaN) cannot change anything and is skipped
+__attribute__((target("avx2"))) inline void argmax_blocks_avx2(const float* u, int begin, int n, float& best, int& arg, uint32_t& ties, bool& nan, Rng& rng) {
+    int i = begin;
+    for (; i + 8 <= n; i += 8) {
+        const __m256 x = _mm256_loadu_ps(u + i);
+        if (_mm256_movemask_ps(_mm256_cmp_ps(x, _mm256_set1_ps(best), _CMP_NLT_UQ)) == 0) continue;  // NLT_UQ: x >= best or unordered
+        argmax_scan(u, i, i + 8, best, arg, ties, nan, rng);
+    }
+    argmax_scan(u, i, n, best, arg, ties, nan, rng);
+}
+#endif
+inline int argmax_random_ties(const float* u, int n, Rng& rng) {
+    float best = u[0];
+    int arg = 0;
+    uint32_t ties = 1;
+    bool nan = u[0] != u[0];
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) argmax_blocks_avx2(u, 1, n, best, arg, ties, nan, rng);
+    else
+#endif
+        argmax_scan(u, 1, n, best, arg, ties, nan, rng);
+    if (nan) throw std::runtime_error("uct is NaN");  // N32::from_inner panics on NaN
+    return arg;
+}
 }  // namespace detail
 
 template <typename Game>
@@ -326,21 +369,41 @@ struct Tree {
 template <typename Game>
 struct Request {
     int node = -1;  // pool index of the node to evaluate
+    int child_start = 0, child_count = 0;  // its freshly created child slots
     Game board;
     bool is_root() const { return node == Tree<Game>::kRoot; }
 };
 
-// step.rs:61-135.  Returns true and fills `req` when an un-evaluated node was reached; false when a terminal node
-// was reached (its outcome has been propagated).
+// One in-flight zero_step_gather (step.rs:61-135), advanced one tree level per descent_step call so that a caller can
+// interleave the descents of several trees: each step ends by prefetching the child slices the next step will scan, and
+// the cache misses of one tree overlap the arithmetic of the others.
 template <typename Game>
-bool zero_step_gather(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Request<Game>& req, std::vector<uint32_t>& scratch) {
+struct Descent {
     int cur = Tree<Game>::kRoot;
-    Game board = tree.root_board;
-    while (true) {
+    Game board;
+    void begin(const Tree<Game>& tree) {
+        cur = Tree<Game>::kRoot;
+        board = tree.root_board;
+    }
+};
+enum class StepResult { kDescend, kRequest, kTerminal };
+
+inline void prefetch_span(const void* p, size_t bytes) {
+    const char* c = static_cast<const char*>(p);
+    for (size_t o = 0; o < bytes + 63; o += 64) __builtin_prefetch(c + o);
+}
+
+// kRequest: an un-evaluated node was reached and `req` is filled; kTerminal: a terminal node was reached and its outcome
+// has been propagated; kDescend: moved one level down, call again.
+template <typename Game>
+StepResult descent_step(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Descent<Game>& d, Request<Game>& req, std::vector<uint32_t>& scratch) {
+    int& cur = d.cur;
+    Game& board = d.board;
+    {
         tree.pool[size_t(cur)].virt += 1;
         if (board.done()) {
             tree.propagate(cur, ValuesAbs::from_outcome(board.outcome(), 0.0f));
-            return false;
+            return StepResult::kTerminal;
         }
         if (tree.pool[size_t(cur)].child_start < 0) {
             // initialise the children with a uniform policy, step.rs:84-103
@@ -352,8 +415,10 @@ bool zero_step_gather(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Reque
             n.child_count = int(scratch.size());
             n.has_net_values = 0;
             req.node = cur;
+            req.child_start = start;
+            req.child_count = n.child_count;
             req.board = board;
-            return true;
+            return StepResult::kRequest;
         }
         const Visited& pn = tree.pool[size_t(cur)];
         const int c0 = pn.child_start, n = pn.child_count;
@@ -413,31 +478,31 @@ bool zero_step_gather(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Reque
 #endif
                 for (int j = 0; j < k; j++)
                     u[tree.vis_pos[size_t(j)]] = detail::uct_one(tree.pool[size_t(tree.vis_idx[size_t(j)])], tree.vis_policy[size_t(j)], up, s, player);
-            // choose_max_by_key with random tie break, kz-util/src/sequence.rs:11-41.  The running maximum is kept with
-            // selects (the "new best" branch is unpredictable); only an exact tie, which is rare, branches.
-            float best = u[0];
-            int arg = 0;
-            bool nan = u[0] != u[0];
-            ties = 1;
-            for (int i = 1; i < n; i++) {
-                const float x = u[i];
-                nan |= x != x;
-                if (__builtin_expect(x == best, 0)) {
-                    ties++;
-                    if (rng.gen_range(ties) == 0) arg = i;
-                    continue;
-                }
-                const bool gt = x > best;
-                best = gt ? x : best;
-                arg = gt ? i : arg;
-                ties = gt ? 1u : ties;
-            }
-            if (nan) throw std::runtime_error("uct is NaN");  // N32::from_inner panics on NaN
-            selected = c0 + arg;
+            // choose_max_by_key with random tie break, kz-util/src/sequence.rs:11-41: a later element replaces the running
+            // best when it is greater, and with probability 1/ties when it is equal.
+            selected = c0 + detail::argmax_random_ties(u, n, rng);
         }
         if (selected < 0) throw std::logic_error("Board is not done, this node should have a child");
         board.play(tree.last_move[size_t(selected)]);
         cur = tree.visit_child(cur, selected);
+        const Visited& next = tree.pool[size_t(cur)];
+        if (next.child_start >= 0) {
+            prefetch_span(tree.stat.data() + next.child_start, size_t(next.child_count) * 4);
+            prefetch_span(tree.net_policy.data() + next.child_start, size_t(next.child_count) * 4);
+        }
+        return StepResult::kDescend;
+    }
+}
+
+// step.rs:61-135 in one go.  Returns true and fills `req` when an un-evaluated node was reached; false when a terminal
+// node was reached (its outcome has been propagated).
+template <typename Game>
+bool zero_step_gather(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Request<Game>& req, std::vector<uint32_t>& scratch) {
+    Descent<Game> d;
+    d.begin(tree);
+    while (true) {
+        const StepResult r = descent_step(tree, s, rng, d, req, scratch);
+        if (r != StepResult::kDescend) return r == StepResult::kRequest;
     }
 }
 

@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <deque>
 #include <list>
 #include <memory>
@@ -69,6 +70,12 @@ struct SectionClock {
 };
 std::mutex g_profile_mu;
 uint64_t g_profile_cycles[kSecCount];
+double g_profile_cpu_s[2];  // CPU seconds of the generator / executor threads
+double thread_cpu_seconds() {
+    timespec ts;
+    clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+    return double(ts.tv_sec) + 1e-9 * double(ts.tv_nsec);
+}
 
 struct Eval {
     ValuesPov values;
@@ -92,6 +99,9 @@ public:
         mask_ = buckets - 1;
         if (cap_) heads_.assign(buckets, -1);
         entries_.reserve(cap_);
+    }
+    void prefetch(uint64_t key) const {
+        if (cap_) __builtin_prefetch(&heads_[size_t(key) & mask_]);
     }
     const Entry* get(uint64_t key) {
         if (cap_ == 0) return nullptr;
@@ -266,6 +276,17 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                 if (slot.waiting) {
                     if (!slot.job.done.load(std::memory_order_acquire)) continue;
                     clock.start();
+                    // the lines the loop below will write were last touched a GPU round trip ago: ask for all of them
+                    // up front so that their misses overlap instead of queueing up one request at a time
+                    prefetch_span(slot.job.probs.data(), slot.job.probs.size() * 4);  // written by the executor's core
+                    prefetch_span(slot.job.values.data(), slot.job.values.size() * 4);
+                    for (int i = 0; i < slot.job.n; i++) {
+                        const Request<Game>& req = slot.requests[size_t(i)];
+                        const Visited& node = slot.tree->pool[size_t(req.node)];
+                        __builtin_prefetch(&node, 1);
+                        slot.cache.prefetch(req.board.hash());
+                        prefetch_span(slot.tree->net_policy.data() + req.child_start, size_t(req.child_count) * 4);
+                    }
                     // answers are back: cache + apply in request order (generator_alphazero.rs:206-210)
                     for (int i = 0; i < slot.job.n; i++) {
                         const float* v = slot.job.values.data() + size_t(i) * 5;
@@ -405,6 +426,7 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
     if (clock.on) {
         std::lock_guard<std::mutex> lk(g_profile_mu);
         for (int i = 0; i < kSecCount; i++) g_profile_cycles[i] += clock.cycles[i];
+        g_profile_cpu_s[0] += thread_cpu_seconds();
     }
 }
 
@@ -418,6 +440,10 @@ void executor_main(Net* net, Shared& sh, const kzb_selfplay_config& c, const Gam
     std::vector<float> scalars(size_t(c.gpu_batch) * shape.scalar_count), values(size_t(c.gpu_batch) * 5), probs;
     std::vector<uint32_t> mv_idx, mv_off;
     std::vector<Job*> jobs;
+    // KZB_SP_DUMMY_LATENCY_US: make the dummy network take as long as a GPU evaluation would, so that a host-only run batches
+    // like a real one (profiling aid)
+    const char* latency_env = std::getenv("KZB_SP_DUMMY_LATENCY_US");
+    const long dummy_latency_us = latency_env ? std::atol(latency_env) : 0;
     try {
         while (true) {
             jobs.clear();
@@ -429,7 +455,7 @@ void executor_main(Net* net, Shared& sh, const kzb_selfplay_config& c, const Gam
                 sh.cv.wait_for(lk, std::chrono::microseconds(200), [&] {
                     return sh.stop.load() || sh.queued_positions >= size_t(c.gpu_batch) || sh.queue.size() >= job_count;
                 });
-                if (sh.stop.load()) return;
+                if (sh.stop.load()) break;
                 while (!sh.queue.empty() && n + size_t(sh.queue.front()->n) <= size_t(c.gpu_batch)) {
                     Job* j = sh.queue.front();
                     sh.queue.pop_front();
@@ -454,6 +480,7 @@ void executor_main(Net* net, Shared& sh, const kzb_selfplay_config& c, const Gam
             if (net) {
                 net->eval_packed(bits.data(), scalars.data(), int(n), mv_idx.data(), mv_off.data(), values.data(), probs.data());
             } else {
+                if (dummy_latency_us > 0) std::this_thread::sleep_for(std::chrono::microseconds(dummy_latency_us));
                 for (size_t i = 0; i < n; i++) {
                     const uint32_t cnt = mv_off[i + 1] - mv_off[i];
                     float* p = probs.data() + mv_off[i];
@@ -508,6 +535,10 @@ void executor_main(Net* net, Shared& sh, const kzb_selfplay_config& c, const Gam
         sh.stop.store(true);
         sh.cv.notify_all();
     }
+    if (std::getenv("KZB_SP_PROFILE")) {
+        std::lock_guard<std::mutex> lk(g_profile_mu);
+        g_profile_cpu_s[1] += thread_cpu_seconds();
+    }
 }
 
 template <typename Game>
@@ -536,6 +567,7 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
     }
     g_stop_requested.store(false);
     for (auto& v : g_profile_cycles) v = 0;
+    g_profile_cpu_s[0] = g_profile_cpu_s[1] = 0.0;
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<std::thread> threads;
     for (int i = 0; i < c.gpu_threads; i++) threads.emplace_back([&, i] { executor_main(c.dummy_network ? nullptr : nets[size_t(i)].get(), sh, c, shape); });
@@ -556,6 +588,8 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
         const double nodes = double(sh.real_evals.load() + sh.cached_evals.load());
         for (int i = 0; i < kSecCount; i++)
             std::fprintf(stderr, "[kzb selfplay] %-22s %8.1f cycles / node\n", kSectionNames[i], double(g_profile_cycles[i]) / std::max(nodes, 1.0));
+        std::fprintf(stderr, "[kzb selfplay] thread CPU time: generators %.3f us / node, executors %.3f us / node\n",
+                     1e6 * g_profile_cpu_s[0] / std::max(nodes, 1.0), 1e6 * g_profile_cpu_s[1] / std::max(nodes, 1.0));
     }
     if (!sh.error.empty()) throw std::runtime_error(sh.error);
     out.seconds = seconds;

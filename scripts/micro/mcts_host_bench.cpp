@@ -18,6 +18,8 @@ struct Slot {
     std::unique_ptr<Tree<Game>> tree;
     Rng rng;
     std::vector<Request<Game>> requests;
+    Descent<Game> descent;
+    int terminal = 0;
     uint64_t seed;
     explicit Slot(uint64_t s) : board(Game::start(s)), rng(s), seed(s) { reset(); }
     void reset() {
@@ -29,6 +31,8 @@ struct Slot {
 int main(int argc, char** argv) {
     const int slots_n = argc > 1 ? atoi(argv[1]) : 48, visits = argc > 2 ? atoi(argv[2]) : 800;
     const double seconds = argc > 3 ? atof(argv[3]) : 4.0;
+    const int group_n = argc > 4 ? atoi(argv[4]) : 1;  // trees whose descents are interleaved
+    std::vector<Slot*> group;
     SearchSettings settings;
     std::vector<std::unique_ptr<Slot>> slots;
     for (int i = 0; i < slots_n; i++) slots.push_back(std::make_unique<Slot>(uint64_t(i) * 7919 + 1));
@@ -71,13 +75,38 @@ int main(int argc, char** argv) {
                 s.reset();
                 continue;
             }
-            int terminal = 0;
-            while (int(s.requests.size()) < 16 && terminal < 16) {
-                Request<Game> req;
-                gathers++;
-                if (zero_step_gather(tree, settings, s.rng, req, scratch)) s.requests.push_back(std::move(req));
-                else terminal++;
+            if (group_n <= 1) {
+                int terminal = 0;
+                while (int(s.requests.size()) < 16 && terminal < 16) {
+                    Request<Game> req;
+                    gathers++;
+                    if (zero_step_gather(tree, settings, s.rng, req, scratch)) s.requests.push_back(std::move(req));
+                    else terminal++;
+                }
+                cyc_gather += __rdtsc() - c1;
+                continue;
             }
+            s.terminal = 0;
+            s.descent.begin(tree);
+            group.push_back(&s);
+            if (int(group.size()) < group_n && &sp != &slots.back()) continue;
+            c1 = __rdtsc();
+            size_t active = group.size();
+            while (active) {
+                for (size_t g = 0; g < group.size(); g++) {
+                    Slot* gs = group[g];
+                    if (!gs) continue;
+                    Request<Game> req;
+                    const StepResult r = descent_step(*gs->tree, settings, gs->rng, gs->descent, req, scratch);
+                    if (r == StepResult::kDescend) continue;
+                    gathers++;
+                    if (r == StepResult::kRequest) gs->requests.push_back(std::move(req));
+                    else gs->terminal++;
+                    if (int(gs->requests.size()) < 16 && gs->terminal < 16) gs->descent.begin(*gs->tree);
+                    else group[g] = nullptr, active--;
+                }
+            }
+            group.clear();
             cyc_gather += __rdtsc() - c1;
         }
         el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
