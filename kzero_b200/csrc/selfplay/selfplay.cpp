@@ -195,6 +195,7 @@ struct Shared {
     std::condition_variable cv;
     std::deque<Job*> queue;
     size_t queued_positions = 0;
+    int executors_busy = 0;  // executors between taking a batch and having its answers (guarded by mu)
     std::atomic<bool> stop{false};
     size_t job_count = 1;  // RunCondition::JobCount
     std::string error;
@@ -450,11 +451,16 @@ void executor_main(Net* net, Shared& sh, const kzb_selfplay_config& c, const Gam
             size_t n = 0;
             {
                 std::unique_lock<std::mutex> lk(sh.mu);
-                // executor.rs:240-253 should_eval: a full batch, or JobCount jobs queued; plus a short timeout so that the
-                // last few games of a run (fewer than JobCount producers left) still get answers
-                sh.cv.wait_for(lk, std::chrono::microseconds(200), [&] {
-                    return sh.stop.load() || sh.queued_positions >= size_t(c.gpu_batch) || sh.queue.size() >= job_count;
-                });
+                // executor.rs:240-253 should_eval: a full batch, or JobCount jobs queued.  A partial batch is taken only
+                // when no executor has work on the GPU -- then waiting buys nothing, and the last few games of a run
+                // (fewer than JobCount producers left) still get answers; while the GPU is busy a partial batch would
+                // only spend a launch on fewer positions.
+                while (true) {
+                    const bool full = sh.cv.wait_for(lk, std::chrono::microseconds(200), [&] {
+                        return sh.stop.load() || sh.queued_positions >= size_t(c.gpu_batch) || sh.queue.size() >= job_count;
+                    });
+                    if (full || (!sh.queue.empty() && sh.executors_busy == 0)) break;
+                }
                 if (sh.stop.load()) break;
                 while (!sh.queue.empty() && n + size_t(sh.queue.front()->n) <= size_t(c.gpu_batch)) {
                     Job* j = sh.queue.front();
@@ -463,6 +469,7 @@ void executor_main(Net* net, Shared& sh, const kzb_selfplay_config& c, const Gam
                     n += size_t(j->n);
                     jobs.push_back(j);
                 }
+                if (!jobs.empty()) sh.executors_busy++;
             }
             if (jobs.empty()) continue;
             mv_off.assign(1, 0);
@@ -507,6 +514,10 @@ void executor_main(Net* net, Shared& sh, const kzb_selfplay_config& c, const Gam
                     std::memcpy(values.data() + i * 5, v, sizeof(v));
                     for (uint32_t k = 0; k < cnt; k++) p[k] = 1.0f / float(cnt);
                 }
+            }
+            {
+                std::lock_guard<std::mutex> lk(sh.mu);
+                sh.executors_busy--;
             }
             row = 0;
             for (Job* j : jobs) {

@@ -27,7 +27,7 @@ ap.add_argument("--visits", type=int, default=800)
 ap.add_argument("--search-batch", type=int, default=16)
 ap.add_argument("--gpu-batch", type=int, default=1024)
 ap.add_argument("--cpu-threads", type=int, default=0, help="0 = host cores / replicas")
-ap.add_argument("--gpu-threads", type=int, default=2)
+ap.add_argument("--gpu-threads", type=int, default=3, help="executor threads, one network instance each")
 ap.add_argument("--concurrent-games", type=int, default=0)
 args = ap.parse_args()
 
@@ -38,19 +38,22 @@ if ctx.world > 1:
 
     torch.cuda.set_device(ctx.local_rank)
     dist = replicas.init_process_group(ctx, "nccl", torch.device("cuda", ctx.local_rank))
-cores = os.cpu_count() or 1
+cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)  # honours taskset
 share = max(1, cores // ctx.world)  # host cores of this replica
 # plenty of cores: executors spin (lowest latency) on cores of their own; few cores: they sleep on a blocking event and
 # every core runs a generator
-blocking = share < 4 * args.gpu_threads + 4
-cpu_threads = args.cpu_threads or (share if blocking else share - args.gpu_threads)
+blocking = share < 12
+# three executors: while one scatters answers and the next assembles its batch, a third already has work queued on the
+# GPU (measured: 1.62 M nodes/s with 2 executors on 4 cores, 2.03 M with 3 -- profiles/r01d_selfplay_host.md)
+gpu_threads = args.gpu_threads
+cpu_threads = args.cpu_threads or (share if blocking else share - gpu_threads)
 if args.game == "chess":
     spec, depth, channels, game = netgen.game_spec("chess"), 16, 128, selfplay.GAME_SYNTH_CHESS
 else:
     spec, depth, channels, game = netgen.game_spec("ataxx-7"), 8, 64, selfplay.GAME_ATAXX7
 onnx_bytes = netgen.build_onnx(spec, depth, channels, seed=0)
 cfg = selfplay.default_config(game=game, visits=args.visits, search_batch=args.search_batch, gpu_batch=args.gpu_batch,
-                              cpu_threads=cpu_threads, gpu_threads=args.gpu_threads, concurrent_games=args.concurrent_games,
+                              cpu_threads=cpu_threads, gpu_threads=gpu_threads, concurrent_games=args.concurrent_games,
                               duration_s=args.seconds, seed=replicas.game_seed(ctx, 0), executor_blocking_sync=int(blocking))
 replicas.barrier(ctx)
 r = selfplay.run(onnx_bytes, cfg, device=ctx.local_rank)
@@ -72,7 +75,7 @@ if ctx.is_root:
         "config": {"workload": f"{args.game} self-play, {args.visits} visits, search batch {args.search_batch} with virtual loss, "
                                f"net {depth}x{channels}, gpu batch {args.gpu_batch}",
                    "game": "chess-shaped synthetic game (13x8x8 + 8 planes, 1880-move policy, 20-45 legal moves)" if args.game == "chess" else "ataxx 7x7",
-                   "cpu_threads_per_gpu": cpu_threads, "gpu_threads_per_gpu": args.gpu_threads, "executor_blocking_sync": bool(blocking), "concurrent_games_per_gpu": r.concurrent_games,
+                   "cpu_threads_per_gpu": cpu_threads, "gpu_threads_per_gpu": gpu_threads, "executor_blocking_sync": bool(blocking), "concurrent_games_per_gpu": r.concurrent_games,
                    "host_cores": cores, **replicas.parallelism_note(ctx)},
         "data": "synthetic"}), flush=True)
 if dist is not None:
