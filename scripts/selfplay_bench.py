@@ -29,6 +29,7 @@ ap.add_argument("--gpu-batch", type=int, default=1024)
 ap.add_argument("--cpu-threads", type=int, default=0, help="0 = host cores / replicas")
 ap.add_argument("--gpu-threads", type=int, default=3, help="executor threads, one network instance each")
 ap.add_argument("--concurrent-games", type=int, default=0)
+ap.add_argument("--pin", action="store_true", help="pin each replica to its own contiguous share of the host cores")
 args = ap.parse_args()
 
 ctx = replicas.context_from_env()
@@ -40,6 +41,9 @@ if ctx.world > 1:
     dist = replicas.init_process_group(ctx, "nccl", torch.device("cuda", ctx.local_rank))
 cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)  # honours taskset
 share = max(1, cores // ctx.world)  # host cores of this replica
+if args.pin and ctx.world > 1 and hasattr(os, "sched_setaffinity"):
+    mine = sorted(os.sched_getaffinity(0))[ctx.local_rank * share:(ctx.local_rank + 1) * share]
+    os.sched_setaffinity(0, mine)  # threads started from here on inherit it
 # plenty of cores: executors spin (lowest latency) on cores of their own; few cores: they sleep on a blocking event and
 # every core runs a generator
 blocking = share < 12
@@ -76,7 +80,7 @@ if ctx.is_root:
                                f"net {depth}x{channels}, gpu batch {args.gpu_batch}",
                    "game": "chess-shaped synthetic game (13x8x8 + 8 planes, 1880-move policy, 20-45 legal moves)" if args.game == "chess" else "ataxx 7x7",
                    "cpu_threads_per_gpu": cpu_threads, "gpu_threads_per_gpu": gpu_threads, "executor_blocking_sync": bool(blocking), "concurrent_games_per_gpu": r.concurrent_games,
-                   "host_cores": cores, **replicas.parallelism_note(ctx)},
+                   "host_cores": cores, "pinned": bool(args.pin), **replicas.parallelism_note(ctx)},
         "data": "synthetic"}), flush=True)
 if dist is not None:
     dist.destroy_process_group()
