@@ -92,13 +92,14 @@ struct SearchSettings {
 // Node storage.  The reference keeps one 64..88-byte Node per child (node.rs:11-34), and most of them are never visited:
 // a node's children are created together (step.rs:89-97) but a search of V visits touches only about V of them.  So the
 // tree is split in two:
-//   child slots   one per created child, ids consecutive per parent (id 0 = the root): last_move, net_policy and `stat`,
-//                 the index of the child's entry in the visited pool, 0 while it has never been visited
+//   child slots   one per created child, ids consecutive per parent (id 0 = the root): last_move and net_policy only
 //   visited pool  one 64-byte (one cache line) entry per node that has been visited at least once: the visit counters,
 //                 the value sums and the links; entry 0 is an all-zero sentinel that stands for every unvisited child
-// A selection step therefore reads the children's policy and stat slices plus one line per VISITED child, instead of
-// seven separate statistics slices, and the pool (about 64 KB for an 800-visit search) stays cache resident while a
-// generator thread rotates over dozens of trees.  Unvisited children all share q = fpu, so their uct is one multiply-add
+//   visited lists per pool entry, the (pool index, child position) pairs of its visited children, sorted by position,
+//                 in one arena that grows by doubling
+// A selection step therefore reads the children's policy slice, the parent's visited list and one line per VISITED
+// child, instead of seven statistics slices over all children; pool and lists (about 100 KB for an 800-visit search)
+// stay cache resident while a generator thread rotates over dozens of trees.  Unvisited children all share q = fpu, so their uct is one multiply-add
 // chain over the policy slice; visited children go through the same scalar formula as before.  The IEEE operations
 // and their order are those of the reference's Node::uct, so trees stay bit-identical to the oracle's.
 struct UctContext {  // node.rs:55-64
@@ -112,8 +113,12 @@ struct alignas(64) Visited {
     float value = 0, win_a = 0, draw = 0, win_b = 0, ml = 0;  // sum_values (abs)
     int32_t parent = -1;                                      // pool index of the parent, -1 for the root
     int32_t child_start = -1, child_count = 0;                // child slots; children == None  <=>  child_start < 0
-    int32_t slot = 0;                                         // this node's own child slot
+    int32_t vis_off = 0;                                      // visited list: offset into the arena,
+    uint16_t vis_count = 0, vis_cap = 0;                      // entries used / reserved
     uint8_t has_net_values = 0;
+};
+struct VisRef {
+    int32_t idx, pos;  // pool index of a visited child, its position among the parent's children
 };
 
 namespace detail {
@@ -277,58 +282,71 @@ struct Tree {
     // child slots
     std::vector<uint32_t> last_move;
     std::vector<float> net_policy;
-    std::vector<int32_t> stat;
     // visited pool; [0] is the sentinel, [1] the root
     std::vector<Visited> pool;
+    std::vector<VisRef> vis_arena;
     std::vector<float> uct_scratch, vis_policy, vis_out;
     std::vector<int32_t> vis_idx, vis_pos;
+    std::vector<uint32_t> visits_scratch;
     static constexpr int kRoot = 1;  // pool index of the root
 
     explicit Tree(const Game& root) : root_board(root) {  // tree.rs:31-39
         if (root.done()) throw std::runtime_error("Cannot build tree for done board");
-        last_move.push_back(0), net_policy.push_back(NAN), stat.push_back(kRoot);
+        last_move.push_back(0), net_policy.push_back(NAN);
         pool.resize(2);
     }
     size_t size() const { return last_move.size(); }  // nodes in the reference's sense: the root and every created child
     void reserve(size_t slots, size_t visited) {
-        last_move.reserve(slots), net_policy.reserve(slots), stat.reserve(slots);
-        pool.reserve(visited + 2);
+        last_move.reserve(slots), net_policy.reserve(slots);
+        pool.reserve(visited + 2), vis_arena.reserve(4 * visited + 64);
     }
     // all children of a node at once (step.rs:89-97), with a uniform prior
     int push_children(const std::vector<uint32_t>& moves, float p) {
         const size_t start = last_move.size(), end = start + moves.size();
-        net_policy.resize(end, p), stat.resize(end, 0);
+        net_policy.resize(end, p);
         last_move.insert(last_move.end(), moves.begin(), moves.end());
         return int(start);
     }
-    int visit_child(int parent, int slot) {  // the pool entry of a child slot, created on its first visit
-        int v = stat[size_t(slot)];
-        if (v == 0) {
-            v = int(pool.size());
-            pool.emplace_back();
-            pool.back().parent = parent;
-            pool.back().slot = slot;
-            stat[size_t(slot)] = v;
+    // the pool entry of the child at position `pos` of `parent`, created (and entered into the parent's visited list,
+    // which stays sorted by position) on its first visit
+    int visit_child(int parent, int pos) {
+        {
+            const Visited& p = pool[size_t(parent)];
+            const VisRef* list = vis_arena.data() + p.vis_off;
+            for (int j = 0; j < p.vis_count; j++)
+                if (list[j].pos == pos) return list[j].idx;
         }
+        const int v = int(pool.size());
+        pool.emplace_back();
+        pool.back().parent = parent;
+        Visited& p = pool[size_t(parent)];
+        if (p.vis_count == p.vis_cap) {  // move the list to the end of the arena with twice the room
+            const int cap = p.vis_cap ? 2 * int(p.vis_cap) : 4;
+            const size_t off = vis_arena.size();
+            vis_arena.resize(off + size_t(cap));
+            std::memcpy(vis_arena.data() + off, vis_arena.data() + p.vis_off, size_t(p.vis_count) * sizeof(VisRef));
+            p.vis_off = int32_t(off);
+            p.vis_cap = uint16_t(cap);
+        }
+        VisRef* list = vis_arena.data() + p.vis_off;
+        int j = p.vis_count;
+        for (; j > 0 && list[j - 1].pos > pos; j--) list[j] = list[j - 1];
+        list[j] = {v, pos};
+        p.vis_count++;
         return v;
+    }
+    // complete visits of every child of a node, in child order
+    void child_visits(int node, std::vector<uint32_t>& out) const {
+        const Visited& p = pool[size_t(node)];
+        out.assign(size_t(p.child_count), 0u);
+        const VisRef* list = vis_arena.data() + p.vis_off;
+        for (int j = 0; j < p.vis_count; j++) out[size_t(list[j].pos)] = pool[size_t(list[j].idx)].complete;
     }
     const Visited& root() const { return pool[kRoot]; }
     uint64_t root_visits() const { return pool[kRoot].complete; }
-    uint32_t child_visits(int slot) const { return pool[size_t(stat[size_t(slot)])].complete; }  // 0 through the sentinel
     static ValuesAbs sum_values(const Visited& v) { return {v.value, v.win_a, v.draw, v.win_b, v.ml}; }
     static ValuesAbs values(const Visited& v) { return sum_values(v).div(float(v.complete)); }  // node.rs:126-128
     ValuesAbs root_values() const { return values(pool[kRoot]); }
-
-    UctContext uct_context(int node) const {  // tree.rs:49-66, node.rs:153-161
-        const Visited& pn = pool[size_t(node)];
-        float mass = 0.0f;
-        const int c0 = pn.child_start, c1 = c0 + pn.child_count;
-        for (int c = c0; c < c1; c++) {
-            const int v = stat[size_t(c)];
-            if (v != 0 && pool[size_t(v)].complete + pool[size_t(v)].virt > 0) mass += net_policy[size_t(c)];
-        }
-        return {uint64_t(pn.complete) + pn.virt, values(pn), mass};
-    }
 
     detail::UctParent uct_parent(const UctContext& par, FpuMode fpu_mode, const SearchSettings& s, int player) const {
         detail::UctParent u;
@@ -360,9 +378,10 @@ struct Tree {
     // tree.rs:132-141: visit distribution over the root's children
     void policy(std::vector<float>& out) const {
         const Visited& r = pool[kRoot];
-        out.resize(size_t(r.child_count));
         const float denom = std::fmax(float(r.complete) - 1.0f, 0.0f);
-        for (int i = 0; i < r.child_count; i++) out[size_t(i)] = float(child_visits(r.child_start + i)) / denom;
+        out.assign(size_t(r.child_count), 0.0f / denom);
+        const VisRef* list = vis_arena.data() + r.vis_off;
+        for (int j = 0; j < r.vis_count; j++) out[size_t(list[j].pos)] = float(pool[size_t(list[j].idx)].complete) / denom;
     }
 };
 
@@ -395,8 +414,15 @@ inline void prefetch_span(const void* p, size_t bytes) {
 
 // kRequest: an un-evaluated node was reached and `req` is filled; kTerminal: a terminal node was reached and its outcome
 // has been propagated; kDescend: moved one level down, call again.
-template <typename Game>
-StepResult descent_step(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Descent<Game>& d, Request<Game>& req, std::vector<uint32_t>& scratch) {
+struct NoLeafHook {
+    template <typename Game>
+    void operator()(const Game&) const {}
+};
+// `on_leaf(board)` runs when an un-evaluated node is reached, before its children are created: the caller's chance to
+// start fetching whatever it will look up for this board (the evaluation cache) while the expansion still has work to do.
+template <typename Game, typename LeafHook = NoLeafHook>
+StepResult descent_step(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Descent<Game>& d, Request<Game>& req, std::vector<uint32_t>& scratch,
+                        LeafHook on_leaf = LeafHook()) {
     int& cur = d.cur;
     Game& board = d.board;
     {
@@ -407,6 +433,7 @@ StepResult descent_step(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Des
         }
         if (tree.pool[size_t(cur)].child_start < 0) {
             // initialise the children with a uniform policy, step.rs:84-103
+            on_leaf(board);
             board.moves(scratch);
             const float p = 1.0f / float(scratch.size());
             const int start = tree.push_children(scratch, p);
@@ -422,16 +449,18 @@ StepResult descent_step(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Des
         }
         const Visited& pn = tree.pool[size_t(cur)];
         const int c0 = pn.child_start, n = pn.child_count;
-        const int32_t* stat = tree.stat.data() + c0;
+        const VisRef* vis = tree.vis_arena.data() + pn.vis_off;
+        const int k = pn.vis_count;
         const int player = board.next_player();
         int selected = -1;
         uint32_t ties = 0;
         if (pn.complete == 0) {
             // a random least-visited child, step.rs:112-114 (choose_max_by_key over Reverse(total_visits))
+            tree.visits_scratch.assign(size_t(n), 0u);
+            for (int j = 0; j < k; j++) tree.visits_scratch[size_t(vis[j].pos)] = tree.pool[size_t(vis[j].idx)].complete + tree.pool[size_t(vis[j].idx)].virt;
             uint64_t best = 0;
             for (int i = 0; i < n; i++) {
-                const Visited& ch = tree.pool[size_t(stat[i])];
-                const uint64_t v = uint64_t(ch.complete) + ch.virt;
+                const uint64_t v = tree.visits_scratch[size_t(i)];
                 if (selected < 0 || v < best) {
                     selected = c0 + i;
                     best = v;
@@ -443,20 +472,12 @@ StepResult descent_step(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Des
             }
         } else {
             const FpuMode fpu = cur == Tree<Game>::kRoot ? s.fpu_root : s.fpu_child;
-            // one pass over the stat slice: the visited children (for the vector evaluation below) and, in child
-            // order, the policy mass of those with visits (uct_context, tree.rs:49-66)
+            // the visited children, in child order (the order uct_context sums the policy mass in, tree.rs:49-66)
             const float* policy = tree.net_policy.data() + c0;
             if (tree.uct_scratch.size() < size_t(n) + 8) tree.uct_scratch.resize(size_t(n) + 8), tree.vis_policy.resize(size_t(n) + 8), tree.vis_out.resize(size_t(n) + 8), tree.vis_idx.resize(size_t(n) + 8), tree.vis_pos.resize(size_t(n) + 8);
-            int k = 0;
-            {
-                int32_t* vis_idx = tree.vis_idx.data();
-                int32_t* vis_pos = tree.vis_pos.data();
-                float* vis_policy = tree.vis_policy.data();
-                for (int i = 0; i < n; i++) {  // branch-free compaction: always write, advance only past visited children
-                    const int v = stat[i];
-                    vis_idx[k] = v, vis_pos[k] = i, vis_policy[k] = policy[i];
-                    k += v != 0;
-                }
+            for (int j = 0; j < k; j++) {
+                tree.vis_idx[size_t(j)] = vis[j].idx, tree.vis_pos[size_t(j)] = vis[j].pos;
+                tree.vis_policy[size_t(j)] = policy[vis[j].pos];
             }
             float mass = 0.0f;
             for (int j = 0; j < k; j++) {
@@ -484,24 +505,20 @@ StepResult descent_step(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Des
         }
         if (selected < 0) throw std::logic_error("Board is not done, this node should have a child");
         board.play(tree.last_move[size_t(selected)]);
-        cur = tree.visit_child(cur, selected);
-        const Visited& next = tree.pool[size_t(cur)];
-        if (next.child_start >= 0) {
-            prefetch_span(tree.stat.data() + next.child_start, size_t(next.child_count) * 4);
-            prefetch_span(tree.net_policy.data() + next.child_start, size_t(next.child_count) * 4);
-        }
+        cur = tree.visit_child(cur, selected - c0);
         return StepResult::kDescend;
     }
 }
 
 // step.rs:61-135 in one go.  Returns true and fills `req` when an un-evaluated node was reached; false when a terminal
 // node was reached (its outcome has been propagated).
-template <typename Game>
-bool zero_step_gather(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Request<Game>& req, std::vector<uint32_t>& scratch) {
+template <typename Game, typename LeafHook = NoLeafHook>
+bool zero_step_gather(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Request<Game>& req, std::vector<uint32_t>& scratch,
+                      LeafHook on_leaf = LeafHook()) {
     Descent<Game> d;
     d.begin(tree);
     while (true) {
-        const StepResult r = descent_step(tree, s, rng, d, req, scratch);
+        const StepResult r = descent_step(tree, s, rng, d, req, scratch, on_leaf);
         if (r != StepResult::kDescend) return r == StepResult::kRequest;
     }
 }

@@ -97,7 +97,7 @@ public:
         size_t buckets = 16;
         while (buckets < cap * 2) buckets *= 2;
         mask_ = buckets - 1;
-        if (cap_) heads_.assign(buckets, -1);
+        if (cap_) heads_.assign(buckets, Bucket{});
         entries_.reserve(cap_);
     }
     void prefetch(uint64_t key) const {
@@ -105,46 +105,65 @@ public:
     }
     const Entry* get(uint64_t key) {
         if (cap_ == 0) return nullptr;
-        for (int32_t i = heads_[size_t(key) & mask_]; i >= 0; i = entries_[size_t(i)].chain)
-            if (entries_[size_t(i)].key == key) {
-                touch(i);
-                return &entries_[size_t(i)];
-            }
-        return nullptr;
+        const int32_t i = find(key);
+        if (i < 0) return nullptr;
+        touch(i);
+        return &entries_[size_t(i)];
     }
     // the entry for `key`, made most recent; the caller fills `values` and `policy`.  nullptr when the cache is disabled.
     Entry* put(uint64_t key) {
         if (cap_ == 0) return nullptr;
-        for (int32_t i = heads_[size_t(key) & mask_]; i >= 0; i = entries_[size_t(i)].chain)
-            if (entries_[size_t(i)].key == key) {
-                touch(i);
-                return &entries_[size_t(i)];
-            }
-        int32_t i;
+        int32_t i = find(key);
+        if (i >= 0) {
+            touch(i);
+            return &entries_[size_t(i)];
+        }
         if (entries_.size() < cap_) {
             i = int32_t(entries_.size());
             entries_.emplace_back();
         } else {  // recycle the least recently used entry
             i = tail_;
             unlink(i);
-            int32_t* link = &heads_[size_t(entries_[size_t(i)].key) & mask_];
-            while (*link != i) link = &entries_[size_t(*link)].chain;
-            *link = entries_[size_t(i)].chain;
+            unchain(i);
         }
         Entry& e = entries_[size_t(i)];
         e.key = key;
-        e.chain = heads_[size_t(key) & mask_];
-        heads_[size_t(key) & mask_] = i;
+        Bucket& b = heads_[size_t(key) & mask_];
+        e.chain = b.head;
+        b.head = i;
+        b.tags |= tag_bit(key);
         push_front(i);
         return &e;
     }
     void clear() {
-        std::fill(heads_.begin(), heads_.end(), -1);
+        std::fill(heads_.begin(), heads_.end(), Bucket{});
         entries_.clear();
         head_ = tail_ = -1;
     }
 
 private:
+    // a bucket carries a 32-bit Bloom word of the keys chained in it: most misses are answered from the bucket's own
+    // cache line without touching an entry
+    struct Bucket {
+        int32_t head = -1;
+        uint32_t tags = 0;
+    };
+    static uint32_t tag_bit(uint64_t key) { return 1u << ((key >> 40) & 31); }
+    int32_t find(uint64_t key) const {
+        const Bucket& b = heads_[size_t(key) & mask_];
+        if (!(b.tags & tag_bit(key))) return -1;
+        for (int32_t i = b.head; i >= 0; i = entries_[size_t(i)].chain)
+            if (entries_[size_t(i)].key == key) return i;
+        return -1;
+    }
+    void unchain(int32_t i) {
+        Bucket& b = heads_[size_t(entries_[size_t(i)].key) & mask_];
+        int32_t* link = &b.head;
+        while (*link != i) link = &entries_[size_t(*link)].chain;
+        *link = entries_[size_t(i)].chain;
+        b.tags = 0;  // rebuild the Bloom word from what is left in the chain
+        for (int32_t j = b.head; j >= 0; j = entries_[size_t(j)].chain) b.tags |= tag_bit(entries_[size_t(j)].key);
+    }
     void unlink(int32_t i) {
         Entry& e = entries_[size_t(i)];
         if (e.prev >= 0) entries_[size_t(e.prev)].next = e.next; else head_ = e.next;
@@ -165,7 +184,7 @@ private:
     }
     size_t cap_, mask_ = 0;
     int32_t head_ = -1, tail_ = -1;
-    std::vector<int32_t> heads_;
+    std::vector<Bucket> heads_;
     std::vector<Entry> entries_;
 };
 
@@ -362,7 +381,7 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                 uint64_t cached = 0;
                 while (int(slot.requests.size()) < c.search_batch && terminal_gathers < c.search_batch) {
                     Request<Game> req;
-                    if (zero_step_gather(tree, settings, slot.rng, req, scratch)) {
+                    if (zero_step_gather(tree, settings, slot.rng, req, scratch, [&](const Game& b) { slot.cache.prefetch(b.hash()); })) {
                         if (const LruCache::Entry* hit = slot.cache.get(req.board.hash())) {
                             cached++;
                             apply_eval(slot, req, hit->values, hit->policy.data(), hit->policy.size(), c, policy_tmp);
@@ -678,9 +697,11 @@ void trace_search(const kzb_selfplay_config& c, uint64_t game_seed, int plies, i
     const int n_children = tree.root().child_count;
     if (n_children > out.capacity) throw std::runtime_error("trace: child capacity too small");
     out.n_children = n_children;
+    std::vector<uint32_t> visits;
+    tree.child_visits(Tree<Game>::kRoot, visits);
     for (int i = 0; i < n_children; i++) {
         const size_t ch = size_t(tree.root().child_start + i);
-        out.child_visits[i] = tree.child_visits(int(ch));
+        out.child_visits[i] = visits[size_t(i)];
         out.child_moves[i] = tree.last_move[ch];
         out.child_policy[i] = tree.net_policy[ch];
     }
