@@ -11,6 +11,7 @@
 //   bool done() const; int outcome() const (+1 player A won, 0 draw, -1 player B won; only if done);
 //   int next_player() const (0 = A, 1 = B); void moves(std::vector<uint32_t>&) const; void play(uint32_t move);
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -91,34 +92,40 @@ struct SearchSettings {
 
 // Node storage.  The reference keeps one 64..88-byte Node per child (node.rs:11-34), and most of them are never visited:
 // a node's children are created together (step.rs:89-97) but a search of V visits touches only about V of them.  So the
-// tree is split in two:
-//   child slots   one per created child, ids consecutive per parent (id 0 = the root): last_move and net_policy only
-//   visited pool  one 64-byte (one cache line) entry per node that has been visited at least once: the visit counters,
-//                 the value sums and the links; entry 0 is an all-zero sentinel that stands for every unvisited child
-//   visited lists per pool entry, the (pool index, child position) pairs of its visited children, sorted by position,
-//                 in one arena that grows by doubling
-// A selection step therefore reads the children's policy slice, the parent's visited list and one line per VISITED
-// child, instead of seven statistics slices over all children; pool and lists (about 100 KB for an 800-visit search)
-// stay cache resident while a generator thread rotates over dozens of trees.  Unvisited children all share q = fpu, so their uct is one multiply-add
-// chain over the policy slice; visited children go through the same scalar formula as before.  The IEEE operations
-// and their order are those of the reference's Node::uct, so trees stay bit-identical to the oracle's.
+// tree is split in three:
+//   child slots     one per created child, ids consecutive per parent: last_move and net_policy only
+//   nodes           one 32-byte entry per node that has been visited at least once: the links (parent, child slots,
+//                   visited block) -- no statistics
+//   visited blocks  per node, the statistics of its VISITED children: one 32-byte row (visit counters, value sums, node
+//                   index) per visited child in first-visit order, preceded by two u16 arrays (the child position of
+//                   every row; the rows sorted by position), in one arena that grows by doubling.  A node's own
+//                   statistics therefore live in its parent's block (the root's in `root_stat`); rows never move within
+//                   a block, and when a block is moved to grow, its children's `row` links are rewritten.
+// A selection step reads the children's policy slice and the parent's block -- a few CONTIGUOUS cache lines -- instead
+// of seven statistics slices over all children or one scattered line per visited child; with dozens of trees per
+// generator thread and thousands per host every tree visit starts cold, so lines touched are what the search costs.
+// Unvisited children all share q = fpu, so their uct is one multiply-add chain over the policy slice; visited children
+// go through the same formula as the reference's Node::uct, 8 rows at a time.  The IEEE operations and their order are
+// the reference's, so trees stay bit-identical to the oracle's.
 struct UctContext {  // node.rs:55-64
     uint64_t total_visits;
     ValuesAbs values;
     float visited_policy_mass;
 };
 
-struct alignas(64) Visited {
+struct alignas(32) ChildStat {
     uint32_t complete = 0, virt = 0;                          // complete_visits, virtual_visits
     float value = 0, win_a = 0, draw = 0, win_b = 0, ml = 0;  // sum_values (abs)
-    int32_t parent = -1;                                      // pool index of the parent, -1 for the root
-    int32_t child_start = -1, child_count = 0;                // child slots; children == None  <=>  child_start < 0
-    int32_t vis_off = 0;                                      // visited list: offset into the arena,
-    uint16_t vis_count = 0, vis_cap = 0;                      // entries used / reserved
-    uint8_t has_net_values = 0;
+    int32_t node = 0;                                         // index of this child in `nodes`
 };
-struct VisRef {
-    int32_t idx, pos;  // pool index of a visited child, its position among the parent's children
+struct Node {
+    int32_t parent = -1;       // index of the parent, -1 for the root
+    int32_t child_start = -1;  // child slots; children == None  <=>  child_start < 0
+    int32_t block = -1;        // visited block: arena offset in 32-byte units, -1 while no child has been visited
+    int32_t row = -1;          // arena index of this node's own statistics row (in the parent's block), -1 for the root
+    uint16_t child_count = 0;
+    uint16_t vis_count = 0, vis_cap = 0;
+    uint8_t has_net_values = 0;
 };
 
 namespace detail {
@@ -126,7 +133,7 @@ struct UctParent {  // the per-parent part of Node::uct, computed once per selec
     float fpu, sqrt_visits, moves_left_m1;
 };
 // node.rs:163-206 + Uct::total :87-98 for one child
-inline float uct_one(const Visited& v, float policy, const UctParent& up, const SearchSettings& s, int player) {
+inline float uct_one(const ChildStat& v, float policy, const UctParent& up, const SearchSettings& s, int player) {
     const float vl = s.virtual_loss;
     const float cv = float(v.complete), vv = float(v.virt);
     const float tvv = cv + vl * vv;
@@ -151,11 +158,11 @@ inline float uct_one(const Visited& v, float policy, const UctParent& up, const 
     return q + w.exploration_weight * u + w.moves_left_weight * m_unit;
 }
 #if defined(__x86_64__)
-// The same formula for 8 visited children at a time: the first 32 bytes of their pool entries (complete, virt, value,
-// win_a, draw, win_b, ml, parent) are loaded as one row each and transposed into columns.  Same IEEE operations in the
-// same order as uct_one.  `idx` / `policy` are padded to a multiple of 8 (index 0 = the sentinel).
-__attribute__((target("avx2"))) inline void uct_visited_avx2(const Visited* pool, const int32_t* idx, const float* policy, int k,
-                                                             const UctParent& up, const SearchSettings& s, int player, float* out) {
+// The same formula for 8 visited children at a time: their rows (complete, virt, value, win_a, draw, win_b, ml, node)
+// are contiguous in the parent's block and are transposed into columns.  Same IEEE operations in the same order as
+// uct_one.  Rows and `policy` must be readable up to the next multiple of 8 (what lies there is computed and ignored).
+__attribute__((target("avx2"))) inline void uct_visited_avx2(const ChildStat* rows, const float* policy, int k, const UctParent& up,
+                                                             const SearchSettings& s, int player, float* out) {
     const __m256 vl = _mm256_set1_ps(s.virtual_loss), fpu = _mm256_set1_ps(up.fpu), sq = _mm256_set1_ps(up.sqrt_visits);
     const __m256 mlm1 = _mm256_set1_ps(up.moves_left_m1), ds = _mm256_set1_ps(s.q_mode.draw_score), zero = _mm256_setzero_ps();
     const UctWeights& w = s.weights;
@@ -164,7 +171,7 @@ __attribute__((target("avx2"))) inline void uct_visited_avx2(const Visited* pool
     const __m256 one = _mm256_set1_ps(1.0f), none = _mm256_set1_ps(-1.0f);
     for (int g = 0; g < k; g += 8) {
         __m256 r[8];
-        for (int j = 0; j < 8; j++) r[j] = _mm256_load_ps(reinterpret_cast<const float*>(pool + idx[g + j]));
+        for (int j = 0; j < 8; j++) r[j] = _mm256_load_ps(reinterpret_cast<const float*>(rows + g + j));
         // 8x8 transpose
         const __m256 t0 = _mm256_unpacklo_ps(r[0], r[1]), t1 = _mm256_unpackhi_ps(r[0], r[1]);
         const __m256 t2 = _mm256_unpacklo_ps(r[2], r[3]), t3 = _mm256_unpackhi_ps(r[2], r[3]);
@@ -282,23 +289,27 @@ struct Tree {
     // child slots
     std::vector<uint32_t> last_move;
     std::vector<float> net_policy;
-    // visited pool; [0] is the sentinel, [1] the root
-    std::vector<Visited> pool;
-    std::vector<VisRef> vis_arena;
+    // visited nodes; [0] is the root
+    std::vector<Node> nodes;
+    ChildStat root_stat;
+    // visited blocks, in 32-byte units
+    std::vector<ChildStat> arena;
+    size_t arena_used = 0;
     std::vector<float> uct_scratch, vis_policy, vis_out;
-    std::vector<int32_t> vis_idx, vis_pos;
     std::vector<uint32_t> visits_scratch;
-    static constexpr int kRoot = 1;  // pool index of the root
+    static constexpr int kRoot = 0;
+    static constexpr size_t kArenaTail = 8;  // rows that may be read (never used) past the last block
 
     explicit Tree(const Game& root) : root_board(root) {  // tree.rs:31-39
         if (root.done()) throw std::runtime_error("Cannot build tree for done board");
         last_move.push_back(0), net_policy.push_back(NAN);
-        pool.resize(2);
+        nodes.emplace_back();
+        arena.resize(kArenaTail);
     }
     size_t size() const { return last_move.size(); }  // nodes in the reference's sense: the root and every created child
     void reserve(size_t slots, size_t visited) {
         last_move.reserve(slots), net_policy.reserve(slots);
-        pool.reserve(visited + 2), vis_arena.reserve(4 * visited + 64);
+        nodes.reserve(visited + 1), arena.reserve(5 * visited + 64);
     }
     // all children of a node at once (step.rs:89-97), with a uniform prior
     int push_children(const std::vector<uint32_t>& moves, float p) {
@@ -307,46 +318,79 @@ struct Tree {
         last_move.insert(last_move.end(), moves.begin(), moves.end());
         return int(start);
     }
-    // the pool entry of the child at position `pos` of `parent`, created (and entered into the parent's visited list,
-    // which stays sorted by position) on its first visit
+
+    // block layout: u16 row_pos[cap] | u16 order[cap] | ChildStat rows[cap]
+    static size_t head_units(size_t cap) { return (cap + 7) / 8; }
+    uint16_t* block_row_pos(const Node& n) { return reinterpret_cast<uint16_t*>(arena.data() + n.block); }
+    const uint16_t* block_row_pos(const Node& n) const { return reinterpret_cast<const uint16_t*>(arena.data() + n.block); }
+    uint16_t* block_order(const Node& n) { return block_row_pos(n) + n.vis_cap; }
+    const uint16_t* block_order(const Node& n) const { return block_row_pos(n) + n.vis_cap; }
+    ChildStat* block_rows(const Node& n) { return arena.data() + n.block + head_units(n.vis_cap); }
+    const ChildStat* block_rows(const Node& n) const { return arena.data() + n.block + head_units(n.vis_cap); }
+
+    // index, in `parent`'s block, of the row of the child at position `pos`; the row (and the child's node) is created
+    // on the first visit
     int visit_child(int parent, int pos) {
         {
-            const Visited& p = pool[size_t(parent)];
-            const VisRef* list = vis_arena.data() + p.vis_off;
-            for (int j = 0; j < p.vis_count; j++)
-                if (list[j].pos == pos) return list[j].idx;
+            const Node& p = nodes[size_t(parent)];
+            if (p.block >= 0) {
+                const uint16_t* rp = block_row_pos(p);
+                for (int j = 0; j < p.vis_count; j++)
+                    if (rp[j] == pos) return j;
+            }
         }
-        const int v = int(pool.size());
-        pool.emplace_back();
-        pool.back().parent = parent;
-        Visited& p = pool[size_t(parent)];
-        if (p.vis_count == p.vis_cap) {  // move the list to the end of the arena with twice the room
-            const int cap = p.vis_cap ? 2 * int(p.vis_cap) : 4;
-            const size_t off = vis_arena.size();
-            vis_arena.resize(off + size_t(cap));
-            std::memcpy(vis_arena.data() + off, vis_arena.data() + p.vis_off, size_t(p.vis_count) * sizeof(VisRef));
-            p.vis_off = int32_t(off);
+        const int v = int(nodes.size());
+        nodes.emplace_back();
+        nodes.back().parent = parent;
+        Node& p = nodes[size_t(parent)];
+        const int k = p.vis_count;
+        if (k == p.vis_cap) {  // move the block to the end of the arena with twice the room
+            const size_t cap = p.vis_cap ? 2 * size_t(p.vis_cap) : 4, off = arena_used;
+            arena_used += head_units(cap) + cap;
+            if (arena.size() < arena_used + kArenaTail) arena.resize(std::max(arena_used + kArenaTail, 2 * arena.size()));
+            uint16_t* head = reinterpret_cast<uint16_t*>(arena.data() + off);
+            ChildStat* rows = arena.data() + off + head_units(cap);
+            if (k) {
+                std::memcpy(head, block_row_pos(p), size_t(k) * sizeof(uint16_t));
+                std::memcpy(head + cap, block_order(p), size_t(k) * sizeof(uint16_t));
+                std::memcpy(rows, block_rows(p), size_t(k) * sizeof(ChildStat));
+                for (int j = 0; j < k; j++) nodes[size_t(rows[j].node)].row = int32_t(rows + j - arena.data());
+            }
+            p.block = int32_t(off);
             p.vis_cap = uint16_t(cap);
         }
-        VisRef* list = vis_arena.data() + p.vis_off;
-        int j = p.vis_count;
-        for (; j > 0 && list[j - 1].pos > pos; j--) list[j] = list[j - 1];
-        list[j] = {v, pos};
+        uint16_t* rp = block_row_pos(p);
+        uint16_t* order = block_order(p);
+        ChildStat* rows = block_rows(p);
+        rp[k] = uint16_t(pos);
+        int t = k;
+        for (; t > 0 && rp[order[t - 1]] > pos; t--) order[t] = order[t - 1];
+        order[t] = uint16_t(k);
+        rows[k] = ChildStat();
+        rows[k].node = v;
+        nodes[size_t(v)].row = int32_t(rows + k - arena.data());
         p.vis_count++;
-        return v;
+        return k;
+    }
+    // the statistics of a visited node: a row of its parent's block
+    ChildStat& stat_of(int node) {
+        const Node& n = nodes[size_t(node)];
+        return n.row < 0 ? root_stat : arena[size_t(n.row)];
     }
     // complete visits of every child of a node, in child order
     void child_visits(int node, std::vector<uint32_t>& out) const {
-        const Visited& p = pool[size_t(node)];
+        const Node& p = nodes[size_t(node)];
         out.assign(size_t(p.child_count), 0u);
-        const VisRef* list = vis_arena.data() + p.vis_off;
-        for (int j = 0; j < p.vis_count; j++) out[size_t(list[j].pos)] = pool[size_t(list[j].idx)].complete;
+        if (p.block < 0) return;
+        const uint16_t* rp = block_row_pos(p);
+        const ChildStat* rows = block_rows(p);
+        for (int j = 0; j < p.vis_count; j++) out[size_t(rp[j])] = rows[j].complete;
     }
-    const Visited& root() const { return pool[kRoot]; }
-    uint64_t root_visits() const { return pool[kRoot].complete; }
-    static ValuesAbs sum_values(const Visited& v) { return {v.value, v.win_a, v.draw, v.win_b, v.ml}; }
-    static ValuesAbs values(const Visited& v) { return sum_values(v).div(float(v.complete)); }  // node.rs:126-128
-    ValuesAbs root_values() const { return values(pool[kRoot]); }
+    const Node& root() const { return nodes[kRoot]; }
+    uint64_t root_visits() const { return root_stat.complete; }
+    static ValuesAbs sum_values(const ChildStat& v) { return {v.value, v.win_a, v.draw, v.win_b, v.ml}; }
+    static ValuesAbs values(const ChildStat& v) { return sum_values(v).div(float(v.complete)); }  // node.rs:126-128
+    ValuesAbs root_values() const { return values(root_stat); }
 
     detail::UctParent uct_parent(const UctContext& par, FpuMode fpu_mode, const SearchSettings& s, int player) const {
         detail::UctParent u;
@@ -364,45 +408,48 @@ struct Tree {
     void propagate(int node, ValuesAbs v) {  // step.rs:171-188
         int cur = node;
         while (true) {
-            Visited& n = pool[size_t(cur)];
+            ChildStat& n = stat_of(cur);
             if (n.virt == 0) throw std::logic_error("propagate: node has no virtual visit");
             n.complete += 1;
             n.virt -= 1;
             n.value += v.value, n.win_a += v.win_a, n.draw += v.draw, n.win_b += v.win_b, n.ml += v.moves_left;
-            if (n.parent < 0) break;
-            cur = n.parent;
+            cur = nodes[size_t(cur)].parent;
+            if (cur < 0) break;
             v = v.parent();
         }
     }
 
     // tree.rs:132-141: visit distribution over the root's children
     void policy(std::vector<float>& out) const {
-        const Visited& r = pool[kRoot];
-        const float denom = std::fmax(float(r.complete) - 1.0f, 0.0f);
+        const Node& r = nodes[kRoot];
+        const float denom = std::fmax(float(root_stat.complete) - 1.0f, 0.0f);
         out.assign(size_t(r.child_count), 0.0f / denom);
-        const VisRef* list = vis_arena.data() + r.vis_off;
-        for (int j = 0; j < r.vis_count; j++) out[size_t(list[j].pos)] = float(pool[size_t(list[j].idx)].complete) / denom;
+        if (r.block < 0) return;
+        const uint16_t* rp = block_row_pos(r);
+        const ChildStat* rows = block_rows(r);
+        for (int j = 0; j < r.vis_count; j++) out[size_t(rp[j])] = float(rows[j].complete) / denom;
     }
 };
 
 template <typename Game>
 struct Request {
-    int node = -1;  // pool index of the node to evaluate
+    int node = -1;  // index (in Tree::nodes) of the node to evaluate
     int child_start = 0, child_count = 0;  // its freshly created child slots
     Game board;
     bool is_root() const { return node == Tree<Game>::kRoot; }
 };
 
-// One in-flight zero_step_gather (step.rs:61-135), advanced one tree level per descent_step call so that a caller can
-// interleave the descents of several trees: each step ends by prefetching the child slices the next step will scan, and
-// the cache misses of one tree overlap the arithmetic of the others.
+// One in-flight zero_step_gather (step.rs:61-135), advanced one tree level per descent_step call.
 template <typename Game>
 struct Descent {
     int cur = Tree<Game>::kRoot;
+    int cur_row = -1;  // arena index of cur's statistics row, -1 for the root
     Game board;
-    void begin(const Tree<Game>& tree) {
+    void begin(Tree<Game>& tree) {
         cur = Tree<Game>::kRoot;
+        cur_row = -1;
         board = tree.root_board;
+        tree.root_stat.virt += 1;
     }
 };
 enum class StepResult { kDescend, kRequest, kTerminal };
@@ -412,102 +459,102 @@ inline void prefetch_span(const void* p, size_t bytes) {
     for (size_t o = 0; o < bytes + 63; o += 64) __builtin_prefetch(c + o);
 }
 
-// kRequest: an un-evaluated node was reached and `req` is filled; kTerminal: a terminal node was reached and its outcome
-// has been propagated; kDescend: moved one level down, call again.
 struct NoLeafHook {
     template <typename Game>
     void operator()(const Game&) const {}
 };
+// kRequest: an un-evaluated node was reached and `req` is filled; kTerminal: a terminal node was reached and its outcome
+// has been propagated; kDescend: moved one level down, call again.  The virtual visit of the node a step arrives at is
+// added when the node is selected (Descent::begin for the root).
 // `on_leaf(board)` runs when an un-evaluated node is reached, before its children are created: the caller's chance to
 // start fetching whatever it will look up for this board (the evaluation cache) while the expansion still has work to do.
 template <typename Game, typename LeafHook = NoLeafHook>
 StepResult descent_step(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Descent<Game>& d, Request<Game>& req, std::vector<uint32_t>& scratch,
                         LeafHook on_leaf = LeafHook()) {
-    int& cur = d.cur;
+    const int cur = d.cur;
     Game& board = d.board;
-    {
-        tree.pool[size_t(cur)].virt += 1;
-        if (board.done()) {
-            tree.propagate(cur, ValuesAbs::from_outcome(board.outcome(), 0.0f));
-            return StepResult::kTerminal;
-        }
-        if (tree.pool[size_t(cur)].child_start < 0) {
-            // initialise the children with a uniform policy, step.rs:84-103
-            on_leaf(board);
-            board.moves(scratch);
-            const float p = 1.0f / float(scratch.size());
-            const int start = tree.push_children(scratch, p);
-            Visited& n = tree.pool[size_t(cur)];
-            n.child_start = start;
-            n.child_count = int(scratch.size());
-            n.has_net_values = 0;
-            req.node = cur;
-            req.child_start = start;
-            req.child_count = n.child_count;
-            req.board = board;
-            return StepResult::kRequest;
-        }
-        const Visited& pn = tree.pool[size_t(cur)];
-        const int c0 = pn.child_start, n = pn.child_count;
-        const VisRef* vis = tree.vis_arena.data() + pn.vis_off;
-        const int k = pn.vis_count;
-        const int player = board.next_player();
-        int selected = -1;
-        uint32_t ties = 0;
-        if (pn.complete == 0) {
-            // a random least-visited child, step.rs:112-114 (choose_max_by_key over Reverse(total_visits))
-            tree.visits_scratch.assign(size_t(n), 0u);
-            for (int j = 0; j < k; j++) tree.visits_scratch[size_t(vis[j].pos)] = tree.pool[size_t(vis[j].idx)].complete + tree.pool[size_t(vis[j].idx)].virt;
-            uint64_t best = 0;
-            for (int i = 0; i < n; i++) {
-                const uint64_t v = tree.visits_scratch[size_t(i)];
-                if (selected < 0 || v < best) {
-                    selected = c0 + i;
-                    best = v;
-                    ties = 1;
-                } else if (v == best) {
-                    ties++;
-                    if (rng.gen_range(ties) == 0) selected = c0 + i;
-                }
-            }
-        } else {
-            const FpuMode fpu = cur == Tree<Game>::kRoot ? s.fpu_root : s.fpu_child;
-            // the visited children, in child order (the order uct_context sums the policy mass in, tree.rs:49-66)
-            const float* policy = tree.net_policy.data() + c0;
-            if (tree.uct_scratch.size() < size_t(n) + 8) tree.uct_scratch.resize(size_t(n) + 8), tree.vis_policy.resize(size_t(n) + 8), tree.vis_out.resize(size_t(n) + 8), tree.vis_idx.resize(size_t(n) + 8), tree.vis_pos.resize(size_t(n) + 8);
-            for (int j = 0; j < k; j++) {
-                tree.vis_idx[size_t(j)] = vis[j].idx, tree.vis_pos[size_t(j)] = vis[j].pos;
-                tree.vis_policy[size_t(j)] = policy[vis[j].pos];
-            }
-            float mass = 0.0f;
-            for (int j = 0; j < k; j++) {
-                const Visited& ch = tree.pool[size_t(tree.vis_idx[size_t(j)])];
-                if (ch.complete + ch.virt > 0) mass += tree.vis_policy[size_t(j)];
-            }
-            const UctContext ctx{uint64_t(pn.complete) + pn.virt, Tree<Game>::values(pn), mass};
-            if (ctx.total_visits == 0) throw std::runtime_error("uct is NaN");  // node.rs:171-173
-            const detail::UctParent up = tree.uct_parent(ctx, fpu, s, player);
-            float* u = tree.uct_scratch.data();
-            detail::uct_unvisited(policy, n, up, s, u);
-#if defined(__x86_64__)
-            static const bool have_avx2 = __builtin_cpu_supports("avx2");
-            if (have_avx2 && k > 2) {
-                for (int j = k; j < ((k + 7) & ~7); j++) tree.vis_idx[size_t(j)] = 0, tree.vis_policy[size_t(j)] = 0.0f;
-                detail::uct_visited_avx2(tree.pool.data(), tree.vis_idx.data(), tree.vis_policy.data(), k, up, s, player, tree.vis_out.data());
-                for (int j = 0; j < k; j++) u[tree.vis_pos[size_t(j)]] = tree.vis_out[size_t(j)];
-            } else
-#endif
-                for (int j = 0; j < k; j++)
-                    u[tree.vis_pos[size_t(j)]] = detail::uct_one(tree.pool[size_t(tree.vis_idx[size_t(j)])], tree.vis_policy[size_t(j)], up, s, player);
-            // choose_max_by_key with random tie break, kz-util/src/sequence.rs:11-41: a later element replaces the running
-            // best when it is greater, and with probability 1/ties when it is equal.
-            selected = c0 + detail::argmax_random_ties(u, n, rng);
-        }
-        if (selected < 0) throw std::logic_error("Board is not done, this node should have a child");
-        board.play(tree.last_move[size_t(selected)]);
-        cur = tree.visit_child(cur, selected - c0);
-        return StepResult::kDescend;
+    if (board.done()) {
+        tree.propagate(cur, ValuesAbs::from_outcome(board.outcome(), 0.0f));
+        return StepResult::kTerminal;
     }
+    if (tree.nodes[size_t(cur)].child_start < 0) {
+        // initialise the children with a uniform policy, step.rs:84-103
+        on_leaf(board);
+        board.moves(scratch);
+        const float p = 1.0f / float(scratch.size());
+        const int start = tree.push_children(scratch, p);
+        Node& n = tree.nodes[size_t(cur)];
+        n.child_start = start;
+        n.child_count = uint16_t(scratch.size());
+        n.has_net_values = 0;
+        req.node = cur;
+        req.child_start = start;
+        req.child_count = n.child_count;
+        req.board = board;
+        return StepResult::kRequest;
+    }
+    const Node& pn = tree.nodes[size_t(cur)];
+    const ChildStat own = d.cur_row < 0 ? tree.root_stat : tree.arena[size_t(d.cur_row)];
+    const int c0 = pn.child_start, n = pn.child_count, k = pn.vis_count;
+    const uint16_t* vis_pos = k ? tree.block_row_pos(pn) : nullptr;  // child position of every row
+    const uint16_t* order = k ? tree.block_order(pn) : nullptr;      // rows sorted by child position
+    const ChildStat* rows = k ? tree.block_rows(pn) : nullptr;
+    const int player = board.next_player();
+    int arg = -1;
+    if (own.complete == 0) {
+        // a random least-visited child, step.rs:112-114 (choose_max_by_key over Reverse(total_visits))
+        tree.visits_scratch.assign(size_t(n), 0u);
+        for (int j = 0; j < k; j++) tree.visits_scratch[size_t(vis_pos[j])] = rows[j].complete + rows[j].virt;
+        uint64_t best = 0;
+        uint32_t ties = 0;
+        for (int i = 0; i < n; i++) {
+            const uint64_t v = tree.visits_scratch[size_t(i)];
+            if (arg < 0 || v < best) {
+                arg = i;
+                best = v;
+                ties = 1;
+            } else if (v == best) {
+                ties++;
+                if (rng.gen_range(ties) == 0) arg = i;
+            }
+        }
+    } else {
+        const FpuMode fpu = cur == Tree<Game>::kRoot ? s.fpu_root : s.fpu_child;
+        const float* policy = tree.net_policy.data() + c0;
+        if (tree.uct_scratch.size() < size_t(n) + 8) tree.uct_scratch.resize(size_t(n) + 8), tree.vis_policy.resize(size_t(n) + 8), tree.vis_out.resize(size_t(n) + 8);
+        // the policy mass of the visited children is summed in child order, like uct_context (tree.rs:49-66)
+        for (int j = 0; j < k; j++) tree.vis_policy[size_t(j)] = policy[vis_pos[j]];
+        float mass = 0.0f;
+        for (int t = 0; t < k; t++) {
+            const int j = order[t];
+            if (rows[j].complete + rows[j].virt > 0) mass += tree.vis_policy[size_t(j)];
+        }
+        const UctContext ctx{uint64_t(own.complete) + own.virt, Tree<Game>::values(own), mass};
+        if (ctx.total_visits == 0) throw std::runtime_error("uct is NaN");  // node.rs:171-173
+        const detail::UctParent up = tree.uct_parent(ctx, fpu, s, player);
+        float* u = tree.uct_scratch.data();
+        detail::uct_unvisited(policy, n, up, s, u);
+#if defined(__x86_64__)
+        static const bool have_avx2 = __builtin_cpu_supports("avx2");
+        if (have_avx2 && k > 2) {
+            detail::uct_visited_avx2(rows, tree.vis_policy.data(), k, up, s, player, tree.vis_out.data());
+            for (int j = 0; j < k; j++) u[vis_pos[j]] = tree.vis_out[size_t(j)];
+        } else
+#endif
+            for (int j = 0; j < k; j++) u[vis_pos[j]] = detail::uct_one(rows[j], tree.vis_policy[size_t(j)], up, s, player);
+        // choose_max_by_key with random tie break, kz-util/src/sequence.rs:11-41: a later element replaces the running
+        // best when it is greater, and with probability 1/ties when it is equal.
+        arg = detail::argmax_random_ties(u, n, rng);
+    }
+    if (arg < 0) throw std::logic_error("Board is not done, this node should have a child");
+    board.play(tree.last_move[size_t(c0 + arg)]);
+    const int j = tree.visit_child(cur, arg);  // may move cur's block: take the row from the tree again
+    const Node& now = tree.nodes[size_t(cur)];
+    ChildStat* row = tree.block_rows(now) + j;
+    row->virt += 1;
+    d.cur = row->node;
+    d.cur_row = int(row - tree.arena.data());
+    return StepResult::kDescend;
 }
 
 // step.rs:61-135 in one go.  Returns true and fills `req` when an un-evaluated node was reached; false when a terminal
@@ -526,7 +573,7 @@ bool zero_step_gather(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Reque
 // step.rs:140-167.  `policy` has one entry per child, in available_moves order.
 template <typename Game>
 void zero_step_apply(Tree<Game>& tree, int node, int next_player, const ValuesPov& values, const float* policy, size_t n_policy) {
-    Visited& n = tree.pool[size_t(node)];
+    Node& n = tree.nodes[size_t(node)];
     if (n.has_net_values) throw std::logic_error("Node was already evaluated by the network");
     n.has_net_values = 1;
     if (n.child_start < 0) throw std::logic_error("Applied node should have initialized children");

@@ -197,7 +197,7 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                     prefetch_span(slot.job.values.data(), slot.job.values.size() * 4);
                     for (int i = 0; i < slot.job.n; i++) {
                         const Request<Game>& req = slot.requests[size_t(i)];
-                        const Visited& node = slot.tree->pool[size_t(req.node)];
+                        const Node& node = slot.tree->nodes[size_t(req.node)];
                         __builtin_prefetch(&node, 1);
                         slot.cache.prefetch(req.board.hash());
                         prefetch_span(slot.tree->net_policy.data() + req.child_start, size_t(req.child_count) * 4);
@@ -299,16 +299,16 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                 job.mv_off.resize(size_t(job.n) + 1);
                 job.mv_off[0] = 0;
                 for (int i = 0; i < job.n; i++)
-                    job.mv_off[size_t(i) + 1] = job.mv_off[size_t(i)] + uint32_t(tree.pool[size_t(slot.requests[size_t(i)].node)].child_count);
+                    job.mv_off[size_t(i) + 1] = job.mv_off[size_t(i)] + uint32_t(tree.nodes[size_t(slot.requests[size_t(i)].node)].child_count);
                 job.mv_idx.resize(job.mv_off[size_t(job.n)]);
                 for (int i = 0; i < job.n; i++) {
                     const Game& b = slot.requests[size_t(i)].board;
                     b.encode(job.bits.data() + size_t(i) * bits_bytes, job.scalars.data() + size_t(i) * shape.scalar_count);
                     // the node's children were created from available_moves() in order (step.rs:89-97): their moves ARE the legal list
                     const int node = slot.requests[size_t(i)].node;
-                    const uint32_t* mv = tree.last_move.data() + size_t(tree.pool[size_t(node)].child_start);
+                    const uint32_t* mv = tree.last_move.data() + size_t(tree.nodes[size_t(node)].child_start);
                     uint32_t* idx = job.mv_idx.data() + job.mv_off[size_t(i)];
-                    const size_t cn = size_t(tree.pool[size_t(node)].child_count);
+                    const size_t cn = size_t(tree.nodes[size_t(node)].child_count);
                     for (size_t k = 0; k < cn; k++) idx[k] = b.move_to_index(mv[k]);
                 }
                 job.values.resize(size_t(job.n) * 5);

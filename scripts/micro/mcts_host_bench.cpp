@@ -48,7 +48,7 @@ int main(int argc, char** argv) {
             uint64_t c0 = __rdtsc();
             for (auto& req : s.requests) {  // answers of the previous round
                 const uint64_t h = req.board.hash();
-                const size_t n = size_t(tree.pool[size_t(req.node)].child_count);
+                const size_t n = size_t(tree.nodes[size_t(req.node)].child_count);
                 policy.resize(n);
                 float sum = 0;
                 for (size_t k = 0; k < n; k++) {

@@ -55,36 +55,36 @@ static int check_uct() {
 #if defined(__x86_64__)
     if (!__builtin_cpu_supports("avx2")) return 0;
     Rng gen(7);
-    std::vector<Visited> pool(64);
+    std::vector<ChildStat> rows(48);
     for (int trial = 0; trial < 20000; trial++) {
         SearchSettings s;
         s.q_mode.wdl = gen.gen_range(2) != 0;
         s.q_mode.draw_score = gen.gen_range(2) ? 0.0f : 0.3f;
         s.virtual_loss = gen.gen_range(3) == 0 ? 2.5f : 1.0f;
         if (gen.gen_range(4) == 0) s.weights.moves_left_weight = 0.0f;
-        for (size_t i = 1; i < pool.size(); i++) {
-            Visited& v = pool[i];
+        for (ChildStat& v : rows) {
             v.complete = gen.gen_range(4) == 0 ? 0 : gen.gen_range(500);
             v.virt = gen.gen_range(3) == 0 ? 0 : gen.gen_range(20);
             const float c = float(v.complete);
             v.win_a = float(gen.uniform()) * c, v.win_b = float(gen.uniform()) * (c - v.win_a), v.draw = c - v.win_a - v.win_b;
             v.value = v.win_a - v.win_b;
             v.ml = float(gen.uniform()) * 60.0f * c;
+            v.node = int32_t(gen.gen_range(1000));
         }
         const detail::UctParent up{float(gen.uniform()) * 2.0f - 1.0f, std::sqrt(float(1 + gen.gen_range(800))), float(gen.uniform()) * 50.0f};
         const int player = int(gen.gen_range(2)), k = 1 + int(gen.gen_range(40));
-        int32_t idx[48] = {};
         float policy[48] = {}, out[48], unvisited[48];
-        for (int j = 0; j < k; j++) idx[j] = int32_t(gen.gen_range(64)), policy[j] = float(gen.uniform());  // index 0 = the sentinel
-        detail::uct_visited_avx2(pool.data(), idx, policy, k, up, s, player, out);
+        for (int j = 0; j < k; j++) policy[j] = float(gen.uniform());
+        detail::uct_visited_avx2(rows.data(), policy, k, up, s, player, out);
         detail::uct_unvisited(policy, k, up, s, unvisited);
+        const ChildStat never;
         for (int j = 0; j < k; j++) {
-            const float want = detail::uct_one(pool[size_t(idx[j])], policy[j], up, s, player);
+            const float want = detail::uct_one(rows[size_t(j)], policy[j], up, s, player);
             if (std::memcmp(&want, &out[j], 4) != 0 && !(want == 0.0f && out[j] == 0.0f)) {
                 std::printf("uct mismatch at trial %d lane %d: scalar %.9g vector %.9g\n", trial, j, want, out[j]);
                 return 1;
             }
-            const float zero_want = detail::uct_one(pool[0], policy[j], up, s, player);
+            const float zero_want = detail::uct_one(never, policy[j], up, s, player);
             if (!(zero_want == unvisited[j])) {
                 std::printf("unvisited uct mismatch at trial %d lane %d: scalar %.9g fast %.9g\n", trial, j, zero_want, unvisited[j]);
                 return 1;
@@ -95,37 +95,51 @@ static int check_uct() {
     return 0;
 }
 
-// visited lists stay sorted by position and map every position to one pool entry
-static int check_visited_lists() {
+// visited blocks: one row per visited position, rows never move inside a block, `order` sorts them by position, and
+// every child's `row` link follows its row when the block is moved to grow
+static int check_visited_blocks() {
     SynthChess board = SynthChess::start(3);
     Tree<SynthChess> tree(board);
     Rng gen(5);
     std::vector<uint32_t> moves(200);
-    Visited& root = tree.pool[Tree<SynthChess>::kRoot];
-    root.child_start = tree.push_children(moves, 0.005f);
-    root.child_count = 200;
-    std::vector<int> seen(200, -1);
+    tree.nodes[0].child_start = tree.push_children(moves, 0.005f);
+    tree.nodes[0].child_count = 200;
+    std::vector<int> node_of(200, -1);
     for (int step = 0; step < 5000; step++) {
         const int pos = int(gen.gen_range(200));
-        const int v = tree.visit_child(Tree<SynthChess>::kRoot, pos);
-        if (seen[size_t(pos)] >= 0 && seen[size_t(pos)] != v) {
-            std::printf("visit_child returned a second entry for position %d\n", pos);
+        const int j = tree.visit_child(0, pos);
+        const Node& r = tree.nodes[0];
+        const ChildStat* rows = tree.block_rows(r);
+        const uint16_t* rp = tree.block_row_pos(r);
+        const uint16_t* order = tree.block_order(r);
+        if (rp[j] != pos || (node_of[size_t(pos)] >= 0 && node_of[size_t(pos)] != rows[j].node)) {
+            std::printf("visit_child returned a wrong row for position %d\n", pos);
             return 1;
         }
-        seen[size_t(pos)] = v;
-        const Visited& r = tree.pool[Tree<SynthChess>::kRoot];
-        const VisRef* list = tree.vis_arena.data() + r.vis_off;
-        for (int j = 0; j < r.vis_count; j++)
-            if ((j > 0 && list[j - 1].pos >= list[j].pos) || seen[size_t(list[j].pos)] != list[j].idx || tree.pool[size_t(list[j].idx)].parent != Tree<SynthChess>::kRoot) {
-                std::printf("visited list broken at step %d entry %d\n", step, j);
+        node_of[size_t(pos)] = rows[j].node;
+        tree.stat_of(rows[j].node).complete += 1;  // through the node's own link
+        for (int t = 0; t < r.vis_count; t++) {
+            const int row = order[t];
+            const Node& child = tree.nodes[size_t(rows[row].node)];
+            if ((t > 0 && rp[order[t - 1]] >= rp[row]) || child.parent != 0 || child.row != int32_t(rows + row - tree.arena.data())) {
+                std::printf("visited block broken at step %d entry %d\n", step, t);
                 return 1;
             }
+        }
+    }
+    std::vector<uint32_t> visits;
+    tree.child_visits(0, visits);
+    uint32_t total = 0;
+    for (uint32_t v : visits) total += v;
+    if (total != 5000) {
+        std::printf("child_visits sums to %u, expected 5000\n", total);
+        return 1;
     }
     return 0;
 }
 
 int main() {
-    if (check_argmax() || check_uct() || check_visited_lists()) return 1;
+    if (check_argmax() || check_uct() || check_visited_blocks()) return 1;
     std::printf("ok\n");
     return 0;
 }
