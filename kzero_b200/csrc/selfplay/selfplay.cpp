@@ -27,6 +27,8 @@
 #include <list>
 #include <memory>
 #include <mutex>
+#include <pthread.h>
+#include <sched.h>
 #include <thread>
 #include <unordered_map>
 #if defined(__x86_64__)
@@ -116,6 +118,7 @@ struct Shared {
     // per generator thread wake-up
     std::vector<std::unique_ptr<std::mutex>> gen_mu;
     std::vector<std::unique_ptr<std::condition_variable>> gen_cv;
+    std::vector<uint64_t> gen_signal;  // answers delivered to each generator thread so far (guarded by its gen_mu)
     // finished games go to one writer, the collector's role (collector.rs:59-85)
     std::mutex writer_mu;
     std::unique_ptr<RecordWriter> writer;
@@ -183,6 +186,22 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
     std::vector<float> policy_tmp;
     SectionClock clock;
     clock.on = std::getenv("KZB_SP_PROFILE") != nullptr;
+    const char* spin_env = std::getenv("KZB_SP_SPIN_US");
+    const long spin_us = spin_env ? std::atol(spin_env) : 0;
+    uint64_t seen_signal = 0;
+    if (std::getenv("KZB_SP_PIN_GENERATORS")) {  // generator t stays on the t-th CPU this process may use
+        cpu_set_t allowed, one;
+        if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+            int seen = 0, want = tid % std::max(1, CPU_COUNT(&allowed));
+            for (int cpu = 0; cpu < CPU_SETSIZE; cpu++)
+                if (CPU_ISSET(cpu, &allowed) && seen++ == want) {
+                    CPU_ZERO(&one);
+                    CPU_SET(cpu, &one);
+                    pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+                    break;
+                }
+        }
+    }
     try {
         while (!sh.stop.load(std::memory_order_relaxed)) {
             bool progressed = false;
@@ -328,8 +347,25 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                 clock.lap(kSecQueue);
             }
             if (!progressed) {
-                std::unique_lock<std::mutex> lk(*sh.gen_mu[size_t(tid)]);
-                sh.gen_cv[size_t(tid)]->wait_for(lk, std::chrono::microseconds(100));
+                // nothing is ready: spin for a moment (a sleeping thread of a busy virtual machine comes back late), then
+                // sleep until an executor has delivered answers to this thread
+                bool arrived = false;
+                if (spin_us > 0) {
+                    const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us);
+                    while (!arrived && std::chrono::steady_clock::now() < until) {
+                        for (int i = 0; i < 64 && !arrived; i++) {
+                            for (auto& sp : slots) arrived |= sp->waiting && sp->job.done.load(std::memory_order_acquire) != 0;
+#if defined(__x86_64__)
+                            _mm_pause();
+#endif
+                        }
+                    }
+                }
+                if (!arrived) {
+                    std::unique_lock<std::mutex> lk(*sh.gen_mu[size_t(tid)]);
+                    sh.gen_cv[size_t(tid)]->wait_for(lk, std::chrono::microseconds(100), [&] { return sh.gen_signal[size_t(tid)] != seen_signal; });
+                    seen_signal = sh.gen_signal[size_t(tid)];
+                }
             }
         }
     } catch (const std::exception& e) {
@@ -359,6 +395,7 @@ void executor_main(Net* net, Shared& sh, const kzb_selfplay_config& c, const Gam
     // like a real one (profiling aid)
     const char* latency_env = std::getenv("KZB_SP_DUMMY_LATENCY_US");
     const long dummy_latency_us = latency_env ? std::atol(latency_env) : 0;
+    const bool dummy_serial = std::getenv("KZB_SP_DUMMY_SERIAL") != nullptr;
     try {
         while (true) {
             jobs.clear();
@@ -401,7 +438,13 @@ void executor_main(Net* net, Shared& sh, const kzb_selfplay_config& c, const Gam
             if (net) {
                 net->eval_packed(bits.data(), scalars.data(), int(n), mv_idx.data(), mv_off.data(), values.data(), probs.data());
             } else {
-                if (dummy_latency_us > 0) std::this_thread::sleep_for(std::chrono::microseconds(dummy_latency_us));
+                if (dummy_latency_us > 0) {
+                    // KZB_SP_DUMMY_SERIAL: one batch at a time, like executors sharing one GPU
+                    static std::mutex one_gpu;
+                    std::unique_lock<std::mutex> gpu(one_gpu, std::defer_lock);
+                    if (dummy_serial) gpu.lock();
+                    std::this_thread::sleep_for(std::chrono::microseconds(dummy_latency_us));
+                }
                 for (size_t i = 0; i < n; i++) {
                     const uint32_t cnt = mv_off[i + 1] - mv_off[i];
                     float* p = probs.data() + mv_off[i];
@@ -445,6 +488,10 @@ void executor_main(Net* net, Shared& sh, const kzb_selfplay_config& c, const Gam
             for (size_t o = 0; o < owner_woken.size(); o++)  // one wake-up per generator thread and batch
                 if (owner_woken[o]) {
                     owner_woken[o] = 0;
+                    {
+                        std::lock_guard<std::mutex> lk(*sh.gen_mu[o]);  // no lost wake-up: the sleeper re-checks gen_signal
+                        sh.gen_signal[o]++;
+                    }
                     sh.gen_cv[o]->notify_one();
                 }
             sh.real_evals.fetch_add(n, std::memory_order_relaxed);
@@ -489,6 +536,7 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
     for (int t = 0; t < c.cpu_threads; t++) {
         sh.gen_mu.push_back(std::make_unique<std::mutex>());
         sh.gen_cv.push_back(std::make_unique<std::condition_variable>());
+        sh.gen_signal.push_back(0);
     }
     g_stop_requested.store(false);
     for (auto& v : g_profile_cycles) v = 0;
