@@ -39,6 +39,28 @@ int main(int argc, char** argv) {
     std::vector<uint32_t> scratch;
     std::vector<float> policy;
     uint64_t nodes = 0, cyc_gather = 0, cyc_apply = 0, gathers = 0;
+    // interleaved mode: the descents of the grouped trees advance one level at a time, round-robin
+    auto flush_group = [&] {
+        if (group.empty()) return;
+        const uint64_t c1 = __rdtsc();
+        size_t active = group.size();
+        while (active) {
+            for (size_t g = 0; g < group.size(); g++) {
+                Slot* gs = group[g];
+                if (!gs) continue;
+                Request<Game> req;
+                const StepResult r = descent_step(*gs->tree, settings, gs->rng, gs->descent, req, scratch);
+                if (r == StepResult::kDescend) continue;
+                gathers++;
+                if (r == StepResult::kRequest) gs->requests.push_back(std::move(req));
+                else gs->terminal++;
+                if (int(gs->requests.size()) < 16 && gs->terminal < 16) gs->descent.begin(*gs->tree);
+                else group[g] = nullptr, active--;
+            }
+        }
+        group.clear();
+        cyc_gather += __rdtsc() - c1;
+    };
     const auto t0 = std::chrono::steady_clock::now();
     double el = 0;
     while (el < seconds) {
@@ -89,26 +111,9 @@ int main(int argc, char** argv) {
             s.terminal = 0;
             s.descent.begin(tree);
             group.push_back(&s);
-            if (int(group.size()) < group_n && &sp != &slots.back()) continue;
-            c1 = __rdtsc();
-            size_t active = group.size();
-            while (active) {
-                for (size_t g = 0; g < group.size(); g++) {
-                    Slot* gs = group[g];
-                    if (!gs) continue;
-                    Request<Game> req;
-                    const StepResult r = descent_step(*gs->tree, settings, gs->rng, gs->descent, req, scratch);
-                    if (r == StepResult::kDescend) continue;
-                    gathers++;
-                    if (r == StepResult::kRequest) gs->requests.push_back(std::move(req));
-                    else gs->terminal++;
-                    if (int(gs->requests.size()) < 16 && gs->terminal < 16) gs->descent.begin(*gs->tree);
-                    else group[g] = nullptr, active--;
-                }
-            }
-            group.clear();
-            cyc_gather += __rdtsc() - c1;
+            if (int(group.size()) == group_n) flush_group();
         }
+        flush_group();
         el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
     printf("slots %d: %.0f nodes/s  (%.2f us/node)  gather %.0f cycles/node  apply %.0f cycles/node  gathers/node %.2f\n", slots_n, nodes / el,
