@@ -1,9 +1,11 @@
 """C++ unit checks of the self-play host code, compiled with g++ and run here -- no GPU.
 
   tests/cpp/lru_cache_test.cpp    the flat LRU evaluation cache against a std::list + std::unordered_map model
-  tests/cpp/mcts_units_test.cpp   the vectorised uct / tie-aware argmax / visited lists against their scalar definitions
+  tests/cpp/mcts_units_test.cpp   the vectorised uct / tie-aware argmax / visited blocks against their scalar definitions
                                   (node.rs:163-206, kz-util/src/sequence.rs:11-41)
+  tests/cpp/selfplay_tsan_main.cpp  the generator / executor threads of the driver under ThreadSanitizer
 """
+import os
 import subprocess
 from pathlib import Path
 
@@ -32,3 +34,19 @@ def test_pseudo_network_run_is_sane():
     assert r.max_batch <= 128 and r.real_evals <= r.potential_evals
     assert 0.0 < r.cached_evals / (r.real_evals + r.cached_evals) < 0.9  # sharp policies revisit positions: the cache gets hits
     assert abs(r.root_visits / r.moves_played - 60) < 8 + 1  # every move was searched to ~`visits` (overshoot < search_batch)
+
+
+@pytest.mark.parametrize("env", [{}, {"KZB_SP_SPIN_US": "50", "KZB_SP_PIN_GENERATORS": "1"}])
+def test_selfplay_threads_under_tsan(tmp_path, env):
+    """The driver's queue / wake-up / record-writer synchronisation, with the evaluator stubbed out (no CUDA linked)."""
+    cuda_include = "/usr/local/cuda/include"
+    if not os.path.isdir(cuda_include):
+        pytest.skip("CUDA headers not found")
+    exe = tmp_path / "selfplay_tsan"
+    build = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-I", cuda_include, "-o", str(exe),
+                            str(ROOT / "cpp" / "selfplay_tsan_main.cpp"), "-lpthread"], capture_output=True, text=True)
+    if build.returncode != 0 and "tsan" in build.stderr.lower():
+        pytest.skip("ThreadSanitizer runtime not available")
+    assert build.returncode == 0, build.stderr[-2000:]
+    out = subprocess.run([str(exe), str(tmp_path / "games")], capture_output=True, text=True, timeout=300, env={**os.environ, **env})
+    assert out.returncode == 0 and "ThreadSanitizer" not in out.stderr, out.stdout + out.stderr[-4000:]
