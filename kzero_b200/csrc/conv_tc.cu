@@ -55,9 +55,14 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* base, int n, int stages) {
     return s;
 }
 
+// CL = CTAs per cluster.  CL = 2: the two CTAs of a pair walk the same (tile, tap, k-block) sequence on different tiles
+// and share every weight tile: each loads half of it (n/2 output channels, map `tmap_bh`) and TMA-multicasts it into both
+// CTAs' rings; a ring slot is free again when the MMAs of BOTH CTAs have read it.  Every CTA then runs the same number
+// of tiles (the surplus ones read zero-filled rows and store nothing) so that the pair stays in lockstep.
+template <int CL>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   const ConvTcParams p) {
+                   const __grid_constant__ CUtensorMap tmap_bh, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -65,13 +70,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int stage_bytes = kABytes + p.n * 128;
     const int iters_per_tile = p.taps * p.kblocks;
+    const int my_tiles = CL == 1 ? (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x)
+                                 : (p.num_tiles + int(gridDim.x) - 1) / int(gridDim.x);
+    constexpr uint16_t kMask = uint16_t((1u << CL) - 1);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(CL == 1 ? &tmap_b : &tmap_bh)) : "memory");
         for (int i = 0; i < p.stages; i++) {
             mbar_init(&sm.full[i], 1);
-            mbar_init(&sm.empty[i], 1);
+            mbar_init(&sm.empty[i], CL);  // released by the MMA warp of every CTA the weight tile was multicast to
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&sm.tmem_full[i], 1);
@@ -89,6 +97,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast / committed to them
+    const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
     const uint32_t tmem_base = *sm.tmem_ptr;
     const uint32_t acc_stride = uint32_t(p.tmem_cols / 2);
 
@@ -97,7 +107,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int ti = 0; ti < my_tiles; ti++) {
+                const int tile = int(blockIdx.x) + ti * int(gridDim.x);
                 for (int tap = 0; tap < p.taps; tap++) {
                     const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
                     const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
@@ -111,7 +122,13 @@ __global__ void __launch_bounds__(kThreads, 1)
                         else
                             tma_load_2d(&tmap_a, &sm.full[stage], a_dst, kb * kBlockK,
                                         tile * kTileM + dy * p.lay.rank_pitch + dx);
-                        tma_load_2d(&tmap_b, &sm.full[stage], b_dst, tap * p.cin_pad + kb * kBlockK, 0);
+                        if (CL == 1) {
+                            tma_load_2d(&tmap_b, &sm.full[stage], b_dst, tap * p.cin_pad + kb * kBlockK, 0);
+                        } else {  // my n/CL rows of the weight tile, into every CTA of the cluster
+                            const int rows = p.n / CL;
+                            tma_load_2d_multicast(&tmap_bh, &sm.full[stage], b_dst + size_t(cta_rank) * rows * 128,
+                                                  tap * p.cin_pad + kb * kBlockK, int(cta_rank) * rows, kMask);
+                        }
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1;
@@ -127,8 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint64_t desc_hi = umma_desc_sw128_hi();
         int stage = 0;
         uint32_t phase = 0;
-        int local = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, local++) {
+        for (int local = 0; local < my_tiles; local++) {
             const int buf = local & 1;
             const uint32_t buf_phase = (local >> 1) & 1;
             mbar_wait(&sm.tmem_empty[buf], buf_phase ^ 1);
@@ -146,7 +162,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                         umma_bf16(tmem_d, desc_hi | uint64_t(a_lo + 2 * k), desc_hi | uint64_t(b_lo + 2 * k), idesc,
                                   (it | k) != 0);
                     }
-                    umma_commit(&sm.empty[stage]);  // frees the smem slot once these MMAs have read it
+                    // frees the smem slot once these MMAs have read it
+                    if (CL == 1) umma_commit(&sm.empty[stage]);
+                    else umma_commit_multicast(&sm.empty[stage], kMask);
                 }
                 __syncwarp();
                 if (++stage == p.stages) {
@@ -160,8 +178,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         const int quarter = warp % 4;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
-        int local = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, local++) {
+        for (int local = 0; local < my_tiles; local++) {
+            const int tile = int(blockIdx.x) + local * int(gridDim.x);
             const int buf = local & 1;
             const uint32_t buf_phase = (local >> 1) & 1;
             const int row = tile * kTileM + quarter * 32 + lane;
@@ -251,6 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or signal its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(p.tmem_cols))
@@ -271,13 +290,33 @@ int conv_tc_pick_stages(int n) {
     return stages;
 }
 
-void conv_tc_prepare() { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }
+void conv_tc_prepare() {
+    cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
 
-void launch_conv_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ConvTcParams& p, int grid,
-                    cudaStream_t s) {
+// p.cluster == 2: `tmap_bh` is the weight map with a box of n/2 rows; the grid is even
+void launch_conv_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_bh, const ConvTcParams& p,
+                    int grid, cudaStream_t s) {
     if (p.num_tiles <= 0) return;
     size_t smem = conv_tc_smem_bytes(p.n, p.stages);
-    conv_tc_kernel<<<std::min(grid, p.num_tiles), kThreads, smem, s>>>(tmap_a, tmap_b, p);
+    if (p.cluster == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(unsigned(std::min(grid & ~1, (p.num_tiles + 1) & ~1)));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, tmap_a, tmap_b, tmap_bh, p);
+    } else {
+        conv_tc_kernel<1><<<std::min(grid, p.num_tiles), kThreads, smem, s>>>(tmap_a, tmap_b, tmap_bh, p);
+    }
 }
 
 }  // namespace kzb

@@ -282,6 +282,11 @@ void Net::build_bf16() {
             uint64_t strides[1] = {uint64_t(ktot) * 2};
             uint32_t box[2] = {64, uint32_t(n)};
             st->tmap_b = make_tmap(st->w_bf16.ptr, 2, dims, strides, box);
+            st->tmap_bh = st->tmap_b;
+            if (n % 32 == 0) {  // half-height box for the 2-CTA multicast variant of conv_tc
+                uint32_t half[2] = {64, uint32_t(n / 2)};
+                st->tmap_bh = make_tmap(st->w_bf16.ptr, 2, dims, strides, half);
+            }
         }
         if (mode_ == 1) {
             uint64_t dims[4] = {uint64_t(in_stride), uint64_t(W), uint64_t(H), uint64_t(rows_alloc_ / (W * H))};
@@ -326,6 +331,10 @@ void Net::build_bf16() {
         int cols = 32;
         while (cols < 2 * n) cols *= 2;
         p.tmem_cols = cols;
+        // KZB_CONV_CLUSTER=2: CTA pairs share every weight tile (TMA multicast); worth it where the weight stream
+        // dominates SM ingress, i.e. wide layers on boards that go through the per-layer kernel
+        const char* cl = std::getenv("KZB_CONV_CLUSTER");
+        p.cluster = (cl && cl[0] == '2' && n % 32 == 0 && st->taps == 9) ? 2 : 1;
         convs_.push_back(std::move(st));
     };
 
@@ -716,7 +725,7 @@ void Net::run_network(int batch, const StepHook& hook) {
                 p.valid_rows = batch * lay_.board_pitch;
                 p.num_tiles = (p.valid_rows + 127) / 128;
             }
-            launch_conv_tc(st->tmap_a, st->tmap_b, p, num_sms_, stream_);
+            launch_conv_tc(st->tmap_a, st->tmap_b, st->tmap_bh, p, num_sms_, stream_);
         } else {
             ConvF32Params p = st->f32;
             p.batch = batch;

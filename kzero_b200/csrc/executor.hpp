@@ -45,7 +45,7 @@ struct ConvStep {
     std::string name;
     int taps = 9;
     // bf16 tensor-core form
-    CUtensorMap tmap_a{}, tmap_b{};
+    CUtensorMap tmap_a{}, tmap_b{}, tmap_bh{};
     ConvTcParams tc{};
     bool use_tc8 = false;  // 8x8-board specialisation (conv_tc8.cu)
     CUtensorMap tmap_a8{};

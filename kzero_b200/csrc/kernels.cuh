@@ -86,11 +86,12 @@ struct ConvTcParams {
     int n_store;  // channels written per row (multiple of 16, <= n)
     int stages;
     int tmem_cols;
+    int cluster;  // conv_tc only: 1, or 2 = CTA pairs share every weight tile through TMA multicast
     // development aid: when non-null, each CTA writes 16 clock64() stamps (see conv_tc8.cu) -- KZB_TIMELINE=1
     unsigned long long* timeline;
 };
-void launch_conv_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ConvTcParams& p, int grid,
-                    cudaStream_t s);
+void launch_conv_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_bh, const ConvTcParams& p,
+                    int grid, cudaStream_t s);
 size_t conv_tc_smem_bytes(int n, int stages);
 int conv_tc_pick_stages(int n);
 void conv_tc_prepare();  // per-device: opt in to 227 KB dynamic shared memory
