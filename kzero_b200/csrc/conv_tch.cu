@@ -1,0 +1,301 @@
+// K1h: conv3x3 on padded rows with the activation tile loaded ONCE per k-block (conv_tc.cu re-loads it for each tap).
+//
+// Same GEMM view, tile shape and epilogue as conv_tc.cu (D[128 rows, cout] += A_tap[128, 64] * W[cout, 64] per tap and
+// k-block), but the A operand lives in shared memory in the SWIZZLE_NONE K-major layout: 8 boxes of (8 channels, R rows)
+// land as [k-chunk][row][16 bytes], R = 128 + 2 * halo rows (rounded up to 8) with halo = rank_pitch + 1.  Rows are then 16 bytes apart
+// (SBO = 128 bytes per 8-row group, LBO = R * 16 bytes per k-chunk), and a descriptor may start at any row: tap (dy, dx)
+// is the same tile read from row halo + dy * rank_pitch + dx.  Per 128-row tile and k-block the SM receives R * 128 bytes
+// of activations instead of 9 * 16 KB, the weight stream (cout * 128 bytes per tap and k-block) is unchanged: 27 % fewer
+// bytes into shared memory per MMA at cout = 256.  profiles/r01d_go9_conv_tc_ncu.md has the measurement that motivates
+// it.  Weights keep the SWIZZLE_128B layout and an own ring.  Default for 3x3 layers in mode 0 (KZB_CONV_HALO=0: conv_tc.cu).
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace kzb {
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;
+constexpr int kThreads = 192;
+constexpr int kASlots = 2;
+
+using namespace tc;
+
+struct SmemLayout {
+    uint8_t* b_base;  // weight ring, `stages` slots of n * 128 bytes (1024-byte aligned)
+    uint8_t* a_base;  // activation slots, kASlots of a_bytes
+    uint64_t* full;
+    uint64_t* empty;
+    uint64_t* a_full;
+    uint64_t* a_empty;
+    uint64_t* tmem_full;
+    uint64_t* tmem_empty;
+    uint32_t* tmem_ptr;
+    float* bias;
+};
+
+__host__ __device__ inline size_t a_slot_bytes(int a_rows) { return (size_t(a_rows) * 128 + 1023) & ~size_t(1023); }
+
+__device__ __forceinline__ SmemLayout carve(uint8_t* base, int n, int stages, int a_rows) {
+    SmemLayout s;
+    s.b_base = base;
+    s.a_base = base + size_t(stages) * n * 128;
+    uint8_t* p = s.a_base + kASlots * a_slot_bytes(a_rows);
+    s.full = reinterpret_cast<uint64_t*>(p);
+    s.empty = s.full + stages;
+    s.a_full = s.empty + stages;
+    s.a_empty = s.a_full + kASlots;
+    s.tmem_full = s.a_empty + kASlots;
+    s.tmem_empty = s.tmem_full + 2;
+    s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tmem_empty + 2);
+    s.bias = reinterpret_cast<float*>(s.tmem_ptr + 4);
+    return s;
+}
+
+// SWIZZLE_NONE K-major descriptor, address-independent part: LBO = k-chunk pitch, SBO = 8-row group pitch, version 1
+__device__ __forceinline__ uint64_t umma_desc_nosw_hi(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t(lbo_bytes >> 4) << 16) | (uint64_t(sbo_bytes >> 4) << 32) | (uint64_t(1) << 46);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+    conv_tch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const SmemLayout sm = carve(smem, p.n, p.stages, p.a_rows);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const uint32_t b_bytes = uint32_t(p.n) * 128u;
+    const uint32_t a_bytes = uint32_t(a_slot_bytes(p.a_rows));
+    const uint32_t chunk_bytes = uint32_t(p.a_rows) * 16u;  // one k-chunk (8 channels) of the activation tile
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+        for (int i = 0; i < p.stages; i++) {
+            mbar_init(&sm.full[i], 1);
+            mbar_init(&sm.empty[i], 1);
+        }
+        for (int i = 0; i < kASlots; i++) {
+            mbar_init(&sm.a_full[i], 1);
+            mbar_init(&sm.a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&sm.tmem_full[i], 1);
+            mbar_init(&sm.tmem_empty[i], 4);  // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem_ptr)),
+                     "r"(uint32_t(p.tmem_cols))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < p.n; i += kThreads) sm.bias[i] = p.bias[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sm.tmem_ptr;
+    const uint32_t acc_stride = uint32_t(p.tmem_cols / 2);
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0, a_slot = 0;
+            uint32_t phase = 0, a_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < p.kblocks; kb++) {
+                    // the activation tile of this k-block, halo rows included (rows off either end are zero-filled)
+                    mbar_wait(&sm.a_empty[a_slot], a_phase ^ 1);
+                    mbar_expect_tx(&sm.a_full[a_slot], 8u * chunk_bytes);
+                    uint8_t* a_dst = sm.a_base + size_t(a_slot) * a_bytes;
+#pragma unroll
+                    for (int kc = 0; kc < 8; kc++)
+                        tma_load_2d(&tmap_a, &sm.a_full[a_slot], a_dst + size_t(kc) * chunk_bytes, kb * kBlockK + kc * 8,
+                                    tile * kTileM - p.halo);
+                    if (++a_slot == kASlots) {
+                        a_slot = 0;
+                        a_phase ^= 1;
+                    }
+                    for (int tap = 0; tap < 9; tap++) {
+                        mbar_wait(&sm.empty[stage], phase ^ 1);
+                        mbar_expect_tx(&sm.full[stage], b_bytes);
+                        tma_load_2d(&tmap_b, &sm.full[stage], sm.b_base + size_t(stage) * b_bytes, tap * p.cin_pad + kb * kBlockK, 0);
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        const uint32_t idesc = umma_idesc_bf16(kTileM, p.n);
+        const uint64_t b_hi = umma_desc_sw128_hi();
+        const uint64_t a_hi = umma_desc_nosw_hi(chunk_bytes, 128);
+        int stage = 0, a_slot = 0;
+        uint32_t phase = 0, a_phase = 0;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, local++) {
+            const int buf = local & 1;
+            const uint32_t buf_phase = (local >> 1) & 1;
+            mbar_wait(&sm.tmem_empty[buf], buf_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + buf * acc_stride;
+            bool first = true;
+            for (int kb = 0; kb < p.kblocks; kb++) {
+                mbar_wait(&sm.a_full[a_slot], a_phase);
+                const uint32_t a_lo = umma_desc_lo(smem_u32(sm.a_base + size_t(a_slot) * a_bytes));
+                for (int tap = 0; tap < 9; tap++) {
+                    mbar_wait(&sm.full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t b_lo = umma_desc_lo(smem_u32(sm.b_base + size_t(stage) * b_bytes));
+                    // tap (dy, dx) = the same tile read from another row; one row is 16 bytes = one descriptor unit
+                    const uint32_t a_t = a_lo + uint32_t(p.halo + (tap / 3 - 1) * p.lay.rank_pitch + (tap % 3 - 1));
+                    if (lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; k++)  // 16 channels = two k-chunks of the activation tile
+                            umma_bf16(tmem_d, a_hi | uint64_t(a_t + uint32_t(k) * (2u * chunk_bytes >> 4)), b_hi | uint64_t(b_lo + 2 * k), idesc,
+                                      (!first || k != 0) ? 1u : 0u);
+                        umma_commit(&sm.empty[stage]);
+                        if (tap == 8) umma_commit(&sm.a_empty[a_slot]);
+                    }
+                    __syncwarp();
+                    first = false;
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                if (++a_slot == kASlots) {
+                    a_slot = 0;
+                    a_phase ^= 1;
+                }
+            }
+            if (lane == 0) umma_commit(&sm.tmem_full[buf]);  // accumulator complete -> epilogue
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp % 4;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+        for (int tile = blockIdx.x, local = 0; tile < p.num_tiles; tile += gridDim.x, local++) {
+            const int buf = local & 1;
+            const uint32_t buf_phase = (local >> 1) & 1;
+            const int row = tile * kTileM + quarter * 32 + lane;
+            bool on_board = true;
+            if (p.mode == 0) {
+                int r = row % p.lay.board_pitch;
+                on_board = (r % p.lay.rank_pitch) < p.lay.W && (r / p.lay.rank_pitch) < p.lay.H;
+            }
+            const bool store = row < p.valid_rows;
+
+            // residual row (bf16) prefetched into registers BEFORE waiting for the accumulator, so its global
+            // latency hides behind the MMAs of this tile (first 128 channels; the rest is loaded in the loop)
+            constexpr int kResPrefetch = 16;  // uint4 = 8 channels each
+            uint4 resq[kResPrefetch];
+            const bool has_res = p.res != nullptr && store;
+            if (has_res) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.res + size_t(row) * p.res_stride);
+#pragma unroll
+                for (int j = 0; j < kResPrefetch; j++)
+                    if (j * 8 < p.n_store) resq[j] = rp[j];
+            }
+
+            mbar_wait(&sm.tmem_full[buf], buf_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * acc_stride + (uint32_t(quarter * 32) << 16);
+
+#pragma unroll
+            for (int cc = 0; cc < 8; cc++) {  // 32 columns per iteration, n <= 256
+                const int c0 = cc * 32;
+                if (c0 >= p.n_store) break;
+                const bool second = c0 + 16 < p.n_store;
+                uint32_t r[32];
+                tmem_ld16(taddr + c0, r);
+                if (second) tmem_ld16(taddr + c0 + 16, r + 16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    if (h == 1 && !second) break;
+                    const int ch = c0 + h * 16;
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        float f = __uint_as_float(r[h * 16 + j]) + sm.bias[ch + j];
+                        if (ch + j < p.relu_n) f = f < 0.0f ? 0.0f : f;  // NaN stays NaN, like torch/ONNX Relu
+                        v[j] = f;
+                    }
+                    if (has_res) {
+                        uint4 q0, q1;
+                        if (cc < kResPrefetch / 4) {
+                            q0 = resq[cc * 4 + h * 2];
+                            q1 = resq[cc * 4 + h * 2 + 1];
+                        } else {
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.res + size_t(row) * p.res_stride + ch);
+                            q0 = rp[0];
+                            q1 = rp[1];
+                        }
+                        const __nv_bfloat16* h0 = reinterpret_cast<const __nv_bfloat16*>(&q0);
+                        const __nv_bfloat16* h1 = reinterpret_cast<const __nv_bfloat16*>(&q1);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            v[j] += __bfloat162float(h0[j]);
+                            v[8 + j] += __bfloat162float(h1[j]);
+                        }
+                    }
+                    if (!on_board) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] = 0.0f;  // keep the padding rows zero for the next layer
+                    }
+                    if (store) {
+                        if (p.out_f32) {
+                            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + size_t(row) * p.out_stride + ch);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+                            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + size_t(row) * p.out_stride + ch);
+                            op[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                            op[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.tmem_empty[buf]);
+        }
+    }
+
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(p.tmem_cols))
+                     : "memory");
+    }
+}
+
+}  // namespace
+
+size_t conv_tch_smem_bytes(int n, int stages, int a_rows) {
+    return 1024 /*alignment slack*/ + size_t(stages) * n * 128 + kASlots * a_slot_bytes(a_rows) + (2 * stages + 2 * kASlots + 4) * 8 + 16 +
+           size_t(n) * 4;
+}
+
+int conv_tch_pick_stages(int n, int a_rows) {
+    const size_t budget = 227 * 1024;
+    int stages = 9;
+    while (stages > 2 && conv_tch_smem_bytes(n, stages, a_rows) > budget) stages--;
+    return stages;
+}
+
+void conv_tch_prepare() { cudaFuncSetAttribute(conv_tch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }
+
+// tmap_a: 2-D map over the channels-last rows with an UNSWIZZLED box of (8 channels, p.a_rows rows)
+void launch_conv_tch(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ConvTcParams& p, int grid, cudaStream_t s) {
+    if (p.num_tiles <= 0) return;
+    conv_tch_kernel<<<std::min(grid, p.num_tiles), kThreads, conv_tch_smem_bytes(p.n, p.stages, p.a_rows), s>>>(tmap_a, tmap_b, p);
+}
+
+}  // namespace kzb

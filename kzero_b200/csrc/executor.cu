@@ -245,6 +245,7 @@ void Net::build_bf16() {
     const char* no_tc8 = std::getenv("KZB_NO_CONV8");
     const bool allow_tc8 = mode_ == 1 && !(no_tc8 && no_tc8[0] == '1');
     conv_tc_prepare();
+    conv_tch_prepare();
     conv_tc8_prepare();
     rows_alloc_ = round_up(boards_alloc * lay_.board_pitch, 128);
     cin_pad_ = round_up(spec_.cin, 64);
@@ -333,6 +334,19 @@ void Net::build_bf16() {
         p.tmem_cols = cols;
         // KZB_CONV_CLUSTER=2: CTA pairs share every weight tile (TMA multicast); worth it where the weight stream
         // dominates SM ingress, i.e. wide layers on boards that go through the per-layer kernel
+        // 3x3 layers on padded rows load their activation tile once per k-block (conv_tch.cu; KZB_CONV_HALO=0 falls back
+        // to conv_tc.cu, which re-loads it for every tap)
+        const char* halo_env = std::getenv("KZB_CONV_HALO");
+        p.halo = lay_.rank_pitch + 1;
+        p.a_rows = (128 + 2 * p.halo + 7) & ~7;  // whole 8-row groups: every k-chunk of the tile starts 128-byte aligned
+        if (!(halo_env && halo_env[0] == '0') && mode_ == 0 && st->taps == 9 && cin_pad % 64 == 0 && p.a_rows <= 256 && !st->use_tc8) {
+            uint64_t dims[2] = {uint64_t(in_stride), uint64_t(rows_alloc_)};
+            uint64_t strides[1] = {uint64_t(in_stride) * 2};
+            uint32_t box[2] = {8, uint32_t(p.a_rows)};
+            st->tmap_ah = make_tmap(in.ptr, 2, dims, strides, box, false);
+            st->use_tch = true;
+            st->tch_stages = conv_tch_pick_stages(n, p.a_rows);
+        }
         const char* cl = std::getenv("KZB_CONV_CLUSTER");
         p.cluster = (cl && cl[0] == '2' && n % 32 == 0 && st->taps == 9) ? 2 : 1;
         convs_.push_back(std::move(st));
@@ -725,7 +739,12 @@ void Net::run_network(int batch, const StepHook& hook) {
                 p.valid_rows = batch * lay_.board_pitch;
                 p.num_tiles = (p.valid_rows + 127) / 128;
             }
-            launch_conv_tc(st->tmap_a, st->tmap_b, st->tmap_bh, p, num_sms_, stream_);
+            if (st->use_tch) {
+                p.stages = st->tch_stages;
+                launch_conv_tch(st->tmap_ah, st->tmap_b, p, num_sms_, stream_);
+            } else {
+                launch_conv_tc(st->tmap_a, st->tmap_b, st->tmap_bh, p, num_sms_, stream_);
+            }
         } else {
             ConvF32Params p = st->f32;
             p.batch = batch;

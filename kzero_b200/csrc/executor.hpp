@@ -45,7 +45,9 @@ struct ConvStep {
     std::string name;
     int taps = 9;
     // bf16 tensor-core form
-    CUtensorMap tmap_a{}, tmap_b{}, tmap_bh{};
+    CUtensorMap tmap_a{}, tmap_b{}, tmap_bh{}, tmap_ah{};
+    bool use_tch = false;  // conv_tch.cu (activation tile with halo, loaded once per k-block)
+    int tch_stages = 0;
     ConvTcParams tc{};
     bool use_tc8 = false;  // 8x8-board specialisation (conv_tc8.cu)
     CUtensorMap tmap_a8{};

@@ -87,11 +87,17 @@ struct ConvTcParams {
     int stages;
     int tmem_cols;
     int cluster;  // conv_tc only: 1, or 2 = CTA pairs share every weight tile through TMA multicast
+    int halo, a_rows;  // conv_tch only: rank_pitch + 1 halo rows on either side, a_rows = 128 + 2 * halo (rounded up to 8) rows per activation tile
     // development aid: when non-null, each CTA writes 16 clock64() stamps (see conv_tc8.cu) -- KZB_TIMELINE=1
     unsigned long long* timeline;
 };
 void launch_conv_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_bh, const ConvTcParams& p,
                     int grid, cudaStream_t s);
+// conv_tch.cu: the same layer with the activation tile loaded once per k-block (3x3 layers on padded rows)
+void launch_conv_tch(const CUtensorMap& tmap_a_rows, const CUtensorMap& tmap_b, const ConvTcParams& p, int grid, cudaStream_t s);
+size_t conv_tch_smem_bytes(int n, int stages, int a_rows);
+int conv_tch_pick_stages(int n, int a_rows);
+void conv_tch_prepare();
 size_t conv_tc_smem_bytes(int n, int stages);
 int conv_tc_pick_stages(int n);
 void conv_tc_prepare();  // per-device: opt in to 227 KB dynamic shared memory
