@@ -9,8 +9,10 @@ namespace kzb {
 
 // `quarter` = warp % 4 selects the TMEM lanes [32*quarter, 32*quarter+32) this warp may read; `tmem_acc` is the
 // accumulator's TMEM address (lane 0); waits for `tmem_full` at `buf_phase`, arrives on `tmem_empty` when done.
+// The accumulator's columns [0, n_cols) are output channels [ch_base, ch_base + n_cols) (a CTA that owns only part of
+// the output channels passes its slice; `bias` always holds all of them).
 __device__ __forceinline__ void conv_epilogue_tile(const ConvTcParams& p, const float* bias, int tile, int quarter, int lane, uint32_t tmem_acc,
-                                                   uint64_t* tmem_full, uint32_t buf_phase, uint64_t* tmem_empty) {
+                                                   uint64_t* tmem_full, uint32_t buf_phase, uint64_t* tmem_empty, int ch_base, int n_cols) {
     using namespace tc;
     const int row = tile * 128 + quarter * 32 + lane;
     bool on_board = true;
@@ -26,10 +28,10 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvTcParams& p, const 
     uint4 resq[kResPrefetch];
     const bool has_res = p.res != nullptr && store;
     if (has_res) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.res + size_t(row) * p.res_stride);
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + size_t(row) * p.res_stride + ch_base);
 #pragma unroll
         for (int j = 0; j < kResPrefetch; j++)
-            if (j * 8 < p.n_store) resq[j] = rp[j];
+            if (j * 8 < n_cols) resq[j] = rp[j];
     }
 
     mbar_wait(tmem_full, buf_phase);
@@ -39,8 +41,8 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvTcParams& p, const 
 #pragma unroll
     for (int cc = 0; cc < 8; cc++) {  // 32 columns per iteration, n <= 256
         const int c0 = cc * 32;
-        if (c0 >= p.n_store) break;
-        const bool second = c0 + 16 < p.n_store;
+        if (c0 >= n_cols) break;
+        const bool second = c0 + 16 < n_cols;
         uint32_t r[32];
         tmem_ld16(taddr + c0, r);
         if (second) tmem_ld16(taddr + c0 + 16, r + 16);
@@ -48,7 +50,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvTcParams& p, const 
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             if (h == 1 && !second) break;
-            const int ch = c0 + h * 16;
+            const int col = c0 + h * 16, ch = ch_base + col;
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; j++) {

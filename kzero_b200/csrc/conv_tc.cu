@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(kThreads, 1)
             const int tile = int(blockIdx.x) + local * int(gridDim.x);
             const int buf = local & 1;
             const uint32_t buf_phase = (local >> 1) & 1;
-            conv_epilogue_tile(p, sm.bias, tile, quarter, lane, tmem_base + buf * acc_stride, &sm.tmem_full[buf], buf_phase, &sm.tmem_empty[buf]);
+            conv_epilogue_tile(p, sm.bias, tile, quarter, lane, tmem_base + buf * acc_stride, &sm.tmem_full[buf], buf_phase, &sm.tmem_empty[buf], 0,
+                               p.n_store);
         }
     }
 

@@ -7,7 +7,8 @@
 // is the same tile read from row halo + dy * rank_pitch + dx.  Per 128-row tile and k-block the SM receives R * 128 bytes
 // of activations instead of 9 * 16 KB, the weight stream (cout * 128 bytes per tap and k-block) is unchanged: 27 % fewer
 // bytes into shared memory per MMA at cout = 256.  profiles/r01d_go9_conv_tc_ncu.md has the measurement that motivates
-// it.  Weights keep the SWIZZLE_128B layout and an own ring.  Default for 3x3 layers in mode 0 (KZB_CONV_HALO=0: conv_tc.cu).
+// it.  Weights keep the SWIZZLE_128B layout and an own ring.  p.n_split = 2 (small batches: fewer tiles than half the SMs)
+// makes a work item one tile x one HALF of the output channels, so that twice as many SMs share the layer.  Default for 3x3 layers in mode 0 (KZB_CONV_HALO=0: conv_tc.cu).
 #include "conv_epilogue.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -64,7 +65,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const SmemLayout sm = carve(smem, p.n, p.stages, p.a_rows);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const uint32_t b_bytes = uint32_t(p.n) * 128u;
+    const int n_eff = p.n / p.n_split;  // output channels per work item
+    const int num_items = p.num_tiles * p.n_split;
+    const uint32_t b_slot = uint32_t(p.n) * 128u;     // ring pitch (sized for the whole n)
+    const uint32_t b_bytes = uint32_t(n_eff) * 128u;  // bytes one weight tile brings
     const uint32_t a_bytes = uint32_t(a_slot_bytes(p.a_rows));
     const uint32_t chunk_bytes = uint32_t(p.a_rows) * 16u;  // one k-chunk (8 channels) of the activation tile
 
@@ -103,7 +107,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (lane == 0) {
             int stage = 0, a_slot = 0;
             uint32_t phase = 0, a_phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const int tile = item / p.n_split, n0 = (item % p.n_split) * n_eff;
                 for (int kb = 0; kb < p.kblocks; kb++) {
                     // the activation tile of this k-block, halo rows included (rows off either end are zero-filled)
                     mbar_wait(&sm.a_empty[a_slot], a_phase ^ 1);
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                     for (int tap = 0; tap < 9; tap++) {
                         mbar_wait(&sm.empty[stage], phase ^ 1);
                         mbar_expect_tx(&sm.full[stage], b_bytes);
-                        tma_load_2d(&tmap_b, &sm.full[stage], sm.b_base + size_t(stage) * b_bytes, tap * p.cin_pad + kb * kBlockK, 0);
+                        tma_load_2d(&tmap_b, &sm.full[stage], sm.b_base + size_t(stage) * b_slot, tap * p.cin_pad + kb * kBlockK, n0);
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1;
@@ -131,13 +136,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        const uint32_t idesc = umma_idesc_bf16(kTileM, p.n);
+        const uint32_t idesc = umma_idesc_bf16(kTileM, n_eff);
         const uint64_t b_hi = umma_desc_sw128_hi();
         const uint64_t a_hi = umma_desc_nosw_hi(chunk_bytes, 128);
         int stage = 0, a_slot = 0;
         uint32_t phase = 0, a_phase = 0;
         int local = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, local++) {
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x, local++) {
             const int buf = local & 1;
             const uint32_t buf_phase = (local >> 1) & 1;
             mbar_wait(&sm.tmem_empty[buf], buf_phase ^ 1);
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 for (int tap = 0; tap < 9; tap++) {
                     mbar_wait(&sm.full[stage], phase);
                     tc_fence_after();
-                    const uint32_t b_lo = umma_desc_lo(smem_u32(sm.b_base + size_t(stage) * b_bytes));
+                    const uint32_t b_lo = umma_desc_lo(smem_u32(sm.b_base + size_t(stage) * b_slot));
                     // tap (dy, dx) = the same tile read from another row; one row is 16 bytes = one descriptor unit
                     const uint32_t a_t = a_lo + uint32_t(p.halo + (tap / 3 - 1) * p.lay.rank_pitch + (tap % 3 - 1));
                     if (lane == 0) {
@@ -179,10 +184,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         const int quarter = warp % 4;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
-        for (int tile = blockIdx.x, local = 0; tile < p.num_tiles; tile += gridDim.x, local++) {
+        for (int item = blockIdx.x, local = 0; item < num_items; item += gridDim.x, local++) {
             const int buf = local & 1;
             const uint32_t buf_phase = (local >> 1) & 1;
-            conv_epilogue_tile(p, sm.bias, tile, quarter, lane, tmem_base + buf * acc_stride, &sm.tmem_full[buf], buf_phase, &sm.tmem_empty[buf]);
+            const int tile = item / p.n_split, n0 = (item % p.n_split) * n_eff;
+            conv_epilogue_tile(p, sm.bias, tile, quarter, lane, tmem_base + buf * acc_stride, &sm.tmem_full[buf], buf_phase, &sm.tmem_empty[buf], n0,
+                               min(n_eff, p.n_store - n0));
         }
     }
 
@@ -212,10 +219,11 @@ int conv_tch_pick_stages(int n, int a_rows) {
 
 void conv_tch_prepare() { cudaFuncSetAttribute(conv_tch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }
 
-// tmap_a: 2-D map over the channels-last rows with an UNSWIZZLED box of (8 channels, p.a_rows rows)
+// tmap_a: 2-D map over the channels-last rows with an UNSWIZZLED box of (8 channels, p.a_rows rows); tmap_b: the weight map
+// whose box holds p.n / p.n_split rows
 void launch_conv_tch(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ConvTcParams& p, int grid, cudaStream_t s) {
     if (p.num_tiles <= 0) return;
-    conv_tch_kernel<<<std::min(grid, p.num_tiles), kThreads, conv_tch_smem_bytes(p.n, p.stages, p.a_rows), s>>>(tmap_a, tmap_b, p);
+    conv_tch_kernel<<<std::min(grid, p.num_tiles * p.n_split), kThreads, conv_tch_smem_bytes(p.n, p.stages, p.a_rows), s>>>(tmap_a, tmap_b, p);
 }
 
 }  // namespace kzb

@@ -337,6 +337,7 @@ void Net::build_bf16() {
         // 3x3 layers on padded rows load their activation tile once per k-block (conv_tch.cu; KZB_CONV_HALO=0 falls back
         // to conv_tc.cu, which re-loads it for every tap)
         const char* halo_env = std::getenv("KZB_CONV_HALO");
+        p.n_split = 1;
         p.halo = lay_.rank_pitch + 1;
         p.a_rows = (128 + 2 * p.halo + 7) & ~7;  // whole 8-row groups: every k-chunk of the tile starts 128-byte aligned
         if (!(halo_env && halo_env[0] == '0') && mode_ == 0 && st->taps == 9 && cin_pad % 64 == 0 && p.a_rows <= 256 && !st->use_tc8) {
@@ -741,7 +742,10 @@ void Net::run_network(int batch, const StepHook& hook) {
             }
             if (st->use_tch) {
                 p.stages = st->tch_stages;
-                launch_conv_tch(st->tmap_ah, st->tmap_b, p, num_sms_, stream_);
+                // small batches: split the output channels so that twice as many SMs share the layer (KZB_CONV_SPLIT=0: never)
+                const char* split = std::getenv("KZB_CONV_SPLIT");
+                p.n_split = (!(split && split[0] == '0') && p.n >= 128 && p.n % 32 == 0 && p.n_store == p.n && 2 * p.num_tiles <= num_sms_) ? 2 : 1;
+                launch_conv_tch(st->tmap_ah, p.n_split == 2 ? st->tmap_bh : st->tmap_b, p, num_sms_, stream_);
             } else {
                 launch_conv_tc(st->tmap_a, st->tmap_b, st->tmap_bh, p, num_sms_, stream_);
             }

@@ -128,7 +128,7 @@ def test_fp32_packed_vs_oracle(game, depth, ch, n):
     _check_packed(values, probs, ref_values, ref_probs, mv_off, FP32_TOL, FP32_TOL)
 
 
-@pytest.mark.parametrize("variant", ["default", "tower_v1", "no_heads8", "no_tower8", "no_conv8", "linear", "no_embed8", "conv_cluster", "no_conv_halo"])
+@pytest.mark.parametrize("variant", ["default", "tower_v1", "no_heads8", "no_tower8", "no_conv8", "linear", "no_embed8", "conv_cluster", "no_conv_halo", "no_conv_split"])
 @pytest.mark.parametrize("game,depth,ch,n", [("ataxx-7", 8, 64, 256), ("chess", 16, 128, 64), ("go-9", 4, 64, 40),
                                               ("chess", 2, 32, 7), ("chess", 3, 64, 130), ("chess", 2, 256, 12)])
 def test_bf16_packed_vs_oracle(game, depth, ch, n, variant, monkeypatch):
@@ -137,18 +137,20 @@ def test_bf16_packed_vs_oracle(game, depth, ch, n, variant, monkeypatch):
     per-layer 8x8 specialisation (conv_tc8.cu, KZB_NO_TOWER8=1), generic 4-D TMA box per tap (KZB_NO_CONV8=1),
     padded-row 2-D TMA (boards larger than 8x8 / KZB_FORCE_LINEAR=1 / KZB_NO_EMBED8=1), the same with CTA pairs sharing every
     weight tile through TMA multicast (KZB_CONV_CLUSTER=2, with KZB_CONV_HALO=0) -- by default 3x3 layers on padded rows load the activation tile once per
-    k-block with its halo (conv_tch.cu), KZB_CONV_HALO=0 re-loads it per tap (conv_tc.cu); boards smaller than 8x8 (ataxx 7x7) are embedded in the 8x8
+    k-block with its halo (conv_tch.cu), KZB_CONV_HALO=0 re-loads it per tap (conv_tc.cu), and two CTAs share a tile's output
+    channels when there are fewer tiles than half the SMs (KZB_CONV_SPLIT=0: never); boards smaller than 8x8 (ataxx 7x7) are embedded in the 8x8
     grid and masked after every layer."""
     if variant == "no_embed8":
         if game != "ataxx-7":
             pytest.skip("only boards smaller than 8x8 are embedded")
-    elif variant in ("conv_cluster", "no_conv_halo"):
+    elif variant in ("conv_cluster", "no_conv_halo", "no_conv_split"):
         if game == "ataxx-7":
             pytest.skip("covered by go-9 and the chess nets on padded rows")
     elif variant != "default" and game != "chess":
         pytest.skip("the kernel variants are 8x8 specialisations")
     monkeypatch.setenv("KZB_NO_EMBED8", "1" if variant == "no_embed8" else "0")
-    force_linear = "1" if variant in ("linear", "conv_cluster", "no_conv_halo") else "0"
+    force_linear = "1" if variant in ("linear", "conv_cluster", "no_conv_halo", "no_conv_split") else "0"
+    monkeypatch.setenv("KZB_CONV_SPLIT", "0" if variant == "no_conv_split" else "1")
     monkeypatch.setenv("KZB_CONV_HALO", "0" if variant in ("no_conv_halo", "conv_cluster") else "1")
     monkeypatch.setenv("KZB_CONV_CLUSTER", "2" if variant == "conv_cluster" else "1")
     monkeypatch.setenv("KZB_FORCE_LINEAR", force_linear)
