@@ -1,6 +1,7 @@
 #!/bin/bash
 # A/B of the search tree layouts under memory contention, host only: P pinned copies of the MCTS microbenchmark
-# (scripts/micro/mcts_host_bench.cpp built from four revisions into scripts/micro/ab/), 64 trees each, aggregate nodes/s.
+# (scripts/micro/mcts_host_bench.cpp built from four revisions into scripts/micro/ab/ by scripts/build_layout_ab.sh), 64 trees each,
+# aggregate nodes/s.
 mkdir -p gpurun_out
 out=gpurun_out/host_layout_ab.txt
 lscpu | egrep "Model name|^CPU\(s\)|L2|L3" > $out
