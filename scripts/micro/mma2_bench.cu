@@ -16,7 +16,7 @@
 using namespace kzb::tc;
 
 constexpr int kAOff = 0;          // A: 128 rows x 64 k, SWIZZLE_128B, 16 KB
-constexpr int kBOff = 16384;      // B half: up to 128 rows x 64 k, SWIZZLE_128B, 16 KB
+constexpr int kBOff = 20480;      // B half: up to 128 rows x 64 k, SWIZZLE_128B, 16 KB (A unswizzled: 8 x 152 x 16 = 19456 bytes)
 
 __device__ __forceinline__ bool bounded_wait(uint64_t* bar, uint32_t parity) {
     for (int spin = 0; spin < (1 << 22); spin++) {
@@ -32,15 +32,19 @@ __device__ __forceinline__ bool bounded_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // img: per CTA rank, 32 KB image of (A, B half).  mode 0: one K=64 pass, D -> out;  mode 1: timing
-__global__ void __launch_bounds__(128, 1) bench2(const uint8_t* img, int n, int iters, float* out, unsigned long long* cyc, int* status) {
+// a_nosw: A is laid out unswizzled, [k-chunk of 8][row][16 bytes] with kARows rows per k-chunk (the halo-tile operand of
+// conv_tch.cu: LBO = kARows * 16, SBO = 128), and read from row `a_row0`
+constexpr int kARows = 152;
+__global__ void __launch_bounds__(128, 1) bench2(const uint8_t* img, int n, int iters, float* out, unsigned long long* cyc, int* status, int a_nosw,
+                                                 int a_row0) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_ptr;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const uint32_t rank = cluster_ctarank();
-    const uint8_t* mine = img + size_t(rank) * 32768;
-    for (int i = threadIdx.x; i < 32768 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = reinterpret_cast<const uint32_t*>(mine)[i];
+    const uint8_t* mine = img + size_t(rank) * 40960;
+    for (int i = threadIdx.x; i < 40960 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = reinterpret_cast<const uint32_t*>(mine)[i];
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -60,13 +64,15 @@ __global__ void __launch_bounds__(128, 1) bench2(const uint8_t* img, int n, int 
         if (rank == 0) {
             const uint32_t idesc = umma_idesc_bf16(256, n);
             const uint64_t hi = umma_desc_sw128_hi();
-            const uint32_t a_lo = umma_desc_lo(smem_u32(smem + kAOff)), b_lo = umma_desc_lo(smem_u32(smem + kBOff));
+            const uint32_t a_lo = umma_desc_lo(smem_u32(smem + kAOff)) + (a_nosw ? uint32_t(a_row0) : 0u), b_lo = umma_desc_lo(smem_u32(smem + kBOff));
+            const uint64_t a_hi = a_nosw ? ((uint64_t(kARows * 16 >> 4) << 16) | (uint64_t(128 >> 4) << 32) | (uint64_t(1) << 46)) : hi;
+            const uint32_t a_step = a_nosw ? uint32_t(2 * kARows * 16 >> 4) : 2u;  // 16 channels further along K
             const unsigned long long t0 = clock64();
             for (int it = 0; it < iters; it++) {
                 if (lane == 0) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const uint64_t da = hi | uint64_t(a_lo + 2 * j), db = hi | uint64_t(b_lo + 2 * j);
+                        const uint64_t da = a_hi | uint64_t(a_lo + a_step * j), db = hi | uint64_t(b_lo + 2 * j);
                         const uint32_t acc = (it | j) != 0;
                         asm volatile(
                             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem),
@@ -119,11 +125,11 @@ static void put_sw128(std::vector<uint8_t>& img, size_t base, int r, int k, floa
     memcpy(&img[off], &h, 2);
 }
 
-static cudaError_t launch(int grid, const uint8_t* d_img, int n, int iters, float* out, unsigned long long* cyc, int* status) {
+static cudaError_t launch(int grid, const uint8_t* d_img, int n, int iters, float* out, unsigned long long* cyc, int* status, int a_nosw, int a_row0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(grid));
     cfg.blockDim = dim3(128);
-    cfg.dynamicSmemBytes = 40 * 1024;
+    cfg.dynamicSmemBytes = 48 * 1024;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
@@ -131,7 +137,7 @@ static cudaError_t launch(int grid, const uint8_t* d_img, int n, int iters, floa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, bench2, d_img, n, iters, out, cyc, status);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, bench2, d_img, n, iters, out, cyc, status, a_nosw, a_row0);
     if (e != cudaSuccess) return e;
     return cudaDeviceSynchronize();
 }
@@ -141,28 +147,39 @@ int main() {
     float* d_out;
     unsigned long long* d_cyc;
     int* d_status;
-    cudaMalloc(&d_img, 65536);
+    cudaMalloc(&d_img, 81920);
     cudaMalloc(&d_out, 256 * 256 * 4);
     cudaMalloc(&d_cyc, 148 * 8);
     cudaMalloc(&d_status, 4);
     cudaFuncSetAttribute(bench2, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(bench2, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    for (int n : {256, 128}) {
+    for (int cfg_i = 0; cfg_i < 4; cfg_i++) {
+        const int n = cfg_i % 2 == 0 ? 256 : 128, a_nosw = cfg_i / 2, a_row0 = a_nosw ? 11 : 0;  // row 11: a tap-shifted start inside the halo tile
+        printf("---- A operand %s\n", a_nosw ? "UNSWIZZLED halo tile (152 rows per k-chunk), read from row 11" : "SWIZZLE_128B");
         std::vector<float> A(256 * 64), B(size_t(n) * 64);
         srand(n);
         for (auto& v : A) v = bf((rand() % 200 - 100) / 64.0f);
         for (auto& v : B) v = bf((rand() % 200 - 100) / 64.0f);
-        std::vector<uint8_t> img(65536, 0);
+        std::vector<uint8_t> img(81920, 0);
         for (int rank = 0; rank < 2; rank++) {
             for (int r = 0; r < 128; r++)
-                for (int k = 0; k < 64; k++) put_sw128(img, size_t(rank) * 32768 + kAOff, r, k, A[size_t(rank * 128 + r) * 64 + k]);
+                for (int k = 0; k < 64; k++) {
+                    const float v = A[size_t(rank * 128 + r) * 64 + k];
+                    if (!a_nosw) {
+                        put_sw128(img, size_t(rank) * 40960 + kAOff, r, k, v);
+                    } else {
+                        __nv_bfloat16 h = __float2bfloat16_rn(v);
+                        const size_t off = size_t(rank) * 40960 + kAOff + size_t(k / 8) * kARows * 16 + size_t(a_row0 + r) * 16 + size_t(k % 8) * 2;
+                        memcpy(&img[off], &h, 2);
+                    }
+                }
             for (int r = 0; r < n / 2; r++)
-                for (int k = 0; k < 64; k++) put_sw128(img, size_t(rank) * 32768 + kBOff, r, k, B[size_t(rank * (n / 2) + r) * 64 + k]);
+                for (int k = 0; k < 64; k++) put_sw128(img, size_t(rank) * 40960 + kBOff, r, k, B[size_t(rank * (n / 2) + r) * 64 + k]);
         }
         cudaMemcpy(d_img, img.data(), img.size(), cudaMemcpyHostToDevice);
         cudaMemset(d_out, 0, 256 * 256 * 4);
         cudaMemset(d_status, 0, 4);
-        cudaError_t e = launch(2, d_img, n, 1, d_out, nullptr, d_status);
+        cudaError_t e = launch(2, d_img, n, 1, d_out, nullptr, d_status, a_nosw, a_row0);
         int status = 0;
         cudaMemcpy(&status, d_status, 4, cudaMemcpyDeviceToHost);
         printf("N=%d correctness launch: %s%s\n", n, cudaGetErrorString(e), status ? "  (a barrier wait timed out)" : "");
@@ -186,7 +203,7 @@ int main() {
             }
         const int iters = 1024;
         cudaMemset(d_status, 0, 4);
-        e = launch(148, d_img, n, iters, nullptr, d_cyc, d_status);
+        e = launch(148, d_img, n, iters, nullptr, d_cyc, d_status, a_nosw, a_row0);
         unsigned long long c[2];
         cudaMemcpy(c, d_cyc, 16, cudaMemcpyDeviceToHost);
         cudaMemcpy(&status, d_status, 4, cudaMemcpyDeviceToHost);
