@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(128, 1) bench2(const uint8_t* img, int n, int 
                                                  int a_row0) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, peer_ready;
     __shared__ uint32_t tmem_ptr;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const uint32_t rank = cluster_ctarank();
@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(128, 1) bench2(const uint8_t* img, int n, int 
     for (int i = threadIdx.x; i < 40960 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = reinterpret_cast<const uint32_t*>(mine)[i];
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
+        mbar_init(&peer_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -61,7 +62,26 @@ __global__ void __launch_bounds__(128, 1) bench2(const uint8_t* img, int n, int 
     const uint32_t tmem = tmem_ptr;
     bool ok = true;
     if (warp == 1) {
+        // the handshake a pipelined kernel needs per stage: the peer tells the leader "my half of the operands is in place"
+        // with a remote arrive on the leader's barrier (here once; the cluster barrier above already made it true)
+        if (rank == 1 && lane == 0) {
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(&peer_ready)));
+            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+        }
         if (rank == 0) {
+            bool peer_ok = false;
+            for (int spin = 0; spin < (1 << 22) && !peer_ok; spin++) {
+                uint32_t done;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(smem_u32(&peer_ready)), "r"(0u)
+                    : "memory");
+                peer_ok = done != 0;
+            }
+            if (!peer_ok && lane == 0) atomicExch(status, 2);
+            tc_fence_after();
             const uint32_t idesc = umma_idesc_bf16(256, n);
             const uint64_t hi = umma_desc_sw128_hi();
             const uint32_t a_lo = umma_desc_lo(smem_u32(smem + kAOff)) + (a_nosw ? uint32_t(a_row0) : 0u), b_lo = umma_desc_lo(smem_u32(smem + kBOff));
@@ -182,7 +202,8 @@ int main() {
         cudaError_t e = launch(2, d_img, n, 1, d_out, nullptr, d_status, a_nosw, a_row0);
         int status = 0;
         cudaMemcpy(&status, d_status, 4, cudaMemcpyDeviceToHost);
-        printf("N=%d correctness launch: %s%s\n", n, cudaGetErrorString(e), status ? "  (a barrier wait timed out)" : "");
+        printf("N=%d correctness launch: %s%s\n", n, cudaGetErrorString(e),
+               status == 2 ? "  (the peer's remote arrive never reached the leader)" : status ? "  (a barrier wait timed out)" : "  (remote arrive handshake ok)");
         if (e != cudaSuccess) return 1;
         std::vector<float> out(256 * 256);
         cudaMemcpy(out.data(), d_out, out.size() * 4, cudaMemcpyDeviceToHost);
