@@ -95,7 +95,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvTcParams& p, const 
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tmem_empty);
+    if (lane == 0 && tmem_empty != nullptr) mbar_arrive(tmem_empty);  // nullptr: the caller signals (a barrier in another CTA)
 }
 
 }  // namespace kzb

@@ -246,6 +246,7 @@ void Net::build_bf16() {
     const bool allow_tc8 = mode_ == 1 && !(no_tc8 && no_tc8[0] == '1');
     conv_tc_prepare();
     conv_tch_prepare();
+    if (const char* pair_env = std::getenv("KZB_CONV_PAIR"); pair_env && pair_env[0] == '1') conv_tchp_prepare();  // experimental kernel: untouched otherwise
     conv_tc8_prepare();
     rows_alloc_ = round_up(boards_alloc * lay_.board_pitch, 128);
     cin_pad_ = round_up(spec_.cin, 64);
@@ -347,6 +348,11 @@ void Net::build_bf16() {
             st->tmap_ah = make_tmap(in.ptr, 2, dims, strides, box, false);
             st->use_tch = true;
             st->tch_stages = conv_tch_pick_stages(n, p.a_rows);
+            const char* pair_env = std::getenv("KZB_CONV_PAIR");  // experimental: the same layer on the CTA-pair MMA
+            if (pair_env && pair_env[0] == '1' && n % 32 == 0 && n >= 64) {
+                st->use_tchp = true;
+                st->tchp_stages = conv_tchp_pick_stages(n, p.a_rows);
+            }
         }
         const char* cl = std::getenv("KZB_CONV_CLUSTER");
         p.cluster = (cl && cl[0] == '2' && n % 32 == 0 && st->taps == 9) ? 2 : 1;
@@ -740,7 +746,11 @@ void Net::run_network(int batch, const StepHook& hook) {
                 p.valid_rows = batch * lay_.board_pitch;
                 p.num_tiles = (p.valid_rows + 127) / 128;
             }
-            if (st->use_tch) {
+            if (st->use_tchp) {
+                p.stages = st->tchp_stages;
+                p.n_split = 1;
+                launch_conv_tchp(st->tmap_ah, st->tmap_bh, p, num_sms_, stream_);
+            } else if (st->use_tch) {
                 p.stages = st->tch_stages;
                 // small batches: split the output channels so that twice as many SMs share the layer (KZB_CONV_SPLIT=0: never)
                 const char* split = std::getenv("KZB_CONV_SPLIT");

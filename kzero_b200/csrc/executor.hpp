@@ -48,6 +48,8 @@ struct ConvStep {
     CUtensorMap tmap_a{}, tmap_b{}, tmap_bh{}, tmap_ah{};
     bool use_tch = false;  // conv_tch.cu (activation tile with halo, loaded once per k-block)
     int tch_stages = 0;
+    bool use_tchp = false;  // conv_tchp.cu (experimental CTA-pair variant, KZB_CONV_PAIR=1)
+    int tchp_stages = 0;
     ConvTcParams tc{};
     bool use_tc8 = false;  // 8x8-board specialisation (conv_tc8.cu)
     CUtensorMap tmap_a8{};

@@ -99,6 +99,11 @@ void launch_conv_tch(const CUtensorMap& tmap_a_rows, const CUtensorMap& tmap_b, 
 size_t conv_tch_smem_bytes(int n, int stages, int a_rows);
 int conv_tch_pick_stages(int n, int a_rows);
 void conv_tch_prepare();
+// conv_tchp.cu (experimental): conv_tch on the CTA-pair MMA, each CTA stages half of every weight tile
+void launch_conv_tchp(const CUtensorMap& tmap_a_rows, const CUtensorMap& tmap_bh, const ConvTcParams& p, int grid, cudaStream_t s);
+size_t conv_tchp_smem_bytes(int n, int stages, int a_rows);
+int conv_tchp_pick_stages(int n, int a_rows);
+void conv_tchp_prepare();
 size_t conv_tc_smem_bytes(int n, int stages);
 int conv_tc_pick_stages(int n);
 void conv_tc_prepare();  // per-device: opt in to 227 KB dynamic shared memory

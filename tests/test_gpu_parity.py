@@ -128,7 +128,7 @@ def test_fp32_packed_vs_oracle(game, depth, ch, n):
     _check_packed(values, probs, ref_values, ref_probs, mv_off, FP32_TOL, FP32_TOL)
 
 
-@pytest.mark.parametrize("variant", ["default", "tower_v1", "no_heads8", "no_tower8", "no_conv8", "linear", "no_embed8", "conv_cluster", "no_conv_halo", "no_conv_split"])
+@pytest.mark.parametrize("variant", ["default", "tower_v1", "no_heads8", "no_tower8", "no_conv8", "linear", "no_embed8", "conv_cluster", "no_conv_halo", "no_conv_split", "conv_pair"])
 @pytest.mark.parametrize("game,depth,ch,n", [("ataxx-7", 8, 64, 256), ("chess", 16, 128, 64), ("go-9", 4, 64, 40),
                                               ("chess", 2, 32, 7), ("chess", 3, 64, 130), ("chess", 2, 256, 12)])
 def test_bf16_packed_vs_oracle(game, depth, ch, n, variant, monkeypatch):
@@ -143,13 +143,16 @@ def test_bf16_packed_vs_oracle(game, depth, ch, n, variant, monkeypatch):
     if variant == "no_embed8":
         if game != "ataxx-7":
             pytest.skip("only boards smaller than 8x8 are embedded")
-    elif variant in ("conv_cluster", "no_conv_halo", "no_conv_split"):
+    elif variant == "conv_pair" and os.environ.get("KZB_TEST_EXPERIMENTAL") != "1":
+        pytest.skip("conv_tchp.cu (CTA-pair MMA) has not been run on hardware yet: set KZB_TEST_EXPERIMENTAL=1 to try it")
+    elif variant in ("conv_cluster", "no_conv_halo", "no_conv_split", "conv_pair"):
         if game == "ataxx-7":
             pytest.skip("covered by go-9 and the chess nets on padded rows")
     elif variant != "default" and game != "chess":
         pytest.skip("the kernel variants are 8x8 specialisations")
     monkeypatch.setenv("KZB_NO_EMBED8", "1" if variant == "no_embed8" else "0")
-    force_linear = "1" if variant in ("linear", "conv_cluster", "no_conv_halo", "no_conv_split") else "0"
+    force_linear = "1" if variant in ("linear", "conv_cluster", "no_conv_halo", "no_conv_split", "conv_pair") else "0"
+    monkeypatch.setenv("KZB_CONV_PAIR", "1" if variant == "conv_pair" else "0")
     monkeypatch.setenv("KZB_CONV_SPLIT", "0" if variant == "no_conv_split" else "1")
     monkeypatch.setenv("KZB_CONV_HALO", "0" if variant in ("no_conv_halo", "conv_cluster") else "1")
     monkeypatch.setenv("KZB_CONV_CLUSTER", "2" if variant == "conv_cluster" else "1")
