@@ -10,6 +10,7 @@
 //   Ataxx        7x7 ataxx with the reference's AtaxxStdMapper encoding (rust/kz-core/src/mapping/ataxx.rs:60-132):
 //                bools = (next player's tiles, other tiles, gaps), scalar = moves_since_last_copy / 100,
 //                policy index: copy -> to, jump -> (1 + FROM_DX_DY index) * A + to, pass -> 17 * A.
+//   Go9          9x9 go with the reference's GoStdMapper encoding (4 bool + 6 scalar planes) and restated rules, see below.
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -211,6 +212,210 @@ struct Ataxx {
                     bits[bit >> 3] |= uint8_t(1u << (bit & 7));  // LSB-first, bit_buffer.rs:27-35
                 }
         scalars[0] = float(since_copy) / 100.0f;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ Go 9x9
+// Go with the reference's GoStdMapper encoding without the territory planes (rust/kz-core/src/mapping/go.rs:46-112 with
+// territory = false, the 4 + 6 plane form python/lib/games.py:180-194 describes): bools = (next player's stones, other
+// stones, in-board, empty-but-illegal), scalars = (black to move, white to move, one pass, two passes, komi from the
+// mover's side / 15, multi-stone suicide allowed), policy index 0 = pass, 1 + y * S + x = place (go.rs:26-31).
+// Rules, restated (the `board-game` crate is not vendored): area scoring with komi, suicide is illegal, SIMPLE ko (the
+// immediate recapture of a single stone), two consecutive passes end the game.  No superko: a driver-side
+// max_game_length bounds cycles.  Start positions follow go_start_pos (start_pos.rs:69-88): komi 7.5 most of the time.
+struct Go9 {
+    static constexpr int S = 9, A = 81;
+    uint8_t stones[A] = {};  // 0 empty, 1 player A (black), 2 player B (white)
+    uint32_t ply = 0;
+    int16_t ko = -1;         // point that may not be played this turn
+    int16_t komi_2 = 15;     // komi in half points, in white's favour
+    uint8_t passes = 0;      // 0 normal, 1 one pass, 2 done
+
+    static GameShape shape() { return {4, 6, S, A + 1}; }
+    static const char* name() { return "go-9"; }
+    static Go9 start(uint64_t seed) {
+        Go9 g;
+        const uint64_t h = splitmix64(seed ^ 0x60B0A4Dull);
+        const uint32_t pick = uint32_t(h % 10);  // weights 4 : 4 : 2 as in go_start_pos
+        if (pick < 4) g.komi_2 = 15;
+        else if (pick < 8) g.komi_2 = int16_t(10 + (h >> 8) % 10);
+        else g.komi_2 = int16_t(int((h >> 8) % 60) - 30);
+        return g;
+    }
+    int next_player() const { return int(ply & 1); }
+    bool done() const { return passes >= 2; }
+    uint64_t hash() const {
+        uint64_t h = 0x9E3779B97F4A7C15ull * (uint64_t(ply & 1) + 3) + uint64_t(uint16_t(ko)) * 0x100000001B3ull + passes * 0xD6E8FEB86659FD93ull +
+                     uint64_t(uint16_t(komi_2)) * 0xA0761D6478BD642Full;
+        for (int i = 0; i < A; i += 8) {
+            uint64_t w = 0;
+            std::memcpy(&w, stones + i, size_t(A - i < 8 ? A - i : 8));
+            h = splitmix64(h ^ w);
+        }
+        return h;
+    }
+
+    // groups and their liberties for the whole board: gid[p] (0 = empty), libs[g] = liberty count of group g
+    struct Groups {
+        uint8_t gid[A];
+        uint8_t libs[A + 1];
+        int count = 0;
+    };
+    template <typename F>
+    static void for_neighbours(int p, F&& f) {
+        const int x = p % S, y = p / S;
+        if (x > 0) f(p - 1);
+        if (x < S - 1) f(p + 1);
+        if (y > 0) f(p - S);
+        if (y < S - 1) f(p + S);
+    }
+    void groups(Groups& g) const {
+        std::memset(g.gid, 0, sizeof(g.gid));
+        g.count = 0;
+        int stack[A];
+        uint8_t seen_lib[A];  // last group that counted this empty point as a liberty
+        std::memset(seen_lib, 0, sizeof(seen_lib));
+        for (int p0 = 0; p0 < A; p0++) {
+            if (!stones[p0] || g.gid[p0]) continue;
+            const int id = ++g.count;
+            int top = 0, libs = 0;
+            stack[top++] = p0;
+            g.gid[p0] = uint8_t(id);
+            while (top) {
+                const int p = stack[--top];
+                for_neighbours(p, [&](int q) {
+                    if (!stones[q]) {
+                        if (seen_lib[q] != id) {
+                            seen_lib[q] = uint8_t(id);
+                            libs++;
+                        }
+                    } else if (stones[q] == stones[p0] && !g.gid[q]) {
+                        g.gid[q] = uint8_t(id);
+                        stack[top++] = q;
+                    }
+                });
+            }
+            g.libs[id] = uint8_t(libs);
+        }
+    }
+    // legal placements of the player to move: empty, not the ko point, and the stone ends up with a liberty
+    void legal_mask(bool legal[A]) const {
+        Groups g;
+        groups(g);
+        const uint8_t me = uint8_t(1 + (ply & 1)), other = uint8_t(3 - me);
+        for (int p = 0; p < A; p++) {
+            legal[p] = false;
+            if (stones[p] || p == ko) continue;
+            bool ok = false;
+            for_neighbours(p, [&](int q) {
+                if (!stones[q]) ok = true;                                            // an empty neighbour
+                else if (stones[q] == me && g.libs[g.gid[q]] >= 2) ok = true;         // joins a group that keeps a liberty
+                else if (stones[q] == other && g.libs[g.gid[q]] == 1) ok = true;      // captures
+            });
+            legal[p] = ok;
+        }
+    }
+    void moves(std::vector<uint32_t>& out) const {  // a move is its policy index; pass first (available_moves order)
+        bool legal[A];
+        legal_mask(legal);
+        out.clear();
+        out.push_back(0);
+        for (int p = 0; p < A; p++)
+            if (legal[p]) out.push_back(uint32_t(1 + p));
+    }
+    uint32_t move_to_index(uint32_t mv) const { return mv; }
+    void play(uint32_t mv) {
+        if (mv == 0) {
+            passes++;
+            ko = -1;
+            ply++;
+            return;
+        }
+        const int p = int(mv) - 1;
+        const uint8_t me = uint8_t(1 + (ply & 1)), other = uint8_t(3 - me);
+        stones[p] = me;
+        Groups g;
+        groups(g);
+        int captured = 0, last_captured = -1;
+        bool dead[A + 1] = {};
+        for_neighbours(p, [&](int q) {
+            if (stones[q] == other && g.libs[g.gid[q]] == 0) dead[g.gid[q]] = true;
+        });
+        for (int q = 0; q < A; q++)
+            if (stones[q] == other && dead[g.gid[q]]) {
+                stones[q] = 0;
+                captured++;
+                last_captured = q;
+            }
+        // simple ko: one stone captured by a single stone that now has exactly that one liberty
+        ko = -1;
+        if (captured == 1) {
+            bool single = true;
+            int libs = 0;
+            for_neighbours(p, [&](int q) {
+                if (stones[q] == me) single = false;
+                if (!stones[q]) libs++;
+            });
+            if (single && libs == 1) ko = int16_t(last_captured);
+        }
+        passes = 0;
+        ply++;
+    }
+    // area score in half points from black's side, komi included
+    int score_2() const {
+        int black = 0, white = 0;
+        bool seen[A] = {};
+        int stack[A];
+        for (int p0 = 0; p0 < A; p0++) {
+            if (stones[p0] == 1) black++;
+            else if (stones[p0] == 2) white++;
+            else if (!seen[p0]) {  // an empty region belongs to a colour when it touches only that colour
+                int top = 0, size = 0, touches = 0;
+                stack[top++] = p0;
+                seen[p0] = true;
+                while (top) {
+                    const int p = stack[--top];
+                    size++;
+                    for_neighbours(p, [&](int q) {
+                        if (stones[q]) touches |= stones[q];
+                        else if (!seen[q]) {
+                            seen[q] = true;
+                            stack[top++] = q;
+                        }
+                    });
+                }
+                if (touches == 1) black += size;
+                else if (touches == 2) white += size;
+            }
+        }
+        return 2 * (black - white) - komi_2;
+    }
+    int outcome() const {
+        const int s2 = score_2();
+        return (s2 > 0) - (s2 < 0);
+    }
+    void encode(uint8_t* bits, float* scalars) const {
+        std::memset(bits, 0, size_t((4 * A + 7) / 8));
+        bool legal[A];
+        legal_mask(legal);
+        const uint8_t me = uint8_t(1 + (ply & 1)), other = uint8_t(3 - me);
+        auto set = [&](int plane, int p) {
+            const int bit = plane * A + p;
+            bits[bit >> 3] |= uint8_t(1u << (bit & 7));  // LSB-first, bit_buffer.rs:27-35
+        };
+        for (int p = 0; p < A; p++) {
+            if (stones[p] == me) set(0, p);
+            if (stones[p] == other) set(1, p);
+            set(2, p);
+            if (!stones[p] && !legal[p]) set(3, p);
+        }
+        const float komi = float(komi_2) * 0.5f;
+        scalars[0] = next_player() == 0 ? 1.0f : 0.0f;
+        scalars[1] = next_player() == 1 ? 1.0f : 0.0f;
+        scalars[2] = passes == 1 ? 1.0f : 0.0f;
+        scalars[3] = passes >= 2 ? 1.0f : 0.0f;
+        scalars[4] = (next_player() == 0 ? komi : -komi) / 15.0f;
+        scalars[5] = 0.0f;  // multi-stone suicide is not allowed
     }
 };
 

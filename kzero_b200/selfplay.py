@@ -17,6 +17,7 @@ from ._abi import SelfplayConfig, SelfplayStats
 
 GAME_SYNTH_CHESS = 0
 GAME_ATAXX7 = 1
+GAME_GO9 = 2
 
 
 def default_config(**overrides) -> SelfplayConfig:

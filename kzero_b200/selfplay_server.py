@@ -57,7 +57,9 @@ def game_id(name: str) -> int:
         return selfplay.GAME_SYNTH_CHESS
     if name in ("ataxx", "ataxx-7"):
         return selfplay.GAME_ATAXX7
-    raise ValueError(f"game {name!r} is not available in this driver (chess-shaped synthetic game and ataxx-7 are)")
+    if name == "go-9":
+        return selfplay.GAME_GO9
+    raise ValueError(f"game {name!r} is not available in this driver (chess-shaped synthetic game, ataxx-7 and go-9 are)")
 
 
 def config_from(startup: dict, settings: dict, seed: int) -> _abi.SelfplayConfig:

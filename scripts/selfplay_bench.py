@@ -7,7 +7,7 @@
 Settings default to the reference's production values (python/main/loop_main_alpha.py:24-52: 800 visits, search batch 16,
 virtual loss 1, LRU cache 800, Dirichlet 0.03/0.25, root temperature 1.4); the net is chess 16x128 random-init
 (synthetic, like bench.py).  The game is the chess-SHAPED synthetic game of kzero_b200/csrc/selfplay/games.hpp (no chess
-move generator in this repo), or real 7x7 ataxx with an 8x64 net.  Prints one JSON line on rank 0:
+move generator in this repo), real 7x7 ataxx with an 8x64 net, or 9x9 go with the 20x256 net (host side tested; not yet timed on a GPU).  Prints one JSON line on rank 0:
   nodes/s = (real + cached evals) / s  (the collector's `evals/s: real / cached`, collector.rs:172-191), NN positions/s,
   mean batch and fill of the evaluator calls.
 """
@@ -21,7 +21,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from kzero_b200 import netgen, replicas, selfplay  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--game", default="chess", choices=["chess", "ataxx"])
+ap.add_argument("--game", default="chess", choices=["chess", "ataxx", "go"])
 ap.add_argument("--seconds", type=float, default=10.0)
 ap.add_argument("--visits", type=int, default=800)
 ap.add_argument("--search-batch", type=int, default=16)
@@ -53,6 +53,8 @@ gpu_threads = args.gpu_threads
 cpu_threads = args.cpu_threads or (share if blocking else share - gpu_threads)
 if args.game == "chess":
     spec, depth, channels, game = netgen.game_spec("chess"), 16, 128, selfplay.GAME_SYNTH_CHESS
+elif args.game == "go":  # the net of BASELINE.json configs[2]
+    spec, depth, channels, game = netgen.game_spec("go-9"), 20, 256, selfplay.GAME_GO9
 else:
     spec, depth, channels, game = netgen.game_spec("ataxx-7"), 8, 64, selfplay.GAME_ATAXX7
 onnx_bytes = netgen.build_onnx(spec, depth, channels, seed=0)
@@ -78,7 +80,8 @@ if ctx.is_root:
         "moves_per_s": moves / seconds, "games_finished": games, "seconds": seconds, "scaling": "weak",
         "config": {"workload": f"{args.game} self-play, {args.visits} visits, search batch {args.search_batch} with virtual loss, "
                                f"net {depth}x{channels}, gpu batch {args.gpu_batch}",
-                   "game": "chess-shaped synthetic game (13x8x8 + 8 planes, 1880-move policy, 20-45 legal moves)" if args.game == "chess" else "ataxx 7x7",
+                   "game": {"chess": "chess-shaped synthetic game (13x8x8 + 8 planes, 1880-move policy, 20-45 legal moves)", "ataxx": "ataxx 7x7",
+                            "go": "go 9x9 (area scoring, simple ko, no suicide)"}[args.game],
                    "cpu_threads_per_gpu": cpu_threads, "gpu_threads_per_gpu": gpu_threads, "executor_blocking_sync": bool(blocking), "concurrent_games_per_gpu": r.concurrent_games,
                    "host_cores": cores, "pinned": bool(args.pin), **replicas.parallelism_note(ctx)},
         "data": "synthetic"}), flush=True)

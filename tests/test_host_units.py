@@ -3,6 +3,7 @@
   tests/cpp/lru_cache_test.cpp    the flat LRU evaluation cache against a std::list + std::unordered_map model
   tests/cpp/mcts_units_test.cpp   the vectorised uct / tie-aware argmax / visited blocks against their scalar definitions
                                   (node.rs:163-206, kz-util/src/sequence.rs:11-41)
+  tests/cpp/go_rules_test.cpp     the 9x9 go restatement: captures, suicide, ko, passes, area scoring, encoding, random playouts
   tests/cpp/selfplay_tsan_main.cpp  the generator / executor threads of the driver under ThreadSanitizer
 """
 import os
@@ -16,7 +17,7 @@ from kzero_b200 import selfplay
 ROOT = Path(__file__).resolve().parent
 
 
-@pytest.mark.parametrize("name", ["lru_cache_test", "mcts_units_test"])
+@pytest.mark.parametrize("name", ["lru_cache_test", "mcts_units_test", "go_rules_test"])
 def test_cpp_unit(tmp_path, name):
     exe = tmp_path / name
     subprocess.run(["g++", "-O2", "-std=c++17", "-o", str(exe), str(ROOT / "cpp" / f"{name}.cpp")], check=True)

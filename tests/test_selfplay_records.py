@@ -53,7 +53,8 @@ def _parse(prefix, bool_count, scalar_count):
 
 
 @pytest.mark.parametrize("game,name,bool_shape,scalar_count,policy_len", [
-    (selfplay.GAME_SYNTH_CHESS, "chess", [13, 8, 8], 8, 1880), (selfplay.GAME_ATAXX7, "ataxx-7", [3, 7, 7], 1, 17 * 49 + 1)])
+    (selfplay.GAME_SYNTH_CHESS, "chess", [13, 8, 8], 8, 1880), (selfplay.GAME_ATAXX7, "ataxx-7", [3, 7, 7], 1, 17 * 49 + 1),
+    (selfplay.GAME_GO9, "go-9", [4, 9, 9], 6, 82)])
 def test_record_files_are_self_consistent(tmp_path, game, name, bool_shape, scalar_count, policy_len):
     prefix, r = _run(tmp_path, game)
     meta, positions, game_starts = _parse(prefix, int(np.prod(bool_shape)), scalar_count)
@@ -88,7 +89,7 @@ def test_record_files_are_self_consistent(tmp_path, game, name, bool_shape, scal
 
 
 @pytest.mark.skipif(not REFERENCE_PY.exists(), reason="the reference tree is only present in the build container")
-@pytest.mark.parametrize("game,name", [(selfplay.GAME_SYNTH_CHESS, "chess"), (selfplay.GAME_ATAXX7, "ataxx-7")])
+@pytest.mark.parametrize("game,name", [(selfplay.GAME_SYNTH_CHESS, "chess"), (selfplay.GAME_ATAXX7, "ataxx-7"), (selfplay.GAME_GO9, "go-9")])
 def test_reference_loader_reads_the_records(tmp_path, game, name):
     """DataFile.open + Position (python/lib/data/file.py:62-130, position.py:34-103) accept the files and agree with the
     independent parser on every field they decode."""
