@@ -18,6 +18,8 @@ SCALARS = 26
 
 def _run(tmp_path, game, **kw):
     prefix = str(tmp_path / "games_0")
+    if game == selfplay.GAME_GO9:
+        kw.setdefault("max_game_length", 20)  # go games are long: let the length cap end them (max_game_length, generator_alphazero.rs:125)
     cfg = selfplay.default_config(game=game, visits=24, search_batch=4, gpu_batch=32, cpu_threads=2, gpu_threads=1, max_moves=400,
                                   duration_s=30.0, dummy_network=1, output_prefix=prefix, seed=5, **kw)
     r = selfplay.run(None, cfg)
