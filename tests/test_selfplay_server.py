@@ -40,7 +40,8 @@ def _serve():
     return server, t
 
 
-def test_protocol_with_raw_socket(tmp_path):
+@pytest.mark.parametrize("game,length_cap", [("ataxx-7", 60), ("go-9", 30)])
+def test_protocol_with_raw_socket(tmp_path, game, length_cap):
     server, thread = _serve()
     s = socket.create_connection(("127.0.0.1", server.port))
     f = s.makefile("r")
@@ -48,8 +49,8 @@ def test_protocol_with_raw_socket(tmp_path):
     def send(m):
         s.sendall((json.dumps(m) + "\n").encode())
 
-    send({"StartupSettings": dict(STARTUP, output_folder=str(tmp_path))})
-    send({"NewSettings": SETTINGS})
+    send({"StartupSettings": dict(STARTUP, game=game, output_folder=str(tmp_path))})
+    send({"NewSettings": dict(SETTINGS, max_game_length=length_cap)})
     send("UseDummyNetwork")
     assert json.loads(f.readline()) == {"FinishedFile": {"index": 3}}
     assert json.loads(f.readline()) == {"FinishedFile": {"index": 4}}
@@ -60,7 +61,7 @@ def test_protocol_with_raw_socket(tmp_path):
     assert not thread.is_alive()
     for gen in (3, 4):
         meta = json.loads((tmp_path / f"games_{gen}.json").read_text())
-        assert meta["game"] == "ataxx-7" and meta["game_count"] >= 6 and meta["max_game_length"] <= 60
+        assert meta["game"] == game and meta["game_count"] >= 6 and meta["max_game_length"] <= length_cap
 
 
 @pytest.mark.skipif(not REFERENCE_PY.exists(), reason="the reference tree is only present in the build container")
