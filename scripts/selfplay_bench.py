@@ -5,7 +5,9 @@
     torchrun --nproc-per-node N scripts/selfplay_bench.py ...      # one replica per GPU, games sharded by replica
 
 Settings default to the reference's production values (python/main/loop_main_alpha.py:24-52: 800 visits, search batch 16,
-virtual loss 1, LRU cache 800, Dirichlet 0.03/0.25, root temperature 1.4); the net is chess 16x128 random-init
+virtual loss 1, LRU cache 800, Dirichlet 0.03/0.25, root temperature 1.4); the TOPOLOGY is this repo's: gpu batch 1024 (BASELINE.json's
+batch; the reference runs 2048), three executor threads and every remaining core as a generator thread (the reference: 1 and 4,
+loop_main_alpha.py:24-26) -- all of them are startup settings on both sides.  The net is chess 16x128 random-init
 (synthetic, like bench.py).  The game is the chess-SHAPED synthetic game of kzero_b200/csrc/selfplay/games.hpp (no chess
 move generator in this repo), real 7x7 ataxx with an 8x64 net, or 9x9 go with the 20x256 net (host side tested; not yet timed on a GPU).  Prints one JSON line on rank 0:
   nodes/s = (real + cached evals) / s  (the collector's `evals/s: real / cached`, collector.rs:172-191), NN positions/s,
