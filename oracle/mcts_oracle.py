@@ -88,6 +88,138 @@ class SynthChess:
         self.ply += 1
 
 
+class Go9:
+    """Twin of kzb::selfplay::Go9 (kzero_b200/csrc/selfplay/games.hpp), written independently from the rules as stated there:
+    area scoring with komi, no suicide, simple ko, two passes end the game; move 0 = pass, 1 + y * 9 + x = place."""
+    S, A = 9, 81
+
+    def __init__(self):
+        self.stones = [0] * self.A  # 0 empty, 1 black (player A), 2 white
+        self.ply, self.ko, self.komi_2, self.passes = 0, -1, 15, 0
+
+    @staticmethod
+    def start(seed: int) -> "Go9":
+        g = Go9()
+        h = splitmix64(seed ^ 0x60B0A4D)
+        pick = h % 10
+        if pick < 4:
+            g.komi_2 = 15
+        elif pick < 8:
+            g.komi_2 = 10 + (h >> 8) % 10
+        else:
+            g.komi_2 = (h >> 8) % 60 - 30
+        return g
+
+    def clone(self):
+        g = Go9()
+        g.stones, g.ply, g.ko, g.komi_2, g.passes = list(self.stones), self.ply, self.ko, self.komi_2, self.passes
+        return g
+
+    def hash(self) -> int:
+        h = (0x9E3779B97F4A7C15 * ((self.ply & 1) + 3) + (self.ko & 0xFFFF) * 0x100000001B3 + self.passes * 0xD6E8FEB86659FD93
+             + (self.komi_2 & 0xFFFF) * 0xA0761D6478BD642F) & M64
+        for i in range(0, self.A, 8):
+            w = int.from_bytes(bytes(self.stones[i:i + 8]), "little")
+            h = splitmix64(h ^ w)
+        return h
+
+    def next_player(self) -> int:
+        return self.ply & 1
+
+    def done(self) -> bool:
+        return self.passes >= 2
+
+    def _neighbours(self, p: int):
+        x, y = p % self.S, p // self.S
+        if x > 0:
+            yield p - 1
+        if x < self.S - 1:
+            yield p + 1
+        if y > 0:
+            yield p - self.S
+        if y < self.S - 1:
+            yield p + self.S
+
+    def _group(self, p: int):
+        """-> (stones of the group containing p, its liberties)"""
+        colour, group, libs, todo = self.stones[p], {p}, set(), [p]
+        while todo:
+            q = todo.pop()
+            for r in self._neighbours(q):
+                if self.stones[r] == 0:
+                    libs.add(r)
+                elif self.stones[r] == colour and r not in group:
+                    group.add(r)
+                    todo.append(r)
+        return group, libs
+
+    def _legal(self, p: int) -> bool:
+        if self.stones[p] or p == self.ko:
+            return False
+        me = 1 + (self.ply & 1)
+        for q in self._neighbours(p):
+            if self.stones[q] == 0:
+                return True
+            libs = self._group(q)[1]
+            if self.stones[q] == me and len(libs) >= 2:
+                return True
+            if self.stones[q] != me and len(libs) == 1:
+                return True
+        return False
+
+    def moves(self) -> List[int]:
+        return [0] + [1 + p for p in range(self.A) if self._legal(p)]
+
+    def play(self, mv: int) -> None:
+        if mv == 0:
+            self.passes += 1
+            self.ko = -1
+            self.ply += 1
+            return
+        p = mv - 1
+        me = 1 + (self.ply & 1)
+        self.stones[p] = me
+        captured = []
+        for q in self._neighbours(p):
+            if self.stones[q] not in (0, me):
+                group, libs = self._group(q)
+                if not libs:
+                    for r in group:
+                        self.stones[r] = 0
+                    captured.extend(group)
+        self.ko = -1
+        if len(captured) == 1:
+            group, libs = self._group(p)
+            if len(group) == 1 and len(libs) == 1:
+                self.ko = captured[0]
+        self.passes = 0
+        self.ply += 1
+
+    def outcome(self) -> int:
+        black = sum(1 for v in self.stones if v == 1)
+        white = sum(1 for v in self.stones if v == 2)
+        seen = set()
+        for p0 in range(self.A):
+            if self.stones[p0] or p0 in seen:
+                continue
+            region, touches, todo = {p0}, set(), [p0]
+            while todo:
+                q = todo.pop()
+                for r in self._neighbours(q):
+                    if self.stones[r]:
+                        touches.add(self.stones[r])
+                    elif r not in region:
+                        region.add(r)
+                        todo.append(r)
+            seen |= region
+            if touches == {1}:
+                black += len(region)
+            elif touches == {2}:
+                white += len(region)
+        score_2 = 2 * (black - white) - self.komi_2
+        return (score_2 > 0) - (score_2 < 0)
+
+
 def pseudo_eval(board, kind: int):
     """-> (values_pov [value, win, draw, loss, moves_left] f32, policy f32); twin of pseudo_eval in selfplay.cpp."""
     n = len(board.moves())
@@ -257,9 +389,9 @@ def zero_step_apply(tree: Tree, idx: int, next_player: int, values_pov: np.ndarr
         tree.nodes[c].net_policy = F(p)
 
 
-def search(game_seed: int, plies: int, rng_seed: int, visits: int, search_batch: int, eval_kind: int, s: Settings):
+def search(game_seed: int, plies: int, rng_seed: int, visits: int, search_batch: int, eval_kind: int, s: Settings, game: str = "chess"):
     """The twin of trace_search in selfplay.cpp: -> dict(child_visits, child_moves, child_policy, root_values, ...)."""
-    board = SynthChess.start(game_seed)
+    board = Go9.start(game_seed) if game == "go-9" else SynthChess.start(game_seed)
     rng = Rng(rng_seed)
     for _ in range(plies):
         if board.done():

@@ -48,10 +48,23 @@ def test_search_variants_match_oracle(kw):
     assert np.allclose(got.root_values, ref["root_values"], rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize("game_seed,plies,rng_seed,eval_kind", [(1, 0, 5, 1), (2, 30, 6, 1), (9, 60, 7, 0)])
+def test_go_search_matches_oracle(game_seed, plies, rng_seed, eval_kind):
+    """9x9 go: the C++ rules (captures, ko, suicide, passes, scoring inside the search's terminal nodes) and the oracle's
+    independent Python restatement of them must agree for the trees to be identical; 82-way nodes with a pass move."""
+    c = _cfg(game=selfplay.GAME_GO9, visits=120, search_batch=8, seed=rng_seed)
+    got = selfplay.mcts_trace(c, game_seed, plies, eval_kind)
+    ref = mo.search(game_seed, plies, rng_seed, 120, 8, eval_kind, _oracle_settings(c), game="go-9")
+    assert np.array_equal(got.child_moves, ref["child_moves"])
+    assert np.array_equal(got.child_visits, ref["child_visits"])
+    assert (got.root_visits, got.tree_nodes, got.evals) == (ref["root_visits"], ref["tree_nodes"], ref["evals"])
+    assert np.allclose(got.root_values, ref["root_values"], rtol=0, atol=1e-6)
+
+
 def test_search_invariants():
     """What the reference asserts along the way: one policy entry per available move (step.rs:163), the visit
     distribution sums to 1 (tree.rs:132-141), a search with a tree smaller than the batch terminates (tests/tree.rs:16-42)."""
-    for game in (selfplay.GAME_SYNTH_CHESS, selfplay.GAME_ATAXX7):
+    for game in (selfplay.GAME_SYNTH_CHESS, selfplay.GAME_ATAXX7, selfplay.GAME_GO9):
         c = _cfg(game=game, visits=64, search_batch=128, seed=5, policy_temperature_root=1.4)
         t = selfplay.mcts_trace(c, 3, 0, 1)
         assert t.root_visits >= 64 and t.child_visits.sum() == t.root_visits - 1
