@@ -220,6 +220,92 @@ class Go9:
         return (score_2 > 0) - (score_2 < 0)
 
 
+class Ataxx7:
+    """Twin of kzb::selfplay::Ataxx (kzero_b200/csrc/selfplay/games.hpp), written independently with sets of (x, y) instead
+    of bitboards: copy to a free tile at distance 1, jump to one at distance exactly 2 (the origin empties), the moved-to
+    tile converts adjacent enemy tiles, pass only when nothing else is possible; the game ends when a side is wiped out,
+    the board is full, nobody can move, or after 100 moves without a copy (draw).  Move = policy index (ataxx.rs:60-81)."""
+    S = 7
+    JUMPS = [(-2, -2), (-1, -2), (0, -2), (1, -2), (2, -2), (-2, -1), (2, -1), (-2, 0), (2, 0), (-2, 1), (2, 1), (-2, 2), (-1, 2), (0, 2),
+             (1, 2), (2, 2)]  # FROM_DX_DY, ataxx.rs:134-151
+
+    def __init__(self):
+        self.tiles = [{(0, 0), (6, 6)}, {(6, 0), (0, 6)}]
+        self.ply, self.since_copy, self.finished, self.result = 0, 0, False, 0
+
+    @staticmethod
+    def start(seed: int) -> "Ataxx7":
+        return Ataxx7()
+
+    def clone(self):
+        g = Ataxx7()
+        g.tiles = [set(self.tiles[0]), set(self.tiles[1])]
+        g.ply, g.since_copy, g.finished, g.result = self.ply, self.since_copy, self.finished, self.result
+        return g
+
+    def _bits(self, tiles) -> int:
+        return sum(1 << (y * self.S + x) for x, y in tiles)
+
+    def hash(self) -> int:
+        inner = (self._bits(self.tiles[1]) * 5 + ((self.ply & 1) << 62) + (self.since_copy << 50)) & M64
+        return splitmix64((self._bits(self.tiles[0]) * 3 + splitmix64(inner)) & M64)
+
+    def next_player(self) -> int:
+        return self.ply & 1
+
+    def done(self) -> bool:
+        return self.finished
+
+    def outcome(self) -> int:
+        return self.result
+
+    def _free(self, x: int, y: int) -> bool:
+        return 0 <= x < self.S and 0 <= y < self.S and (x, y) not in self.tiles[0] and (x, y) not in self.tiles[1]
+
+    def _reach(self, tiles, distance: int):
+        out = set()
+        for x, y in tiles:
+            for dy in range(-distance, distance + 1):
+                for dx in range(-distance, distance + 1):
+                    if max(abs(dx), abs(dy)) == distance and self._free(x + dx, y + dy):
+                        out.add((x + dx, y + dy))
+        return out
+
+    def moves(self) -> List[int]:
+        mine = self.tiles[self.ply & 1]
+        out = [y * self.S + x for x, y in sorted(self._reach(mine, 1), key=lambda t: t[1] * self.S + t[0])]
+        for fx, fy in sorted(mine, key=lambda t: t[1] * self.S + t[0]):
+            for tx, ty in sorted(self._reach({(fx, fy)}, 2), key=lambda t: t[1] * self.S + t[0]):
+                out.append((1 + self.JUMPS.index((fx - tx, fy - ty))) * self.S * self.S + ty * self.S + tx)
+        return out if out else [17 * self.S * self.S]
+
+    def play(self, mv: int) -> None:
+        area = self.S * self.S
+        me, other = self.ply & 1, (self.ply & 1) ^ 1
+        if mv == 17 * area:
+            self.since_copy += 1
+        else:
+            to = (mv % area % self.S, mv % area // self.S)
+            if mv >= area:
+                dx, dy = self.JUMPS[mv // area - 1]
+                self.tiles[me].discard((to[0] + dx, to[1] + dy))
+                self.since_copy += 1
+            else:
+                self.since_copy = 0
+            self.tiles[me].add(to)
+            converted = {t for t in self.tiles[other] if max(abs(t[0] - to[0]), abs(t[1] - to[1])) == 1}
+            self.tiles[me] |= converted
+            self.tiles[other] -= converted
+        self.ply += 1
+        a, b = len(self.tiles[0]), len(self.tiles[1])
+        free_tiles = self.S * self.S - a - b
+        any_move = any(self._reach(self.tiles[k], 1) or self._reach(self.tiles[k], 2) for k in (0, 1))
+        if a == 0 or b == 0 or free_tiles == 0 or not any_move or self.since_copy >= 100:
+            self.finished = True
+            stalled_only = self.since_copy >= 100 and a and b and free_tiles and any_move
+            self.result = 0 if stalled_only else (a > b) - (a < b)
+
+
 def pseudo_eval(board, kind: int):
     """-> (values_pov [value, win, draw, loss, moves_left] f32, policy f32); twin of pseudo_eval in selfplay.cpp."""
     n = len(board.moves())
@@ -391,7 +477,7 @@ def zero_step_apply(tree: Tree, idx: int, next_player: int, values_pov: np.ndarr
 
 def search(game_seed: int, plies: int, rng_seed: int, visits: int, search_batch: int, eval_kind: int, s: Settings, game: str = "chess"):
     """The twin of trace_search in selfplay.cpp: -> dict(child_visits, child_moves, child_policy, root_values, ...)."""
-    board = Go9.start(game_seed) if game == "go-9" else SynthChess.start(game_seed)
+    board = {"go-9": Go9, "ataxx-7": Ataxx7, "chess": SynthChess}[game].start(game_seed)
     rng = Rng(rng_seed)
     for _ in range(plies):
         if board.done():

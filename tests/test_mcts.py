@@ -61,6 +61,18 @@ def test_go_search_matches_oracle(game_seed, plies, rng_seed, eval_kind):
     assert np.allclose(got.root_values, ref["root_values"], rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize("plies,rng_seed,eval_kind", [(0, 5, 1), (12, 6, 1), (40, 7, 0), (70, 8, 1)])
+def test_ataxx_search_matches_oracle(plies, rng_seed, eval_kind):
+    """7x7 ataxx (BASELINE.json configs[0]'s game): bitboard rules in C++ against the oracle's set-based restatement."""
+    c = _cfg(game=selfplay.GAME_ATAXX7, visits=150, search_batch=8, seed=rng_seed)
+    got = selfplay.mcts_trace(c, 1, plies, eval_kind)
+    ref = mo.search(1, plies, rng_seed, 150, 8, eval_kind, _oracle_settings(c), game="ataxx-7")
+    assert np.array_equal(got.child_moves, ref["child_moves"])
+    assert np.array_equal(got.child_visits, ref["child_visits"])
+    assert (got.root_visits, got.tree_nodes, got.evals) == (ref["root_visits"], ref["tree_nodes"], ref["evals"])
+    assert np.allclose(got.root_values, ref["root_values"], rtol=0, atol=1e-6)
+
+
 def test_search_invariants():
     """What the reference asserts along the way: one policy entry per available move (step.rs:163), the visit
     distribution sums to 1 (tree.rs:132-141), a search with a tree smaller than the batch terminates (tests/tree.rs:16-42)."""
