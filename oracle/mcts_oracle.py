@@ -195,6 +195,20 @@ class Go9:
         self.passes = 0
         self.ply += 1
 
+    def encode(self):
+        """-> (bools [4, 9, 9] u8, scalars f32): GoStdMapper::encode_input without territory, rust/kz-core/src/mapping/go.rs:62-112."""
+        me = 1 + (self.ply & 1)
+        planes = np.zeros((4, self.S, self.S), np.uint8)
+        for p, v in enumerate(self.stones):
+            y, x = divmod(p, self.S)
+            planes[0, y, x] = v == me
+            planes[1, y, x] = v not in (0, me)
+            planes[2, y, x] = 1
+            planes[3, y, x] = v == 0 and not self._legal(p)
+        komi = F(self.komi_2) * F(0.5)
+        black = self.next_player() == 0
+        return planes, np.array([black, not black, self.passes == 1, self.passes >= 2, (komi if black else -komi) / F(15.0), 0], F)
+
     def outcome(self) -> int:
         black = sum(1 for v in self.stones if v == 1)
         white = sum(1 for v in self.stones if v == 2)
@@ -278,6 +292,14 @@ class Ataxx7:
             for tx, ty in sorted(self._reach({(fx, fy)}, 2), key=lambda t: t[1] * self.S + t[0]):
                 out.append((1 + self.JUMPS.index((fx - tx, fy - ty))) * self.S * self.S + ty * self.S + tx)
         return out if out else [17 * self.S * self.S]
+
+    def encode(self):
+        """-> (bools [3, 7, 7] u8, scalars f32): AtaxxStdMapper::encode_input, rust/kz-core/src/mapping/ataxx.rs:106-115."""
+        planes = np.zeros((3, self.S, self.S), np.uint8)
+        for k, tiles in enumerate((self.tiles[self.ply & 1], self.tiles[(self.ply & 1) ^ 1])):
+            for x, y in tiles:
+                planes[k, y, x] = 1
+        return planes, np.array([F(self.since_copy) / F(100.0)], F)
 
     def play(self, mv: int) -> None:
         area = self.S * self.S

@@ -122,3 +122,37 @@ def test_reference_loader_reads_the_records(tmp_path, game, name):
     # the simulations view walks the whole file through the start indices
     sims = [f.simulations[i] for i in range(len(f.simulations))]
     assert sum(sim.position_count for sim in sims) == f.info.position_count
+
+
+@pytest.mark.parametrize("game,name,twin", [(selfplay.GAME_ATAXX7, "ataxx-7", "Ataxx7"), (selfplay.GAME_GO9, "go-9", "Go9")])
+def test_recorded_games_replay_under_the_oracle_rules(tmp_path, game, name, twin):
+    """Every recorded game is replayed move by move with the oracle's independent restatement of the rules: at each
+    position the recorded input planes and scalars are the twin's encoding, the recorded policy indices are the twin's
+    legal moves in order, and the recorded played move leads to the next recorded position (N1 + N2 end to end)."""
+    from oracle import mcts_oracle as mo
+
+    prefix, r = _run(tmp_path, game)
+    shape = {"ataxx-7": (3, 7, 7), "go-9": (4, 9, 9)}[name]
+    meta, positions, game_starts = _parse(prefix, int(np.prod(shape)), {"ataxx-7": 1, "go-9": 6}[name])
+    checked = 0
+    for g in range(meta["game_count"]):
+        first = int(game_starts[g])
+        length = int(positions[first]["scalars"][2])
+        # the driver reseeds every new game; go's komi is the only seed-dependent part of a start position and is in the record
+        board = getattr(mo, twin).start(0)
+        if name == "go-9":
+            komi_pov = float(positions[first]["input_scalars"][4]) * 15.0
+            board.komi_2 = int(round(2 * komi_pov))  # black moves first: komi from black's side
+        for k in range(length + 1):
+            p = positions[first + k]
+            planes, scalars = board.encode()
+            bools = np.unpackbits(p["bits"], bitorder="little")[:planes.size].reshape(planes.shape)
+            assert np.array_equal(bools, planes), (g, k)
+            assert np.array_equal(p["input_scalars"], scalars), (g, k, p["input_scalars"], scalars)
+            if k == length:  # the final position carries no policy
+                assert bool(p["scalars"][5]) and bool(p["scalars"][6]) == board.done()
+                break
+            assert p["indices"].tolist() == board.moves(), (g, k)
+            board.play(int(p["scalars"][9]))
+            checked += 1
+    assert checked >= 40
