@@ -155,4 +155,11 @@ def test_recorded_games_replay_under_the_oracle_rules(tmp_path, game, name, twin
             assert p["indices"].tolist() == board.moves(), (g, k)
             board.play(int(p["scalars"][9]))
             checked += 1
+        # the recorded result of the game, from every position's side to move (Outcome::Draw when the length cap ended it,
+        # binary_output.rs:141-164)
+        outcome = board.outcome() if board.done() else 0
+        for k in range(length + 1):
+            sc = positions[first + k]["scalars"]
+            pov = outcome if k % 2 == 0 else -outcome  # player A moves first in both games
+            assert sc[11] == pov and sc[12:15].tolist() == [float(pov > 0), float(pov == 0), float(pov < 0)], (g, k, sc[11:15], pov)
     assert checked >= 40
