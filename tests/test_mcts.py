@@ -1,5 +1,8 @@
 """The self-play driver's tree search (C++, behind kzb_mcts_trace; host-only, no GPU) against the oracle's restatement of
 rust/kz-core/src/zero/{step,node,tree}.rs (oracle/mcts_oracle.py): identical trees, visit for visit."""
+import json
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -112,3 +115,35 @@ def test_trace_rejects_bad_arguments():
     c = _cfg(visits=10)
     with pytest.raises(KzbError, match="capacity"):
         selfplay.mcts_trace(c, 0, 0, 0, capacity=4)
+
+
+def test_ataxx_move_indexing_matches_the_reference_tables():
+    """Row A7 for ataxx: policy index <-> move.  tests/golden/ataxx7_moves.json is the reference's own table
+    (python/lib/mapping/ataxx_index_to_move_input.txt + ataxx_valid.txt, written by gen_ataxx_moves_golden.py):
+    every index that is a move decodes to the same (pass / copy-to / jump-from, jump-to) under the indexing this repo
+    uses (games.hpp and its oracle twin: copy -> to, jump -> (1 + FROM_DX_DY index) * 49 + to, pass -> 17 * 49), and the
+    moves generated from every origin on an otherwise empty board are exactly the reference's valid set."""
+    golden = json.loads((Path(__file__).parent / "golden" / "ataxx7_moves.json").read_text())
+    table, valid = golden["index_to_move_input"], set(golden["valid"])
+    S, area = 7, 49
+    for index in valid:
+        is_pass, copy_to, jump_from, jump_to = table[index]
+        if index == 17 * area:
+            assert (is_pass, copy_to, jump_from, jump_to) == (1, -1, -1, -1)
+        elif index < area:
+            assert (is_pass, copy_to, jump_from, jump_to) == (0, index, -1, -1)
+        else:
+            dx, dy = mo.Ataxx7.JUMPS[index // area - 1]
+            to = index % area
+            fx, fy = to % S + dx, to // S + dy
+            assert 0 <= fx < S and 0 <= fy < S
+            assert (is_pass, copy_to, jump_from, jump_to) == (0, -1, fy * S + fx, to)
+    for index, row in enumerate(table):
+        assert (index in valid) == (row != [0, -1, -1, -1]) or index == 17 * area
+    # generation side: a lone tile of the side to move at every origin, through the C++-pinned twin
+    generated = {17 * area}
+    for origin in range(area):
+        b = mo.Ataxx7()
+        b.tiles = [{(origin % S, origin // S)}, set()]
+        generated |= set(b.moves())
+    assert generated == valid
