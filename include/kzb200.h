@@ -132,6 +132,7 @@ int kzb_launches_per_eval(const kzb_net* net);
 #define KZB_GAME_SYNTH_CHESS 0 /* chess-shaped synthetic game: 13x8x8 bools + 8 scalars, 1880-move policy, 20..45 legal moves */
 #define KZB_GAME_ATAXX7 1      /* 7x7 ataxx, AtaxxStdMapper encoding (rust/kz-core/src/mapping/ataxx.rs)                      */
 #define KZB_GAME_GO9 2         /* 9x9 go, GoStdMapper encoding without territory planes (rust/kz-core/src/mapping/go.rs)      */
+#define KZB_GAME_CHESS 3       /* chess with legal move generation, ChessStdMapper encoding and the flat 1880-move policy      */
 
 /* Field for field the reference's settings: StartupSettings (rust/kz-selfplay/src/server/protocol.rs:11-40:
  * cpu_threads_per_device, gpu_threads_per_device, gpu_batch_size, search_batch_size) and Settings (protocol.rs:58-110). */

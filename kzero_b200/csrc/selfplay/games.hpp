@@ -11,6 +11,7 @@
 //                bools = (next player's tiles, other tiles, gaps), scalar = moves_since_last_copy / 100,
 //                policy index: copy -> to, jump -> (1 + FROM_DX_DY index) * A + to, pass -> 17 * A.
 //   Go9          9x9 go with the reference's GoStdMapper encoding (4 bool + 6 scalar planes) and restated rules, see below.
+//   Chess        legal chess, in chess_game.hpp.
 #pragma once
 #include <cstdint>
 #include <cstring>

@@ -37,6 +37,7 @@
 
 #include "../../../include/kzb200.h"
 #include "../executor.hpp"
+#include "chess_game.hpp"
 #include "games.hpp"
 #include "lru_cache.hpp"
 #include "mcts.hpp"
@@ -723,6 +724,7 @@ KZB_API int kzb_selfplay_run(int device, const void* onnx_bytes, size_t onnx_len
         if (config->game == KZB_GAME_SYNTH_CHESS) run_selfplay<SynthChess>(device, onnx_bytes, onnx_len, precision, *config, *stats);
         else if (config->game == KZB_GAME_ATAXX7) run_selfplay<Ataxx>(device, onnx_bytes, onnx_len, precision, *config, *stats);
         else if (config->game == KZB_GAME_GO9) run_selfplay<Go9>(device, onnx_bytes, onnx_len, precision, *config, *stats);
+        else if (config->game == KZB_GAME_CHESS) run_selfplay<Chess>(device, onnx_bytes, onnx_len, precision, *config, *stats);
         else throw std::runtime_error("unknown game");
     });
 }
@@ -736,6 +738,7 @@ KZB_API int kzb_mcts_trace(const kzb_selfplay_config* config, uint64_t game_seed
         if (config->game == KZB_GAME_SYNTH_CHESS) trace_search<SynthChess>(*config, game_seed, plies, eval_kind, *out);
         else if (config->game == KZB_GAME_ATAXX7) trace_search<Ataxx>(*config, game_seed, plies, eval_kind, *out);
         else if (config->game == KZB_GAME_GO9) trace_search<Go9>(*config, game_seed, plies, eval_kind, *out);
+        else if (config->game == KZB_GAME_CHESS) trace_search<Chess>(*config, game_seed, plies, eval_kind, *out);
         else throw std::runtime_error("unknown game");
     });
 }

@@ -13,9 +13,10 @@ Messages are one JSON value per line, externally tagged like serde's enums (prot
 Differences that are deliberate (documented in DESIGN.md): a generation is one `kzb_selfplay_run` call, so a new network
 or new settings take effect at the next generation boundary (the reference hot-swaps inside a generation) and games still
 running at the boundary are dropped instead of carried over; `eval_random_symmetries`, `start_pos`, `top_moves`,
-`saved_state_channels` and `gpu_batch_size_root` are accepted and ignored (muzero-only or above the boundary); `chess`
-is served by the chess-SHAPED synthetic game (no chess move generator in this repo), `ataxx-7` by the real rules; one
-server process drives ONE device (the reference takes several `--device` flags, server.rs:49-51) -- start one process per
+`saved_state_channels` and `gpu_batch_size_root` are accepted and ignored (muzero-only or above the boundary); `chess`,
+`ataxx-7` and `go-9` are served with this repo's restated rules (`chess-synth` is the chess-shaped synthetic game the
+B200 self-play numbers were taken with); one server process drives ONE device (the reference takes several `--device`
+flags, server.rs:49-51) -- start one process per
 GPU on different ports, the games are independent.
 """
 from __future__ import annotations
@@ -54,12 +55,14 @@ def parse_q_mode(text: str):
 def game_id(name: str) -> int:
     """Game::parse + the per-game dispatch of server.rs:103-199, for the games this driver bundles."""
     if name == "chess":
+        return selfplay.GAME_CHESS
+    if name == "chess-synth":  # the chess-shaped synthetic game the B200 self-play numbers were taken with
         return selfplay.GAME_SYNTH_CHESS
     if name in ("ataxx", "ataxx-7"):
         return selfplay.GAME_ATAXX7
     if name == "go-9":
         return selfplay.GAME_GO9
-    raise ValueError(f"game {name!r} is not available in this driver (chess-shaped synthetic game, ataxx-7 and go-9 are)")
+    raise ValueError(f"game {name!r} is not available in this driver (chess, ataxx-7, go-9 and the chess-shaped synthetic game 'chess-synth' are)")
 
 
 def config_from(startup: dict, settings: dict, seed: int) -> _abi.SelfplayConfig:

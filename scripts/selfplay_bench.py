@@ -23,7 +23,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from kzero_b200 import netgen, replicas, selfplay  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--game", default="chess", choices=["chess", "ataxx", "go"])
+ap.add_argument("--game", default="chess", choices=["chess", "chess-real", "ataxx", "go"])
 ap.add_argument("--seconds", type=float, default=10.0)
 ap.add_argument("--visits", type=int, default=800)
 ap.add_argument("--search-batch", type=int, default=16)
@@ -55,6 +55,8 @@ gpu_threads = args.gpu_threads
 cpu_threads = args.cpu_threads or (share if blocking else share - gpu_threads)
 if args.game == "chess":
     spec, depth, channels, game = netgen.game_spec("chess"), 16, 128, selfplay.GAME_SYNTH_CHESS
+elif args.game == "chess-real":  # legal chess instead of the chess-shaped synthetic game; host side tested, not yet timed on a GPU
+    spec, depth, channels, game = netgen.game_spec("chess"), 16, 128, selfplay.GAME_CHESS
 elif args.game == "go":  # the net of BASELINE.json configs[2]
     spec, depth, channels, game = netgen.game_spec("go-9"), 20, 256, selfplay.GAME_GO9
 else:
@@ -83,6 +85,7 @@ if ctx.is_root:
         "config": {"workload": f"{args.game} self-play, {args.visits} visits, search batch {args.search_batch} with virtual loss, "
                                f"net {depth}x{channels}, gpu batch {args.gpu_batch}",
                    "game": {"chess": "chess-shaped synthetic game (13x8x8 + 8 planes, 1880-move policy, 20-45 legal moves)", "ataxx": "ataxx 7x7",
+                            "chess-real": "chess (legal move generation, ChessStdMapper encoding)",
                             "go": "go 9x9 (area scoring, simple ko, no suicide)"}[args.game],
                    "cpu_threads_per_gpu": cpu_threads, "gpu_threads_per_gpu": gpu_threads, "executor_blocking_sync": bool(blocking), "concurrent_games_per_gpu": r.concurrent_games,
                    "host_cores": cores, "pinned": bool(args.pin), **replicas.parallelism_note(ctx)},

@@ -4,6 +4,7 @@
   tests/cpp/mcts_units_test.cpp   the vectorised uct / tie-aware argmax / visited blocks against their scalar definitions
                                   (node.rs:163-206, kz-util/src/sequence.rs:11-41)
   tests/cpp/go_rules_test.cpp     the 9x9 go restatement: captures, suicide, ko, passes, area scoring, encoding, random playouts
+  tests/cpp/chess_perft_test.cpp  the chess move generator: perft counts of five standard positions through the policy-index interface
   tests/cpp/selfplay_tsan_main.cpp  the generator / executor threads of the driver under ThreadSanitizer
 """
 import os
@@ -17,7 +18,7 @@ from kzero_b200 import selfplay
 ROOT = Path(__file__).resolve().parent
 
 
-@pytest.mark.parametrize("name", ["lru_cache_test", "mcts_units_test", "go_rules_test"])
+@pytest.mark.parametrize("name", ["lru_cache_test", "mcts_units_test", "go_rules_test", "chess_perft_test"])
 def test_cpp_unit(tmp_path, name):
     exe = tmp_path / name
     subprocess.run(["g++", "-O2", "-std=c++17", "-o", str(exe), str(ROOT / "cpp" / f"{name}.cpp")], check=True)

@@ -79,7 +79,7 @@ def test_ataxx_search_matches_oracle(plies, rng_seed, eval_kind):
 def test_search_invariants():
     """What the reference asserts along the way: one policy entry per available move (step.rs:163), the visit
     distribution sums to 1 (tree.rs:132-141), a search with a tree smaller than the batch terminates (tests/tree.rs:16-42)."""
-    for game in (selfplay.GAME_SYNTH_CHESS, selfplay.GAME_ATAXX7, selfplay.GAME_GO9):
+    for game in (selfplay.GAME_SYNTH_CHESS, selfplay.GAME_ATAXX7, selfplay.GAME_GO9, selfplay.GAME_CHESS):
         c = _cfg(game=game, visits=64, search_batch=128, seed=5, policy_temperature_root=1.4)
         t = selfplay.mcts_trace(c, 3, 0, 1)
         assert t.root_visits >= 64 and t.child_visits.sum() == t.root_visits - 1

@@ -18,7 +18,7 @@ SCALARS = 26
 
 def _run(tmp_path, game, **kw):
     prefix = str(tmp_path / "games_0")
-    if game == selfplay.GAME_GO9:
+    if game in (selfplay.GAME_GO9, selfplay.GAME_CHESS):
         kw.setdefault("max_game_length", 20)  # go games are long: let the length cap end them (max_game_length, generator_alphazero.rs:125)
     cfg = selfplay.default_config(game=game, visits=24, search_batch=4, gpu_batch=32, cpu_threads=2, gpu_threads=1, max_moves=400,
                                   duration_s=30.0, dummy_network=1, output_prefix=prefix, seed=5, **kw)
@@ -56,7 +56,7 @@ def _parse(prefix, bool_count, scalar_count):
 
 @pytest.mark.parametrize("game,name,bool_shape,scalar_count,policy_len", [
     (selfplay.GAME_SYNTH_CHESS, "chess", [13, 8, 8], 8, 1880), (selfplay.GAME_ATAXX7, "ataxx-7", [3, 7, 7], 1, 17 * 49 + 1),
-    (selfplay.GAME_GO9, "go-9", [4, 9, 9], 6, 82)])
+    (selfplay.GAME_GO9, "go-9", [4, 9, 9], 6, 82), (selfplay.GAME_CHESS, "chess", [13, 8, 8], 8, 1880)])
 def test_record_files_are_self_consistent(tmp_path, game, name, bool_shape, scalar_count, policy_len):
     prefix, r = _run(tmp_path, game)
     meta, positions, game_starts = _parse(prefix, int(np.prod(bool_shape)), scalar_count)
@@ -91,7 +91,8 @@ def test_record_files_are_self_consistent(tmp_path, game, name, bool_shape, scal
 
 
 @pytest.mark.skipif(not REFERENCE_PY.exists(), reason="the reference tree is only present in the build container")
-@pytest.mark.parametrize("game,name", [(selfplay.GAME_SYNTH_CHESS, "chess"), (selfplay.GAME_ATAXX7, "ataxx-7"), (selfplay.GAME_GO9, "go-9")])
+@pytest.mark.parametrize("game,name", [(selfplay.GAME_SYNTH_CHESS, "chess"), (selfplay.GAME_ATAXX7, "ataxx-7"), (selfplay.GAME_GO9, "go-9"),
+                                       (selfplay.GAME_CHESS, "chess")])
 def test_reference_loader_reads_the_records(tmp_path, game, name):
     """DataFile.open + Position (python/lib/data/file.py:62-130, position.py:34-103) accept the files and agree with the
     independent parser on every field they decode."""

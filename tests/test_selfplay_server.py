@@ -40,7 +40,7 @@ def _serve():
     return server, t
 
 
-@pytest.mark.parametrize("game,length_cap", [("ataxx-7", 60), ("go-9", 30)])
+@pytest.mark.parametrize("game,length_cap", [("ataxx-7", 60), ("go-9", 30), ("chess", 30)])
 def test_protocol_with_raw_socket(tmp_path, game, length_cap):
     server, thread = _serve()
     s = socket.create_connection(("127.0.0.1", server.port))
