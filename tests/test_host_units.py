@@ -8,6 +8,7 @@
   tests/cpp/selfplay_tsan_main.cpp  the generator / executor threads of the driver under ThreadSanitizer
 """
 import os
+import json
 import subprocess
 from pathlib import Path
 
@@ -52,3 +53,14 @@ def test_selfplay_threads_under_tsan(tmp_path, env):
     assert build.returncode == 0, build.stderr[-2000:]
     out = subprocess.run([str(exe), str(tmp_path / "games")], capture_output=True, text=True, timeout=300, env={**os.environ, **env})
     assert out.returncode == 0 and "ThreadSanitizer" not in out.stderr, out.stdout + out.stderr[-4000:]
+
+
+def test_chess_policy_table_matches_the_reference(tmp_path):
+    """Row A7 for chess on the C++ side: the 1880-entry flat move table of chess_game.hpp against the reference's own
+    python/lib/mapping/chess_flat_to_move_input.txt (tests/golden/chess_flat_moves.json, gen_chess_moves_golden.py)."""
+    exe = tmp_path / "chess_flat_dump"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-o", str(exe), str(ROOT / "cpp" / "chess_flat_dump.cpp")], check=True)
+    lines = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")[:-1]
+    mine = [[int(a), int(b), "" if c == "-" else c] for a, b, c in (line.split() for line in lines)]
+    golden = json.loads((ROOT / "golden" / "chess_flat_moves.json").read_text())
+    assert len(mine) == 1880 and mine == golden
