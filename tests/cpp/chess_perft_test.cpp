@@ -3,6 +3,7 @@
 // indices of a position's legal moves are pairwise distinct.  Compiled and run by tests/test_host_units.py.
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 
 #include "../../kzero_b200/csrc/selfplay/chess_game.hpp"
 
@@ -57,6 +58,57 @@ int main() {
         const uint64_t got = perft(Chess::from_fen(c.fen), c.depth);
         if (got != c.nodes) {
             std::printf("perft(%d) of %s: %llu, expected %llu\n", c.depth, c.fen, (unsigned long long)got, (unsigned long long)c.nodes);
+            return 1;
+        }
+    }
+    // encoding (ChessStdMapper, chess.rs:136-170): planes from the mover's side, ranks flipped for black
+    {
+        Chess b = Chess::from_fen("rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1");
+        uint8_t bits[104];
+        float sc[8];
+        uint64_t planes[13];
+        b.encode(bits, sc);
+        std::memcpy(planes, bits, 104);
+        const float want_w[8] = {1, 0, 1, 1, 1, 1, 0, 0};
+        if (std::memcmp(sc, want_w, sizeof(sc)) != 0 || planes[0] != 0xFF00ull || planes[6] != 0x00FF000000000000ull || planes[5] != 0x10ull ||
+            planes[11] != 0x1000000000000000ull || planes[3] != 0x81ull || planes[12] != 0) {
+            std::printf("encoding of the initial position is wrong\n");
+            return 1;
+        }
+        // 1. e4 c5 2. e5 d5: white may capture en passant on d6; then it is white's view, no flip
+        const auto& t = kzb::selfplay::chess_detail::flat_moves();
+        auto play = [&](int from, int to) {  // absolute squares; the index is looked up from the mover's side
+            const int f = Chess::pov_square(from, b.side), o = Chess::pov_square(to, b.side);
+            b.play(uint32_t(t.index[f][o][0]));
+        };
+        play(12, 28), play(50, 34), play(28, 36), play(51, 35);
+        b.encode(bits, sc);
+        std::memcpy(planes, bits, 104);
+        if (b.ep != 43 || planes[12] != (1ull << 43) || sc[0] != 1.0f || sc[7] != 0.0f) {
+            std::printf("en passant after 1. e4 c5 2. e5 d5 is wrong (ep %d)\n", int(b.ep));
+            return 1;
+        }
+        play(6, 21);  // 3. Nf3: black to move, everything flipped; the en-passant right is gone, one quiet ply on the clock
+        b.encode(bits, sc);
+        std::memcpy(planes, bits, 104);
+        const uint64_t black_pawns_pov = (0xFF00ull & ~((1ull << 10) | (1ull << 11))) | (1ull << 26) | (1ull << 27);  // c5, d5 seen from black
+        if (sc[0] != 0.0f || sc[1] != 1.0f || sc[7] != 1.0f || planes[12] != 0 || planes[0] != black_pawns_pov) {
+            std::printf("black's view after 3. Nf3 is wrong (pawns %llx)\n", (unsigned long long)planes[0]);
+            return 1;
+        }
+        // fool's mate: 1. f3 e5 2. g4 Qh4#
+        Chess m = Chess::from_fen("rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1");
+        b = m;
+        play(13, 21), play(52, 36), play(14, 30), play(59, 31);
+        if (!b.done() || b.outcome() != -1) {
+            std::printf("fool's mate is not a win for black\n");
+            return 1;
+        }
+        // threefold repetition by shuffling knights
+        b = m;
+        for (int rep = 0; rep < 2; rep++) play(6, 21), play(62, 45), play(21, 6), play(45, 62);
+        if (!b.done() || b.outcome() != 0 || b.reps != 2) {
+            std::printf("threefold repetition is not a draw (reps %d)\n", int(b.reps));
             return 1;
         }
     }
