@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "../../kzero_b200/csrc/selfplay/chess_game.hpp"
+#include "../../kzero_b200/csrc/selfplay/mcts.hpp"
 
 using namespace kzb::selfplay;
 
@@ -29,7 +30,44 @@ static uint64_t perft(const Chess& b, int depth) {
     return n;
 }
 
+// random playouts: the cached fields stay consistent with what they cache, and the bookkeeping of play() with a brute-force history
+static int check_playouts() {
+    int mates = 0, draws_rep = 0, draws_50 = 0, draws_material = 0, stalemates = 0;
+    for (uint64_t seed = 1; seed <= 300; seed++) {
+        Chess b = Chess::start(seed);
+        Rng rng(seed);
+        std::vector<uint32_t> m;
+        std::vector<uint64_t> keys;  // keys of all earlier positions since the last irreversible move
+        for (int ply = 0; ply < 400 && !b.done(); ply++) {
+            b.moves(m);
+            if (m.empty()) return std::printf("no moves in a running game\n"), 1;
+            const uint32_t mv = m[rng.gen_range(uint32_t(m.size()))];
+            const Chess before = b;
+            b.play(mv);
+            const auto& t = kzb::selfplay::chess_detail::flat_moves();
+            const int from = Chess::pov_square(t.from[mv], before.side), to = Chess::pov_square(t.to[mv], before.side);
+            const bool pawn = std::abs(int(before.sq[from])) == 1, capture = before.sq[to] != 0 || (pawn && to == before.ep);
+            if (pawn || capture || b.castle != before.castle) keys.clear();
+            else keys.push_back(before.key);
+            int reps = 0;
+            for (uint64_t k : keys) reps += k == b.key;
+            if (b.key != b.position_key() || b.reps != reps || b.halfmove != ((pawn || capture) ? 0 : before.halfmove + 1)) return std::printf("bookkeeping broken at seed %llu ply %d\n", (unsigned long long)seed, ply), 1;
+            if (b.sq[b.king[0]] != 6 || b.sq[b.king[1]] != -6 || b.low_material != b.insufficient_material()) return std::printf("cached fields broken\n"), 1;
+            if (b.attacked(b.king[b.side ^ 1], b.side)) return std::printf("the side that just moved left its king in check\n"), 1;
+            const bool any = b.has_legal_move();
+            const int want = !any ? (b.in_check() ? 1 : 2) : (b.halfmove >= 100 || b.reps >= 2 || b.low_material) ? 2 : 0;
+            if (b.terminal != want) return std::printf("terminal flag %d, expected %d\n", int(b.terminal), want), 1;
+            if (b.terminal == 1) mates++;
+            else if (b.terminal == 2) (!any ? stalemates : b.low_material ? draws_material : b.reps >= 2 ? draws_rep : draws_50)++;
+        }
+    }
+    // random play reaches every kind of ending except (rarely) none of some kind; require the common ones
+    if (mates == 0 || draws_material + draws_rep + draws_50 + stalemates == 0) return std::printf("playouts ended in no mate or no draw at all\n"), 1;
+    return 0;
+}
+
 int main() {
+    if (check_playouts()) return 1;
     struct Case {
         const char* fen;
         int depth;
