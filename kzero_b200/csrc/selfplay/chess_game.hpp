@@ -86,6 +86,7 @@ struct Chess {
     uint8_t low_material = 0;  // insufficient mating material (recomputed when material changes)
     uint8_t hist_n = 0;
     uint64_t key = 0;        // position_key() of the current position
+    uint64_t piece_key = 0;  // the placement part of it, kept incrementally
     uint64_t hist[100];      // position keys since the last irreversible move (not including the current one)
 
     Chess() = default;
@@ -148,7 +149,8 @@ struct Chess {
             if (b.sq[s] == -kKing) b.king[1] = uint8_t(s);
         }
         b.low_material = b.insufficient_material();
-        b.key = b.position_key();
+        b.piece_key = b.placement_key();
+        b.key = b.piece_key ^ b.state_key();
         b.update_terminal();
         return b;
     }
@@ -157,20 +159,26 @@ struct Chess {
     bool done() const { return terminal != 0; }
     int outcome() const { return terminal == 1 ? (side == 0 ? -1 : 1) : 0; }  // the mated side is the one to move
 
-    uint64_t position_key() const {  // what repetition compares: placement, side, castling rights, en-passant square
-        using namespace chess_detail;
-        uint64_t h = side ? 0x9E3779B97F4A7C15ull : 0;
+    uint64_t placement_key() const {
+        uint64_t h = 0;
         for (int s = 0; s < 64; s++)
-            if (sq[s]) h ^= zobrist(sq[s], s);
+            if (sq[s]) h ^= chess_detail::zobrist(sq[s], s);
+        return h;
+    }
+    uint64_t state_key() const {  // side, castling rights, en-passant square
+        uint64_t h = side ? 0x9E3779B97F4A7C15ull : 0;
         h ^= splitmix64(0xCA57ull + castle);
         if (ep >= 0) h ^= splitmix64(0xE9ull + uint64_t(ep));
         return h;
     }
+    uint64_t position_key() const { return placement_key() ^ state_key(); }  // what repetition compares (from scratch)
     uint64_t hash() const { return splitmix64(key ^ (uint64_t(halfmove) << 8) ^ (uint64_t(reps) << 20)); }  // + what the net sees
 
     static int colour_of(int8_t p) { return p > 0 ? 0 : 1; }
     int king_square(int colour) const { return king[colour]; }
-    bool attacked(int s, int by) const {  // is square s attacked by colour `by`
+    // is square s attacked by colour `by`; the square `transparent` counts as empty (a king that steps away does not
+    // shelter the squares behind it)
+    bool attacked(int s, int by, int transparent = -1) const {
         using namespace chess_detail;
         const int r = s / 8, f = s % 8, sign = by == 0 ? 1 : -1;
         const int pr = r - sign;  // a pawn of colour `by` attacks from the rank behind (from its own side)
@@ -188,7 +196,7 @@ struct Chess {
             int rr = r + dirs[d][0], ff = f + dirs[d][1];
             for (int dist = 1; rr >= 0 && rr < 8 && ff >= 0 && ff < 8; rr += dirs[d][0], ff += dirs[d][1], dist++) {
                 const int8_t p = sq[rr * 8 + ff];
-                if (!p) continue;
+                if (!p || rr * 8 + ff == transparent) continue;
                 if (p * sign > 0) {
                     const int type = p * sign;
                     if (type == kQueen || (d < 4 && type == kRook) || (d >= 4 && type == kBishop) || (dist == 1 && type == kKing)) return true;
@@ -286,19 +294,56 @@ struct Chess {
         c.apply_placement(m);
         return !c.attacked(c.king_square(side), side ^ 1);
     }
-    static bool aligned(int a, int b) {  // same rank, file or diagonal
-        const int dr = a / 8 - b / 8, df = a % 8 - b % 8;
-        return dr == 0 || df == 0 || dr == df || dr == -df;
+    // pin_dir[s] = index (0..7) of the ray from the own king on which the own piece on s is pinned, -1 otherwise
+    void find_pins(int8_t pin_dir[64]) const {
+        using namespace chess_detail;
+        static const int dirs[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
+        std::memset(pin_dir, -1, 64);
+        const int sign = side == 0 ? 1 : -1, k = king[side], kr = k / 8, kf = k % 8;
+        for (int d = 0; d < 8; d++) {
+            int candidate = -1;
+            for (int rr = kr + dirs[d][0], ff = kf + dirs[d][1]; rr >= 0 && rr < 8 && ff >= 0 && ff < 8; rr += dirs[d][0], ff += dirs[d][1]) {
+                const int8_t p = sq[rr * 8 + ff];
+                if (!p) continue;
+                if (p * sign > 0) {
+                    if (candidate >= 0) break;  // two own pieces in a row: nothing is pinned on this ray
+                    candidate = rr * 8 + ff;
+                } else {
+                    const int type = -p * sign;
+                    if (candidate >= 0 && (type == kQueen || (d < 4 && type == kRook) || (d >= 4 && type == kBishop))) pin_dir[candidate] = int8_t(d);
+                    break;
+                }
+            }
+        }
+    }
+    static bool on_ray(int k, int s, int d) {  // is s on ray d (one of the 8 directions) from k
+        const int dr = s / 8 - k / 8, df = s % 8 - k % 8;
+        switch (d) {
+            case 0: return df == 0 && dr > 0;
+            case 1: return df == 0 && dr < 0;
+            case 2: return dr == 0 && df > 0;
+            case 3: return dr == 0 && df < 0;
+            case 4: return dr == df && dr > 0;
+            case 5: return dr == -df && dr > 0;
+            case 6: return dr == -df && dr < 0;
+            default: return dr == df && dr < 0;
+        }
     }
     template <typename F>
     void legal_moves(F&& emit) const {
-        // when the king is not in check, a move can only expose it if the moving piece leaves a line through the king
-        // (or is the king, or captures en passant): everything else is legal without looking
+        // not in check: a piece other than the king may move unless it is pinned, and a pinned piece may move along its
+        // pin ray; a king may step onto a square the other side does not attack once the king itself is off the board;
+        // en-passant captures and every other move while in check take the full test
         const bool check = in_check();
         const int k = king[side];
+        int8_t pin_dir[64];
+        if (!check) find_pins(pin_dir);
         pseudo_moves([&](const Mv& m) {
-            const bool quick = !check && m.from != k && !aligned(m.from, k) && !(m.to == ep && std::abs(int(sq[m.from])) == chess_detail::kPawn);
-            return !(quick || legal(m)) || emit(m);
+            bool ok;
+            if (m.from == k) ok = !attacked(m.to, side ^ 1, k);  // the squares a castling king crosses were tested by the generator
+            else if (check || (m.to == ep && std::abs(int(sq[m.from])) == chess_detail::kPawn)) ok = legal(m);
+            else ok = pin_dir[m.from] < 0 || on_ray(k, m.to, pin_dir[m.from]);
+            return !ok || emit(m);
         });
     }
     bool has_legal_move() const {
@@ -347,6 +392,17 @@ struct Chess {
         const int type = sq[m.from] * sign;
         const bool capture = sq[m.to] != 0 || (type == kPawn && m.to == ep);
         const uint64_t key_before = key;
+        {  // placement key: the mover leaves `from`, whatever stood on `to` (or the pawn passed en passant) goes, the mover or
+           // its promotion arrives, a castling rook changes squares
+            const int8_t p = sq[m.from];
+            piece_key ^= zobrist(p, m.from) ^ zobrist(m.promo ? int8_t(sign * m.promo) : p, m.to);
+            if (sq[m.to]) piece_key ^= zobrist(sq[m.to], m.to);
+            else if (type == kPawn && m.to == ep) piece_key ^= zobrist(int8_t(-sign * kPawn), (m.from / 8) * 8 + m.to % 8);
+            if (type == kKing && std::abs(int(m.to) - int(m.from)) == 2) {
+                const int rook_from = m.to > m.from ? m.from + 3 : m.from - 4, rook_to = m.to > m.from ? m.from + 1 : m.from - 1;
+                piece_key ^= zobrist(int8_t(sign * kRook), rook_from) ^ zobrist(int8_t(sign * kRook), rook_to);
+            }
+        }
         apply_placement(m);
         if (capture || m.promo) low_material = insufficient_material();
         // castling rights: a king or rook that moves, or a rook that is captured, loses them
@@ -374,7 +430,7 @@ struct Chess {
         side ^= 1;
         ply++;
         reps = 0;
-        key = position_key();
+        key = piece_key ^ state_key();
         for (int i = int(hist_n) - 2; i >= 0; i -= 2)  // same side to move: every second entry back
             if (hist[i] == key) reps++;
         update_terminal();
