@@ -328,6 +328,235 @@ class Ataxx7:
             self.result = 0 if stalled_only else (a > b) - (a < b)
 
 
+class Chess:
+    """Twin of kzb::selfplay::Chess (kzero_b200/csrc/selfplay/chess_game.hpp), written independently: a mailbox board,
+    legality by making the move and looking at the king (no pins, no shortcuts).  What the two must share is the
+    SPECIFICATION: moves are policy indices from the mover's side (ranks flipped for black) in the reference's flat table
+    (chess.rs:439-481); they are generated square by square from a1, per piece in the order pawn push (promotions Q R B N),
+    double push, capture towards the a-file, capture towards the h-file; knight / king steps in the orders below, castling
+    king side then queen side; sliders direction by direction, near to far.  The en-passant square exists only while an
+    enemy pawn stands next to the pushed pawn; a position repeats when placement, side, castling rights and en-passant
+    square agree; draw on the third occurrence, after 100 quiet plies, or with K (+ one minor) v K."""
+    KNIGHT = [(2, 1), (1, 2), (-1, 2), (-2, 1), (-2, -1), (-1, -2), (1, -2), (2, -1)]  # (rank, file) steps
+    KING = [(1, 0), (-1, 0), (0, 1), (0, -1), (1, 1), (1, -1), (-1, 1), (-1, -1)]
+    SLIDES = {3: KING[4:], 4: KING[:4], 5: KING}  # bishop, rook, queen
+    _flat = None
+
+    def __init__(self):
+        back = [4, 2, 3, 5, 6, 3, 2, 4]
+        self.sq = back + [1] * 8 + [0] * 32 + [-1] * 8 + [-v for v in back]
+        self.side, self.castle, self.ep, self.halfmove, self.ply = 0, 15, -1, 0, 0
+        self.history: List[int] = []  # keys of earlier positions since the last irreversible move
+        self.reps, self.terminal = 0, 0
+
+    @staticmethod
+    def start(seed: int) -> "Chess":
+        return Chess()
+
+    def clone(self):
+        c = Chess.__new__(Chess)
+        c.sq, c.history = list(self.sq), list(self.history)
+        c.side, c.castle, c.ep, c.halfmove, c.ply, c.reps, c.terminal = self.side, self.castle, self.ep, self.halfmove, self.ply, self.reps, self.terminal
+        return c
+
+    @classmethod
+    def flat(cls):
+        if cls._flat is None:
+            table = []
+            for f in range(64):
+                for t in range(64):
+                    df, dr = f % 8 - t % 8, f // 8 - t // 8
+                    if ((df == 0) != (dr == 0)) or (df != 0 and abs(df) == abs(dr)):
+                        table.append((f, t, 0))
+            for f in range(64):
+                for t in range(64):
+                    df, dr = abs(f % 8 - t % 8), abs(f // 8 - t // 8)
+                    if (df, dr) in ((1, 2), (2, 1)):
+                        table.append((f, t, 0))
+            for piece in (5, 4, 3, 2):
+                for ff in range(8):
+                    for tf in range(8):
+                        if abs(ff - tf) <= 1:
+                            table.append((48 + ff, 56 + tf, piece))
+            cls._flat = (table, {m: i for i, m in enumerate(table)})
+        return cls._flat
+
+    def _pov(self, s: int) -> int:
+        return s if self.side == 0 else (7 - s // 8) * 8 + s % 8
+
+    def position_key(self) -> int:
+        h = 0x9E3779B97F4A7C15 if self.side else 0
+        for s, p in enumerate(self.sq):
+            if p:
+                h ^= splitmix64((p + 16) * 64 + s + 0xC0FFEE)
+        h ^= splitmix64(0xCA57 + self.castle)
+        if self.ep >= 0:
+            h ^= splitmix64(0xE9 + self.ep)
+        return h
+
+    def hash(self) -> int:
+        return splitmix64(self.position_key() ^ (self.halfmove << 8) ^ (self.reps << 20))
+
+    def next_player(self) -> int:
+        return self.side
+
+    def done(self) -> bool:
+        return self.terminal != 0
+
+    def outcome(self) -> int:
+        return (-1 if self.side == 0 else 1) if self.terminal == 1 else 0
+
+    def _attacked(self, s: int, by: int) -> bool:
+        sign = 1 if by == 0 else -1
+        r, f = divmod(s, 8)
+        for df in (-1, 1):
+            rr, ff = r - sign, f + df
+            if 0 <= rr < 8 and 0 <= ff < 8 and self.sq[rr * 8 + ff] == sign:
+                return True
+        for steps, piece in ((self.KNIGHT, 2), (self.KING, 6)):
+            for dr, df in steps:
+                rr, ff = r + dr, f + df
+                if 0 <= rr < 8 and 0 <= ff < 8 and self.sq[rr * 8 + ff] == sign * piece:
+                    return True
+        for i, (dr, df) in enumerate(self.KING):
+            rr, ff = r + dr, f + df
+            while 0 <= rr < 8 and 0 <= ff < 8:
+                p = self.sq[rr * 8 + ff]
+                if p:
+                    if p * sign in (5, 4 if i < 4 else 3):
+                        return True
+                    break
+                rr, ff = rr + dr, ff + df
+        return False
+
+    def _king(self, colour: int) -> int:
+        return self.sq.index(6 if colour == 0 else -6)
+
+    def _pseudo(self):
+        sign = 1 if self.side == 0 else -1
+        enemy = self.side ^ 1
+        for s in range(64):
+            p = self.sq[s] * sign
+            if p <= 0:
+                continue
+            r, f = divmod(s, 8)
+            if p == 1:
+                last, first = (7, 1) if self.side == 0 else (0, 6)
+                r1 = r + sign
+                targets = []
+                if not self.sq[r1 * 8 + f]:
+                    targets.append(r1 * 8 + f)
+                    if r == first and not self.sq[(r + 2 * sign) * 8 + f]:
+                        targets.append((r + 2 * sign) * 8 + f)
+                for df in (-1, 1):
+                    if 0 <= f + df < 8:
+                        t = r1 * 8 + f + df
+                        if self.sq[t] * sign < 0 or t == self.ep:
+                            targets.append(t)
+                for t in targets:
+                    if t // 8 == last:
+                        for promo in (5, 4, 3, 2):
+                            yield s, t, promo
+                    else:
+                        yield s, t, 0
+            elif p in (2, 6):
+                for dr, df in (self.KNIGHT if p == 2 else self.KING):
+                    rr, ff = r + dr, f + df
+                    if 0 <= rr < 8 and 0 <= ff < 8 and self.sq[rr * 8 + ff] * sign <= 0:
+                        yield s, rr * 8 + ff, 0
+                home = 4 if self.side == 0 else 60
+                if p == 6 and s == home and not self._attacked(home, enemy):
+                    k_right, q_right = (1, 2) if self.side == 0 else (4, 8)
+                    if self.castle & k_right and not self.sq[home + 1] and not self.sq[home + 2] and self.sq[home + 3] == 4 * sign \
+                            and not self._attacked(home + 1, enemy) and not self._attacked(home + 2, enemy):
+                        yield s, home + 2, 0
+                    if self.castle & q_right and not any(self.sq[home - 3:home]) and self.sq[home - 4] == 4 * sign \
+                            and not self._attacked(home - 1, enemy) and not self._attacked(home - 2, enemy):
+                        yield s, home - 2, 0
+            else:
+                for dr, df in self.SLIDES[p]:
+                    rr, ff = r + dr, f + df
+                    while 0 <= rr < 8 and 0 <= ff < 8:
+                        q = self.sq[rr * 8 + ff] * sign
+                        if q > 0:
+                            break
+                        yield s, rr * 8 + ff, 0
+                        if q:
+                            break
+                        rr, ff = rr + dr, ff + df
+
+    def encode(self):
+        """-> (bools [13, 8, 8] u8, scalars f32): ChessStdMapper::encode_input, rust/kz-core/src/mapping/chess.rs:136-170."""
+        sign = 1 if self.side == 0 else -1
+        planes = np.zeros((13, 8, 8), np.uint8)
+        for s, p in enumerate(self.sq):
+            if p:
+                r, f = divmod(self._pov(s), 8)
+                planes[(0 if p * sign > 0 else 6) + abs(p) - 1, r, f] = 1
+        if self.ep >= 0:
+            r, f = divmod(self._pov(self.ep), 8)
+            planes[12, r, f] = 1
+        own_k, own_q, opp_k, opp_q = (1, 2, 4, 8) if self.side == 0 else (4, 8, 1, 2)
+        scalars = [self.side == 0, self.side == 1, bool(self.castle & own_k), bool(self.castle & own_q), bool(self.castle & opp_k),
+                   bool(self.castle & opp_q), self.reps, self.halfmove]
+        return planes, np.array(scalars, F)
+
+    def _place(self, frm: int, to: int, promo: int) -> None:
+        sign = 1 if self.side == 0 else -1
+        p = self.sq[frm]
+        if abs(p) == 1 and to == self.ep and not self.sq[to]:
+            self.sq[(frm // 8) * 8 + to % 8] = 0
+        self.sq[to] = sign * promo if promo else p
+        self.sq[frm] = 0
+        if abs(p) == 6 and abs(to - frm) == 2:
+            rook_from, rook_to = (frm + 3, frm + 1) if to > frm else (frm - 4, frm - 1)
+            self.sq[rook_to], self.sq[rook_from] = self.sq[rook_from], 0
+
+    def _legal(self):
+        for frm, to, promo in self._pseudo():
+            c = self.clone()
+            c._place(frm, to, promo)
+            if not c._attacked(c._king(self.side), self.side ^ 1):
+                yield frm, to, promo
+
+    def moves(self) -> List[int]:
+        index = self.flat()[1]
+        return [index[(self._pov(f), self._pov(t), promo)] for f, t, promo in self._legal()]
+
+    def play(self, mv: int) -> None:
+        f, t, promo = self.flat()[0][mv]
+        frm, to = self._pov(f), self._pov(t)
+        sign = 1 if self.side == 0 else -1
+        piece = abs(self.sq[frm])
+        capture = self.sq[to] != 0 or (piece == 1 and to == self.ep)
+        key_before, castle_before = self.position_key(), self.castle
+        self._place(frm, to, promo)
+        for s in (frm, to):
+            self.castle &= {4: ~3, 60: ~12, 7: ~1, 0: ~2, 63: ~4, 56: ~8}.get(s, 15) & 15
+        self.ep = -1
+        if piece == 1 and abs(to - frm) == 16:
+            file = to % 8
+            if (file > 0 and self.sq[to - 1] == -sign) or (file < 7 and self.sq[to + 1] == -sign):
+                self.ep = (frm + to) // 2
+        if piece == 1 or capture:
+            self.halfmove = 0
+        else:
+            self.halfmove += 1
+        if piece == 1 or capture or self.castle != castle_before:
+            self.history = []
+        else:
+            self.history.append(key_before)
+        self.side ^= 1
+        self.ply += 1
+        self.reps = self.history.count(self.position_key())
+        others = [abs(p) for p in self.sq if p and abs(p) != 6]
+        low_material = all(p in (2, 3) for p in others) and len(others) <= 1
+        if not any(True for _ in self._legal()):
+            self.terminal = 1 if self._attacked(self._king(self.side), self.side ^ 1) else 2
+        else:
+            self.terminal = 2 if (self.halfmove >= 100 or self.reps >= 2 or low_material) else 0
+
+
 def pseudo_eval(board, kind: int):
     """-> (values_pov [value, win, draw, loss, moves_left] f32, policy f32); twin of pseudo_eval in selfplay.cpp."""
     n = len(board.moves())
@@ -499,7 +728,7 @@ def zero_step_apply(tree: Tree, idx: int, next_player: int, values_pov: np.ndarr
 
 def search(game_seed: int, plies: int, rng_seed: int, visits: int, search_batch: int, eval_kind: int, s: Settings, game: str = "chess"):
     """The twin of trace_search in selfplay.cpp: -> dict(child_visits, child_moves, child_policy, root_values, ...)."""
-    board = {"go-9": Go9, "ataxx-7": Ataxx7, "chess": SynthChess}[game].start(game_seed)
+    board = {"go-9": Go9, "ataxx-7": Ataxx7, "chess": SynthChess, "chess-real": Chess}[game].start(game_seed)
     rng = Rng(rng_seed)
     for _ in range(plies):
         if board.done():

@@ -76,6 +76,19 @@ def test_ataxx_search_matches_oracle(plies, rng_seed, eval_kind):
     assert np.allclose(got.root_values, ref["root_values"], rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize("plies,rng_seed,eval_kind", [(0, 5, 1), (16, 6, 1), (60, 7, 0), (120, 8, 1)])
+def test_chess_search_matches_oracle(plies, rng_seed, eval_kind):
+    """Legal chess: the C++ generator (pins, incremental keys, cached terminal state) against the oracle's plain
+    make-and-test mailbox restatement, on positions up to 120 random plies into a game."""
+    c = _cfg(game=selfplay.GAME_CHESS, visits=100, search_batch=8, seed=rng_seed)
+    got = selfplay.mcts_trace(c, 1, plies, eval_kind)
+    ref = mo.search(1, plies, rng_seed, 100, 8, eval_kind, _oracle_settings(c), game="chess-real")
+    assert np.array_equal(got.child_moves, ref["child_moves"])
+    assert np.array_equal(got.child_visits, ref["child_visits"])
+    assert (got.root_visits, got.tree_nodes, got.evals) == (ref["root_visits"], ref["tree_nodes"], ref["evals"])
+    assert np.allclose(got.root_values, ref["root_values"], rtol=0, atol=1e-6)
+
+
 def test_search_invariants():
     """What the reference asserts along the way: one policy entry per available move (step.rs:163), the visit
     distribution sums to 1 (tree.rs:132-141), a search with a tree smaller than the batch terminates (tests/tree.rs:16-42)."""

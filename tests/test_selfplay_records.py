@@ -125,7 +125,8 @@ def test_reference_loader_reads_the_records(tmp_path, game, name):
     assert sum(sim.position_count for sim in sims) == f.info.position_count
 
 
-@pytest.mark.parametrize("game,name,twin", [(selfplay.GAME_ATAXX7, "ataxx-7", "Ataxx7"), (selfplay.GAME_GO9, "go-9", "Go9")])
+@pytest.mark.parametrize("game,name,twin", [(selfplay.GAME_ATAXX7, "ataxx-7", "Ataxx7"), (selfplay.GAME_GO9, "go-9", "Go9"),
+                                            (selfplay.GAME_CHESS, "chess", "Chess")])
 def test_recorded_games_replay_under_the_oracle_rules(tmp_path, game, name, twin):
     """Every recorded game is replayed move by move with the oracle's independent restatement of the rules: at each
     position the recorded input planes and scalars are the twin's encoding, the recorded policy indices are the twin's
@@ -133,8 +134,8 @@ def test_recorded_games_replay_under_the_oracle_rules(tmp_path, game, name, twin
     from oracle import mcts_oracle as mo
 
     prefix, r = _run(tmp_path, game)
-    shape = {"ataxx-7": (3, 7, 7), "go-9": (4, 9, 9)}[name]
-    meta, positions, game_starts = _parse(prefix, int(np.prod(shape)), {"ataxx-7": 1, "go-9": 6}[name])
+    shape = {"ataxx-7": (3, 7, 7), "go-9": (4, 9, 9), "chess": (13, 8, 8)}[name]
+    meta, positions, game_starts = _parse(prefix, int(np.prod(shape)), {"ataxx-7": 1, "go-9": 6, "chess": 8}[name])
     checked = 0
     for g in range(meta["game_count"]):
         first = int(game_starts[g])
@@ -161,6 +162,6 @@ def test_recorded_games_replay_under_the_oracle_rules(tmp_path, game, name, twin
         outcome = board.outcome() if board.done() else 0
         for k in range(length + 1):
             sc = positions[first + k]["scalars"]
-            pov = outcome if k % 2 == 0 else -outcome  # player A moves first in both games
+            pov = outcome if k % 2 == 0 else -outcome  # player A moves first in all three games
             assert sc[11] == pov and sc[12:15].tolist() == [float(pov > 0), float(pov == 0), float(pov < 0)], (g, k, sc[11:15], pov)
     assert checked >= 40
