@@ -101,12 +101,24 @@ __global__ void __launch_bounds__(kThreads, 1)
     tc_fence_after();
     const uint32_t tmem_base = *sm.tmem_ptr;
     const uint32_t acc_stride = uint32_t(p.tmem_cols / 2);
+    if (p.pdl) grid_dep_launch_dependents();  // the next layer may set itself up while this one computes
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0, a_slot = 0;
             uint32_t phase = 0, a_phase = 0;
+            int pre = 0;  // weight tiles issued before the previous layer had finished (they do not depend on it)
+            if (p.pdl) {
+                if (int(blockIdx.x) < num_items) {
+                    const int n0 = (int(blockIdx.x) % p.n_split) * n_eff;
+                    for (; pre < p.stages && pre < 9 * p.kblocks; pre++) {
+                        mbar_expect_tx(&sm.full[pre], b_bytes);
+                        tma_load_2d(&tmap_b, &sm.full[pre], sm.b_base + size_t(pre) * b_slot, (pre % 9) * p.cin_pad + (pre / 9) * kBlockK, n0);
+                    }
+                }
+                grid_dep_wait();
+            }
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
                 const int tile = item / p.n_split, n0 = (item % p.n_split) * n_eff;
                 for (int kb = 0; kb < p.kblocks; kb++) {
@@ -123,9 +135,13 @@ __global__ void __launch_bounds__(kThreads, 1)
                         a_phase ^= 1;
                     }
                     for (int tap = 0; tap < 9; tap++) {
-                        mbar_wait(&sm.empty[stage], phase ^ 1);
-                        mbar_expect_tx(&sm.full[stage], b_bytes);
-                        tma_load_2d(&tmap_b, &sm.full[stage], sm.b_base + size_t(stage) * b_slot, tap * p.cin_pad + kb * kBlockK, n0);
+                        if (pre > 0) {
+                            pre--;  // already in flight
+                        } else {
+                            mbar_wait(&sm.empty[stage], phase ^ 1);
+                            mbar_expect_tx(&sm.full[stage], b_bytes);
+                            tma_load_2d(&tmap_b, &sm.full[stage], sm.b_base + size_t(stage) * b_slot, tap * p.cin_pad + kb * kBlockK, n0);
+                        }
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1;
@@ -184,6 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         const int quarter = warp % 4;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+        if (p.pdl) grid_dep_wait();    // the residual rows are the previous layers' output
         for (int item = blockIdx.x, local = 0; item < num_items; item += gridDim.x, local++) {
             const int buf = local & 1;
             const uint32_t buf_phase = (local >> 1) & 1;
@@ -223,7 +240,17 @@ void conv_tch_prepare() { cudaFuncSetAttribute(conv_tch_kernel, cudaFuncAttribut
 // whose box holds p.n / p.n_split rows
 void launch_conv_tch(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ConvTcParams& p, int grid, cudaStream_t s) {
     if (p.num_tiles <= 0) return;
-    conv_tch_kernel<<<std::min(grid, p.num_tiles * p.n_split), kThreads, conv_tch_smem_bytes(p.n, p.stages, p.a_rows), s>>>(tmap_a, tmap_b, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(std::min(grid, p.num_tiles * p.n_split)));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = conv_tch_smem_bytes(p.n, p.stages, p.a_rows);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, conv_tch_kernel, tmap_a, tmap_b, p);
 }
 
 }  // namespace kzb

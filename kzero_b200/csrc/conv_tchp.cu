@@ -122,12 +122,24 @@ __global__ void __launch_bounds__(kThreads, 1)
     tc_fence_after();
     const uint32_t tmem_base = *sm.tmem_ptr;
     const uint32_t acc_stride = uint32_t(p.tmem_cols / 2);
+    if (p.pdl) grid_dep_launch_dependents();  // the next layer may set itself up while this one computes
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs, own rows / own weight half)
         if (lane == 0) {
             int stage = 0, a_slot = 0;
             uint32_t phase = 0, a_phase = 0;
+            int pre = 0;  // weight tiles issued before the previous layer had finished (they do not depend on it)
+            if (p.pdl) {
+                if (cluster_id < num_pairs) {
+                    for (; pre < p.stages && pre < 9 * p.kblocks; pre++) {
+                        mbar_expect_tx(&sm.full[pre], b_bytes);
+                        tma_load_2d(&tmap_bh, &sm.full[pre], sm.b_base + size_t(pre) * b_stage, (pre % 9) * p.cin_pad + (pre / 9) * kBlockK,
+                                    int(rank) * (p.n / 2));
+                    }
+                }
+                grid_dep_wait();
+            }
             for (int pt = cluster_id; pt < num_pairs; pt += num_clusters) {
                 const int tile = 2 * pt + int(rank);  // may be one past the last tile: its rows are zero-filled and never stored
                 for (int kb = 0; kb < p.kblocks; kb++) {
@@ -143,10 +155,14 @@ __global__ void __launch_bounds__(kThreads, 1)
                         a_phase ^= 1;
                     }
                     for (int tap = 0; tap < 9; tap++) {
-                        mbar_wait(&sm.empty[stage], phase ^ 1);
-                        mbar_expect_tx(&sm.full[stage], b_bytes);
-                        tma_load_2d(&tmap_bh, &sm.full[stage], sm.b_base + size_t(stage) * b_stage, tap * p.cin_pad + kb * kBlockK,
-                                    int(rank) * (p.n / 2));
+                        if (pre > 0) {
+                            pre--;  // already in flight
+                        } else {
+                            mbar_wait(&sm.empty[stage], phase ^ 1);
+                            mbar_expect_tx(&sm.full[stage], b_bytes);
+                            tma_load_2d(&tmap_bh, &sm.full[stage], sm.b_base + size_t(stage) * b_stage, tap * p.cin_pad + kb * kBlockK,
+                                        int(rank) * (p.n / 2));
+                        }
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1;
@@ -212,6 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         // ------------------------------------------------------------------ epilogue (warps 2..5), each CTA drains its own 128 rows
         const int quarter = warp % 4;
         int local = 0;
+        if (p.pdl) grid_dep_wait();  // the residual rows are the previous layers' output
         for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, local++) {
             const int buf = local & 1;
             const uint32_t buf_phase = (local >> 1) & 1;
@@ -256,13 +273,15 @@ void launch_conv_tchp(const CUtensorMap& tmap_a, const CUtensorMap& tmap_bh, con
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = conv_tchp_smem_bytes(p.n, p.stages, p.a_rows);
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = p.pdl ? 2 : 1;
     cudaLaunchKernelEx(&cfg, conv_tchp_kernel, tmap_a, tmap_bh, p);
 }
 

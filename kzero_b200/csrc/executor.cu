@@ -354,6 +354,8 @@ void Net::build_bf16() {
                 st->tchp_stages = conv_tchp_pick_stages(n, p.a_rows);
             }
         }
+        const char* pdl_env = std::getenv("KZB_PDL");  // programmatic dependent launch of consecutive 3x3 layers (conv_tch / conv_tchp)
+        p.pdl = (pdl_env && pdl_env[0] == '1') ? 1 : 0;
         const char* cl = std::getenv("KZB_CONV_CLUSTER");
         p.cluster = (cl && cl[0] == '2' && n % 32 == 0 && st->taps == 9) ? 2 : 1;
         convs_.push_back(std::move(st));

@@ -88,6 +88,7 @@ struct ConvTcParams {
     int tmem_cols;
     int cluster;  // conv_tc only: 1, or 2 = CTA pairs share every weight tile through TMA multicast
     int n_split;       // conv_tch only: 1, or 2 = a work item is one tile x one half of the output channels
+    int pdl;           // conv_tch / conv_tchp: launched with programmatic stream serialization (the prologue and the first weight tiles overlap the previous layer's tail)
     int halo, a_rows;  // conv_tch only: rank_pitch + 1 halo rows on either side, a_rows = 128 + 2 * halo (rounded up to 8) rows per activation tile
     // development aid: when non-null, each CTA writes 16 clock64() stamps (see conv_tc8.cu) -- KZB_TIMELINE=1
     unsigned long long* timeline;

@@ -89,6 +89,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         "r"(parity)
         : "memory");
 }
+// Programmatic dependent launch (kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization): the next kernel of
+// the stream may start once every CTA of this one has called launch_dependents (or exited); it must call grid_dep_wait before
+// it touches anything the previous kernel wrote.
+__device__ __forceinline__ void grid_dep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -91,10 +91,12 @@ class _GraphBuilder:
         self.nodes: List[bytes] = []
         self.inits: List[bytes] = []
         self.ops: List[str] = []
+        self.arrays: dict = {}
         self._n = 0
 
     def init(self, name: str, arr: np.ndarray) -> str:
         self.inits.append(_tensor(name, arr))
+        self.arrays[name] = arr
         return name
 
     def node(self, op: str, inputs: Sequence[str], out: Optional[str] = None, **attrs) -> str:
@@ -183,11 +185,15 @@ _BN = dict(epsilon=float(np.float32(1e-5)), momentum=float(np.float32(0.9)))
 
 
 def build_onnx(game: GameSpec, depth: int, channels: int, seed: int = 0, scalar_hidden_channels: int = 4,
-               scalar_hidden_size: int = 32, query_channels: int = 32, fold_bn: bool = True) -> bytes:
+               scalar_hidden_size: int = 32, query_channels: int = 32, fold_bn: bool = True,
+               weights_out: Optional[dict] = None) -> bytes:
     """ONNX bytes for PredictionHeads(ResTower(depth, C_in, channels), ScalarHead, <policy head>).
 
     fold_bn=False keeps Conv -> BatchNormalization -> Relu un-folded inside blocks (what older torch
-    versions / train-mode exports produce; Kyanite's optimiser folds those itself)."""
+    versions / train-mode exports produce; Kyanite's optimiser folds those itself).
+
+    weights_out: optional dict that receives every initializer (name -> array; tower convs are w1/b1 = input conv,
+    w2.. = block convs in order) -- what bench.py's library comparator builds the same tower from."""
     rng = np.random.default_rng(seed)
     g = _GraphBuilder()
     c, a, s = channels, game.area, game.board_size
@@ -292,6 +298,8 @@ def build_onnx(game: GameSpec, depth: int, channels: int, seed: int = 0, scalar_
     else:
         raise KeyError(game.head)
 
+    if weights_out is not None:
+        weights_out.update(g.arrays)
     return g.finish([("input", ["batch_size", game.input_channels, s, s])],
                     [("scalars", ["batch_size", 5]), ("policy", ["batch_size", policy_dim])])
 

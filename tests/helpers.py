@@ -29,3 +29,32 @@ def load_net_fixture(name):
     scalars = data[n_in:n_in + b * 5].reshape(b, 5)
     policy = data[n_in + b * 5:].reshape(b, p)
     return onnx_bytes, x, scalars, policy
+
+
+def bf16_round(a):
+    """f32 array rounded to the nearest bf16 (ties to even) and widened back -- what a bf16 operand holds."""
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def bf16_emulation(onnx_bytes, residual_bf16=True):
+    """The oracle's op-by-op interpreter with the ARITHMETIC of a bf16 tensor-core path: every Conv reads bf16-rounded
+    activations and weights and accumulates in f32; the residual stream (every Add) is stored as bf16 when
+    `residual_bf16` -- the product's layout -- or kept in f32.  Separates 'the kernel computes something else' from
+    'bf16 operands cannot be closer than this to the f32 oracle'.  Conv via torch's CPU kernels (f32 accumulate)."""
+    from oracle.graph_exec import OnnxOracle
+
+    class Emulation(OnnxOracle):
+        def _run_node(self, node, env):
+            if node.op == "Conv":
+                env = dict(env)
+                env[node.inputs[0]] = bf16_round(env[node.inputs[0]])
+                env[node.inputs[1]] = bf16_round(env[node.inputs[1]])
+                return super()._run_node(node, env)
+            out = super()._run_node(node, env)
+            if node.op == "Add" and residual_bf16:
+                out = [bf16_round(out[0])]
+            return out
+
+    return Emulation(onnx_bytes, conv_backend="torch")
