@@ -1,19 +1,20 @@
-// K1p (EXPERIMENTAL, not yet run on hardware as a whole; off unless KZB_CONV_PAIR=1): conv_tch.cu on the CTA-pair MMA.
+// K1p: conv_tch.cu on the CTA-pair MMA (tcgen05.mma.cta_group::2), the 3x3 layers of boards larger than 8x8 (go).
 //
 // Two CTAs of a cluster own 256 consecutive padded rows (128 each).  Each stages its own activation tile (with halo, as in
 // conv_tch.cu) and only HALF of every weight tile (n/2 output channels); the leader issues tcgen05.mma.cta_group::2 with
 // M = 256 and both CTAs' TMEM receive their own 128 rows x n columns.  Per SM that is n/2 * 128 bytes of weights written
-// into shared memory per (tap, k-block) instead of n * 128, and 8 KB instead of 12 KB read per MMA at n = 256 -- the
-// quantity profiles/r01d_go9_conv_tc_ncu.md points at.  Every primitive used here was verified in isolation by
-// scripts/micro/mma2_bench.cu (profiles/r01d_mma2_bench.txt): operand / accumulator placement of the pair MMA, the
-// unswizzled halo-tile A operand in pair mode, full rate at N = 256 and N = 128, the remote-arrive handshake.
+// into shared memory per (tap, k-block) instead of n * 128, and 8 KB instead of 12 KB read per MMA at n = 256.  The
+// primitives were verified in isolation by scripts/micro/mma2_bench.cu (profiles/r01d_mma2_bench.txt): operand /
+// accumulator placement of the pair MMA, the unswizzled halo-tile A operand in pair mode, full rate at N = 256 and N = 128.
 //
-// Synchronisation (L = leader = cluster rank 0, P = peer):
-//   full[s] / a_full[a]     own TMA landed (per CTA)
-//   peer_full[s] (on L)     P's MMA warp relays "my stage s (and, at tap 0, my activation slot) is in place" by a remote arrive
-//   empty[s] / a_empty[a]   L's commit, multicast to both CTAs: the MMAs that read the slot are done
-//   tmem_full[b]            L's commit, multicast: accumulator b is complete in both CTAs' TMEM
-//   tmem_empty[b] (on L)    8 arrivals: the 4 epilogue warps of L (local) and of P (remote) have drained accumulator b
+// Synchronisation (L = leader = cluster rank 0, P = peer).  Only L's MMA thread issues, so its per-stage work must stay well
+// below the 512 cycles four MMAs take: it waits on ONE barrier per stage.  (The first version relayed P's "stage landed"
+// through a second barrier with an acquire.cluster wait per stage; it ran at 0.65x of conv_tch -- profiles/r02_go_pair.md.)
+//   full[s] / a_full[a] (L's copy)  armed by L's producer with the bytes of BOTH CTAs; P's TMA loads complete their bytes on L's
+//                                   barrier (cp.async.bulk.tensor .cta_group::2 with the peer bit of the barrier address cleared)
+//   empty[s] / a_empty[a]           L's commit, multicast to both CTAs: the MMAs that read the slot are done
+//   tmem_full[b]                    L's commit, multicast: accumulator b is complete in both CTAs' TMEM
+//   tmem_empty[b] (on L)            8 arrivals: the 4 epilogue warps of L (local) and of P (remote) have drained accumulator b
 #include "conv_epilogue.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -32,7 +33,7 @@ using namespace tc;
 struct SmemLayout {
     uint8_t* b_base;  // ring of `stages` half weight tiles, n/2 * 128 bytes each (1024-byte aligned)
     uint8_t* a_base;  // activation slots
-    uint64_t *full, *empty, *peer_full, *a_full, *a_empty, *tmem_full, *tmem_empty;
+    uint64_t *full, *empty, *a_full, *a_empty, *tmem_full, *tmem_empty;
     uint32_t* tmem_ptr;
     float* bias;
 };
@@ -47,8 +48,7 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* base, int n, int stages, in
     uint8_t* p = s.a_base + kASlots * a_slot_bytes(a_rows);
     s.full = reinterpret_cast<uint64_t*>(p);
     s.empty = s.full + stages;
-    s.peer_full = s.empty + stages;
-    s.a_full = s.peer_full + stages;
+    s.a_full = s.empty + stages;
     s.a_empty = s.a_full + kASlots;
     s.tmem_full = s.a_empty + kASlots;
     s.tmem_empty = s.tmem_full + 2;
@@ -68,6 +68,15 @@ __device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t a_desc, uin
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// TMA load issued by either CTA of the pair; the bytes are completed on the LEADER's barrier (same offset, peer bit cleared)
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
         : "memory");
 }
 __device__ __forceinline__ void umma2_commit(uint64_t* bar) {  // arrives on `bar` in both CTAs of the pair
@@ -97,7 +106,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int i = 0; i < p.stages; i++) {
             mbar_init(&sm.full[i], 1);
             mbar_init(&sm.empty[i], 1);
-            mbar_init(&sm.peer_full[i], 1);
         }
         for (int i = 0; i < kASlots; i++) {
             mbar_init(&sm.a_full[i], 1);
@@ -133,9 +141,9 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (p.pdl) {
                 if (cluster_id < num_pairs) {
                     for (; pre < p.stages && pre < 9 * p.kblocks; pre++) {
-                        mbar_expect_tx(&sm.full[pre], b_bytes);
-                        tma_load_2d(&tmap_bh, &sm.full[pre], sm.b_base + size_t(pre) * b_stage, (pre % 9) * p.cin_pad + (pre / 9) * kBlockK,
-                                    int(rank) * (p.n / 2));
+                        if (leader) mbar_expect_tx(&sm.full[pre], 2 * b_bytes);
+                        tma2_load_2d(&tmap_bh, &sm.full[pre], sm.b_base + size_t(pre) * b_stage, (pre % 9) * p.cin_pad + (pre / 9) * kBlockK,
+                                     int(rank) * (p.n / 2));
                     }
                 }
                 grid_dep_wait();
@@ -144,12 +152,12 @@ __global__ void __launch_bounds__(kThreads, 1)
                 const int tile = 2 * pt + int(rank);  // may be one past the last tile: its rows are zero-filled and never stored
                 for (int kb = 0; kb < p.kblocks; kb++) {
                     mbar_wait(&sm.a_empty[a_slot], a_phase ^ 1);
-                    mbar_expect_tx(&sm.a_full[a_slot], 8u * chunk_bytes);
+                    if (leader) mbar_expect_tx(&sm.a_full[a_slot], 2u * 8u * chunk_bytes);
                     uint8_t* a_dst = sm.a_base + size_t(a_slot) * a_bytes;
 #pragma unroll
                     for (int kc = 0; kc < 8; kc++)
-                        tma_load_2d(&tmap_a, &sm.a_full[a_slot], a_dst + size_t(kc) * chunk_bytes, kb * kBlockK + kc * 8,
-                                    tile * kTileM - p.halo);
+                        tma2_load_2d(&tmap_a, &sm.a_full[a_slot], a_dst + size_t(kc) * chunk_bytes, kb * kBlockK + kc * 8,
+                                     tile * kTileM - p.halo);
                     if (++a_slot == kASlots) {
                         a_slot = 0;
                         a_phase ^= 1;
@@ -159,9 +167,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                             pre--;  // already in flight
                         } else {
                             mbar_wait(&sm.empty[stage], phase ^ 1);
-                            mbar_expect_tx(&sm.full[stage], b_bytes);
-                            tma_load_2d(&tmap_bh, &sm.full[stage], sm.b_base + size_t(stage) * b_stage, tap * p.cin_pad + kb * kBlockK,
-                                        int(rank) * (p.n / 2));
+                            if (leader) mbar_expect_tx(&sm.full[stage], 2 * b_bytes);
+                            tma2_load_2d(&tmap_bh, &sm.full[stage], sm.b_base + size_t(stage) * b_stage, tap * p.cin_pad + kb * kBlockK,
+                                         int(rank) * (p.n / 2));
                         }
                         if (++stage == p.stages) {
                             stage = 0;
@@ -172,31 +180,26 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA warp: the leader issues, the peer relays readiness
-        const uint32_t idesc = umma_idesc_bf16(2 * kTileM, p.n);
-        const uint64_t b_hi = umma_desc_sw128_hi();
-        const uint64_t a_hi = umma_desc_nosw_hi(chunk_bytes, 128);
-        int stage = 0, a_slot = 0;
-        uint32_t phase = 0, a_phase = 0;
-        int local = 0;
-        for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, local++) {
-            const int buf = local & 1;
-            const uint32_t buf_phase = (local >> 1) & 1;
-            if (leader) {
+        // ------------------------------------------------------------------ MMA warp: only the leader's issues
+        if (leader) {
+            const uint32_t idesc = umma_idesc_bf16(2 * kTileM, p.n);
+            const uint64_t b_hi = umma_desc_sw128_hi();
+            const uint64_t a_hi = umma_desc_nosw_hi(chunk_bytes, 128);
+            int stage = 0, a_slot = 0;
+            uint32_t phase = 0, a_phase = 0;
+            int local = 0;
+            for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, local++) {
+                const int buf = local & 1;
+                const uint32_t buf_phase = (local >> 1) & 1;
                 mbar_wait_cluster(&sm.tmem_empty[buf], buf_phase ^ 1);
                 tc_fence_after();
-            }
-            const uint32_t tmem_d = tmem_base + buf * acc_stride;
-            bool first = true;
-            for (int kb = 0; kb < p.kblocks; kb++) {
-                mbar_wait(&sm.a_full[a_slot], a_phase);
-                const uint32_t a_lo = umma_desc_lo(smem_u32(sm.a_base + size_t(a_slot) * a_bytes));
-                for (int tap = 0; tap < 9; tap++) {
-                    mbar_wait(&sm.full[stage], phase);
-                    if (!leader) {
-                        if (lane == 0) mbar_arrive_remote(&sm.peer_full[stage], 0);
-                    } else {
-                        mbar_wait_cluster(&sm.peer_full[stage], phase);
+                const uint32_t tmem_d = tmem_base + buf * acc_stride;
+                bool first = true;
+                for (int kb = 0; kb < p.kblocks; kb++) {
+                    mbar_wait(&sm.a_full[a_slot], a_phase);  // both CTAs' activation tiles
+                    const uint32_t a_lo = umma_desc_lo(smem_u32(sm.a_base + size_t(a_slot) * a_bytes));
+                    for (int tap = 0; tap < 9; tap++) {
+                        mbar_wait(&sm.full[stage], phase);  // both halves of the weight tile
                         tc_fence_after();
                         const uint32_t b_lo = umma_desc_lo(smem_u32(sm.b_base + size_t(stage) * b_stage));
                         const uint32_t a_t = a_lo + uint32_t(p.halo + (tap / 3 - 1) * p.lay.rank_pitch + (tap % 3 - 1));
@@ -208,21 +211,21 @@ __global__ void __launch_bounds__(kThreads, 1)
                             umma2_commit(&sm.empty[stage]);
                             if (tap == 8) umma2_commit(&sm.a_empty[a_slot]);
                         }
+                        __syncwarp();
+                        first = false;
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
                     }
-                    __syncwarp();
-                    first = false;
-                    if (++stage == p.stages) {
-                        stage = 0;
-                        phase ^= 1;
+                    if (++a_slot == kASlots) {
+                        a_slot = 0;
+                        a_phase ^= 1;
                     }
                 }
-                if (++a_slot == kASlots) {
-                    a_slot = 0;
-                    a_phase ^= 1;
-                }
+                if (lane == 0) umma2_commit(&sm.tmem_full[buf]);  // accumulator complete in both CTAs -> both epilogues
+                __syncwarp();
             }
-            if (leader && lane == 0) umma2_commit(&sm.tmem_full[buf]);  // accumulator complete in both CTAs -> both epilogues
-            __syncwarp();
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5), each CTA drains its own 128 rows
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 }  // namespace
 
 size_t conv_tchp_smem_bytes(int n, int stages, int a_rows) {
-    return 1024 /*alignment slack*/ + size_t(stages) * b_stage_bytes(n) + kASlots * a_slot_bytes(a_rows) + (3 * stages + 2 * kASlots + 4) * 8 + 16 +
+    return 1024 /*alignment slack*/ + size_t(stages) * b_stage_bytes(n) + kASlots * a_slot_bytes(a_rows) + (2 * stages + 2 * kASlots + 4) * 8 + 16 +
            size_t(n) * 4;
 }
 

@@ -4,7 +4,7 @@
 //
 // The rules live in the un-vendored `chess` / `board-game` crates and are restated here from the rules of chess:
 // castling, en passant, promotions, check / mate / stalemate, the 50-move rule (100 plies without a pawn move or capture),
-// threefold repetition, insufficient material (K v K, K + minor v K).  The move generator is pinned by perft counts
+// threefold repetition, bare kings (K + minor v K plays on, like board-game Rules::default: tests/mapper/chess/pairs.rs:98-136).  The move generator is pinned by perft counts
 // (tests/cpp/chess_perft_test.cpp: initial position, Kiwipete and three more standard positions), through the
 // policy-index interface, so the indexing is checked to be one-to-one on every position visited as well.  Two details
 // of the ENCODING cannot be pinned without the crates and are choices: the en-passant plane marks the capture target
@@ -354,15 +354,12 @@ struct Chess {
         });
         return any;
     }
+    // board-game's Rules::is_draw ends a game on material only when nothing but the two kings is left; K + minor v K plays on --
+    // the reference's own tests play knight moves on "8/8/6k1/8/3N4/6K1/8/8 w" (rust/kz-core/tests/mapper/chess/pairs.rs:98-136)
     bool insufficient_material() const {
-        using namespace chess_detail;
-        int minors = 0;
-        for (int s = 0; s < 64; s++) {
-            const int t = std::abs(int(sq[s]));
-            if (t == kPawn || t == kRook || t == kQueen) return false;
-            if (t == kKnight || t == kBishop) minors++;
-        }
-        return minors <= 1;
+        int pieces = 0;
+        for (int s = 0; s < 64; s++) pieces += sq[s] != 0;
+        return pieces <= 2;
     }
     void update_terminal() {
         if (!has_legal_move()) terminal = in_check() ? 1 : 2;
@@ -446,7 +443,10 @@ struct Chess {
             if (p) planes[(p > 0 ? 0 : 6) + std::abs(p) - 1] |= 1ull << pov_square(s, side);
         }
         std::memcpy(bits, planes, sizeof(planes));  // BitBuffer::push_block: little-endian u64 per plane
-        const uint64_t epb = ep >= 0 ? 1ull << pov_square(ep, side) : 0;
+        // `inner.en_passant()` of the `chess` 3.2.0 crate is the square of the PAWN that just advanced two ranks (make_move calls
+        // set_ep(dest); the capture's destination is ep_sq.uforward(side_to_move)), not the capture target this struct keeps
+        // for move generation: one rank towards the mover's own side of the target
+        const uint64_t epb = ep >= 0 ? 1ull << pov_square(ep + (side == 0 ? -8 : 8), side) : 0;
         std::memcpy(bits + 12 * 8, &epb, 8);
         scalars[0] = side == 0 ? 1.0f : 0.0f;
         scalars[1] = side == 1 ? 1.0f : 0.0f;

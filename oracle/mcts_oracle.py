@@ -336,7 +336,7 @@ class Chess:
     double push, capture towards the a-file, capture towards the h-file; knight / king steps in the orders below, castling
     king side then queen side; sliders direction by direction, near to far.  The en-passant square exists only while an
     enemy pawn stands next to the pushed pawn; a position repeats when placement, side, castling rights and en-passant
-    square agree; draw on the third occurrence, after 100 quiet plies, or with K (+ one minor) v K."""
+    square agree; draw on the third occurrence, after 100 quiet plies, or with bare kings."""
     KNIGHT = [(2, 1), (1, 2), (-1, 2), (-2, 1), (-2, -1), (-1, -2), (1, -2), (2, -1)]  # (rank, file) steps
     KING = [(1, 0), (-1, 0), (0, 1), (0, -1), (1, 1), (1, -1), (-1, 1), (-1, -1)]
     SLIDES = {3: KING[4:], 4: KING[:4], 5: KING}  # bishop, rook, queen
@@ -493,8 +493,8 @@ class Chess:
             if p:
                 r, f = divmod(self._pov(s), 8)
                 planes[(0 if p * sign > 0 else 6) + abs(p) - 1, r, f] = 1
-        if self.ep >= 0:
-            r, f = divmod(self._pov(self.ep), 8)
+        if self.ep >= 0:  # the plane marks the pawn that just advanced two ranks (chess 3.2.0: Board::en_passant()), not the target
+            r, f = divmod(self._pov(self.ep + (-8 if self.side == 0 else 8)), 8)
             planes[12, r, f] = 1
         own_k, own_q, opp_k, opp_q = (1, 2, 4, 8) if self.side == 0 else (4, 8, 1, 2)
         scalars = [self.side == 0, self.side == 1, bool(self.castle & own_k), bool(self.castle & own_q), bool(self.castle & opp_k),
@@ -550,7 +550,7 @@ class Chess:
         self.ply += 1
         self.reps = self.history.count(self.position_key())
         others = [abs(p) for p in self.sq if p and abs(p) != 6]
-        low_material = all(p in (2, 3) for p in others) and len(others) <= 1
+        low_material = not others  # bare kings only (K + minor v K plays on: rust/kz-core/tests/mapper/chess/pairs.rs:98-136)
         if not any(True for _ in self._legal()):
             self.terminal = 1 if self._attacked(self._king(self.side), self.side ^ 1) else 2
         else:

@@ -113,7 +113,8 @@ int main() {
             std::printf("encoding of the initial position is wrong\n");
             return 1;
         }
-        // 1. e4 c5 2. e5 d5: white may capture en passant on d6; then it is white's view, no flip
+        // 1. e4 c5 2. e5 d5: white may capture en passant on d6 (43); the en-passant PLANE marks the pawn that just advanced, d5 (35),
+        // which is what `inner.en_passant()` of the chess 3.2.0 crate returns (mapping/chess.rs:168); white's view, no flip
         const auto& t = kzb::selfplay::chess_detail::flat_moves();
         auto play = [&](int from, int to) {  // absolute squares; the index is looked up from the mover's side
             const int f = Chess::pov_square(from, b.side), o = Chess::pov_square(to, b.side);
@@ -122,7 +123,7 @@ int main() {
         play(12, 28), play(50, 34), play(28, 36), play(51, 35);
         b.encode(bits, sc);
         std::memcpy(planes, bits, 104);
-        if (b.ep != 43 || planes[12] != (1ull << 43) || sc[0] != 1.0f || sc[7] != 0.0f) {
+        if (b.ep != 43 || planes[12] != (1ull << 35) || sc[0] != 1.0f || sc[7] != 0.0f) {
             std::printf("en passant after 1. e4 c5 2. e5 d5 is wrong (ep %d)\n", int(b.ep));
             return 1;
         }
