@@ -38,7 +38,7 @@ EncodeTiledFn encode_tiled_fn() {
 
 // bf16 tensor map, SWIZZLE_128B, zero OOB fill.  dims/box innermost first; strides in bytes for dims 1..rank-1.
 CUtensorMap make_tmap(void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                      bool swizzle128 = true) {
+                      bool swizzle128 = true, bool swizzle64 = false) {
     CUtensorMap m;
     cuuint64_t gdim[5], gstr[4];
     cuuint32_t bdim[5], estr[5];
@@ -49,10 +49,41 @@ CUtensorMap make_tmap(void* base, int rank, const uint64_t* dims, const uint64_t
         if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
     }
     CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cuuint32_t(rank), base, gdim, gstr, bdim, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+    return m;
+}
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                   const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// bf16 im2col map over channels-last activations [boards][H][W][C] for a 3x3 filter with zero padding 1: a load brings `pixels`
+// consecutive output pixels x `channels` channels, shifted by the instruction's tap offset, zero-filled off the board
+CUtensorMap make_tmap_im2col3x3(void* base, int C, int W, int H, int boards, int channels, int pixels) {
+    static EncodeIm2colFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cuda_check(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q), "cudaGetDriverEntryPoint");
+        if (q != cudaDriverEntryPointSuccess || !p) throw std::runtime_error("cuTensorMapEncodeIm2col not available in this driver");
+        return reinterpret_cast<EncodeIm2colFn>(p);
+    }();
+    CUtensorMap m;
+    cuuint64_t gdim[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(boards)};
+    cuuint64_t gstr[3] = {cuuint64_t(C) * 2, cuuint64_t(C) * 2 * W, cuuint64_t(C) * 2 * W * H};
+    int lower[2] = {-1, -1}, upper[2] = {-1, -1};  // -padding, padding - (filter - 1)
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, lower, upper, cuuint32_t(channels), cuuint32_t(pixels), estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeIm2col failed with CUresult " + std::to_string(int(r)));
+    // drivers up to CUDA 13.1 mis-encode im2col maps of tensors smaller than 128 KiB (bit 21 of the second descriptor word must be
+    // clear); the same correction CUTLASS applies in make_im2col_tma_copy_desc
+    int driver = 0;
+    if (cudaDriverGetVersion(&driver) == cudaSuccess && driver <= 13010 && size_t(C) * 2 * W * H * boards < 131072)
+        reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
     return m;
 }
 
@@ -235,7 +266,13 @@ void Net::build_bf16() {
     }
     const int W = embed8_ ? 8 : spec_.board_w, H = embed8_ ? 8 : spec_.board_h;  // the board as the kernels see it
     mode_ = (W == 8 && H == 8 && !(force && force[0] == '1')) ? 1 : 0;
-    if (mode_ == 1)
+    // boards the 8x8 kernels do not cover run their 3x3 layers on conv_i2c.cu: dense rows, padding by the TMA engine's im2col mode
+    // (KZB_NO_I2C=1: the padded-row kernels conv_tch / conv_tchp / conv_tc)
+    {
+        const char* no_i2c = std::getenv("KZB_NO_I2C");
+        dense_i2c_ = mode_ == 0 && !(no_i2c && no_i2c[0] == '1') && W <= 255 && H <= 255;
+    }
+    if (mode_ == 1 || dense_i2c_)
         lay_ = RowLayout{W, H, W, W * H};
     else
         lay_ = RowLayout{W, H, W + 1, (W + 1) * (H + 1)};
@@ -249,6 +286,12 @@ void Net::build_bf16() {
     if (const char* pair_env = std::getenv("KZB_CONV_PAIR"); pair_env && pair_env[0] == '1') conv_tchp_prepare();  // experimental kernel: untouched otherwise
     conv_tc8_prepare();
     rows_alloc_ = round_up(boards_alloc * lay_.board_pitch, 128);
+    if (dense_i2c_) {  // whole 256-pixel pair tiles, and whole boards under every one of them
+        conv_i2c_prepare();
+        const int pixels = round_up(max_batch_ * W * H, 256);
+        boards_i2c_ = (pixels + W * H - 1) / (W * H);
+        rows_alloc_ = round_up(std::max(pixels, boards_i2c_ * W * H), 128);
+    }
     cin_pad_ = round_up(spec_.cin, 64);
     c_pad_ = round_up(C, 64);
     cp_pad_ = round_up(spec_.policy_conv1.cout, 64);
@@ -301,6 +344,26 @@ void Net::build_bf16() {
             uint32_t box[2] = {64, 128};
             st->tmap_a = make_tmap(in.ptr, 2, dims, strides, box);
         }
+        if (dense_i2c_ && st->taps == 9 && cin_pad % 64 == 0 && n % 32 == 0 && n >= 32 && !out_f32 && (relu_n == 0 || relu_n == n) && out_off == 0) {
+            st->tmap_i2c = make_tmap_im2col3x3(in.ptr, in_stride, W, H, boards_i2c_, 64, 128);
+            auto rows_map = [&](void* ptr, int stride) {
+                uint64_t dims[2] = {uint64_t(stride), uint64_t(rows_alloc_)};
+                uint64_t strides[1] = {uint64_t(stride) * 2};
+                uint32_t box[2] = {32, 32};
+                return make_tmap(ptr, 2, dims, strides, box, false, true);
+            };
+            st->tmap_out = rows_map(out.ptr, out_stride);
+            st->tmap_res = res ? rows_map(res->ptr, c_pad_) : st->tmap_out;
+            st->tmap_bq = st->tmap_bh;
+            if (n % 64 == 0) {
+                uint64_t dims[2] = {uint64_t(ktot), uint64_t(n)};
+                uint64_t strides[1] = {uint64_t(ktot) * 2};
+                uint32_t quarter[2] = {64, uint32_t(n / 4)};
+                st->tmap_bq = make_tmap(st->w_bf16.ptr, 2, dims, strides, quarter);
+            }
+            st->use_i2c = true;
+            st->i2c_stages = conv_i2c_pick_stages(n);
+        }
         if (allow_tc8 && st->taps == 9 && n <= 128 && !out_f32) {
             // (c, x, board, y)-ordered view of the same rows, box (64, 8, 4 boards, 10 ranks incl. halo)
             uint64_t dims[4] = {uint64_t(in_stride), 8, uint64_t(rows_alloc_ / 64), 8};
@@ -341,7 +404,7 @@ void Net::build_bf16() {
         p.n_split = 1;
         p.halo = lay_.rank_pitch + 1;
         p.a_rows = (128 + 2 * p.halo + 7) & ~7;  // whole 8-row groups: every k-chunk of the tile starts 128-byte aligned
-        if (!(halo_env && halo_env[0] == '0') && mode_ == 0 && st->taps == 9 && cin_pad % 64 == 0 && p.a_rows <= 256 && !st->use_tc8) {
+        if (!(halo_env && halo_env[0] == '0') && mode_ == 0 && !dense_i2c_ && st->taps == 9 && cin_pad % 64 == 0 && p.a_rows <= 256 && !st->use_tc8) {
             uint64_t dims[2] = {uint64_t(in_stride), uint64_t(rows_alloc_)};
             uint64_t strides[1] = {uint64_t(in_stride) * 2};
             uint32_t box[2] = {8, uint32_t(p.a_rows)};
@@ -748,7 +811,13 @@ void Net::run_network(int batch, const StepHook& hook) {
                 p.valid_rows = batch * lay_.board_pitch;
                 p.num_tiles = (p.valid_rows + 127) / 128;
             }
-            if (st->use_tchp) {
+            if (st->use_i2c) {
+                p.stages = st->i2c_stages;
+                // small batches: split the output channels so that twice as many SM pairs share the layer
+                const char* split = std::getenv("KZB_CONV_SPLIT");
+                p.n_split = (!(split && split[0] == '0') && p.n % 64 == 0 && p.n_store == p.n && 2 * ((p.num_tiles + 1) / 2) <= num_sms_ / 2) ? 2 : 1;
+                launch_conv_i2c(st->tmap_i2c, p.n_split == 2 ? st->tmap_bq : st->tmap_bh, st->tmap_out, st->tmap_res, p, num_sms_, stream_);
+            } else if (st->use_tchp) {
                 p.stages = st->tchp_stages;
                 p.n_split = 1;
                 launch_conv_tchp(st->tmap_ah, st->tmap_bh, p, num_sms_, stream_);

@@ -48,8 +48,12 @@ struct ConvStep {
     CUtensorMap tmap_a{}, tmap_b{}, tmap_bh{}, tmap_ah{};
     bool use_tch = false;  // conv_tch.cu (activation tile with halo, loaded once per k-block)
     int tch_stages = 0;
-    bool use_tchp = false;  // conv_tchp.cu (experimental CTA-pair variant, KZB_CONV_PAIR=1)
+    bool use_tchp = false;  // conv_tchp.cu (CTA-pair variant of conv_tch, KZB_CONV_PAIR=1)
     int tchp_stages = 0;
+    bool use_i2c = false;  // conv_i2c.cu (dense rows, TMA im2col, CTA-pair MMA)
+    int i2c_stages = 0;
+    CUtensorMap tmap_out{}, tmap_res{};  // conv_i2c: output / residual rows, box (32 channels, 32 rows), SWIZZLE_64B
+    CUtensorMap tmap_i2c{}, tmap_bq{};  // im2col map of the input rows; weight box of n / 4 rows (output channels split in two)
     ConvTcParams tc{};
     bool use_tc8 = false;  // 8x8-board specialisation (conv_tc8.cu)
     CUtensorMap tmap_a8{};
@@ -113,6 +117,8 @@ private:
     int cin_pad_ = 0, c_pad_ = 0, cp_pad_ = 0, s1_stride_ = 16, pm_stride_ = 0;
     bool act_bf16_ = true;
     bool embed8_ = false;  // a board smaller than 8x8 embedded in the 8x8 grid of the whole-tower kernel
+    bool dense_i2c_ = false;  // boards the 8x8 kernels do not cover: dense rows, 3x3 layers on conv_i2c.cu
+    int boards_i2c_ = 0;      // boards covered by the im2col tensor maps (>= every 256-pixel tile of a full batch)
 
     DeviceBuffer d_bits_, d_scalars_, d_mv_idx_, d_mv_off_, d_nchw_;
     DeviceBuffer act_in_, act_x_, act_t_, act_h1_, act_s1_, act_pm_, act_att_;

@@ -87,7 +87,7 @@ struct ConvTcParams {
     int stages;
     int tmem_cols;
     int cluster;  // conv_tc only: 1, or 2 = CTA pairs share every weight tile through TMA multicast
-    int n_split;       // conv_tch only: 1, or 2 = a work item is one tile x one half of the output channels
+    int n_split;       // conv_tch / conv_i2c: 1, or 2 = a work item is one tile x one half of the output channels
     int pdl;           // conv_tch / conv_tchp: launched with programmatic stream serialization (the prologue and the first weight tiles overlap the previous layer's tail)
     int halo, a_rows;  // conv_tch only: rank_pitch + 1 halo rows on either side, a_rows = 128 + 2 * halo (rounded up to 8) rows per activation tile
     // development aid: when non-null, each CTA writes 16 clock64() stamps (see conv_tc8.cu) -- KZB_TIMELINE=1
@@ -105,6 +105,12 @@ void launch_conv_tchp(const CUtensorMap& tmap_a_rows, const CUtensorMap& tmap_bh
 size_t conv_tchp_smem_bytes(int n, int stages, int a_rows);
 int conv_tchp_pick_stages(int n, int a_rows);
 void conv_tchp_prepare();
+// conv_i2c.cu: conv3x3 on DENSE rows, activation tiles by TMA im2col, CTA-pair MMA (tmap_bh: weight box of p.n / p.n_split / 2 rows)
+void launch_conv_i2c(const CUtensorMap& tmap_a_im2col, const CUtensorMap& tmap_bh, const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
+                     const ConvTcParams& p, int grid, cudaStream_t s);
+size_t conv_i2c_smem_bytes(int n, int stages);
+int conv_i2c_pick_stages(int n);
+void conv_i2c_prepare();
 size_t conv_tc_smem_bytes(int n, int stages);
 int conv_tc_pick_stages(int n);
 void conv_tc_prepare();  // per-device: opt in to 227 KB dynamic shared memory

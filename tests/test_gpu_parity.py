@@ -128,32 +128,35 @@ def test_fp32_packed_vs_oracle(game, depth, ch, n):
     _check_packed(values, probs, ref_values, ref_probs, mv_off, FP32_TOL, FP32_TOL)
 
 
-@pytest.mark.parametrize("variant", ["default", "tower_v1", "no_heads8", "no_tower8", "no_conv8", "linear", "no_embed8", "conv_cluster", "no_conv_halo", "no_conv_split", "conv_pair"])
+@pytest.mark.parametrize("variant", ["default", "tower_v1", "no_heads8", "no_tower8", "no_conv8", "linear", "no_embed8", "pdl", "no_conv_split", "no_i2c",
+                                     "conv_cluster", "no_conv_halo", "no_i2c_no_split", "conv_pair"])
 @pytest.mark.parametrize("game,depth,ch,n", [("ataxx-7", 8, 64, 256), ("chess", 16, 128, 64), ("go-9", 4, 64, 40),
                                               ("chess", 2, 32, 7), ("chess", 3, 64, 130), ("chess", 2, 256, 12)])
 def test_bf16_packed_vs_oracle(game, depth, ch, n, variant, monkeypatch):
     """The tensor-core path in all its forms: whole-tower persistent kernel + fused heads kernel (tower8k.cu, heads8.cu,
     default for 8x8 boards), the first-generation tower kernel (tower8.cu, KZB_TOWER_V1=1), the same tower with per-op head convs + tail kernel (KZB_NO_HEADS8=1),
     per-layer 8x8 specialisation (conv_tc8.cu, KZB_NO_TOWER8=1), generic 4-D TMA box per tap (KZB_NO_CONV8=1),
-    padded-row 2-D TMA (boards larger than 8x8 / KZB_FORCE_LINEAR=1 / KZB_NO_EMBED8=1), the same with CTA pairs sharing every
-    weight tile through TMA multicast (KZB_CONV_CLUSTER=2, with KZB_CONV_HALO=0) -- by default 3x3 layers on padded rows load the activation tile once per
-    k-block with its halo (conv_tch.cu), KZB_CONV_HALO=0 re-loads it per tap (conv_tc.cu), and two CTAs share a tile's output
-    channels when there are fewer tiles than half the SMs (KZB_CONV_SPLIT=0: never); boards smaller than 8x8 (ataxx 7x7) are embedded in the 8x8
-    grid and masked after every layer."""
+    dense rows with TMA im2col loads and the CTA-pair MMA (conv_i2c.cu: boards larger than 8x8 / KZB_FORCE_LINEAR=1 / KZB_NO_EMBED8=1; with
+    programmatic dependent launch, KZB_PDL=1; two SM pairs share a tile's output channels at small batches, KZB_CONV_SPLIT=0: never), and the
+    padded-row kernels it replaced (KZB_NO_I2C=1: conv_tch.cu with the halo tile, its CTA-pair form conv_tchp.cu with KZB_CONV_PAIR=1, conv_tc.cu
+    re-loading the tile per tap with KZB_CONV_HALO=0, plus weight multicast with KZB_CONV_CLUSTER=2); boards smaller than 8x8 (ataxx 7x7) are
+    embedded in the 8x8 grid and masked after every layer."""
+    padded_row_variants = ("no_i2c", "conv_cluster", "no_conv_halo", "no_i2c_no_split", "conv_pair")  # KZB_NO_I2C=1: the padded-row kernels
+    row_variants = ("linear", "pdl", "no_conv_split") + padded_row_variants                           # everything off the 8x8 kernels
     if variant == "no_embed8":
         if game != "ataxx-7":
             pytest.skip("only boards smaller than 8x8 are embedded")
-    elif variant == "conv_pair" and os.environ.get("KZB_TEST_EXPERIMENTAL") != "1":
-        pytest.skip("conv_tchp.cu (CTA-pair MMA) has not been run on hardware yet: set KZB_TEST_EXPERIMENTAL=1 to try it")
-    elif variant in ("conv_cluster", "no_conv_halo", "no_conv_split", "conv_pair"):
+    elif variant in row_variants:
         if game == "ataxx-7":
-            pytest.skip("covered by go-9 and the chess nets on padded rows")
+            pytest.skip("covered by go-9 and the chess nets on the row kernels")
     elif variant != "default" and game != "chess":
         pytest.skip("the kernel variants are 8x8 specialisations")
     monkeypatch.setenv("KZB_NO_EMBED8", "1" if variant == "no_embed8" else "0")
-    force_linear = "1" if variant in ("linear", "conv_cluster", "no_conv_halo", "no_conv_split", "conv_pair") else "0"
+    force_linear = "1" if variant in row_variants else "0"
+    monkeypatch.setenv("KZB_NO_I2C", "1" if variant in padded_row_variants else "0")
+    monkeypatch.setenv("KZB_PDL", "1" if variant == "pdl" else "0")
     monkeypatch.setenv("KZB_CONV_PAIR", "1" if variant == "conv_pair" else "0")
-    monkeypatch.setenv("KZB_CONV_SPLIT", "0" if variant == "no_conv_split" else "1")
+    monkeypatch.setenv("KZB_CONV_SPLIT", "0" if variant in ("no_conv_split", "no_i2c_no_split") else "1")
     monkeypatch.setenv("KZB_CONV_HALO", "0" if variant in ("no_conv_halo", "conv_cluster") else "1")
     monkeypatch.setenv("KZB_CONV_CLUSTER", "2" if variant == "conv_cluster" else "1")
     monkeypatch.setenv("KZB_FORCE_LINEAR", force_linear)
