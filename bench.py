@@ -435,9 +435,9 @@ def rooflines(m, peaks):
     tower_s = m["tower_ms"] * 1e-3
     achieved = tower_flops / tower_s / 1e12
     if "tower8" in share:
-        kernel = "tower8_kernel" if os.environ.get("KZB_TOWER_V1") == "1" else "tower8k_kernel"
+        kernel = "tower8k_kernel"
     else:
-        kernel = "conv_tchp_kernel" if os.environ.get("KZB_CONV_PAIR") == "1" else "conv_tch_kernel"
+        kernel = "conv_tc_kernel" if os.environ.get("KZB_NO_I2C") == "1" else "conv_i2c_kernel"
     traffic = None
     tpath = ROOT / "profiles" / "tower_dram_traffic.json"
     if tpath.exists() and "tower8" in share:

@@ -197,8 +197,23 @@ int kzb_selfplay_run(int device, const void* onnx_bytes, size_t onnx_len, int pr
                      kzb_selfplay_stats* stats);
 
 /* Ask every kzb_selfplay_run in this process to return as soon as possible (the `Stop` command, protocol.rs:37);
- * callable from any thread.  The flag is cleared when the next run starts. */
+ * callable from any thread.  The flag stays set -- a run that starts while it is set returns at once -- until
+ * kzb_selfplay_clear_stop: a Stop that arrives while a network is still loading must not be lost. */
 void kzb_selfplay_request_stop(void);
+void kzb_selfplay_clear_stop(void);
+
+/* A session keeps the concurrent games of one server connection alive BETWEEN runs: every kzb_selfplay_session_run plays until
+ * config->max_games more games have finished (one record file = games_per_gen games), writes them to config->output_prefix and
+ * returns; the games still in flight -- boards, search trees, per-game caches, the positions recorded so far -- continue in the
+ * next run, with that run's network and settings.  This is what the reference's server does: its generators run across file
+ * boundaries, the collector only rotates the output file (rust/kz-selfplay/src/server/collector.rs:59-116), and a new network is
+ * swapped in under running games (executor.rs:320-342) -- so long games are not dropped and the data has no length bias.
+ * The game, cpu_threads and the derived number of concurrent games are fixed by the first run (StartupSettings, protocol.rs:11-28). */
+typedef struct kzb_selfplay_session kzb_selfplay_session;
+int kzb_selfplay_session_create(int game, kzb_selfplay_session** out);
+int kzb_selfplay_session_run(kzb_selfplay_session* session, int device, const void* onnx_bytes, size_t onnx_len, int precision,
+                             const kzb_selfplay_config* config, kzb_selfplay_stats* stats);
+void kzb_selfplay_session_destroy(kzb_selfplay_session* session);
 
 /* Host-only (no GPU): one tree search of `config->visits` visits from the position `plies` random moves into game
  * `game_seed`, gathered in rounds of `config->search_batch` (virtual loss) and answered by a deterministic stand-in

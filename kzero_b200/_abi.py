@@ -69,6 +69,10 @@ SYMBOLS = {
     "kzb_selfplay_default_config": (None, [ctypes.POINTER(SelfplayConfig)]),
     "kzb_selfplay_run": (_i, [_i, _vp, _sz, _i, ctypes.POINTER(SelfplayConfig), ctypes.POINTER(SelfplayStats)]),
     "kzb_selfplay_request_stop": (None, []),
+    "kzb_selfplay_clear_stop": (None, []),
+    "kzb_selfplay_session_create": (_i, [_i, ctypes.POINTER(_vp)]),
+    "kzb_selfplay_session_run": (_i, [_vp, _i, _vp, _sz, _i, ctypes.POINTER(SelfplayConfig), ctypes.POINTER(SelfplayStats)]),
+    "kzb_selfplay_session_destroy": (None, [_vp]),
     "kzb_mcts_trace": (_i, [ctypes.POINTER(SelfplayConfig), ctypes.c_uint64, _i, _i, ctypes.POINTER(MctsTraceOut)]),
 }
 

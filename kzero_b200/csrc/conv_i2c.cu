@@ -1,4 +1,4 @@
-// K1i: conv3x3 as an implicit GEMM on DENSE rows -- TMA im2col loads + the CTA-pair MMA.  The 3x3 layers of every board the
+// K1i: conv3x3 (and conv1x1: p.taps = 1) as an implicit GEMM on DENSE rows -- TMA im2col loads + the CTA-pair MMA.  The 3x3 layers of every board the
 // 8x8 whole-tower kernel does not cover (go 9x9 / 19x19, wide nets).
 //
 // GEMM view: D[pixels, cout] += A_tap[pixels, 64 ch] * W_tap[cout, 64 ch] over 9 taps x cin/64 k-blocks.  Activations are plain
@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int num_items = num_pairs * p.n_split;
     const int cluster_id = int(blockIdx.x) / 2, num_clusters = int(gridDim.x) / 2;
     const int area = p.lay.W * p.lay.H;
+    const int taps = p.taps, pad = p.taps == 9 ? 1 : 0;  // 3x3 with zero padding 1, or 1x1
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
@@ -165,9 +166,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                 // weights do not depend on the previous layer: fill the ring's weight halves before waiting for it
                 if (cluster_id < num_items) {
                     const int n0 = (cluster_id % p.n_split) * n_eff;
-                    for (; pre < p.stages && pre < 9 * p.kblocks; pre++) {
+                    for (; pre < p.stages && pre < taps * p.kblocks; pre++) {
                         if (leader) mbar_expect_tx(&sm.full[pre], 2 * (kABytes + b_bytes));
-                        tma2_load_2d(&tmap_bh, &sm.full[pre], sm.stages + size_t(pre) * kStageBytes + kABytes, (pre % 9) * p.cin_pad + (pre / 9) * kBlockK,
+                        tma2_load_2d(&tmap_bh, &sm.full[pre], sm.stages + size_t(pre) * kStageBytes + kABytes, (pre % taps) * p.cin_pad + (pre / taps) * kBlockK,
                                      n0 + int(rank) * (n_eff / 2));
                     }
                 }
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 const int img = pix / area, rem = pix - img * area;
                 const int h0 = rem / p.lay.W, w0 = rem - h0 * p.lay.W;
                 for (int kb = 0; kb < p.kblocks; kb++) {
-                    for (int tap = 0; tap < 9; tap++) {
+                    for (int tap = 0; tap < taps; tap++) {
                         uint8_t* dst = sm.stages + size_t(stage) * kStageBytes;
                         if (pre > 0) {
                             pre--;
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                             if (leader) mbar_expect_tx(&sm.full[stage], 2 * (kABytes + b_bytes));
                             tma2_load_2d(&tmap_bh, &sm.full[stage], dst + kABytes, tap * p.cin_pad + kb * kBlockK, n0 + int(rank) * (n_eff / 2));
                         }
-                        tma2_load_im2col(&tmap_a, &sm.full[stage], dst, kb * kBlockK, w0 - 1, h0 - 1, img, uint16_t(tap % 3), uint16_t(tap / 3));
+                        tma2_load_im2col(&tmap_a, &sm.full[stage], dst, kb * kBlockK, w0 - pad, h0 - pad, img, uint16_t(tap % 3), uint16_t(tap / 3));
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1;
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 mbar_wait_cluster(&sm.tmem_empty[buf], buf_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * acc_stride;
-                const int steps = 9 * p.kblocks;
+                const int steps = taps * p.kblocks;
                 for (int it = 0; it < steps; it++) {
                     mbar_wait(&sm.full[stage], phase);  // both CTAs' pixels and both halves of the weight tile
                     tc_fence_after();

@@ -1,4 +1,6 @@
-// K1: the conv tower's workhorse -- implicit-GEMM conv3x3 / conv1x1 on the 5th-gen tensor cores.
+// K1 (generic form): implicit-GEMM conv3x3 / conv1x1 on the 5th-gen tensor cores, one CTA per 128-row tile.  Today it runs the
+// layers conv_i2c.cu / tower8k.cu / heads8.cu do not take: head 1x1 convs with f32 output (scalar conv, policy conv2, attention
+// convs) and, with KZB_NO_I2C=1, 3x3 layers on padded rows (the A/B baseline of conv_i2c.cu).
 //
 // Replaces the per-layer `cudnnConvolutionBiasActivationForward` (fp32 NCHW) + separate residual-add
 // and relu autokernels of the reference's CUDA executor (kn-cuda-eval 0.7.3 planner, evidence
@@ -56,14 +58,8 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* base, int n, int stages) {
     return s;
 }
 
-// CL = CTAs per cluster.  CL = 2: the two CTAs of a pair walk the same (tile, tap, k-block) sequence on different tiles
-// and share every weight tile: each loads half of it (n/2 output channels, map `tmap_bh`) and TMA-multicasts it into both
-// CTAs' rings; a ring slot is free again when the MMAs of BOTH CTAs have read it.  Every CTA then runs the same number
-// of tiles (the surplus ones read zero-filled rows and store nothing) so that the pair stays in lockstep.
-template <int CL>
 __global__ void __launch_bounds__(kThreads, 1)
-    conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   const __grid_constant__ CUtensorMap tmap_bh, const ConvTcParams p) {
+    conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -71,16 +67,14 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int stage_bytes = kABytes + p.n * 128;
     const int iters_per_tile = p.taps * p.kblocks;
-    const int my_tiles = CL == 1 ? (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x)
-                                 : (p.num_tiles + int(gridDim.x) - 1) / int(gridDim.x);
-    constexpr uint16_t kMask = uint16_t((1u << CL) - 1);
+    const int my_tiles = (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(CL == 1 ? &tmap_b : &tmap_bh)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
         for (int i = 0; i < p.stages; i++) {
             mbar_init(&sm.full[i], 1);
-            mbar_init(&sm.empty[i], CL);  // released by the MMA warp of every CTA the weight tile was multicast to
+            mbar_init(&sm.empty[i], 1);
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&sm.tmem_full[i], 1);
@@ -98,8 +92,6 @@ __global__ void __launch_bounds__(kThreads, 1)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast / committed to them
-    const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
     const uint32_t tmem_base = *sm.tmem_ptr;
     const uint32_t acc_stride = uint32_t(p.tmem_cols / 2);
 
@@ -123,13 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                         else
                             tma_load_2d(&tmap_a, &sm.full[stage], a_dst, kb * kBlockK,
                                         tile * kTileM + dy * p.lay.rank_pitch + dx);
-                        if (CL == 1) {
-                            tma_load_2d(&tmap_b, &sm.full[stage], b_dst, tap * p.cin_pad + kb * kBlockK, 0);
-                        } else {  // my n/CL rows of the weight tile, into every CTA of the cluster
-                            const int rows = p.n / CL;
-                            tma_load_2d_multicast(&tmap_bh, &sm.full[stage], b_dst + size_t(cta_rank) * rows * 128,
-                                                  tap * p.cin_pad + kb * kBlockK, int(cta_rank) * rows, kMask);
-                        }
+                        tma_load_2d(&tmap_b, &sm.full[stage], b_dst, tap * p.cin_pad + kb * kBlockK, 0);
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1;
@@ -164,8 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                                   (it | k) != 0);
                     }
                     // frees the smem slot once these MMAs have read it
-                    if (CL == 1) umma_commit(&sm.empty[stage]);
-                    else umma_commit_multicast(&sm.empty[stage], kMask);
+                    umma_commit(&sm.empty[stage]);
                 }
                 __syncwarp();
                 if (++stage == p.stages) {
@@ -190,7 +175,6 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     tc_fence_before();
     __syncthreads();
-    if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or signal its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(p.tmem_cols))
@@ -211,33 +195,11 @@ int conv_tc_pick_stages(int n) {
     return stages;
 }
 
-void conv_tc_prepare() {
-    cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-}
+void conv_tc_prepare() { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }
 
-// p.cluster == 2: `tmap_bh` is the weight map with a box of n/2 rows; the grid is even
-void launch_conv_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_bh, const ConvTcParams& p,
-                    int grid, cudaStream_t s) {
+void launch_conv_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ConvTcParams& p, int grid, cudaStream_t s) {
     if (p.num_tiles <= 0) return;
-    size_t smem = conv_tc_smem_bytes(p.n, p.stages);
-    if (p.cluster == 2) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(unsigned(std::min(grid & ~1, (p.num_tiles + 1) & ~1)));
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, tmap_a, tmap_b, tmap_bh, p);
-    } else {
-        conv_tc_kernel<1><<<std::min(grid, p.num_tiles), kThreads, smem, s>>>(tmap_a, tmap_b, tmap_bh, p);
-    }
+    conv_tc_kernel<<<std::min(grid, p.num_tiles), kThreads, conv_tc_smem_bytes(p.n, p.stages), s>>>(tmap_a, tmap_b, p);
 }
 
 }  // namespace kzb

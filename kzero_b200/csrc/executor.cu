@@ -61,9 +61,9 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// bf16 im2col map over channels-last activations [boards][H][W][C] for a 3x3 filter with zero padding 1: a load brings `pixels`
-// consecutive output pixels x `channels` channels, shifted by the instruction's tap offset, zero-filled off the board
-CUtensorMap make_tmap_im2col3x3(void* base, int C, int W, int H, int boards, int channels, int pixels) {
+// bf16 im2col map over channels-last activations [boards][H][W][C] for a (2 * pad + 1)^2 filter with zero padding `pad`: a load
+// brings `pixels` consecutive output pixels x `channels` channels, shifted by the instruction's tap offset, zero-filled off the board
+CUtensorMap make_tmap_im2col(void* base, int C, int W, int H, int boards, int channels, int pixels, int pad) {
     static EncodeIm2colFn fn = [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -74,7 +74,7 @@ CUtensorMap make_tmap_im2col3x3(void* base, int C, int W, int H, int boards, int
     CUtensorMap m;
     cuuint64_t gdim[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(boards)};
     cuuint64_t gstr[3] = {cuuint64_t(C) * 2, cuuint64_t(C) * 2 * W, cuuint64_t(C) * 2 * W * H};
-    int lower[2] = {-1, -1}, upper[2] = {-1, -1};  // -padding, padding - (filter - 1)
+    int lower[2] = {-pad, -pad}, upper[2] = {-pad, -pad};  // -padding, padding - (filter - 1)
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, lower, upper, cuuint32_t(channels), cuuint32_t(pixels), estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -261,16 +261,17 @@ void Net::build_bf16() {
         auto off = [](const char* name) { const char* v = std::getenv(name); return v && v[0] == '1'; };
         const bool small = spec_.board_w <= 8 && spec_.board_h <= 8 && (spec_.board_w < 8 || spec_.board_h < 8);
         const int units = (((max_batch_ + 3) / 4 + 1) & ~1);
-        embed8_ = small && !off("KZB_FORCE_LINEAR") && !off("KZB_NO_CONV8") && !off("KZB_NO_TOWER8") && !off("KZB_TOWER_V1") &&
+        embed8_ = small && !off("KZB_FORCE_LINEAR") && !off("KZB_NO_CONV8") && !off("KZB_NO_TOWER8") &&
                   !off("KZB_NO_EMBED8") && round_up(C, 64) <= 128 && (units + num_sms_ - 1) / num_sms_ <= tower8k_max_local_units();
     }
     const int W = embed8_ ? 8 : spec_.board_w, H = embed8_ ? 8 : spec_.board_h;  // the board as the kernels see it
     mode_ = (W == 8 && H == 8 && !(force && force[0] == '1')) ? 1 : 0;
-    // boards the 8x8 kernels do not cover run their 3x3 layers on conv_i2c.cu: dense rows, padding by the TMA engine's im2col mode
-    // (KZB_NO_I2C=1: the padded-row kernels conv_tch / conv_tchp / conv_tc)
+    // boards the 8x8 kernels do not cover run on DENSE rows: conv_i2c.cu gets a 3x3 layer's zero padding from the TMA engine's
+    // im2col mode (KZB_NO_I2C=1: padded rows and conv_tc.cu, which multiplies the padding rows as well)
     {
         const char* no_i2c = std::getenv("KZB_NO_I2C");
-        dense_i2c_ = mode_ == 0 && !(no_i2c && no_i2c[0] == '1') && W <= 255 && H <= 255;
+        i2c_ok_ = !(no_i2c && no_i2c[0] == '1') && W <= 255 && H <= 255;
+        dense_i2c_ = mode_ == 0 && i2c_ok_;
     }
     if (mode_ == 1 || dense_i2c_)
         lay_ = RowLayout{W, H, W, W * H};
@@ -282,15 +283,15 @@ void Net::build_bf16() {
     const char* no_tc8 = std::getenv("KZB_NO_CONV8");
     const bool allow_tc8 = mode_ == 1 && !(no_tc8 && no_tc8[0] == '1');
     conv_tc_prepare();
-    conv_tch_prepare();
-    if (const char* pair_env = std::getenv("KZB_CONV_PAIR"); pair_env && pair_env[0] == '1') conv_tchp_prepare();  // experimental kernel: untouched otherwise
     conv_tc8_prepare();
+    if (i2c_ok_) conv_i2c_prepare();
     rows_alloc_ = round_up(boards_alloc * lay_.board_pitch, 128);
     if (dense_i2c_) {  // whole 256-pixel pair tiles, and whole boards under every one of them
-        conv_i2c_prepare();
         const int pixels = round_up(max_batch_ * W * H, 256);
         boards_i2c_ = (pixels + W * H - 1) / (W * H);
         rows_alloc_ = round_up(std::max(pixels, boards_i2c_ * W * H), 128);
+    } else if (mode_ == 1) {
+        boards_i2c_ = rows_alloc_ / 64;  // boards_alloc is a multiple of 8: whole 256-pixel tiles
     }
     cin_pad_ = round_up(spec_.cin, 64);
     c_pad_ = round_up(C, 64);
@@ -328,7 +329,7 @@ void Net::build_bf16() {
             uint32_t box[2] = {64, uint32_t(n)};
             st->tmap_b = make_tmap(st->w_bf16.ptr, 2, dims, strides, box);
             st->tmap_bh = st->tmap_b;
-            if (n % 32 == 0) {  // half-height box for the 2-CTA multicast variant of conv_tc
+            if (n % 32 == 0) {  // half-height box: each CTA of a pair stages half of every weight tile (conv_i2c.cu)
                 uint32_t half[2] = {64, uint32_t(n / 2)};
                 st->tmap_bh = make_tmap(st->w_bf16.ptr, 2, dims, strides, half);
             }
@@ -344,8 +345,8 @@ void Net::build_bf16() {
             uint32_t box[2] = {64, 128};
             st->tmap_a = make_tmap(in.ptr, 2, dims, strides, box);
         }
-        if (dense_i2c_ && st->taps == 9 && cin_pad % 64 == 0 && n % 32 == 0 && n >= 32 && !out_f32 && (relu_n == 0 || relu_n == n) && out_off == 0) {
-            st->tmap_i2c = make_tmap_im2col3x3(in.ptr, in_stride, W, H, boards_i2c_, 64, 128);
+        if ((dense_i2c_ || (mode_ == 1 && i2c_ok_)) && cin_pad % 64 == 0 && n % 32 == 0 && n >= 32 && !out_f32 && (relu_n == 0 || relu_n == n) && out_off == 0) {
+            st->tmap_i2c = make_tmap_im2col(in.ptr, in_stride, W, H, boards_i2c_, 64, 128, st->taps == 9 ? 1 : 0);
             auto rows_map = [&](void* ptr, int stride) {
                 uint64_t dims[2] = {uint64_t(stride), uint64_t(rows_alloc_)};
                 uint64_t strides[1] = {uint64_t(stride) * 2};
@@ -365,6 +366,7 @@ void Net::build_bf16() {
             st->i2c_stages = conv_i2c_pick_stages(n);
         }
         if (allow_tc8 && st->taps == 9 && n <= 128 && !out_f32) {
+            st->use_i2c = false;  // 8x8 boards, narrow layers: the per-layer 8x8 kernel (it only runs when the whole-tower kernel does not)
             // (c, x, board, y)-ordered view of the same rows, box (64, 8, 4 boards, 10 ranks incl. halo)
             uint64_t dims[4] = {uint64_t(in_stride), 8, uint64_t(rows_alloc_ / 64), 8};
             uint64_t strides[3] = {uint64_t(in_stride) * 2, uint64_t(in_stride) * 2 * 64, uint64_t(in_stride) * 2 * 8};
@@ -396,31 +398,9 @@ void Net::build_bf16() {
         int cols = 32;
         while (cols < 2 * n) cols *= 2;
         p.tmem_cols = cols;
-        // KZB_CONV_CLUSTER=2: CTA pairs share every weight tile (TMA multicast); worth it where the weight stream
-        // dominates SM ingress, i.e. wide layers on boards that go through the per-layer kernel
-        // 3x3 layers on padded rows load their activation tile once per k-block (conv_tch.cu; KZB_CONV_HALO=0 falls back
-        // to conv_tc.cu, which re-loads it for every tap)
-        const char* halo_env = std::getenv("KZB_CONV_HALO");
         p.n_split = 1;
-        p.halo = lay_.rank_pitch + 1;
-        p.a_rows = (128 + 2 * p.halo + 7) & ~7;  // whole 8-row groups: every k-chunk of the tile starts 128-byte aligned
-        if (!(halo_env && halo_env[0] == '0') && mode_ == 0 && !dense_i2c_ && st->taps == 9 && cin_pad % 64 == 0 && p.a_rows <= 256 && !st->use_tc8) {
-            uint64_t dims[2] = {uint64_t(in_stride), uint64_t(rows_alloc_)};
-            uint64_t strides[1] = {uint64_t(in_stride) * 2};
-            uint32_t box[2] = {8, uint32_t(p.a_rows)};
-            st->tmap_ah = make_tmap(in.ptr, 2, dims, strides, box, false);
-            st->use_tch = true;
-            st->tch_stages = conv_tch_pick_stages(n, p.a_rows);
-            const char* pair_env = std::getenv("KZB_CONV_PAIR");  // experimental: the same layer on the CTA-pair MMA
-            if (pair_env && pair_env[0] == '1' && n % 32 == 0 && n >= 64) {
-                st->use_tchp = true;
-                st->tchp_stages = conv_tchp_pick_stages(n, p.a_rows);
-            }
-        }
-        const char* pdl_env = std::getenv("KZB_PDL");  // programmatic dependent launch of consecutive 3x3 layers (conv_tch / conv_tchp)
-        p.pdl = (pdl_env && pdl_env[0] == '1') ? 1 : 0;
-        const char* cl = std::getenv("KZB_CONV_CLUSTER");
-        p.cluster = (cl && cl[0] == '2' && n % 32 == 0 && st->taps == 9) ? 2 : 1;
+        const char* pdl_env = std::getenv("KZB_PDL");  // programmatic dependent launch of consecutive conv_i2c layers (KZB_PDL=0: off)
+        p.pdl = (pdl_env && pdl_env[0] == '0') ? 0 : 1;
         convs_.push_back(std::move(st));
     };
 
@@ -472,40 +452,22 @@ void Net::build_bf16() {
         }
     }
 
-    // whole-tower persistent kernel: all 2*depth+1 conv3x3 layers in one launch (tower8.cu)
+    // whole-tower persistent kernel: all 2*depth+1 conv3x3 layers in one launch (tower8k.cu)
     const char* no_t8 = std::getenv("KZB_NO_TOWER8");
     const int units_max = ((max_batch_ + 3) / 4 + 1) & ~1;
     if (allow_tc8 && c_pad_ <= 128 && !(no_t8 && no_t8[0] == '1') &&
-        (units_max + num_sms_ - 1) / num_sms_ <= tower8_max_local_units()) {
-        tower8_prepare();
+        (units_max + num_sms_ - 1) / num_sms_ <= tower8k_max_local_units()) {
+        tower8k_prepare();
         tower_layers_ = 1 + 2 * spec_.depth;
         const int n = c_pad_;
-        auto amap = [&](DeviceBuffer& buf, int stride) {
-            uint64_t dims[4] = {uint64_t(stride), 8, uint64_t(rows_alloc_ / 64), 8};
-            uint64_t strides[3] = {uint64_t(stride) * 2, uint64_t(stride) * 2 * 64, uint64_t(stride) * 2 * 8};
-            uint32_t box[4] = {64, 8, 4, 8};
-            return make_tmap(buf.ptr, 4, dims, strides, box);
-        };
-        tower_maps_.a[0] = amap(act_in_, cin_pad_);
-        tower_maps_.a[1] = amap(act_x_, c_pad_);
-        tower_maps_.a[2] = amap(act_t_, c_pad_);
-        auto omap = [&](DeviceBuffer& buf) {  // TMA store of one rank of a 4-board unit: [4 boards][8 x][c_pad]
-            uint64_t dims[4] = {uint64_t(c_pad_), 8, uint64_t(rows_alloc_ / 64), 8};
-            uint64_t strides[3] = {uint64_t(c_pad_) * 2, uint64_t(c_pad_) * 2 * 64, uint64_t(c_pad_) * 2 * 8};
-            uint32_t box[4] = {32, 8, 4, 1};  // one epilogue warp's 32 channels
-            return make_tmap(buf.ptr, 4, dims, strides, box, false);
-        };
-        tower_maps_.out[0] = omap(act_x_);
-        tower_maps_.out[1] = omap(act_t_);
         act_xt_.alloc(size_t(std::max(rows_alloc_ / 256 + 1, 2 * num_sms_ + 2)) * 128 * 256 * 2);  // one slot per (CTA, local unit)
-        const char* cl_env = std::getenv("KZB_TOWER_CLUSTER");
-        const int cluster = (cl_env && cl_env[0] == '1') ? 1 : 2;
+        const int cluster = 2;  // CTA pairs: each loads half of every weight tile and multicasts it
         {
             ConvStep& f = *convs_[0];
             uint64_t dims[2] = {uint64_t(9 * cin_pad_), uint64_t(n)};
             uint64_t strides[1] = {uint64_t(9 * cin_pad_) * 2};
             uint32_t box[2] = {64, uint32_t(n / cluster)};
-            tower_maps_.w[0] = make_tmap(f.w_bf16.ptr, 2, dims, strides, box);
+            tower_kmaps_.w[0] = make_tmap(f.w_bf16.ptr, 2, dims, strides, box);
         }
         const size_t layer_w_bytes = size_t(n) * 9 * c_pad_ * 2;
         w_tower_.alloc(std::max<size_t>(layer_w_bytes * 2 * spec_.depth, 256), true);
@@ -515,7 +477,7 @@ void Net::build_bf16() {
             uint64_t dims[2] = {uint64_t(9 * c_pad_), uint64_t(std::max(1, 2 * spec_.depth) * n)};
             uint64_t strides[1] = {uint64_t(9 * c_pad_) * 2};
             uint32_t box[2] = {64, uint32_t(n / cluster)};
-            tower_maps_.w[1] = make_tmap(w_tower_.ptr, 2, dims, strides, box);
+            tower_kmaps_.w[1] = make_tmap(w_tower_.ptr, 2, dims, strides, box);
         }
         std::vector<TowerLayerDev> layers(tower_layers_);
         for (int i = 0; i < tower_layers_; i++) {
@@ -530,7 +492,7 @@ void Net::build_bf16() {
             l.has_res = conv2 ? 1 : 0;
             l.out_buf = (first || conv2) ? 1 : 2;
             l.bias = convs_[i]->bias.as<float>();
-            // second-generation kernel: a narrow single-k-block first layer only stages / multiplies the chunks that exist
+            // a narrow single-k-block first layer only stages / multiplies the chunks that exist
             l.ksteps = (first && l.kblocks == 1) ? std::max(1, (spec_.cin + 15) / 16) : 4;
             l.kchunks = 2 * l.ksteps;
             l.out_rowmajor = (i == tower_layers_ - 1) ? 1 : 0;
@@ -545,59 +507,51 @@ void Net::build_bf16() {
         tp.t = act_t_.as<__nv_bfloat16>();
         tp.xt = act_xt_.as<__nv_bfloat16>();
         tp.stride = c_pad_;
-        tp.b_slots = tower8_pick_b_slots(n);
         tp.cluster = cluster;
         tp.board_w = spec_.board_w;
         tp.board_h = spec_.board_h;
         int cols = 32;
         while (cols < 4 * n) cols *= 2;
         tp.tmem_cols = cols;
-        // second generation (tower8k.cu): k-chunk-major activations, one staged copy per k-block
-        const char* v1 = std::getenv("KZB_TOWER_V1");
-        if (!(v1 && v1[0] == '1')) {
-            tower8k_prepare();
-            const uint64_t boards_total = uint64_t(rows_alloc_ / 64);
-            act_ink_.alloc(size_t(cin_pad_ / 8) * boards_total * 1024);
-            act_xk_.alloc(size_t(c_pad_ / 8) * boards_total * 1024);
-            act_tk_.alloc(size_t(c_pad_ / 8) * boards_total * 1024);
-            auto kload = [&](DeviceBuffer& buf, int kc_total, int nb) {  // (x*8+c8, board, y, kc)
-                uint64_t dims[4] = {64, boards_total, 8, uint64_t(kc_total)};
-                uint64_t strides[3] = {1024, 128, boards_total * 1024};
-                // 72 > 64: the engine zero-fills the pad row of every 8-position group; 9 > 8: and a zero rank behind the board
-                uint32_t box[4] = {72, uint32_t(nb), 9, 1};
-                return make_tmap(buf.ptr, 4, dims, strides, box, false);
-            };
-            auto kstore = [&](DeviceBuffer& buf, int kc_total, int nb) {  // (x*8+c8, kc, board, y)
-                uint64_t dims[4] = {64, uint64_t(kc_total), boards_total, 8};
-                uint64_t strides[3] = {boards_total * 1024, 1024, 128};
-                uint32_t box[4] = {80, 4, uint32_t(nb), 1};  // staging rows are 160 bytes (bank spreading); elements 64..79 are clipped
-                return make_tmap(buf.ptr, 4, dims, strides, box, false);
-            };
-            auto rstore = [&](DeviceBuffer& buf, int nb) {  // row-major rows, one rank of an nb-board unit: (c, x, board, y)
-                uint64_t dims[4] = {uint64_t(c_pad_), 8, uint64_t(rows_alloc_ / 64), 8};
-                uint64_t strides[3] = {uint64_t(c_pad_) * 2, uint64_t(c_pad_) * 2 * 64, uint64_t(c_pad_) * 2 * 8};
-                uint32_t box[4] = {32, 8, uint32_t(nb), 1};
-                return make_tmap(buf.ptr, 4, dims, strides, box, false);
-            };
-            for (int nb = 3; nb <= 4; nb++) {
-                tower_kmaps_.a[0][nb - 3] = kload(act_ink_, cin_pad_ / 8, nb);
-                tower_kmaps_.a[1][nb - 3] = kload(act_xk_, c_pad_ / 8, nb);
-                tower_kmaps_.a[2][nb - 3] = kload(act_tk_, c_pad_ / 8, nb);
-                tower_kmaps_.out[0][nb - 3] = kstore(act_xk_, c_pad_ / 8, nb);
-                tower_kmaps_.out[1][nb - 3] = kstore(act_tk_, c_pad_ / 8, nb);
-                tower_kmaps_.out[2][nb - 3] = rstore(act_x_, nb);
-            }
-            tower_kmaps_.w[0] = tower_maps_.w[0];
-            tower_kmaps_.w[1] = tower_maps_.w[1];
-            tower_k_b_slots_ = tower8k_pick_b_slots();
-            use_tower8k_ = true;
+        // k-chunk-major activations, one staged copy per k-block
+        const uint64_t boards_total = uint64_t(rows_alloc_ / 64);
+        act_ink_.alloc(size_t(cin_pad_ / 8) * boards_total * 1024);
+        act_xk_.alloc(size_t(c_pad_ / 8) * boards_total * 1024);
+        act_tk_.alloc(size_t(c_pad_ / 8) * boards_total * 1024);
+        auto kload = [&](DeviceBuffer& buf, int kc_total, int nb) {  // (x*8+c8, board, y, kc)
+            uint64_t dims[4] = {64, boards_total, 8, uint64_t(kc_total)};
+            uint64_t strides[3] = {1024, 128, boards_total * 1024};
+            // 72 > 64: the engine zero-fills the pad row of every 8-position group; 9 > 8: and a zero rank behind the board
+            uint32_t box[4] = {72, uint32_t(nb), 9, 1};
+            return make_tmap(buf.ptr, 4, dims, strides, box, false);
+        };
+        auto kstore = [&](DeviceBuffer& buf, int kc_total, int nb) {  // (x*8+c8, kc, board, y)
+            uint64_t dims[4] = {64, uint64_t(kc_total), boards_total, 8};
+            uint64_t strides[3] = {boards_total * 1024, 1024, 128};
+            uint32_t box[4] = {80, 4, uint32_t(nb), 1};  // staging rows are 160 bytes (bank spreading); elements 64..79 are clipped
+            return make_tmap(buf.ptr, 4, dims, strides, box, false);
+        };
+        auto rstore = [&](DeviceBuffer& buf, int nb) {  // row-major rows, one rank of an nb-board unit: (c, x, board, y)
+            uint64_t dims[4] = {uint64_t(c_pad_), 8, uint64_t(rows_alloc_ / 64), 8};
+            uint64_t strides[3] = {uint64_t(c_pad_) * 2, uint64_t(c_pad_) * 2 * 64, uint64_t(c_pad_) * 2 * 8};
+            uint32_t box[4] = {32, 8, uint32_t(nb), 1};
+            return make_tmap(buf.ptr, 4, dims, strides, box, false);
+        };
+        for (int nb = 3; nb <= 4; nb++) {
+            tower_kmaps_.a[0][nb - 3] = kload(act_ink_, cin_pad_ / 8, nb);
+            tower_kmaps_.a[1][nb - 3] = kload(act_xk_, c_pad_ / 8, nb);
+            tower_kmaps_.a[2][nb - 3] = kload(act_tk_, c_pad_ / 8, nb);
+            tower_kmaps_.out[0][nb - 3] = kstore(act_xk_, c_pad_ / 8, nb);
+            tower_kmaps_.out[1][nb - 3] = kstore(act_tk_, c_pad_ / 8, nb);
+            tower_kmaps_.out[2][nb - 3] = rstore(act_x_, nb);
         }
+        tp.b_slots = tower8k_pick_b_slots();
+        const char* bs = std::getenv("KZB_B_SLOTS");
+        if (bs && std::atoi(bs) >= 2 && std::atoi(bs) <= tp.b_slots) tp.b_slots = std::atoi(bs);
         tp.timeline = nullptr;
         const char* dbg = std::getenv("KZB_DEBUG");
         tp.debug = dbg ? std::atoi(dbg) : 0;
-        const char* bs = std::getenv("KZB_B_SLOTS");
-        if (bs && std::atoi(bs) >= 2 && std::atoi(bs) <= tp.b_slots) tp.b_slots = std::atoi(bs);
-        use_tower8_ = true;
+        use_tower8k_ = true;
     }
 }
 
@@ -763,28 +717,22 @@ void Net::run_encode(int batch, const StepHook& hook) {
 
 void Net::run_network(int batch, const StepHook& hook) {
     size_t first_step = 0;
-    if (use_tower8_) {
+    if (use_tower8k_) {
         Tower8Params tp = tower_params_;
-        tp.num_units = (batch + 3) / 4;
-        if (tp.cluster == 2) tp.num_units = (tp.num_units + 1) & ~1;  // rows of the padding unit exist (boards_alloc) and are never read back
+        tp.num_units = (((batch + 3) / 4) + 1) & ~1;  // cluster pairs: rows of the padding unit exist (boards_alloc) and are never read back
         tp.valid_rows = batch * 64;
         if (timeline_step_ == "tower8") tp.timeline = d_timeline_.as<unsigned long long>();
-        if (use_tower8k_) {
-            tp.b_slots = tower_k_b_slots_;
-            // balanced assignment: every CTA owns 6..8 contiguous boards (two units of 4 / 3); otherwise 4-board units
-            const int grid = num_sms_ & ~1;
-            const char* nobal = std::getenv("KZB_NO_BALANCE");
-            tp.balanced = 0;
-            if (!(nobal && nobal[0] == '1') && batch / grid >= 6 && (batch + grid - 1) / grid <= 8) {
-                tp.balanced = 1;
-                tp.bal_grid = grid;
-                tp.bal_base = batch / grid;
-                tp.bal_rem = batch % grid;
-            }
-            launch_tower8k(tower_kmaps_, tp, num_sms_, stream_);
-        } else {
-            launch_tower8(tower_maps_, tp, num_sms_, stream_);
+        // balanced assignment: every CTA owns 6..8 contiguous boards (two units of 4 / 3); otherwise 4-board units
+        const int grid = num_sms_ & ~1;
+        const char* nobal = std::getenv("KZB_NO_BALANCE");
+        tp.balanced = 0;
+        if (!(nobal && nobal[0] == '1') && batch / grid >= 6 && (batch + grid - 1) / grid <= 8) {
+            tp.balanced = 1;
+            tp.bal_grid = grid;
+            tp.bal_base = batch / grid;
+            tp.bal_rem = batch % grid;
         }
+        launch_tower8k(tower_kmaps_, tp, num_sms_, stream_);
         if (hook) hook("tower8");
         first_step = size_t(tower_layers_);
     }
@@ -817,18 +765,8 @@ void Net::run_network(int batch, const StepHook& hook) {
                 const char* split = std::getenv("KZB_CONV_SPLIT");
                 p.n_split = (!(split && split[0] == '0') && p.n % 64 == 0 && p.n_store == p.n && 2 * ((p.num_tiles + 1) / 2) <= num_sms_ / 2) ? 2 : 1;
                 launch_conv_i2c(st->tmap_i2c, p.n_split == 2 ? st->tmap_bq : st->tmap_bh, st->tmap_out, st->tmap_res, p, num_sms_, stream_);
-            } else if (st->use_tchp) {
-                p.stages = st->tchp_stages;
-                p.n_split = 1;
-                launch_conv_tchp(st->tmap_ah, st->tmap_bh, p, num_sms_, stream_);
-            } else if (st->use_tch) {
-                p.stages = st->tch_stages;
-                // small batches: split the output channels so that twice as many SMs share the layer (KZB_CONV_SPLIT=0: never)
-                const char* split = std::getenv("KZB_CONV_SPLIT");
-                p.n_split = (!(split && split[0] == '0') && p.n >= 128 && p.n % 32 == 0 && p.n_store == p.n && 2 * p.num_tiles <= num_sms_) ? 2 : 1;
-                launch_conv_tch(st->tmap_ah, p.n_split == 2 ? st->tmap_bh : st->tmap_b, p, num_sms_, stream_);
             } else {
-                launch_conv_tc(st->tmap_a, st->tmap_b, st->tmap_bh, p, num_sms_, stream_);
+                launch_conv_tc(st->tmap_a, st->tmap_b, p, num_sms_, stream_);
             }
         } else {
             ConvF32Params p = st->f32;

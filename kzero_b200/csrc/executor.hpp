@@ -45,11 +45,7 @@ struct ConvStep {
     std::string name;
     int taps = 9;
     // bf16 tensor-core form
-    CUtensorMap tmap_a{}, tmap_b{}, tmap_bh{}, tmap_ah{};
-    bool use_tch = false;  // conv_tch.cu (activation tile with halo, loaded once per k-block)
-    int tch_stages = 0;
-    bool use_tchp = false;  // conv_tchp.cu (CTA-pair variant of conv_tch, KZB_CONV_PAIR=1)
-    int tchp_stages = 0;
+    CUtensorMap tmap_a{}, tmap_b{}, tmap_bh{};
     bool use_i2c = false;  // conv_i2c.cu (dense rows, TMA im2col, CTA-pair MMA)
     int i2c_stages = 0;
     CUtensorMap tmap_out{}, tmap_res{};  // conv_i2c: output / residual rows, box (32 channels, 32 rows), SWIZZLE_64B
@@ -82,7 +78,7 @@ public:
     // kzb_eval_packed waits for the GPU by spinning (lowest latency, default) or by sleeping on a blocking event
     void set_blocking_sync(bool on) { blocking_sync_ = on; }
     int launches_per_eval() const {
-        int n = int(convs_.size()) + 2 - (use_tower8_ ? tower_layers_ - 1 : 0);
+        int n = int(convs_.size()) + 2 - (use_tower8k_ ? tower_layers_ - 1 : 0);
         if (use_heads8_) n -= int(convs_.size() - head_first_);  // head convs + tail become one launch
         return n;
     }
@@ -117,6 +113,7 @@ private:
     int cin_pad_ = 0, c_pad_ = 0, cp_pad_ = 0, s1_stride_ = 16, pm_stride_ = 0;
     bool act_bf16_ = true;
     bool embed8_ = false;  // a board smaller than 8x8 embedded in the 8x8 grid of the whole-tower kernel
+    bool i2c_ok_ = true;      // conv_i2c.cu may be used (KZB_NO_I2C=1: never)
     bool dense_i2c_ = false;  // boards the 8x8 kernels do not cover: dense rows, 3x3 layers on conv_i2c.cu
     int boards_i2c_ = 0;      // boards covered by the im2col tensor maps (>= every 256-pixel tile of a full batch)
 
@@ -149,14 +146,12 @@ private:
     Heads8Maps heads_maps_{};
     Heads8Params heads_params_{};
 
-    // whole-tower persistent kernel (8x8 boards): covers convs_[0 .. tower_layers_)
-    bool use_tower8_ = false;
+    // whole-tower persistent kernel (8x8 boards, tower8k.cu): covers convs_[0 .. tower_layers_); k-chunk-major activation
+    // tensors A[kc][board][y][x][8]
+    bool use_tower8k_ = false;
     int tower_layers_ = 0;
-    Tower8Maps tower_maps_{};
     Tower8Params tower_params_{};
     DeviceBuffer d_tower_layers_, w_tower_, act_xt_;
-    // second generation (tower8k.cu): k-chunk-major activation tensors A[kc][board][y][x][8]
-    bool use_tower8k_ = false;
     Tower8kMaps tower_kmaps_{};
     int tower_k_b_slots_ = 0;
     DeviceBuffer act_ink_, act_xk_, act_tk_;

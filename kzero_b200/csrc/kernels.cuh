@@ -86,26 +86,13 @@ struct ConvTcParams {
     int n_store;  // channels written per row (multiple of 16, <= n)
     int stages;
     int tmem_cols;
-    int cluster;  // conv_tc only: 1, or 2 = CTA pairs share every weight tile through TMA multicast
-    int n_split;       // conv_tch / conv_i2c: 1, or 2 = a work item is one tile x one half of the output channels
-    int pdl;           // conv_tch / conv_tchp: launched with programmatic stream serialization (the prologue and the first weight tiles overlap the previous layer's tail)
-    int halo, a_rows;  // conv_tch only: rank_pitch + 1 halo rows on either side, a_rows = 128 + 2 * halo (rounded up to 8) rows per activation tile
+    int n_split;  // conv_i2c: 1, or 2 = a work item is one 256-pixel tile x one half of the output channels
+    int pdl;      // conv_i2c: launched with programmatic stream serialization (set-up and the first weight tiles overlap the previous layer's tail)
     // development aid: when non-null, each CTA writes 16 clock64() stamps (see conv_tc8.cu) -- KZB_TIMELINE=1
     unsigned long long* timeline;
 };
-void launch_conv_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_bh, const ConvTcParams& p,
-                    int grid, cudaStream_t s);
-// conv_tch.cu: the same layer with the activation tile loaded once per k-block (3x3 layers on padded rows)
-void launch_conv_tch(const CUtensorMap& tmap_a_rows, const CUtensorMap& tmap_b, const ConvTcParams& p, int grid, cudaStream_t s);
-size_t conv_tch_smem_bytes(int n, int stages, int a_rows);
-int conv_tch_pick_stages(int n, int a_rows);
-void conv_tch_prepare();
-// conv_tchp.cu (experimental): conv_tch on the CTA-pair MMA, each CTA stages half of every weight tile
-void launch_conv_tchp(const CUtensorMap& tmap_a_rows, const CUtensorMap& tmap_bh, const ConvTcParams& p, int grid, cudaStream_t s);
-size_t conv_tchp_smem_bytes(int n, int stages, int a_rows);
-int conv_tchp_pick_stages(int n, int a_rows);
-void conv_tchp_prepare();
-// conv_i2c.cu: conv3x3 on DENSE rows, activation tiles by TMA im2col, CTA-pair MMA (tmap_bh: weight box of p.n / p.n_split / 2 rows)
+void launch_conv_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ConvTcParams& p, int grid, cudaStream_t s);
+// conv_i2c.cu: conv3x3 / conv1x1 (p.taps) on DENSE rows, activation tiles by TMA im2col, CTA-pair MMA (tmap_bh: weight box of p.n / p.n_split / 2 rows)
 void launch_conv_i2c(const CUtensorMap& tmap_a_im2col, const CUtensorMap& tmap_bh, const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                      const ConvTcParams& p, int grid, cudaStream_t s);
 size_t conv_i2c_smem_bytes(int n, int stages);
@@ -123,7 +110,7 @@ size_t conv_tc8_smem_bytes(int n, int b_slots);
 int conv_tc8_pick_b_slots(int n);
 void conv_tc8_prepare();
 
-// whole-tower persistent kernel for 8x8 boards (tower8.cu)
+// whole-tower persistent kernel for 8x8 boards (tower8k.cu)
 struct TowerLayerDev {
     int a_map;   // input activations: 0 = encoded planes, 1 = X (residual stream), 2 = T (block-internal)
     int w_map;   // 0 = first-layer weights, 1 = concatenated block weights
@@ -137,11 +124,6 @@ struct TowerLayerDev {
     int kchunks;       // 8-channel chunks staged per k-block (8, fewer for a narrow first layer)
     int ksteps;        // K=16 MMA steps per k-block and tap (kchunks / 2)
     int out_rowmajor;  // last layer: store [position][C] rows (what the head kernels read) instead of k-chunk-major
-};
-struct Tower8Maps {
-    CUtensorMap a[3];    // loads: encoded planes, X, T   -- (c, x, board, y) order, box (64, 8, 4, 8), SWIZZLE_128B
-    CUtensorMap w[2];    // loads: first-layer weights, concatenated block weights -- box (64, n / cluster)
-    CUtensorMap out[2];  // stores: X, T                  -- (c, x, board, y) order, box (32, 8, 4, 1), no swizzle
 };
 struct Tower8Params {
     int num_layers;
@@ -163,8 +145,6 @@ struct Tower8Params {
     unsigned long long* timeline;
     int debug;  // development aid (KZB_DEBUG): 1 = skip A loads, 2 = skip B loads, 4 = skip epilogue memory traffic
 };
-void launch_tower8(const Tower8Maps& maps, const Tower8Params& p, int grid, cudaStream_t s);
-
 // second generation (tower8k.cu): k-chunk-major activations A[kc][board][y][x][8], every tap = a descriptor offset
 struct Tower8kMaps {
     // second index: boards per unit - 3 (units of 3 or 4 boards)
@@ -182,10 +162,6 @@ void tower8k_prepare();
 void launch_encode_kc(const EncodeParams& p, int kc_total, int boards_total, cudaStream_t s);
 void launch_nchw_to_kc(const float* in, int batch, int channels, int rec_w, int rec_h, int kc_total, int boards_total, void* out,
                        cudaStream_t s);
-size_t tower8_smem_bytes(int w_slots);
-int tower8_pick_b_slots(int n);
-int tower8_max_local_units();
-void tower8_prepare();
 
 // ---------------------------------------------------------------------------------------------- K3
 struct AttEntryDev {  // same layout as NetSpec::AttEntry

@@ -515,7 +515,14 @@ void executor_main(Net* net, Shared& sh, const kzb_selfplay_config& c, const Gam
 }
 
 template <typename Game>
-void run_selfplay(int device, const void* onnx, size_t len, int precision, const kzb_selfplay_config& c, kzb_selfplay_stats& out) {
+using SlotTable = std::vector<std::vector<std::unique_ptr<Slot<Game>>>>;  // [generator thread][its games]
+
+// `kept`: the games of a session (kzb_selfplay_session_*).  Empty on the first run: filled here; afterwards every game continues
+// where the previous run left it -- board, tree, per-game cache and the positions recorded so far -- like the reference's generators,
+// which run across file boundaries (collector.rs:59-116 only rotates the output file).  nullptr: games live for this run only.
+template <typename Game>
+void run_selfplay(int device, const void* onnx, size_t len, int precision, const kzb_selfplay_config& c, kzb_selfplay_stats& out,
+                  SlotTable<Game>* kept = nullptr) {
     const GameShape shape = Game::shape();
     if (c.visits < 1 || c.search_batch < 1 || c.gpu_batch < c.search_batch || c.cpu_threads < 1 || c.gpu_threads < 1)
         throw std::runtime_error("selfplay config: need visits >= 1, 1 <= search_batch <= gpu_batch, cpu_threads >= 1, gpu_threads >= 1");
@@ -531,15 +538,31 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
     if (c.output_prefix && c.output_prefix[0])
         sh.writer = std::make_unique<RecordWriter>(c.output_prefix, Game::name(), shape.bool_channels, shape.board, shape.scalar_count, shape.policy_len);
     sh.job_count = size_t(std::max(1, c.gpu_batch / std::max(1, c.search_batch)));
-    std::vector<std::vector<std::unique_ptr<Slot<Game>>>> per_thread(size_t(c.cpu_threads));
-    for (int g = 0; g < games; g++)
-        per_thread[size_t(g % c.cpu_threads)].push_back(std::make_unique<Slot<Game>>(c.seed * 1000003ull + uint64_t(g) * 7919ull + 1, size_t(c.cache_size), size_t(c.visits)));
+    SlotTable<Game> local;
+    SlotTable<Game>& per_thread = kept ? *kept : local;
+    if (per_thread.empty()) {
+        per_thread.resize(size_t(c.cpu_threads));
+        for (int g = 0; g < games; g++)
+            per_thread[size_t(g % c.cpu_threads)].push_back(std::make_unique<Slot<Game>>(c.seed * 1000003ull + uint64_t(g) * 7919ull + 1, size_t(c.cache_size), size_t(c.visits)));
+    } else {
+        if (per_thread.size() != size_t(c.cpu_threads)) throw std::runtime_error("selfplay session: cpu_threads is a startup setting and cannot change between runs");
+        games = 0;
+        for (auto& slots : per_thread) {
+            games += int(slots.size());
+            // requests that were queued or never answered when the previous run stopped go back into the (new) queue; answered ones
+            // are picked up by their generator thread as usual
+            for (auto& sp : slots)
+                if (sp->waiting && !sp->job.done.load(std::memory_order_acquire)) {
+                    sh.queue.push_back(&sp->job);
+                    sh.queued_positions += size_t(sp->job.n);
+                }
+        }
+    }
     for (int t = 0; t < c.cpu_threads; t++) {
         sh.gen_mu.push_back(std::make_unique<std::mutex>());
         sh.gen_cv.push_back(std::make_unique<std::condition_variable>());
         sh.gen_signal.push_back(0);
     }
-    g_stop_requested.store(false);
     for (auto& v : g_profile_cycles) v = 0;
     g_profile_cpu_s[0] = g_profile_cpu_s[1] = 0.0;
     const auto t0 = std::chrono::steady_clock::now();
@@ -660,6 +683,20 @@ void trace_search(const kzb_selfplay_config& c, uint64_t game_seed, int plies, i
     out.evals = evals;
 }
 
+// a session = the games of one self-play server connection, kept between generations
+struct SessionBase {
+    virtual ~SessionBase() = default;
+    virtual void run(int device, const void* onnx, size_t len, int precision, const kzb_selfplay_config& c, kzb_selfplay_stats& out) = 0;
+    int game = -1;
+};
+template <typename Game>
+struct Session : SessionBase {
+    SlotTable<Game> slots;
+    void run(int device, const void* onnx, size_t len, int precision, const kzb_selfplay_config& c, kzb_selfplay_stats& out) override {
+        run_selfplay<Game>(device, onnx, len, precision, c, out, &slots);
+    }
+};
+
 template <typename F>
 int guarded(F&& f) {
     try {
@@ -730,6 +767,40 @@ KZB_API int kzb_selfplay_run(int device, const void* onnx_bytes, size_t onnx_len
 }
 
 KZB_API void kzb_selfplay_request_stop(void) { kzb::selfplay::g_stop_requested.store(true); }
+KZB_API void kzb_selfplay_clear_stop(void) { kzb::selfplay::g_stop_requested.store(false); }
+
+struct kzb_selfplay_session {
+    std::unique_ptr<kzb::selfplay::SessionBase> impl;
+};
+
+KZB_API int kzb_selfplay_session_create(int game, kzb_selfplay_session** out) {
+    using namespace kzb::selfplay;
+    return guarded([&] {
+        if (!out) throw std::runtime_error("out must not be NULL");
+        auto s = std::make_unique<kzb_selfplay_session>();
+        if (game == KZB_GAME_SYNTH_CHESS) s->impl = std::make_unique<Session<SynthChess>>();
+        else if (game == KZB_GAME_ATAXX7) s->impl = std::make_unique<Session<Ataxx>>();
+        else if (game == KZB_GAME_GO9) s->impl = std::make_unique<Session<Go9>>();
+        else if (game == KZB_GAME_CHESS) s->impl = std::make_unique<Session<Chess>>();
+        else throw std::runtime_error("unknown game");
+        s->impl->game = game;
+        *out = s.release();
+    });
+}
+
+KZB_API int kzb_selfplay_session_run(kzb_selfplay_session* session, int device, const void* onnx_bytes, size_t onnx_len, int precision,
+                                     const kzb_selfplay_config* config, kzb_selfplay_stats* stats) {
+    using namespace kzb::selfplay;
+    return guarded([&] {
+        if (!session || !config || !stats) throw std::runtime_error("session, config and stats must not be NULL");
+        if (!onnx_bytes && !config->dummy_network) throw std::runtime_error("onnx_bytes must not be NULL unless dummy_network is set");
+        if (config->game != session->impl->game) throw std::runtime_error("selfplay session: the game is a startup setting and cannot change between runs");
+        std::memset(stats, 0, sizeof(*stats));
+        session->impl->run(device, onnx_bytes, onnx_len, precision, *config, *stats);
+    });
+}
+
+KZB_API void kzb_selfplay_session_destroy(kzb_selfplay_session* session) { delete session; }
 
 KZB_API int kzb_mcts_trace(const kzb_selfplay_config* config, uint64_t game_seed, int plies, int eval_kind, kzb_mcts_trace_out* out) {
     using namespace kzb::selfplay;

@@ -69,9 +69,37 @@ class SelfplayResult:
 def run(onnx_bytes: Optional[bytes], config: SelfplayConfig, device: int = 0, precision: int = 1) -> SelfplayResult:
     """onnx_bytes may be None when config.dummy_network is set (uniform evaluations, no GPU)."""
     stats = SelfplayStats()
+    _abi.lib().kzb_selfplay_clear_stop()  # a stand-alone run starts fresh; the server manages the flag itself (kzb_selfplay_request_stop)
     _abi.check(_abi.lib().kzb_selfplay_run(device, onnx_bytes, len(onnx_bytes) if onnx_bytes else 0, precision, ctypes.byref(config),
                                            ctypes.byref(stats)))
     return SelfplayResult(**{f[0]: getattr(stats, f[0]) for f in SelfplayStats._fields_})
+
+
+class Session:
+    """The concurrent games of one server connection, kept alive between runs (kzb_selfplay_session_*): every `run` plays until
+    config.max_games more games have finished and returns; games in flight continue in the next run, with that run's network and
+    settings -- like the reference's generators, which run across file boundaries (collector.rs:59-116)."""
+
+    def __init__(self, game: int):
+        self._handle = ctypes.c_void_p()
+        _abi.check(_abi.lib().kzb_selfplay_session_create(game, ctypes.byref(self._handle)))
+
+    def run(self, onnx_bytes: Optional[bytes], config: SelfplayConfig, device: int = 0, precision: int = 1) -> SelfplayResult:
+        stats = SelfplayStats()
+        _abi.check(_abi.lib().kzb_selfplay_session_run(self._handle, device, onnx_bytes, len(onnx_bytes) if onnx_bytes else 0, precision,
+                                                       ctypes.byref(config), ctypes.byref(stats)))
+        return SelfplayResult(**{f[0]: getattr(stats, f[0]) for f in SelfplayStats._fields_})
+
+    def close(self) -> None:
+        if self._handle:
+            _abi.lib().kzb_selfplay_session_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 @dataclass

@@ -10,9 +10,11 @@ read one `StartupSettings` line, then
                                     `<output_folder>/games_<gen>.{bin,off,json}`, `"Stopped"` at the end
 Messages are one JSON value per line, externally tagged like serde's enums (protocol.rs:30-84).
 
-Differences that are deliberate (documented in DESIGN.md): a generation is one `kzb_selfplay_run` call, so a new network
-or new settings take effect at the next generation boundary (the reference hot-swaps inside a generation) and games still
-running at the boundary are dropped instead of carried over; `eval_random_symmetries`, `start_pos`, `top_moves`,
+Games live in a session (kzb_selfplay_session_*): a generation is one run of it, which returns after `games_per_gen` more games
+have been written; the games still in flight at that point -- boards, trees, caches, recorded positions -- continue in the next
+generation, so long games are never dropped (the reference's generators run across file boundaries the same way).  A new
+network or new settings take effect at the next generation boundary, under the running games (the reference swaps them in
+as soon as they arrive).  Differences that are deliberate (documented in DESIGN.md): `eval_random_symmetries`, `start_pos`, `top_moves`,
 `saved_state_channels` and `gpu_batch_size_root` are accepted and ignored (muzero-only or above the boundary); `chess`,
 `ataxx-7` and `go-9` are served with this repo's restated rules (`chess-synth` is the chess-shaped synthetic game the
 B200 self-play numbers were taken with); one server process drives ONE device (the reference takes several `--device`
@@ -148,6 +150,7 @@ class SelfplayServer:
             conn.sendall((json.dumps(message) + "\n").encode())
 
         gen = int(startup["first_gen"])
+        session = selfplay.Session(game_id(startup["game"]))
         try:
             while True:
                 with self.lock:
@@ -156,13 +159,15 @@ class SelfplayServer:
                     if self.stop:
                         break
                     settings, network = dict(self.settings), self.network
-                cfg = config_from(startup, settings, seed=gen)
+                    # under the lock the commander also takes: a Stop can no longer slip between this check and the run
+                    _abi.lib().kzb_selfplay_clear_stop()
+                cfg = config_from(startup, settings, seed=int(startup["first_gen"]))
                 cfg.output_prefix = str(Path(startup["output_folder"]) / f"games_{gen}").encode()
                 if network == "dummy":
                     cfg.dummy_network = 1
-                    result = selfplay.run(None, cfg, device=self.device)
+                    result = session.run(None, cfg, device=self.device)
                 else:
-                    result = selfplay.run(network, cfg, device=self.device)
+                    result = session.run(network, cfg, device=self.device)
                 if self.stop:
                     break
                 print(f"generation {gen}: {result.games_written} games, {result.moves_played} moves, "
@@ -170,6 +175,7 @@ class SelfplayServer:
                 send({"FinishedFile": {"index": gen}})  # ServerUpdate::FinishedFile, protocol.rs:80-84
                 gen += 1
         finally:
+            session.close()
             try:
                 send("Stopped")
             except OSError:

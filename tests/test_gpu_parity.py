@@ -5,8 +5,6 @@ Bars (BASELINE.json north_star):
   fp32 path               <= 1e-4 max-abs on scalars and policy logits
   bf16 tensor-core path   <= 2e-2 max-abs on policy logits, value sign agreement reported/checked
 """
-import os
-
 import numpy as np
 import pytest
 
@@ -128,21 +126,18 @@ def test_fp32_packed_vs_oracle(game, depth, ch, n):
     _check_packed(values, probs, ref_values, ref_probs, mv_off, FP32_TOL, FP32_TOL)
 
 
-@pytest.mark.parametrize("variant", ["default", "tower_v1", "no_heads8", "no_tower8", "no_conv8", "linear", "no_embed8", "pdl", "no_conv_split", "no_i2c",
-                                     "conv_cluster", "no_conv_halo", "no_i2c_no_split", "conv_pair"])
+@pytest.mark.parametrize("variant", ["default", "no_heads8", "no_tower8", "no_conv8", "linear", "no_embed8", "no_pdl", "no_conv_split", "no_i2c"])
 @pytest.mark.parametrize("game,depth,ch,n", [("ataxx-7", 8, 64, 256), ("chess", 16, 128, 64), ("go-9", 4, 64, 40),
                                               ("chess", 2, 32, 7), ("chess", 3, 64, 130), ("chess", 2, 256, 12)])
 def test_bf16_packed_vs_oracle(game, depth, ch, n, variant, monkeypatch):
-    """The tensor-core path in all its forms: whole-tower persistent kernel + fused heads kernel (tower8k.cu, heads8.cu,
-    default for 8x8 boards), the first-generation tower kernel (tower8.cu, KZB_TOWER_V1=1), the same tower with per-op head convs + tail kernel (KZB_NO_HEADS8=1),
-    per-layer 8x8 specialisation (conv_tc8.cu, KZB_NO_TOWER8=1), generic 4-D TMA box per tap (KZB_NO_CONV8=1),
-    dense rows with TMA im2col loads and the CTA-pair MMA (conv_i2c.cu: boards larger than 8x8 / KZB_FORCE_LINEAR=1 / KZB_NO_EMBED8=1; with
-    programmatic dependent launch, KZB_PDL=1; two SM pairs share a tile's output channels at small batches, KZB_CONV_SPLIT=0: never), and the
-    padded-row kernels it replaced (KZB_NO_I2C=1: conv_tch.cu with the halo tile, its CTA-pair form conv_tchp.cu with KZB_CONV_PAIR=1, conv_tc.cu
-    re-loading the tile per tap with KZB_CONV_HALO=0, plus weight multicast with KZB_CONV_CLUSTER=2); boards smaller than 8x8 (ataxx 7x7) are
-    embedded in the 8x8 grid and masked after every layer."""
-    padded_row_variants = ("no_i2c", "conv_cluster", "no_conv_halo", "no_i2c_no_split", "conv_pair")  # KZB_NO_I2C=1: the padded-row kernels
-    row_variants = ("linear", "pdl", "no_conv_split") + padded_row_variants                           # everything off the 8x8 kernels
+    """The tensor-core path in all its forms: whole-tower persistent kernel + fused heads kernel (tower8k.cu, heads8.cu, default for 8x8
+    boards), the same tower with per-op head convs + tail kernel (KZB_NO_HEADS8=1), the per-layer 8x8 specialisation (conv_tc8.cu,
+    KZB_NO_TOWER8=1), conv_i2c.cu on 8x8 boards (KZB_NO_CONV8=1, and always for layers wider than 128 channels), and the row kernels of
+    every other board (go; KZB_FORCE_LINEAR=1 / KZB_NO_EMBED8=1 push chess / ataxx there): dense rows with TMA im2col loads and the
+    CTA-pair MMA (conv_i2c.cu), without programmatic dependent launch (KZB_PDL=0), without sharing a tile's output channels between
+    two SM pairs at small batches (KZB_CONV_SPLIT=0), and the padded-row kernel it replaced (KZB_NO_I2C=1: conv_tc.cu).  Boards
+    smaller than 8x8 (ataxx 7x7) are embedded in the 8x8 grid and masked after every layer."""
+    row_variants = ("linear", "no_pdl", "no_conv_split", "no_i2c")  # everything off the 8x8 kernels
     if variant == "no_embed8":
         if game != "ataxx-7":
             pytest.skip("only boards smaller than 8x8 are embedded")
@@ -153,16 +148,12 @@ def test_bf16_packed_vs_oracle(game, depth, ch, n, variant, monkeypatch):
         pytest.skip("the kernel variants are 8x8 specialisations")
     monkeypatch.setenv("KZB_NO_EMBED8", "1" if variant == "no_embed8" else "0")
     force_linear = "1" if variant in row_variants else "0"
-    monkeypatch.setenv("KZB_NO_I2C", "1" if variant in padded_row_variants else "0")
-    monkeypatch.setenv("KZB_PDL", "1" if variant == "pdl" else "0")
-    monkeypatch.setenv("KZB_CONV_PAIR", "1" if variant == "conv_pair" else "0")
-    monkeypatch.setenv("KZB_CONV_SPLIT", "0" if variant in ("no_conv_split", "no_i2c_no_split") else "1")
-    monkeypatch.setenv("KZB_CONV_HALO", "0" if variant in ("no_conv_halo", "conv_cluster") else "1")
-    monkeypatch.setenv("KZB_CONV_CLUSTER", "2" if variant == "conv_cluster" else "1")
+    monkeypatch.setenv("KZB_NO_I2C", "1" if variant == "no_i2c" else "0")
+    monkeypatch.setenv("KZB_PDL", "0" if variant == "no_pdl" else "1")
+    monkeypatch.setenv("KZB_CONV_SPLIT", "0" if variant == "no_conv_split" else "1")
     monkeypatch.setenv("KZB_FORCE_LINEAR", force_linear)
     monkeypatch.setenv("KZB_NO_CONV8", "1" if variant == "no_conv8" else "0")
     monkeypatch.setenv("KZB_NO_TOWER8", "1" if variant == "no_tower8" else "0")
-    monkeypatch.setenv("KZB_TOWER_V1", "1" if variant == "tower_v1" else "0")
     monkeypatch.setenv("KZB_NO_HEADS8", "1" if variant in ("no_heads8", "no_conv8") else "0")
     spec = netgen.game_spec(game)
     onnx_bytes = netgen.build_onnx(spec, depth, ch, seed=9)

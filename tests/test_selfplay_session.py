@@ -1,0 +1,65 @@
+"""kzb_selfplay_session_*: the games of a server connection live BETWEEN generations, like the reference's generators, which run across
+file boundaries while the collector only rotates the output file (rust/kz-selfplay/src/server/collector.rs:59-116).  A generation
+that ends must not drop the games still in flight (dropping them biases the data towards short games).  No GPU
+(DummyNetwork stand-in)."""
+import json
+from pathlib import Path
+
+import pytest
+
+from kzero_b200 import selfplay
+from test_selfplay_records import _parse
+
+
+def _cfg(prefix, **kw):
+    base = dict(game=selfplay.GAME_SYNTH_CHESS, visits=16, search_batch=4, gpu_batch=32, cpu_threads=2, gpu_threads=1, concurrent_games=8,
+                max_games=1, duration_s=120.0, dummy_network=2, output_prefix=prefix, seed=11)
+    base.update(kw)
+    return selfplay.default_config(**base)
+
+
+def test_games_in_flight_continue_in_the_next_generation(tmp_path):
+    moves, lengths = [], []
+    with selfplay.Session(selfplay.GAME_SYNTH_CHESS) as session:
+        for gen in range(8):
+            prefix = str(tmp_path / f"games_{gen}")
+            r = session.run(None, _cfg(prefix))
+            assert r.games_written >= 1 and r.concurrent_games == 8
+            meta, positions, starts = _parse(prefix, 13 * 64, 8)
+            assert meta["game_count"] == r.games_written
+            lengths.append([int(positions[int(s)]["scalars"][2]) for s in starts])
+            moves.append(r.moves_played)
+            # every file is complete on its own: per-game position indices run 0..length
+            for s, length in zip(starts, lengths[-1]):
+                for k in range(length + 1):
+                    assert int(positions[int(s) + k]["scalars"][1]) == k
+    # a generation cannot have played a game from its start to its end if the whole generation -- all 8 games together -- played
+    # fewer moves than that game is long: such games were carried over from earlier generations
+    carried = [gen for gen in range(1, len(moves)) if max(lengths[gen]) > moves[gen]]
+    assert len(carried) >= 2, (moves, lengths)
+    # and nothing is invented: the files never hold more positions than were played
+    assert sum(sum(lens) for lens in lengths) <= sum(moves)
+
+
+def test_a_session_keeps_its_startup_settings(tmp_path):
+    with selfplay.Session(selfplay.GAME_SYNTH_CHESS) as session:
+        session.run(None, _cfg(str(tmp_path / "a")))
+        with pytest.raises(Exception, match="cpu_threads"):
+            session.run(None, _cfg(str(tmp_path / "b"), cpu_threads=3))
+        with pytest.raises(Exception, match="game"):
+            session.run(None, _cfg(str(tmp_path / "c"), game=selfplay.GAME_ATAXX7))
+        r = session.run(None, _cfg(str(tmp_path / "d"), visits=8))  # Settings may change between generations
+        assert r.games_written >= 1
+
+
+def test_stop_requested_before_a_run_is_not_lost(tmp_path):
+    """a Stop that arrives while the network is still being built must end the run; only an explicit clear resets it."""
+    from kzero_b200 import _abi
+
+    with selfplay.Session(selfplay.GAME_SYNTH_CHESS) as session:
+        _abi.lib().kzb_selfplay_request_stop()
+        r = session.run(None, _cfg(str(tmp_path / "a"), max_games=1000, duration_s=60.0))
+        assert r.seconds < 5.0 and r.games_written < 1000
+        _abi.lib().kzb_selfplay_clear_stop()
+        r = session.run(None, _cfg(str(tmp_path / "b")))
+        assert r.games_written >= 1
