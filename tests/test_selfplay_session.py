@@ -11,6 +11,16 @@ from kzero_b200 import selfplay
 from test_selfplay_records import _parse
 
 
+@pytest.fixture(autouse=True)
+def _fresh_stop_flag():
+    """The process-wide stop flag stays set until it is cleared (a server that was stopped earlier in this process leaves it set)."""
+    from kzero_b200 import _abi
+
+    _abi.lib().kzb_selfplay_clear_stop()
+    yield
+    _abi.lib().kzb_selfplay_clear_stop()
+
+
 def _cfg(prefix, **kw):
     base = dict(game=selfplay.GAME_SYNTH_CHESS, visits=16, search_batch=4, gpu_batch=32, cpu_threads=2, gpu_threads=1, concurrent_games=8,
                 max_games=1, duration_s=120.0, dummy_network=2, output_prefix=prefix, seed=11)
