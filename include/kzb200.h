@@ -56,6 +56,42 @@ typedef struct kzb_net_info {
 int kzb_net_create_from_onnx(int device, const void* onnx_bytes, size_t onnx_len, int max_batch, int precision,
                              kzb_net** out);
 
+/* The same network from weights the caller already holds -- for a host that keeps the reference's `load_graph` untouched
+ * (`load_graph_from_onnx_path` + `optimize_graph`, server_alphazero.rs:126-128) and hands the optimised Graph's constants over,
+ * exactly what `CudaExecutor::new(device, &graph, batch)` receives today (network/cudnn.rs:32).  All pointers are read during the
+ * call only.  Convolutions are [cout][cin][k][k] f32 + [cout] bias with their in-block BatchNorm already folded (optimize_graph
+ * does that; kzb_net_create_from_onnx does it itself); the tower's trailing BatchNormalization (post_act.py:207) is passed as the
+ * per-channel affine y = final_scale * x + final_shift and folded into the head convs here.  Conv-policy heads only (chess conv +
+ * gather, ataxx, go); a network with the attention policy head goes through kzb_net_create_from_onnx. */
+typedef struct kzb_conv_weights {
+    int32_t cin, cout, ksize; /* ksize 3 (stride 1, zero padding 1) or 1 */
+    const float* w;           /* [cout][cin][ksize][ksize] */
+    const float* b;           /* [cout] */
+} kzb_conv_weights;
+typedef struct kzb_fc_weights {
+    int32_t in, out;
+    const float* w; /* [out][in] (Gemm with transB = 1) */
+    const float* b; /* [out] */
+} kzb_fc_weights;
+typedef struct kzb_net_spec {
+    int32_t input_channels, board_h, board_w, channels, depth;
+    kzb_conv_weights first;         /* conv3x3 input_channels -> channels, bias, no ReLU (post_act.py:203)             */
+    const kzb_conv_weights* blocks; /* 2 * depth conv3x3 channels -> channels, ReLU after each, residual add after every second */
+    const float* final_scale;       /* [channels] or NULL (with final_shift): the trailing BatchNormalization as an affine */
+    const float* final_shift;
+    kzb_conv_weights scalar_conv;   /* conv1x1 channels -> hc, ReLU (post_act.py:10-23)                                */
+    kzb_fc_weights fc1, fc2;        /* hc * H * W -> hs (ReLU) -> 5                                                    */
+    kzb_conv_weights policy_conv1;  /* conv1x1 channels -> cp, ReLU (post_act.py:54-112)                               */
+    kzb_conv_weights policy_conv2;  /* conv1x1 cp -> pc                                                                */
+    int32_t has_extra;              /* go: extra pass-move logit = fc(flatten(conv1x1(channels -> 1)))  (post_act.py:63-84) */
+    kzb_conv_weights extra_conv;
+    kzb_fc_weights extra_fc;
+    int32_t policy_len;
+    const int32_t* policy_src;      /* [policy_len]: >= 0: element pc * H * W + sq of policy_conv2's output (what Flatten / Gather
+                                       select); -1: constant zero (ataxx pass); -2 - e: output e of extra_fc (go pass)          */
+} kzb_net_spec;
+int kzb_net_create(int device, const kzb_net_spec* spec, int max_batch, int precision, kzb_net** out);
+
 /* Twin of check_graph_shapes (network/common.rs:165-198): verifies the graph input is
  * [BATCH, scalar_count + bool_channels, board_h, board_w] and the policy has `policy_len` entries, and
  * tells the network how a packed record splits into scalar and bool planes (InputMapper::input_bool_shape /

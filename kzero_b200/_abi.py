@@ -15,6 +15,28 @@ class NetInfo(ctypes.Structure):
                 ("conv_mode", ctypes.c_int32), ("flops_per_position", ctypes.c_double)]
 
 
+_fp = ctypes.POINTER(ctypes.c_float)
+
+
+class ConvWeights(ctypes.Structure):
+    """kzb_conv_weights (include/kzb200.h)."""
+    _fields_ = [("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("ksize", ctypes.c_int32), ("w", _fp), ("b", _fp)]
+
+
+class FcWeights(ctypes.Structure):
+    """kzb_fc_weights (include/kzb200.h)."""
+    _fields_ = [("in_", ctypes.c_int32), ("out", ctypes.c_int32), ("w", _fp), ("b", _fp)]
+
+
+class NetSpecC(ctypes.Structure):
+    """kzb_net_spec (include/kzb200.h)."""
+    _fields_ = [("input_channels", ctypes.c_int32), ("board_h", ctypes.c_int32), ("board_w", ctypes.c_int32), ("channels", ctypes.c_int32),
+                ("depth", ctypes.c_int32), ("first", ConvWeights), ("blocks", ctypes.POINTER(ConvWeights)), ("final_scale", _fp),
+                ("final_shift", _fp), ("scalar_conv", ConvWeights), ("fc1", FcWeights), ("fc2", FcWeights), ("policy_conv1", ConvWeights),
+                ("policy_conv2", ConvWeights), ("has_extra", ctypes.c_int32), ("extra_conv", ConvWeights), ("extra_fc", FcWeights),
+                ("policy_len", ctypes.c_int32), ("policy_src", ctypes.POINTER(ctypes.c_int32))]
+
+
 class SelfplayConfig(ctypes.Structure):
     """kzb_selfplay_config (include/kzb200.h)."""
     _fields_ = [("game", ctypes.c_int32), ("visits", ctypes.c_int32), ("search_batch", ctypes.c_int32), ("gpu_batch", ctypes.c_int32),
@@ -53,6 +75,7 @@ SYMBOLS = {
     "kzb_device_count": (_i, []),
     "kzb_last_error": (ctypes.c_char_p, []),
     "kzb_net_create_from_onnx": (_i, [_i, _vp, _sz, _i, _i, ctypes.POINTER(_vp)]),
+    "kzb_net_create": (_i, [_i, ctypes.POINTER(NetSpecC), _i, _i, ctypes.POINTER(_vp)]),
     "kzb_net_bind_mapper": (_i, [_vp, _i, _i, _i, _i, _i]),
     "kzb_net_get_info": (_i, [_vp, ctypes.POINTER(NetInfo)]),
     "kzb_onnx_inspect": (_i, [_vp, _sz, ctypes.POINTER(NetInfo)]),

@@ -17,6 +17,7 @@ struct kzb_net {
     kzb::Net impl;
     kzb_net(int device, const void* onnx, size_t len, int max_batch, int precision)
         : impl(device, onnx, len, max_batch, precision) {}
+    kzb_net(int device, kzb::NetSpec spec, int max_batch, int precision) : impl(device, std::move(spec), max_batch, precision) {}
 };
 
 namespace {
@@ -57,6 +58,30 @@ KZB_API int kzb_net_create_from_onnx(int device, const void* onnx_bytes, size_t 
         *out = nullptr;
         need(onnx_bytes, "onnx_bytes");
         *out = new kzb_net(device, onnx_bytes, onnx_len, max_batch, precision);
+    });
+}
+
+KZB_API int kzb_net_create(int device, const kzb_net_spec* spec, int max_batch, int precision, kzb_net** out) {
+    return guarded([&] {
+        need(out, "out");
+        *out = nullptr;
+        need(spec, "spec");
+        auto conv = [](const kzb_conv_weights& c) { return kzb::RawConv{c.cin, c.cout, c.ksize, c.w, c.b}; };
+        auto fc = [](const kzb_fc_weights& f) { return kzb::RawFc{f.in, f.out, f.w, f.b}; };
+        std::vector<kzb::RawConv> blocks;
+        if (spec->depth > 0) need(spec->blocks, "spec->blocks");
+        for (int i = 0; i < 2 * spec->depth; i++) blocks.push_back(conv(spec->blocks[i]));
+        kzb::RawNet r{};
+        r.cin = spec->input_channels, r.board_h = spec->board_h, r.board_w = spec->board_w, r.channels = spec->channels, r.depth = spec->depth;
+        r.first = conv(spec->first);
+        r.blocks = blocks.data();
+        r.final_scale = spec->final_scale, r.final_shift = spec->final_shift;
+        r.scalar_conv = conv(spec->scalar_conv), r.fc1 = fc(spec->fc1), r.fc2 = fc(spec->fc2);
+        r.policy_conv1 = conv(spec->policy_conv1), r.policy_conv2 = conv(spec->policy_conv2);
+        r.has_extra = spec->has_extra != 0;
+        r.extra_conv = conv(spec->extra_conv), r.extra_fc = fc(spec->extra_fc);
+        r.policy_len = spec->policy_len, r.policy_src = spec->policy_src;
+        *out = new kzb_net(device, kzb::net_spec_from_raw(r), max_batch, precision);
     });
 }
 

@@ -123,6 +123,9 @@ static void upload(DeviceBuffer& buf, const std::vector<T>& host) {
 
 // ---------------------------------------------------------------------------------------------- Net
 Net::Net(int device, const void* onnx, size_t len, int max_batch, int precision)
+    : Net(device, build_net_spec(parse_onnx(onnx, len)), max_batch, precision) {}
+
+Net::Net(int device, NetSpec spec, int max_batch, int precision)
     : device_(device), max_batch_(max_batch), precision_(precision) {
     if (max_batch < 1) throw std::runtime_error("max_batch must be >= 1");
     if (precision != 0 && precision != 1) throw std::runtime_error("precision must be 0 (fp32) or 1 (bf16)");
@@ -137,7 +140,7 @@ Net::Net(int device, const void* onnx, size_t len, int max_batch, int precision)
     if (prop.major != 10) throw std::runtime_error("libkzb200 is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
     num_sms_ = prop.multiProcessorCount;
 
-    spec_ = build_net_spec(parse_onnx(onnx, len));
+    spec_ = std::move(spec);
     if (spec_.scalar_conv.cout + (spec_.has_extra ? 1 : 0) > 16) throw std::runtime_error("scalar head with more than 15 hidden channels is not supported");
     if (spec_.fc1.out > 128) throw std::runtime_error("scalar head hidden size > 128 is not supported");
     if (spec_.has_extra && spec_.extra_fc.out != 1) throw std::runtime_error("policy head with more than one extra move is not supported");
@@ -199,7 +202,8 @@ Net::~Net() {
     delete[] trace_;
     cudaSetDevice(device_);
     if (done_event_) cudaEventDestroy(done_event_);
-    if (full_batch_graph_) cudaGraphExecDestroy(full_batch_graph_);
+    for (auto& kv : graphs_)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (stream_) {
         cudaStreamSynchronize(stream_);
         cudaStreamDestroy(stream_);
@@ -911,29 +915,35 @@ void Net::eval_packed(const uint8_t* bits, const float* scalars, int batch, cons
     upload_packed(bits, scalars, batch, mv_idx, mv_off);
     if (trace) t1 = clk::now();
     *h_out_.as<volatile int>() = 0;  // error word; the tail kernel only ever writes non-zero into it
-    // The kernel sequence of a FULL batch without symmetries is captured once into a CUDA graph and replayed: one launch call
-    // instead of one per kernel (self-play batches are full 99 % of the time).  Every other shape takes the direct path.
-    const bool graphable = use_graph_ && batch == max_batch_ && cur_sym_ == nullptr;
-    if (graphable && full_batch_graph_) {
-        CK(cudaGraphLaunch(full_batch_graph_, stream_));
-    } else if (graphable) {
+    // The kernel sequence of a batch size that keeps coming back (the full batch above all: self-play batches are full 99 % of the
+    // time) is captured once into a CUDA graph and replayed: one launch call instead of one per kernel (46 for a 20-block go net).
+    // Evaluations with symmetries and one-off sizes take the direct path.
+    BatchGraph* bg = nullptr;
+    if (use_graph_ && cur_sym_ == nullptr) {
+        auto it = graphs_.find(batch);
+        if (it != graphs_.end()) bg = &it->second;
+        else if (graphs_.size() < kMaxGraphs) bg = &graphs_[batch];
+    }
+    if (bg && bg->exec) {
+        CK(cudaGraphLaunch(bg->exec, stream_));
+    } else if (bg && (++bg->seen >= 2 || batch == max_batch_)) {
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
         run_encode(batch, nullptr);
         run_network(batch, nullptr);
         run_tail(batch, true, nullptr, /*to_host=*/true);
         CK(cudaStreamEndCapture(stream_, &graph));
-        cudaError_t ge = cudaGraphInstantiate(&full_batch_graph_, graph, 0);
+        cudaError_t ge = cudaGraphInstantiate(&bg->exec, graph, 0);
         cudaGraphDestroy(graph);
         if (ge != cudaSuccess) {  // fall back to direct launches for good
             cudaGetLastError();
-            full_batch_graph_ = nullptr;
+            bg->exec = nullptr;
             use_graph_ = false;
             run_encode(batch, nullptr);
             run_network(batch, nullptr);
             run_tail(batch, true, nullptr, /*to_host=*/true);
         } else {
-            CK(cudaGraphLaunch(full_batch_graph_, stream_));
+            CK(cudaGraphLaunch(bg->exec, stream_));
         }
     } else {
         run_encode(batch, nullptr);

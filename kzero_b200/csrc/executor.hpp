@@ -5,6 +5,7 @@
 #include <functional>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "kernels.cuh"
@@ -64,6 +65,7 @@ struct ConvStep {
 class Net {
 public:
     Net(int device, const void* onnx, size_t len, int max_batch, int precision);
+    Net(int device, NetSpec spec, int max_batch, int precision);
     ~Net();
 
     void bind_mapper(int scalar_count, int bool_channels, int h, int w, int policy_len);
@@ -127,8 +129,16 @@ private:
     PinnedBuffer h_in_, h_out_;
     size_t mv_cap_ = 0;
     bool blocking_sync_ = false;
-    bool use_graph_ = true;                         // replay a captured graph for full batches (KZB_NO_GRAPH=1 disables)
-    cudaGraphExec_t full_batch_graph_ = nullptr;
+    // CUDA graphs of the kernel sequence, one per batch size that keeps coming back (KZB_NO_GRAPH=1 disables): the role of the
+    // reference's MultiBatchNetwork (rust/kz-core/src/network/multibatch.rs:19-35), without its padding -- a graph computes exactly
+    // its batch.  A size is captured the second time it is seen (the full batch: the first time); at most kMaxGraphs are kept.
+    bool use_graph_ = true;
+    static constexpr size_t kMaxGraphs = 48;
+    struct BatchGraph {
+        cudaGraphExec_t exec = nullptr;
+        int seen = 0;
+    };
+    std::unordered_map<int, BatchGraph> graphs_;
     int n_sym_ = 0;
     const uint8_t* cur_sym_ = nullptr;  // device pointer while an evaluation with symmetries is in flight
     DeviceBuffer d_sym_square_, d_sym_policy_, d_sym_;

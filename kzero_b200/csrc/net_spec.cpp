@@ -671,6 +671,9 @@ struct Matcher {
     void match_heads() {
         // network/common.rs:176-196: (scalars [B,5], policy [B]+policy_shape); the 3-output legacy form
         // (value, wdl, policy) is not produced by the reference's current exporter
+        if (g.outputs.size() == 3)
+            fail("3-output graphs (value, wdl, policy: the legacy form of rust/kz-core/src/network/common.rs:43-50) are not supported: no model class "
+                 "of the reference exports that form any more (save_onnx.py writes scalars, policy), so there is no architecture to recognise");
         if (g.outputs.size() != 2)
             fail("Wrong number of outputs, expected (scalars, policy), got " + std::to_string(g.outputs.size()));
         match_scalar_head(g.outputs[0].name);
@@ -697,6 +700,81 @@ double NetSpec::flops_per_position() const {
     f += 2.0 * fc1.in * fc1.out + 2.0 * fc2.in * fc2.out;
     if (has_extra) f += 2.0 * a * channels + 2.0 * extra_fc.in * extra_fc.out;
     return f;
+}
+
+namespace {
+[[noreturn]] void raw_fail(const std::string& what) { throw std::runtime_error("kzb_net_create: " + what); }
+ConvParams raw_conv(const RawConv& c, int cin, int cout, int ksize, const char* name) {
+    if (!c.w || !c.b) raw_fail(std::string(name) + ": weight / bias pointer is NULL");
+    if (c.cin != cin || c.ksize != ksize || (cout > 0 && c.cout != cout) || c.cout < 1)
+        raw_fail(std::string(name) + ": expected a " + std::to_string(ksize) + "x" + std::to_string(ksize) + " conv over " + std::to_string(cin) +
+                 " channels" + (cout > 0 ? " with " + std::to_string(cout) + " outputs" : "") + ", got cin " + std::to_string(c.cin) + ", cout " +
+                 std::to_string(c.cout) + ", ksize " + std::to_string(c.ksize));
+    ConvParams p;
+    p.cin = c.cin, p.cout = c.cout, p.ksize = c.ksize;
+    p.w.assign(c.w, c.w + size_t(c.cout) * c.cin * c.ksize * c.ksize);
+    p.b.assign(c.b, c.b + c.cout);
+    return p;
+}
+FcParams raw_fc(const RawFc& f, int in, int out, const char* name) {
+    if (!f.w || !f.b) raw_fail(std::string(name) + ": weight / bias pointer is NULL");
+    if (f.in != in || (out > 0 && f.out != out) || f.out < 1)
+        raw_fail(std::string(name) + ": expected " + std::to_string(in) + " inputs" + (out > 0 ? ", " + std::to_string(out) + " outputs" : "") + ", got " +
+                 std::to_string(f.in) + " -> " + std::to_string(f.out));
+    FcParams p;
+    p.in = f.in, p.out = f.out;
+    p.w.assign(f.w, f.w + size_t(f.in) * f.out);
+    p.b.assign(f.b, f.b + f.out);
+    return p;
+}
+// y = conv1x1(scale * x + shift): W' = W diag(scale), bias' = bias + W shift (exact: a 1x1 conv has no padding)
+void fold_affine_into(ConvParams& c, const float* scale, const float* shift) {
+    for (int o = 0; o < c.cout; o++) {
+        double extra = 0;
+        for (int i = 0; i < c.cin; i++) {
+            const double w = c.w[size_t(o) * c.cin + i];
+            extra += w * shift[i];
+            c.w[size_t(o) * c.cin + i] = float(w * scale[i]);
+        }
+        c.b[size_t(o)] = float(double(c.b[size_t(o)]) + extra);
+    }
+}
+}  // namespace
+
+NetSpec net_spec_from_raw(const RawNet& r) {
+    if (r.cin < 1 || r.board_h < 1 || r.board_w < 1 || r.channels < 1 || r.depth < 0) raw_fail("invalid shape");
+    if (r.depth > 0 && !r.blocks) raw_fail("blocks is NULL");
+    if ((r.final_scale == nullptr) != (r.final_shift == nullptr)) raw_fail("final_scale and final_shift must both be given or both be NULL");
+    NetSpec s;
+    s.cin = r.cin, s.board_h = r.board_h, s.board_w = r.board_w, s.channels = r.channels, s.depth = r.depth;
+    const int C = r.channels, A = r.board_h * r.board_w;
+    s.first = raw_conv(r.first, r.cin, C, 3, "first conv");
+    for (int i = 0; i < 2 * r.depth; i++) s.blocks.push_back(raw_conv(r.blocks[i], C, C, 3, "block conv"));
+    s.scalar_conv = raw_conv(r.scalar_conv, C, 0, 1, "scalar head conv");
+    s.fc1 = raw_fc(r.fc1, s.scalar_conv.cout * A, 0, "scalar head fc1");
+    s.fc2 = raw_fc(r.fc2, s.fc1.out, 5, "scalar head fc2");
+    s.policy_conv1 = raw_conv(r.policy_conv1, C, 0, 1, "policy conv1");
+    s.policy_conv2 = raw_conv(r.policy_conv2, s.policy_conv1.cout, 0, 1, "policy conv2");
+    s.has_extra = r.has_extra;
+    if (r.has_extra) {
+        s.extra_conv = raw_conv(r.extra_conv, C, 1, 1, "extra policy conv");
+        s.extra_fc = raw_fc(r.extra_fc, A, 0, "extra policy fc");
+    }
+    if (r.final_scale) {
+        fold_affine_into(s.scalar_conv, r.final_scale, r.final_shift);
+        fold_affine_into(s.policy_conv1, r.final_scale, r.final_shift);
+        if (r.has_extra) fold_affine_into(s.extra_conv, r.final_scale, r.final_shift);
+    }
+    if (r.policy_len < 1 || !r.policy_src) raw_fail("policy_src is NULL or policy_len < 1");
+    s.policy_len = r.policy_len;
+    s.policy_src.assign(r.policy_src, r.policy_src + r.policy_len);
+    for (int32_t v : s.policy_src) {
+        const bool conv_ok = v >= 0 && v < s.policy_conv2.cout * A;
+        const bool extra_ok = r.has_extra && v <= kPolicySrcExtra && v > kPolicySrcExtra - s.extra_fc.out;
+        if (!conv_ok && v != kPolicySrcZero && !extra_ok) raw_fail("policy_src entry " + std::to_string(v) + " is out of range");
+    }
+    s.policy_shape = {int64_t(r.policy_len)};
+    return s;
 }
 
 NetSpec build_net_spec(const OnnxGraph& g) {

@@ -81,4 +81,31 @@ struct NetSpec {
 // Throws std::runtime_error describing the first thing that does not match.
 NetSpec build_net_spec(const OnnxGraph& g);
 
+// The same NetSpec from weights the caller already holds (kzb_net_create, include/kzb200.h): convs with their in-block BatchNorm
+// already folded, the tower's trailing BatchNormalization as a per-channel affine y = scale * x + shift (folded into the head
+// convs here, like build_net_spec does).  Checks every shape and throws on the first mismatch.
+struct RawConv {
+    int cin, cout, ksize;
+    const float *w, *b;
+};
+struct RawFc {
+    int in, out;
+    const float *w, *b;
+};
+struct RawNet {
+    int cin, board_h, board_w, channels, depth;
+    RawConv first;
+    const RawConv* blocks;  // 2 * depth
+    const float *final_scale, *final_shift;  // [channels] or both null
+    RawConv scalar_conv;
+    RawFc fc1, fc2;
+    RawConv policy_conv1, policy_conv2;
+    bool has_extra;
+    RawConv extra_conv;
+    RawFc extra_fc;
+    int policy_len;
+    const int32_t* policy_src;  // [policy_len]
+};
+NetSpec net_spec_from_raw(const RawNet& r);
+
 }  // namespace kzb

@@ -154,9 +154,10 @@ def game_spec(name: str) -> GameSpec:
     if name.startswith("ataxx-"):  # games.py:144-159, ataxx.rs:21,94-104
         s = int(name.split("-")[1])
         return GameSpec(name, s, 3, 1, 17 * s * s + 1, 17, "ataxx")
-    if name.startswith("go-"):  # games.py:178-194 (4 bool + 6 scalar, the Python-exportable form)
+    if name.startswith("go-"):  # games.py:178-194 (4 bool + 6 scalar, the Python-exportable form); "go-N-territory": GoStdMapper::new(size,
+        # true), what the self-play server constructs (server.rs:193): three more bool planes (territory of us / them / nobody, go.rs:46-59)
         s = int(name.split("-")[1])
-        return GameSpec(name, s, 4, 6, s * s + 1, 1, "go")
+        return GameSpec(name, s, 7 if name.endswith("-territory") else 4, 6, s * s + 1, 1, "go")
     raise KeyError(name)
 
 
@@ -186,11 +187,14 @@ _BN = dict(epsilon=float(np.float32(1e-5)), momentum=float(np.float32(0.9)))
 
 def build_onnx(game: GameSpec, depth: int, channels: int, seed: int = 0, scalar_hidden_channels: int = 4,
                scalar_hidden_size: int = 32, query_channels: int = 32, fold_bn: bool = True,
-               weights_out: Optional[dict] = None) -> bytes:
+               weights_out: Optional[dict] = None, legacy_three_outputs: bool = False) -> bytes:
     """ONNX bytes for PredictionHeads(ResTower(depth, C_in, channels), ScalarHead, <policy head>).
 
     fold_bn=False keeps Conv -> BatchNormalization -> Relu un-folded inside blocks (what older torch
     versions / train-mode exports produce; Kyanite's optimiser folds those itself).
+
+    legacy_three_outputs: declare the outputs as (value [B], wdl [B, 3], policy), the legacy form network/common.rs:43-50 still accepts
+    and this library rejects at load time (only used to test that rejection).
 
     weights_out: optional dict that receives every initializer (name -> array; tower convs are w1/b1 = input conv,
     w2.. = block convs in order) -- what bench.py's library comparator builds the same tower from."""
@@ -300,6 +304,13 @@ def build_onnx(game: GameSpec, depth: int, channels: int, seed: int = 0, scalar_
 
     if weights_out is not None:
         weights_out.update(g.arrays)
+    if legacy_three_outputs:
+        i64 = lambda *v: g.node("Constant", [], value=np.array(v, dtype=np.int64))  # noqa: E731
+        v = g.node("Slice", ["scalars", i64(0), i64(1), i64(1), i64(1)])
+        g.node("Flatten", [v], out="value", axis=0)
+        g.node("Slice", ["scalars", i64(1), i64(4), i64(1), i64(1)], out="wdl")
+        return g.finish([("input", ["batch_size", game.input_channels, s, s])],
+                        [("value", ["batch_size"]), ("wdl", ["batch_size", 3]), ("policy", ["batch_size", policy_dim])])
     return g.finish([("input", ["batch_size", game.input_channels, s, s])],
                     [("scalars", ["batch_size", 5]), ("policy", ["batch_size", policy_dim])])
 
@@ -363,6 +374,10 @@ def synthetic_positions(game: GameSpec, n: int, seed: int = 0, min_moves: int = 
         planes[:, 2, :] = 1
         ko = rng.random(n) < 0.1
         planes[np.nonzero(ko)[0], 3, rng.integers(0, a, size=int(ko.sum()))] = 1
+        if cb == 7:  # territory planes: every point belongs to exactly one of us / them / nobody
+            owner = rng.integers(0, 3, size=(n, a))
+            for p in range(3):
+                planes[:, 4 + p, :] = owner == p
         stm = rng.integers(0, 2, n)
         scalars[:, 0] = stm
         scalars[:, 1] = 1 - stm

@@ -91,16 +91,64 @@ def inspect_onnx(onnx_bytes: bytes) -> NetInfo:
     return info
 
 
+class RawWeights:
+    """A kzb_net_spec built from numpy arrays (kept alive here): the input of kzb_net_create.
+
+    first / blocks[i] / scalar_conv / policy_conv1 / policy_conv2 / extra_conv: (w [cout, cin, k, k], b [cout]);
+    fc1 / fc2 / extra_fc: (w [out, in], b [out]); final_affine: (scale [C], shift [C]) or None; policy_src: int32 [policy_len]."""
+
+    def __init__(self, board, first, blocks, final_affine, scalar_conv, fc1, fc2, policy_conv1, policy_conv2, policy_src,
+                 extra_conv=None, extra_fc=None):
+        self._keep = []
+
+        def f32(a):
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            self._keep.append(a)
+            return a.ctypes.data_as(_abi._fp)
+
+        def conv(wb):
+            w, b = wb
+            return _abi.ConvWeights(int(w.shape[1]), int(w.shape[0]), int(w.shape[2]), f32(w), f32(b))
+
+        def fc(wb):
+            w, b = wb
+            return _abi.FcWeights(int(w.shape[1]), int(w.shape[0]), f32(w), f32(b))
+
+        s = _abi.NetSpecC()
+        s.board_h, s.board_w = (board, board) if isinstance(board, int) else board
+        s.input_channels, s.channels, s.depth = int(first[0].shape[1]), int(first[0].shape[0]), len(blocks) // 2
+        s.first = conv(first)
+        self._blocks = (_abi.ConvWeights * max(len(blocks), 1))(*[conv(b) for b in blocks])
+        s.blocks = ctypes.cast(self._blocks, ctypes.POINTER(_abi.ConvWeights))
+        if final_affine is not None:
+            s.final_scale, s.final_shift = f32(final_affine[0]), f32(final_affine[1])
+        s.scalar_conv, s.fc1, s.fc2 = conv(scalar_conv), fc(fc1), fc(fc2)
+        s.policy_conv1, s.policy_conv2 = conv(policy_conv1), conv(policy_conv2)
+        s.has_extra = int(extra_conv is not None)
+        if extra_conv is not None:
+            s.extra_conv, s.extra_fc = conv(extra_conv), fc(extra_fc)
+        src = np.ascontiguousarray(policy_src, dtype=np.int32)
+        self._keep.append(src)
+        s.policy_len, s.policy_src = int(src.size), src.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+        self.spec = s
+
+
 class B200Network:
     """Drop-in for `CudaNetwork<B, M>` (network/cudnn.rs:18-88) behind the same evaluate_batch contract."""
 
-    def __init__(self, mapper: Mapper, onnx_bytes: bytes, max_batch_size: int, device: int = 0,
+    def __init__(self, mapper: Mapper, onnx_bytes, max_batch_size: int, device: int = 0,
                  precision: int = PRECISION_BF16):
+        """onnx_bytes: the ONNX file's bytes (kzb_net_create_from_onnx), or a `RawWeights` (kzb_net_create: weights the caller
+        already holds, e.g. the constants of a Graph the reference's own `load_graph` produced)."""
         self._lib = _abi.lib()
         self._handle = ctypes.c_void_p()
         self.mapper = mapper
-        _abi.check(self._lib.kzb_net_create_from_onnx(device, onnx_bytes, len(onnx_bytes), int(max_batch_size),
-                                                      int(precision), ctypes.byref(self._handle)))
+        if isinstance(onnx_bytes, RawWeights):
+            _abi.check(self._lib.kzb_net_create(device, ctypes.byref(onnx_bytes.spec), int(max_batch_size), int(precision),
+                                                ctypes.byref(self._handle)))
+        else:
+            _abi.check(self._lib.kzb_net_create_from_onnx(device, onnx_bytes, len(onnx_bytes), int(max_batch_size),
+                                                          int(precision), ctypes.byref(self._handle)))
         try:
             _, w, h = mapper.input_bool_shape
             # check_graph_shapes(mapper, graph), network/common.rs:165-198

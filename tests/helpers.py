@@ -58,3 +58,30 @@ def bf16_emulation(onnx_bytes, residual_bf16=True):
             return out
 
     return Emulation(onnx_bytes, conv_backend="torch")
+
+
+def raw_weights_from_netgen(spec, depth, weights):
+    """kzero_b200.network.RawWeights (the input of kzb_net_create) from the initializers netgen.build_onnx reports through
+    `weights_out` (conv-policy heads: chess conv + gather, ataxx, go)."""
+    from kzero_b200 import mapping
+    from kzero_b200.network import RawWeights
+
+    a = spec.area
+    conv = lambda k: (weights[f"w{k}"], weights[f"b{k}"])  # noqa: E731
+    fc = lambda k: (weights[f"fc_w{k}"], weights[f"fc_b{k}"])  # noqa: E731
+    k = 2 * depth + 1
+    gamma, beta, mean, var = (weights[f"final_bn.{n}"].astype(np.float64) for n in ("weight", "bias", "running_mean", "running_var"))
+    scale = gamma / np.sqrt(var + np.float64(np.float32(1e-5)))
+    affine = (scale.astype(np.float32), (beta - scale * mean).astype(np.float32))
+    extra = {}
+    if spec.head == "chess_conv":
+        src = mapping.chess_flat_to_conv()
+    elif spec.head == "ataxx":
+        src = np.concatenate([np.arange(spec.policy_size - 1), [-1]])
+    elif spec.head == "go":
+        src = np.concatenate([np.arange(a), [-2]])
+        extra = dict(extra_conv=conv(k + 6), extra_fc=fc(k + 7))
+    else:
+        raise KeyError(spec.head)
+    return RawWeights(spec.board_size, conv(1), [conv(i) for i in range(2, k + 1)], affine, conv(k + 1), fc(k + 2), fc(k + 3),
+                      conv(k + 4), conv(k + 5), src, **extra)

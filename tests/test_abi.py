@@ -99,3 +99,45 @@ def test_product_does_not_import_oracle():
         if path.suffix in (".py", ".cu", ".cpp", ".hpp", ".cuh", ".h"):
             text = path.read_text()
             assert "import oracle" not in text and "from oracle" not in text and "kz_oracle" not in text, path
+
+
+def test_net_create_from_raw_weights_checks_shapes_before_touching_a_device():
+    """kzb_net_create (weights the caller already holds, so the reference's load_graph stays untouched): shape errors are reported
+    with a message, and a well-formed spec gets as far as the device -- which is missing here."""
+    import numpy as np
+    import pytest
+
+    from helpers import raw_weights_from_netgen
+    from kzero_b200 import netgen
+    from kzero_b200.network import B200Network, KzbError, mapper_for
+
+    spec = netgen.game_spec("go-9")
+    weights = {}
+    netgen.build_onnx(spec, 2, 32, seed=3, weights_out=weights)
+    raw = raw_weights_from_netgen(spec, 2, weights)
+    assert (raw.spec.input_channels, raw.spec.channels, raw.spec.depth, raw.spec.policy_len, raw.spec.has_extra) == (10, 32, 2, 82, 1)
+    with pytest.raises(KzbError, match="no CUDA device|CUDA"):  # everything host-side was accepted
+        B200Network(mapper_for(spec), raw, 4)
+    bad = dict(weights)
+    bad["w3"] = np.zeros((32, 31, 3, 3), np.float32)
+    with pytest.raises(KzbError, match="block conv: expected a 3x3 conv over 32 channels"):
+        B200Network(mapper_for(spec), raw_weights_from_netgen(spec, 2, bad), 4)
+    raw = raw_weights_from_netgen(spec, 2, weights)
+    raw.spec.policy_src[5] = 81 * 1 + 7  # beyond the 1-channel policy map
+    with pytest.raises(KzbError, match="policy_src entry"):
+        B200Network(mapper_for(spec), raw, 4)
+
+
+def test_three_output_graphs_are_rejected_with_a_message():
+    """The legacy 3-output graph form (value [B], wdl [B, 3], policy; rust/kz-core/src/network/common.rs:43-50,181-196) is not
+    produced by the reference's exporter (save_onnx.py:111-119 writes `scalars`, `policy`) and is not supported here: loading one
+    fails at inspect / create time with a message that says so -- it never evaluates to something else."""
+    import pytest
+
+    from kzero_b200 import netgen
+    from kzero_b200.network import KzbError, inspect_onnx
+
+    spec = netgen.game_spec("ataxx-7")
+    onnx_bytes = netgen.build_onnx(spec, 1, 16, seed=1, legacy_three_outputs=True)
+    with pytest.raises(KzbError, match="3-output"):
+        inspect_onnx(onnx_bytes)

@@ -403,3 +403,66 @@ def test_concurrent_instances_match(tmp_path):
     for t in threads:
         t.join()
     assert not failures, failures
+
+
+# ------------------------------------------------------------------------------------------- boundary loose ends
+@pytest.mark.parametrize("game,depth,ch", [("chess", 2, 64), ("ataxx-7", 2, 32), ("go-9", 2, 64)])
+def test_net_created_from_raw_weights_equals_the_onnx_net(game, depth, ch):
+    """kzb_net_create (weights the caller already holds: the reference's load_graph stays untouched and hands the optimised Graph's
+    constants over, network/cudnn.rs:29-43) must give the network kzb_net_create_from_onnx builds from the file."""
+    from helpers import raw_weights_from_netgen
+
+    spec = netgen.game_spec(game)
+    weights = {}
+    onnx_bytes = netgen.build_onnx(spec, depth, ch, seed=71, weights_out=weights)
+    bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, 21, seed=72)
+    for precision, tol in ((PRECISION_FP32, 2e-6), (PRECISION_BF16, 2e-3)):
+        with B200Network(mapper_for(spec), onnx_bytes, 24, precision=precision) as a:
+            va, pa = a.evaluate_packed(bits, scalars, mv_idx, mv_off)
+        with B200Network(mapper_for(spec), raw_weights_from_netgen(spec, depth, weights), 24, precision=precision) as b:
+            assert (b.info().channels, b.info().depth, b.info().policy_len) == (ch, depth, spec.policy_size)
+            vb, pb = b.evaluate_packed(bits, scalars, mv_idx, mv_off)
+        # not bit-identical: the final BN reaches this path as an f32 affine, the ONNX path folds it in f64
+        assert np.abs(va - vb).max() <= tol and np.abs(pa - pb).max() <= tol
+
+
+def test_go_with_territory_planes_13_channels():
+    """GoStdMapper::new(size, true), what the reference's self-play SERVER constructs (rust/kz-selfplay/src/server/server.rs:193;
+    mapping/go.rs:46-59): 6 scalar + 7 bool planes = 13 input channels.  Same encode / tower / heads path as the 10-channel form."""
+    spec = netgen.game_spec("go-9-territory")
+    assert (spec.scalar_channels, spec.bool_channels, spec.input_channels) == (6, 7, 13)
+    onnx_bytes = netgen.build_onnx(spec, 3, 64, seed=81)
+    bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, 33, seed=82)
+    ref_s, ref_p, ref_values, ref_probs = _oracle_packed(spec, onnx_bytes, bits, scalars, mv_idx, mv_off)
+    with B200Network(mapper_for(spec), onnx_bytes, 40, precision=PRECISION_FP32) as net:
+        planes = net.encode_planes(bits, scalars)
+        values, probs = net.evaluate_packed(bits, scalars, mv_idx, mv_off)
+    assert np.array_equal(planes.view(np.uint32), _oracle_planes(spec, bits, scalars).view(np.uint32))
+    _check_packed(values, probs, ref_values, ref_probs, mv_off, FP32_TOL, FP32_TOL)
+    with B200Network(mapper_for(spec), onnx_bytes, 40, precision=PRECISION_BF16) as net:
+        values, probs = net.evaluate_packed(bits, scalars, mv_idx, mv_off)
+        s, p = net.evaluate_planes(_oracle_planes(spec, bits, scalars))
+    assert np.abs(p - ref_p).max() <= BF16_POLICY_TOL
+    _check_packed(values, probs, ref_values, ref_probs, mv_off, 5e-2, 1e-2)
+
+
+@pytest.mark.parametrize("game,depth,ch", [("chess", 3, 64), ("go-9", 3, 64)])
+def test_partial_batches_replay_their_own_cuda_graph(game, depth, ch, monkeypatch):
+    """Batch sizes that keep coming back get a CUDA graph of their own (the role of MultiBatchNetwork, network/multibatch.rs:19-35,
+    without padding rows): first call direct launches, second call captures + launches, third call replays -- all bit-identical to
+    each other and to a network that never uses graphs; interleaved sizes keep their own graphs."""
+    spec = netgen.game_spec(game)
+    onnx_bytes = netgen.build_onnx(spec, depth, ch, seed=91)
+    bits, scalars, mv_idx, mv_off = netgen.synthetic_positions(spec, 64, seed=92)
+
+    def part(n):
+        return bits[:n], scalars[:n], mv_idx[:mv_off[n]], mv_off[:n + 1]
+
+    monkeypatch.setenv("KZB_NO_GRAPH", "1")
+    with B200Network(mapper_for(spec), onnx_bytes, 64) as net:
+        want = {n: net.evaluate_packed(*part(n)) for n in (64, 37, 5)}
+    monkeypatch.setenv("KZB_NO_GRAPH", "0")
+    with B200Network(mapper_for(spec), onnx_bytes, 64) as net:
+        for n in (37, 64, 37, 5, 37, 64, 5, 5, 37):
+            v, p = net.evaluate_packed(*part(n))
+            assert np.array_equal(v, want[n][0]) and np.array_equal(p, want[n][1]), n

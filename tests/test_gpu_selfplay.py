@@ -22,6 +22,24 @@ def test_selfplay_runs_and_counts_are_consistent(game, game_name, gpu_threads):
     assert r.mcts_nodes_per_s >= r.nn_positions_per_s > 0
 
 
+@pytest.mark.parametrize("game,name,twin", [(selfplay.GAME_ATAXX7, "ataxx-7", "Ataxx7"), (selfplay.GAME_GO9, "go-9", "Go9"),
+                                            (selfplay.GAME_CHESS, "chess", "Chess")])
+def test_games_the_gpu_played_replay_under_the_oracle_rules(tmp_path, game, name, twin):
+    """What the GPU driver PLAYED, not only how much: every recorded game -- searched with a real network on the B200 evaluator,
+    ragged batches, several executors -- is replayed under the oracle's independent restatement of the rules (legal move lists,
+    encodings, transitions, outcomes), and the file is read by the same checks as the host-only records."""
+    from test_selfplay_records import replay_under_oracle_rules
+
+    spec = netgen.game_spec(name)
+    onnx_bytes = netgen.build_onnx(spec, 2, 32, seed=41)
+    prefix = str(tmp_path / "games_0")
+    cfg = selfplay.default_config(game=game, visits=40, search_batch=8, gpu_batch=64, cpu_threads=2, gpu_threads=2, max_moves=300,
+                                  max_game_length=30 if game != selfplay.GAME_ATAXX7 else 400, duration_s=60.0, output_prefix=prefix, seed=9)
+    r = selfplay.run(onnx_bytes, cfg)
+    assert r.games_written > 0 and r.real_evals > 0 and r.batches > 0
+    assert replay_under_oracle_rules(prefix, name, twin) >= 40
+
+
 def test_selfplay_rejects_mismatched_network():
     from kzero_b200.network import KzbError
 

@@ -125,15 +125,12 @@ def test_reference_loader_reads_the_records(tmp_path, game, name):
     assert sum(sim.position_count for sim in sims) == f.info.position_count
 
 
-@pytest.mark.parametrize("game,name,twin", [(selfplay.GAME_ATAXX7, "ataxx-7", "Ataxx7"), (selfplay.GAME_GO9, "go-9", "Go9"),
-                                            (selfplay.GAME_CHESS, "chess", "Chess")])
-def test_recorded_games_replay_under_the_oracle_rules(tmp_path, game, name, twin):
-    """Every recorded game is replayed move by move with the oracle's independent restatement of the rules: at each
-    position the recorded input planes and scalars are the twin's encoding, the recorded policy indices are the twin's
-    legal moves in order, and the recorded played move leads to the next recorded position (N1 + N2 end to end)."""
+def replay_under_oracle_rules(prefix, name, twin):
+    """Replays every game of a record file move by move with the oracle's independent restatement of the rules: at each position
+    the recorded input planes and scalars are the twin's encoding, the recorded policy indices are the twin's legal moves in
+    order, and the recorded played move leads to the next recorded position.  -> number of moves checked."""
     from oracle import mcts_oracle as mo
 
-    prefix, r = _run(tmp_path, game)
     shape = {"ataxx-7": (3, 7, 7), "go-9": (4, 9, 9), "chess": (13, 8, 8)}[name]
     meta, positions, game_starts = _parse(prefix, int(np.prod(shape)), {"ataxx-7": 1, "go-9": 6, "chess": 8}[name])
     checked = 0
@@ -155,6 +152,8 @@ def test_recorded_games_replay_under_the_oracle_rules(tmp_path, game, name, twin
                 assert bool(p["scalars"][5]) and bool(p["scalars"][6]) == board.done()
                 break
             assert p["indices"].tolist() == board.moves(), (g, k)
+            assert int(p["scalars"][9]) in p["indices"].tolist()         # the played move is one of the available moves
+            assert abs(float(p["values"].sum()) - 1.0) < 1e-3, (g, k)  # the visit distribution over them
             board.play(int(p["scalars"][9]))
             checked += 1
         # the recorded result of the game, from every position's side to move (Outcome::Draw when the length cap ended it,
@@ -164,4 +163,12 @@ def test_recorded_games_replay_under_the_oracle_rules(tmp_path, game, name, twin
             sc = positions[first + k]["scalars"]
             pov = outcome if k % 2 == 0 else -outcome  # player A moves first in all three games
             assert sc[11] == pov and sc[12:15].tolist() == [float(pov > 0), float(pov == 0), float(pov < 0)], (g, k, sc[11:15], pov)
-    assert checked >= 40
+    return checked
+
+
+@pytest.mark.parametrize("game,name,twin", [(selfplay.GAME_ATAXX7, "ataxx-7", "Ataxx7"), (selfplay.GAME_GO9, "go-9", "Go9"),
+                                            (selfplay.GAME_CHESS, "chess", "Chess")])
+def test_recorded_games_replay_under_the_oracle_rules(tmp_path, game, name, twin):
+    """N1 + N2 end to end on the host (DummyNetwork stand-in); tests/test_gpu_selfplay.py does the same with games the GPU played."""
+    prefix, r = _run(tmp_path, game)
+    assert replay_under_oracle_rules(prefix, name, twin) >= 40
