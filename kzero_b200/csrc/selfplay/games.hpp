@@ -32,6 +32,37 @@ struct GameShape {
     int bits_bytes() const { return (bool_channels * board * board + 7) / 8; }
 };
 
+// ------------------------------------------------------------------------------------------------ MaxMoves
+// board-game's MaxMovesBoard, which the reference wraps every self-play board in BEFORE it builds a search tree
+// (rust/kz-selfplay/src/server/generator_alphazero.rs:86-87): the game is over -- a draw -- once `max_moves` moves have been played,
+// and the search sees that as well: a position at the limit is a terminal draw inside the tree, not a leaf the network evaluates.
+// The move count is part of the board's identity (the wrapper derives Hash / Eq over it), so it is part of the cache key here.
+template <typename G>
+struct MaxMoves {
+    G inner;
+    uint32_t moves_played = 0, max_moves = 0xFFFFFFFFu;
+
+    static GameShape shape() { return G::shape(); }
+    static const char* name() { return G::name(); }
+    static MaxMoves start(uint64_t seed) {
+        MaxMoves b;
+        b.inner = G::start(seed);
+        return b;
+    }
+    bool at_limit() const { return moves_played >= max_moves; }
+    bool done() const { return inner.done() || at_limit(); }
+    int outcome() const { return inner.done() ? inner.outcome() : 0; }
+    int next_player() const { return inner.next_player(); }
+    void moves(std::vector<uint32_t>& out) const { inner.moves(out); }
+    uint32_t move_to_index(uint32_t mv) const { return inner.move_to_index(mv); }
+    void play(uint32_t mv) {
+        inner.play(mv);
+        moves_played++;
+    }
+    uint64_t hash() const { return splitmix64(inner.hash() ^ (uint64_t(moves_played) * 0x9E3779B97F4A7C15ull)); }
+    void encode(uint8_t* bits, float* scalars) const { inner.encode(bits, scalars); }
+};
+
 // ------------------------------------------------------------------------------------------------ SynthChess
 struct SynthChess {
     uint64_t h = 0;

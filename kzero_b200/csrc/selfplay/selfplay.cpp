@@ -143,8 +143,9 @@ struct Slot {
     Job job;
     RecordedGame record;   // only filled when records are written
     Eval root_net_eval;    // the network's own evaluation of the root (generator_alphazero.rs:226-229)
-    Slot(uint64_t seed, size_t cache_size, size_t visits)
+    Slot(uint64_t seed, size_t cache_size, size_t visits, uint32_t max_game_length)
         : board(Game::start(seed)), cache(cache_size), rng(seed ^ 0x5EEDull), next_seed(seed + 0x1000) {
+        board.max_moves = max_game_length;
         tree = std::make_unique<Tree<Game>>(board);
         tree->reserve(visits * 48 + 64, visits * 2 + 64);
     }
@@ -269,11 +270,12 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                     slot.board.play(mv);
                     slot.move_count++;
                     slot.target_visits = 0;
-                    if (slot.board.done() || slot.move_count >= uint32_t(c.max_game_length)) {
+                    slot.board.max_moves = uint32_t(c.max_game_length);  // Settings::max_game_length may change between generations
+                    if (slot.board.done()) {  // the game's own end, or the length cap (a draw: MaxMovesBoard)
                         if (sh.writer) {
                             encode_record(slot.board, shape, slot.record.final_position);
-                            slot.record.final_done = slot.board.done();
-                            slot.record.outcome = slot.board.done() ? slot.board.outcome() : 0;
+                            slot.record.final_done = slot.board.inner.done();
+                            slot.record.outcome = slot.board.outcome();
                             {
                                 std::lock_guard<std::mutex> lk(sh.writer_mu);
                                 sh.writer->append(slot.record);
@@ -282,6 +284,7 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                         }
                         sh.games.fetch_add(1, std::memory_order_relaxed);
                         slot.board = Game::start(slot.next_seed++);
+                        slot.board.max_moves = uint32_t(c.max_game_length);
                         slot.move_count = 0;
                         slot.cache.clear();  // a new cache for every game (generator_alphazero.rs:77-79)
                     }
@@ -543,7 +546,8 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
     if (per_thread.empty()) {
         per_thread.resize(size_t(c.cpu_threads));
         for (int g = 0; g < games; g++)
-            per_thread[size_t(g % c.cpu_threads)].push_back(std::make_unique<Slot<Game>>(c.seed * 1000003ull + uint64_t(g) * 7919ull + 1, size_t(c.cache_size), size_t(c.visits)));
+            per_thread[size_t(g % c.cpu_threads)].push_back(std::make_unique<Slot<Game>>(c.seed * 1000003ull + uint64_t(g) * 7919ull + 1, size_t(c.cache_size), size_t(c.visits),
+                                                                                         uint32_t(c.max_game_length)));
     } else {
         if (per_thread.size() != size_t(c.cpu_threads)) throw std::runtime_error("selfplay session: cpu_threads is a startup setting and cannot change between runs");
         games = 0;
@@ -758,10 +762,10 @@ KZB_API int kzb_selfplay_run(int device, const void* onnx_bytes, size_t onnx_len
         if (!config || !stats) throw std::runtime_error("config and stats must not be NULL");
         if (!onnx_bytes && !config->dummy_network) throw std::runtime_error("onnx_bytes must not be NULL unless dummy_network is set");
         std::memset(stats, 0, sizeof(*stats));
-        if (config->game == KZB_GAME_SYNTH_CHESS) run_selfplay<SynthChess>(device, onnx_bytes, onnx_len, precision, *config, *stats);
-        else if (config->game == KZB_GAME_ATAXX7) run_selfplay<Ataxx>(device, onnx_bytes, onnx_len, precision, *config, *stats);
-        else if (config->game == KZB_GAME_GO9) run_selfplay<Go9>(device, onnx_bytes, onnx_len, precision, *config, *stats);
-        else if (config->game == KZB_GAME_CHESS) run_selfplay<Chess>(device, onnx_bytes, onnx_len, precision, *config, *stats);
+        if (config->game == KZB_GAME_SYNTH_CHESS) run_selfplay<MaxMoves<SynthChess>>(device, onnx_bytes, onnx_len, precision, *config, *stats);
+        else if (config->game == KZB_GAME_ATAXX7) run_selfplay<MaxMoves<Ataxx>>(device, onnx_bytes, onnx_len, precision, *config, *stats);
+        else if (config->game == KZB_GAME_GO9) run_selfplay<MaxMoves<Go9>>(device, onnx_bytes, onnx_len, precision, *config, *stats);
+        else if (config->game == KZB_GAME_CHESS) run_selfplay<MaxMoves<Chess>>(device, onnx_bytes, onnx_len, precision, *config, *stats);
         else throw std::runtime_error("unknown game");
     });
 }
@@ -778,10 +782,10 @@ KZB_API int kzb_selfplay_session_create(int game, kzb_selfplay_session** out) {
     return guarded([&] {
         if (!out) throw std::runtime_error("out must not be NULL");
         auto s = std::make_unique<kzb_selfplay_session>();
-        if (game == KZB_GAME_SYNTH_CHESS) s->impl = std::make_unique<Session<SynthChess>>();
-        else if (game == KZB_GAME_ATAXX7) s->impl = std::make_unique<Session<Ataxx>>();
-        else if (game == KZB_GAME_GO9) s->impl = std::make_unique<Session<Go9>>();
-        else if (game == KZB_GAME_CHESS) s->impl = std::make_unique<Session<Chess>>();
+        if (game == KZB_GAME_SYNTH_CHESS) s->impl = std::make_unique<Session<MaxMoves<SynthChess>>>();
+        else if (game == KZB_GAME_ATAXX7) s->impl = std::make_unique<Session<MaxMoves<Ataxx>>>();
+        else if (game == KZB_GAME_GO9) s->impl = std::make_unique<Session<MaxMoves<Go9>>>();
+        else if (game == KZB_GAME_CHESS) s->impl = std::make_unique<Session<MaxMoves<Chess>>>();
         else throw std::runtime_error("unknown game");
         s->impl->game = game;
         *out = s.release();

@@ -33,7 +33,7 @@ def test_games_the_gpu_played_replay_under_the_oracle_rules(tmp_path, game, name
     spec = netgen.game_spec(name)
     onnx_bytes = netgen.build_onnx(spec, 2, 32, seed=41)
     prefix = str(tmp_path / "games_0")
-    cfg = selfplay.default_config(game=game, visits=40, search_batch=8, gpu_batch=64, cpu_threads=2, gpu_threads=2, max_moves=300,
+    cfg = selfplay.default_config(game=game, visits=40, search_batch=8, gpu_batch=64, cpu_threads=2, gpu_threads=2, max_games=6,
                                   max_game_length=30 if game != selfplay.GAME_ATAXX7 else 400, duration_s=60.0, output_prefix=prefix, seed=9)
     r = selfplay.run(onnx_bytes, cfg)
     assert r.games_written > 0 and r.real_evals > 0 and r.batches > 0
