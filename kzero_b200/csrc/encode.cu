@@ -127,6 +127,8 @@ __global__ void encode_kc_kernel(EncodeParams p, const float* __restrict__ nchw,
     float* s_scalars = reinterpret_cast<float*>(smem);
     uint8_t* s_bits = smem + ((p.scalar_count * 4 + 15) / 16) * 16;
     const int b = blockIdx.x;
+    // the tower kernel is launched with programmatic stream serialization: let it set itself up (it waits before it reads the planes)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (PACKED) {
         for (int i = threadIdx.x; i < p.scalar_count; i += blockDim.x) s_scalars[i] = p.scalars[size_t(b) * p.scalar_count + i];
         for (int i = threadIdx.x; i < p.bits_stride; i += blockDim.x) s_bits[i] = p.bits[size_t(b) * p.bits_stride + i];

@@ -553,6 +553,10 @@ void Net::build_bf16() {
         const char* bs = std::getenv("KZB_B_SLOTS");
         if (bs && std::atoi(bs) >= 2 && std::atoi(bs) <= tp.b_slots) tp.b_slots = std::atoi(bs);
         tp.timeline = nullptr;
+        {
+            const char* pdl_env = std::getenv("KZB_PDL");  // KZB_PDL=0: plain stream order between encode, tower and heads
+            tp.pdl = (pdl_env && pdl_env[0] == '0') ? 0 : 1;
+        }
         const char* dbg = std::getenv("KZB_DEBUG");
         tp.debug = dbg ? std::atoi(dbg) : 0;
         use_tower8k_ = true;
@@ -807,6 +811,7 @@ void Net::run_tail(int batch, bool packed, const StepHook& hook, bool to_host) {
             p.out_probs = reinterpret_cast<float*>(out + 16 + align16(size_t(max_batch_) * 5 * 4));
         }
         p.timeline = timeline_step_ == "heads8" ? d_timeline_.as<unsigned long long>() : nullptr;
+        p.pdl = (use_tower8k_ && tower_params_.pdl) ? 1 : 0;  // only behind the tower kernel, which triggers the dependent launch
         launch_heads8(heads_maps_, p, num_sms_, stream_);
         if (hook) hook("heads8");
         return;

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 tma_load_2d(&maps.ws, sm.w_full, sm.ws + size_t(k) * 16 * 128, k * 64, 0);
             }
             for (int k = 0; k < kb2; k++) tma_load_2d(&maps.w2, sm.w_full, sm.w2 + size_t(k) * p.n2 * 128, k * 64, 0);
+            if (p.pdl) grid_dep_wait();  // the tower's output rows; the weights above do not depend on it
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -440,7 +441,17 @@ void heads8_prepare() { cudaFuncSetAttribute(heads8_kernel, cudaFuncAttributeMax
 
 void launch_heads8(const Heads8Maps& maps, const Heads8Params& p, int grid, cudaStream_t s) {
     if (p.num_tiles <= 0) return;
-    heads8_kernel<<<std::min(grid, p.num_tiles), kThreads, heads8_smem_bytes(p), s>>>(maps, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(std::min(grid, p.num_tiles)));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = heads8_smem_bytes(p);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, heads8_kernel, maps, p);
 }
 
 }  // namespace kzb

@@ -142,6 +142,7 @@ struct Tower8Params {
     int board_w, board_h;
     // tower8k only: balanced board assignment (CTA c owns bal_base + (c < bal_rem) contiguous boards as two units of 4 / 3)
     int balanced, bal_base, bal_rem, bal_grid;
+    int pdl;  // launched with programmatic stream serialization: set-up overlaps the encode kernel, which runs right before it
     unsigned long long* timeline;
     int debug;  // development aid (KZB_DEBUG): 1 = skip A loads, 2 = skip B loads, 4 = skip epilogue memory traffic
 };
@@ -234,6 +235,7 @@ struct Heads8Params {
     int* err_flag;
     float* out_scalars;
     float* out_logits;
+    int pdl;  // launched with programmatic stream serialization: set-up and the resident weights' loads overlap the tower's tail
     unsigned long long* timeline;  // development aid (KZB_TIMELINE=heads8): per-CTA clock64() stamps
 };
 size_t heads8_smem_bytes(const Heads8Params& p);

@@ -160,10 +160,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
     constexpr uint16_t kMask = uint16_t((1u << CL) - 1);
     if (tl && threadIdx.x == 0) tl[1] = clock64();
+    if (p.pdl) grid_dep_launch_dependents();  // the head kernel may set itself up on every SM this kernel leaves
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
+            if (p.pdl) grid_dep_wait();  // the planes of layer 0 are the encode kernel's output (everything above overlapped it)
             const uint32_t w_bytes = uint32_t(p.n) * 128u;
             const int n_local = local_units(p);
             int x_slot = 0, w_slot = 0;
@@ -439,13 +441,15 @@ void launch_tower8k(const Tower8kMaps& maps, const Tower8Params& p, int grid, cu
         cfg.blockDim = dim3(kThreads);
         cfg.dynamicSmemBytes = tower8k_smem_bytes(p.b_slots);
         cfg.stream = s;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = p.pdl ? 2 : 1;
         cudaLaunchKernelEx(&cfg, tower8k_kernel<2>, maps, p);
     } else {
         tower8k_kernel<1><<<p.balanced ? p.bal_grid : std::min(grid, p.num_units), kThreads, tower8k_smem_bytes(p.b_slots), s>>>(maps, p);
