@@ -288,8 +288,8 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                         slot.move_count = 0;
                         slot.cache.clear();  // a new cache for every game (generator_alphazero.rs:77-79)
                     }
-                    slot.tree = std::make_unique<Tree<Game>>(slot.board);
-                    slot.tree->reserve(size_t(c.visits) * 48 + 64, size_t(c.visits) * 2 + 64);
+                    slot.tree->reset(slot.board);
+                    slot.tree->reserve(size_t(c.visits) * 48 + 64, size_t(c.visits) * 2 + 64);  // no-op unless `visits` grew
                     clock.lap(kSecMove);
                     continue;
                 }
