@@ -382,6 +382,16 @@ struct Chess {
     }
     uint32_t move_to_index(uint32_t mv) const { return mv; }
     void play(uint32_t index) {
+        apply_move(index);
+        update_terminal();
+    }
+    // the same move into a position the caller knows not to be terminal (mcts.hpp: the tree already holds its children): skips the
+    // search for a legal reply; everything later tests need (repetitions, material, clocks) is kept
+    void play_interior(uint32_t index) {
+        apply_move(index);
+        terminal = 0;
+    }
+    void apply_move(uint32_t index) {
         using namespace chess_detail;
         const auto& t = flat_moves();
         const Mv m{uint8_t(pov_square(t.from[index], side)), uint8_t(pov_square(t.to[index], side)), int8_t(t.promo[index])};
@@ -430,7 +440,6 @@ struct Chess {
         key = piece_key ^ state_key();
         for (int i = int(hist_n) - 2; i >= 0; i -= 2)  // same side to move: every second entry back
             if (hist[i] == key) reps++;
-        update_terminal();
     }
 
     void encode(uint8_t* bits, float* scalars) const {  // ChessStdMapper::encode_input, chess.rs:138-170

@@ -59,6 +59,14 @@ struct MaxMoves {
         inner.play(mv);
         moves_played++;
     }
+    void play_interior(uint32_t mv) {  // into a position known not to be terminal (neither the game's end nor the length cap)
+        play_inner_interior(inner, mv, 0);
+        moves_played++;
+    }
+    template <typename T>
+    static auto play_inner_interior(T& b, uint32_t mv, int) -> decltype(b.play_interior(mv), void()) { b.play_interior(mv); }
+    template <typename T>
+    static void play_inner_interior(T& b, uint32_t mv, long) { b.play(mv); }
     uint64_t hash() const { return splitmix64(inner.hash() ^ (uint64_t(moves_played) * 0x9E3779B97F4A7C15ull)); }
     void encode(uint8_t* bits, float* scalars) const { inner.encode(bits, scalars); }
 };

@@ -267,6 +267,17 @@ __attribute__((target("avx2"))) inline void argmax_blocks_avx2(const float* u, i
     argmax_scan(u, i, n, best, arg, ties, nan, rng);
 }
 #endif
+// Game::play_interior(move), where a game offers it: play a move into a position that is KNOWN not to be terminal (the search tree
+// already holds its children), skipping whatever the game does to find out -- for chess the search for a legal reply
+template <typename Game>
+auto play_move(Game& b, uint32_t mv, bool known_not_terminal) -> decltype(b.play_interior(mv), void()) {
+    if (known_not_terminal) b.play_interior(mv);
+    else b.play(mv);
+}
+template <typename Game, typename... Ignored>
+void play_move(Game& b, uint32_t mv, bool, Ignored...) {
+    b.play(mv);
+}
 inline int argmax_random_ties(const float* u, int n, Rng& rng) {
     float best = u[0];
     int arg = 0;
@@ -559,13 +570,14 @@ StepResult descent_step(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Des
         arg = detail::argmax_random_ties(u, n, rng);
     }
     if (arg < 0) throw std::logic_error("Board is not done, this node should have a child");
-    board.play(tree.last_move[size_t(c0 + arg)]);
     const int j = tree.visit_child(cur, arg);  // may move cur's block: take the row from the tree again
     const Node& now = tree.nodes[size_t(cur)];
     ChildStat* row = tree.block_rows(now) + j;
     row->virt += 1;
     d.cur = row->node;
     d.cur_row = int(row - tree.arena.data());
+    // a child that has children of its own was found not to be terminal when it was first reached: the game may skip that test
+    detail::play_move(board, tree.last_move[size_t(c0 + arg)], tree.nodes[size_t(d.cur)].child_start >= 0);
     return StepResult::kDescend;
 }
 
