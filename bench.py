@@ -489,8 +489,13 @@ def selfplay_record(ctx, game_name, seconds, dist):
     blocking = share < 12
     gpu_threads = 3
     cpu_threads = share if blocking else share - gpu_threads
+    # games in flight per GPU: half as many again as the reference's formula gives for three executors ((3 + 1) * 1024 / 16 = 256,
+    # server_alphazero.rs:47).  With 4 host cores per GPU the extra games hide the executor <-> generator wake-up latency: 6.88x -> 7.15x
+    # of one GPU at N = 8 (profiles/r02_n8_selfplay_ab.txt); with plenty of cores the loop is GPU-bound either way.
+    concurrent_games = 384
     cfg = selfplay.default_config(game=game, visits=800, search_batch=16, gpu_batch=1024, cpu_threads=cpu_threads, gpu_threads=gpu_threads,
-                                  duration_s=seconds, seed=replicas.game_seed(ctx, 1), executor_blocking_sync=int(blocking))
+                                  concurrent_games=concurrent_games, duration_s=seconds, seed=replicas.game_seed(ctx, 1),
+                                  executor_blocking_sync=int(blocking))
     replicas.barrier(ctx)
     r = selfplay.run(onnx_bytes, cfg, device=ctx.local_rank)
     counts = [r.real_evals, r.cached_evals, r.batches, r.moves_played, r.games_finished]
@@ -508,6 +513,7 @@ def selfplay_record(ctx, game_name, seconds, dist):
             "game": {"chess-synthetic": "chess-shaped synthetic game (13x8x8 + 8 planes, 1880-move policy, 20-45 legal moves)",
                      "chess": "chess (legal move generation, ChessStdMapper encoding)"}[game_name],
             "settings": "800 visits, search batch 16 with virtual loss, LRU cache 800, net chess 16x128, gpu batch 1024",
+            "concurrent_games_per_gpu": int(r.concurrent_games),
             "host_cores": cores, "cpu_threads_per_gpu": cpu_threads, "gpu_threads_per_gpu": gpu_threads,
             "executor_blocking_sync": bool(blocking)}
 
