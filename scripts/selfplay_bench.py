@@ -8,8 +8,8 @@ Settings default to the reference's production values (python/main/loop_main_alp
 virtual loss 1, LRU cache 800, Dirichlet 0.03/0.25, root temperature 1.4); the TOPOLOGY is this repo's: gpu batch 1024 (BASELINE.json's
 batch; the reference runs 2048), three executor threads and every remaining core as a generator thread (the reference: 1 and 4,
 loop_main_alpha.py:24-26) -- all of them are startup settings on both sides.  The net is chess 16x128 random-init
-(synthetic, like bench.py).  The game is the chess-SHAPED synthetic game of kzero_b200/csrc/selfplay/games.hpp (no chess
-move generator in this repo), real 7x7 ataxx with an 8x64 net, or 9x9 go with the 20x256 net (host side tested; not yet timed on a GPU).  Prints one JSON line on rank 0:
+(synthetic, like bench.py).  The game is the chess-SHAPED synthetic game of kzero_b200/csrc/selfplay/games.hpp (--game chess), real chess
+(--game chess-real, chess_game.hpp), real 7x7 ataxx with an 8x64 net, or 9x9 go with the 20x256 net.  Prints one JSON line on rank 0:
   nodes/s = (real + cached evals) / s  (the collector's `evals/s: real / cached`, collector.rs:172-191), NN positions/s,
   mean batch and fill of the evaluator calls.
 """
@@ -55,7 +55,7 @@ gpu_threads = args.gpu_threads
 cpu_threads = args.cpu_threads or (share if blocking else share - gpu_threads)
 if args.game == "chess":
     spec, depth, channels, game = netgen.game_spec("chess"), 16, 128, selfplay.GAME_SYNTH_CHESS
-elif args.game == "chess-real":  # legal chess instead of the chess-shaped synthetic game; host side tested, not yet timed on a GPU
+elif args.game == "chess-real":  # legal chess instead of the chess-shaped synthetic game
     spec, depth, channels, game = netgen.game_spec("chess"), 16, 128, selfplay.GAME_CHESS
 elif args.game == "go":  # the net of BASELINE.json configs[2]
     spec, depth, channels, game = netgen.game_spec("go-9"), 20, 256, selfplay.GAME_GO9
