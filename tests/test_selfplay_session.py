@@ -43,9 +43,9 @@ def test_games_in_flight_continue_in_the_next_generation(tmp_path):
             for s, length in zip(starts, lengths[-1]):
                 for k in range(length + 1):
                     assert int(positions[int(s) + k]["scalars"][1]) == k
-    # a generation cannot have played a game from its start to its end if the whole generation -- all 8 games together -- played
-    # fewer moves than that game is long: such games were carried over from earlier generations
-    carried = [gen for gen in range(1, len(moves)) if max(lengths[gen]) > moves[gen]]
+    # a generation cannot have played the games it wrote from their start to their end if the whole generation -- all 8 games
+    # together -- played fewer moves than those games are long: such games were carried over from earlier generations
+    carried = [gen for gen in range(1, len(moves)) if sum(lengths[gen]) > moves[gen]]
     assert len(carried) >= 2, (moves, lengths)
     # and nothing is invented: the files never hold more positions than were played
     assert sum(sum(lens) for lens in lengths) <= sum(moves)
