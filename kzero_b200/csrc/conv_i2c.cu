@@ -414,8 +414,8 @@ void conv_i2c_prepare() { cudaFuncSetAttribute(conv_i2c_kernel, cudaFuncAttribut
 // One launch runs p.num_layers consecutive layers of p.layers starting at p.layer0.  num_layers == 1: an ordinary launch (with
 // programmatic stream serialization when p.pdl).  num_layers > 1: the persistent mode for small batches -- a cooperative launch (all
 // CTAs co-resident) with a grid-wide barrier between layers on p.grid_barrier, which the caller has zeroed on the same stream.
-void launch_conv_i2c(const I2cMaps& maps, const I2cParams& p, int grid, cudaStream_t s) {
-    if (p.num_tiles <= 0 || p.num_layers <= 0) return;
+cudaError_t launch_conv_i2c(const I2cMaps& maps, const I2cParams& p, int grid, cudaStream_t s) {
+    if (p.num_tiles <= 0 || p.num_layers <= 0) return cudaSuccess;
     const int items = (p.num_tiles + 1) / 2 * p.n_split;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(2 * std::min(grid / 2, items)));
@@ -439,7 +439,7 @@ void launch_conv_i2c(const I2cMaps& maps, const I2cParams& p, int grid, cudaStre
     }
     cfg.attrs = attr;
     cfg.numAttrs = unsigned(n_attr);
-    cudaLaunchKernelEx(&cfg, conv_i2c_kernel, maps, p);
+    return cudaLaunchKernelEx(&cfg, conv_i2c_kernel, maps, p);
 }
 
 }  // namespace kzb

@@ -852,13 +852,18 @@ void Net::run_network(int batch, const StepHook& hook) {
                     ip.num_layers = tower;
                     ip.pdl = 0;
                     CK(cudaMemsetAsync(d_i2c_barrier_.ptr, 0, 4, stream_));
-                    launch_conv_i2c(i2c_maps_, ip, num_sms_, stream_);
-                    if (hook) hook("tower_i2c");
-                    si += size_t(tower) - 1;
-                    continue;
+                    if (launch_conv_i2c(i2c_maps_, ip, num_sms_, stream_) == cudaSuccess) {
+                        if (hook) hook("tower_i2c");
+                        si += size_t(tower) - 1;
+                        continue;
+                    }
+                    // the grid cannot be made co-resident on this device (cooperative launch refused): one launch per layer from now on
+                    cudaGetLastError();
+                    i2c_persist_items_ = 0;
+                    ip.num_layers = 1;
                 }
                 ip.pdl = i2c_pdl_ ? 1 : 0;
-                launch_conv_i2c(i2c_maps_, ip, num_sms_, stream_);
+                CK(launch_conv_i2c(i2c_maps_, ip, num_sms_, stream_));
             } else {
                 launch_conv_tc(st->tmap_a, st->tmap_b, p, num_sms_, stream_);
             }

@@ -117,7 +117,7 @@ struct I2cParams {
     RowLayout lay;  // dense
     unsigned* grid_barrier;  // persistent mode: zeroed by the caller on the same stream before the launch
 };
-void launch_conv_i2c(const I2cMaps& maps, const I2cParams& p, int grid, cudaStream_t s);
+cudaError_t launch_conv_i2c(const I2cMaps& maps, const I2cParams& p, int grid, cudaStream_t s);
 size_t conv_i2c_smem_bytes(int n, int stages);
 int conv_i2c_pick_stages(int n);
 void conv_i2c_prepare();

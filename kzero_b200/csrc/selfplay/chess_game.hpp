@@ -1,15 +1,25 @@
-// Chess for the self-play driver: legal move generation, the reference's ChessStdMapper encoding
+// Chess for the self-play driver: legal move generation on bitboards, the reference's ChessStdMapper encoding
 // (rust/kz-core/src/mapping/chess.rs:126-170: 13 bool planes + 8 scalars from the mover's point of view) and its flat
 // 1880-move policy indexing (generate_all_flat_moves_pov, chess.rs:439-481; move_pov flips ranks for black).
 //
 // The rules live in the un-vendored `chess` / `board-game` crates and are restated here from the rules of chess:
 // castling, en passant, promotions, check / mate / stalemate, the 50-move rule (100 plies without a pawn move or capture),
-// threefold repetition, bare kings (K + minor v K plays on, like board-game Rules::default: tests/mapper/chess/pairs.rs:98-136).  The move generator is pinned by perft counts
-// (tests/cpp/chess_perft_test.cpp: initial position, Kiwipete and three more standard positions), through the
-// policy-index interface, so the indexing is checked to be one-to-one on every position visited as well.  Two details
-// of the ENCODING cannot be pinned without the crates and are choices: the en-passant plane marks the capture target
-// square, and only when an enemy pawn stands next to the pushed pawn; `repetitions` counts earlier occurrences of the
-// position since the last irreversible move.
+// threefold repetition, bare kings (K + minor v K plays on, like board-game Rules::default: tests/mapper/chess/pairs.rs:98-136).
+// Pinned by perft counts (tests/cpp/chess_perft_test.cpp: initial position, Kiwipete and three more standard positions), by the
+// reference's own known answers (tests/test_chess_pairs.py <- tests/mapper/chess/pairs.rs), by a second, mailbox implementation
+// (tests/cpp/chess_mailbox.hpp) on random playouts and by the oracle's third one through whole search trees (tests/test_mcts.py).
+//
+// Why bitboards: with four host cores per B200 the self-play loop was bound by this file (round 2, profiles/r02_selfplay.md: 2.5 us of
+// generator CPU per node with the mailbox generator against 0.96 us for the synthetic game).  A position is two colour sets and six
+// piece-type sets; one generation computes the enemy's attack map (king lifted off the board), the checkers and the pinned pieces
+// once, and every piece's targets are then a few mask operations; sliders use hyperbola quintessence (files, diagonals) and a
+// first-rank table (no BMI2 dependency, 2.5 KB of tables).  play() generates the replies once -- that is the mate / stalemate test --
+// and keeps them in a per-thread one-entry cache that the search's moves() call right afterwards reads back.
+//
+// Canonical move order (shared with the oracle): origin squares ascending from a1, per piece its destination squares ascending,
+// promotions Q R B N.  The en-passant square exists only while an enemy pawn stands next to the pushed pawn; the en-passant PLANE
+// marks the pushed pawn (`Board::en_passant()` of the `chess` 3.2.0 crate), not the capture's destination; `repetitions` counts
+// earlier occurrences of the position since the last irreversible move.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -59,32 +69,127 @@ inline const FlatMoves& flat_moves() {
     static const FlatMoves t;
     return t;
 }
-struct ZobristTable {
-    uint64_t v[13][64];  // [piece code + 6][square]
-    ZobristTable() {
+
+inline uint64_t bit(int s) { return 1ull << s; }
+inline int lsb(uint64_t b) { return __builtin_ctzll(b); }
+
+// attack sets on an empty board, the masks hyperbola quintessence works on, the squares between two aligned squares and the
+// line through them, zobrist keys
+struct Tables {
+    uint64_t knight[64], king[64], pawn_att[2][64];  // pawn_att[colour][s]: squares a pawn of `colour` on s attacks
+    uint64_t file_mask[64], diag_mask[64], anti_mask[64];  // the line through s, without s
+    uint8_t rank_att[8][64];                               // [file][inner six occupancy bits of the rank] -> attacked files
+    uint64_t between[64][64], line[64][64];                // 0 unless the squares share a rank, file or diagonal
+    uint64_t zob[13][64];                                  // [piece code + 6][square]
+    uint64_t zob_castle[16], zob_ep[64];
+    uint8_t castle_keep[64];                               // the rights that survive a move from / to this square
+    Tables() {
+        auto on = [](int r, int f) { return r >= 0 && r < 8 && f >= 0 && f < 8; };
+        static const int kn[8][2] = {{2, 1}, {1, 2}, {-1, 2}, {-2, 1}, {-2, -1}, {-1, -2}, {1, -2}, {2, -1}};
+        static const int kg[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
+        for (int s = 0; s < 64; s++) {
+            const int r = s / 8, f = s % 8;
+            knight[s] = king[s] = pawn_att[0][s] = pawn_att[1][s] = file_mask[s] = diag_mask[s] = anti_mask[s] = 0;
+            for (auto& d : kn)
+                if (on(r + d[0], f + d[1])) knight[s] |= bit((r + d[0]) * 8 + f + d[1]);
+            for (auto& d : kg)
+                if (on(r + d[0], f + d[1])) king[s] |= bit((r + d[0]) * 8 + f + d[1]);
+            for (int df : {-1, 1}) {
+                if (on(r + 1, f + df)) pawn_att[0][s] |= bit((r + 1) * 8 + f + df);
+                if (on(r - 1, f + df)) pawn_att[1][s] |= bit((r - 1) * 8 + f + df);
+            }
+            for (int t = 0; t < 64; t++) {
+                if (t == s) continue;
+                const int dr = t / 8 - r, df = t % 8 - f;
+                if (df == 0) file_mask[s] |= bit(t);
+                if (dr == df) diag_mask[s] |= bit(t);
+                if (dr == -df) anti_mask[s] |= bit(t);
+            }
+        }
+        for (int f = 0; f < 8; f++)
+            for (int o = 0; o < 64; o++) {
+                const int occ = o << 1;  // files b..g
+                uint8_t a = 0;
+                for (int x = f + 1; x < 8; x++) {
+                    a |= uint8_t(1 << x);
+                    if (occ & (1 << x)) break;
+                }
+                for (int x = f - 1; x >= 0; x--) {
+                    a |= uint8_t(1 << x);
+                    if (occ & (1 << x)) break;
+                }
+                rank_att[f][o] = a;
+            }
+        std::memset(between, 0, sizeof(between));
+        std::memset(line, 0, sizeof(line));
+        for (int s = 0; s < 64; s++)
+            for (auto& d : kg) {
+                uint64_t whole = bit(s);  // the whole line through s in direction +-d
+                for (int sg : {1, -1})
+                    for (int r = s / 8 + sg * d[0], f = s % 8 + sg * d[1]; on(r, f); r += sg * d[0], f += sg * d[1]) whole |= bit(r * 8 + f);
+                uint64_t walked = 0;
+                for (int r = s / 8 + d[0], f = s % 8 + d[1]; on(r, f); r += d[0], f += d[1]) {
+                    between[s][r * 8 + f] = walked;
+                    line[s][r * 8 + f] = whole;
+                    walked |= bit(r * 8 + f);
+                }
+            }
         for (int p = 0; p < 13; p++)
-            for (int s = 0; s < 64; s++) v[p][s] = splitmix64(uint64_t(p + 10) * 64 + uint64_t(s) + 0xC0FFEEull);
+            for (int s = 0; s < 64; s++) zob[p][s] = splitmix64(uint64_t(p + 10) * 64 + uint64_t(s) + 0xC0FFEEull);
+        std::memset(castle_keep, 15, sizeof(castle_keep));
+        castle_keep[4] = 15 & ~3, castle_keep[60] = 15 & ~12, castle_keep[7] = 15 & ~1, castle_keep[0] = 15 & ~2, castle_keep[63] = 15 & ~4, castle_keep[56] = 15 & ~8;
+        for (int c = 0; c < 16; c++) zob_castle[c] = splitmix64(0xCA57ull + uint64_t(c));
+        for (int s = 0; s < 64; s++) zob_ep[s] = splitmix64(0xE9ull + uint64_t(s));
     }
 };
-inline uint64_t zobrist(int piece_code, int square) {
-    static const ZobristTable t;
-    return t.v[piece_code + 6][square];
+inline const Tables& tables() {
+    static const Tables t;
+    return t;
+}
+inline uint64_t zobrist(int piece_code, int square) { return tables().zob[piece_code + 6][square]; }
+
+// hyperbola quintessence: the squares a slider on s reaches along `mask` (a file or a diagonal: one bit per rank, so a byte swap
+// reverses the line) with blockers `occ`
+inline uint64_t hq_line(uint64_t occ, uint64_t mask, int s) {
+    const uint64_t o = occ & mask, b = bit(s);  // mask does not contain s: o - b borrows through the empty squares above s
+    const uint64_t fwd = o - b, rev = __builtin_bswap64(__builtin_bswap64(o) - __builtin_bswap64(b));
+    return (fwd ^ rev) & mask;
+}
+inline uint64_t rank_line(const Tables& t, uint64_t occ, int s) {
+    const int sh = s & 56;
+    return uint64_t(t.rank_att[s & 7][(occ >> (sh + 1)) & 63]) << sh;
+}
+inline uint64_t bishop_att(const Tables& t, uint64_t occ, int s) { return hq_line(occ, t.diag_mask[s], s) | hq_line(occ, t.anti_mask[s], s); }
+inline uint64_t rook_att(const Tables& t, uint64_t occ, int s) { return hq_line(occ, t.file_mask[s], s) | rank_line(t, occ, s); }
+
+// the replies of the position play() generated last on this thread (its mate / stalemate test): the search asks for exactly
+// that list next (descent_step: done(), then moves())
+struct ReplyCache {
+    uint64_t key = 0;
+    int n = -1;
+    uint16_t mv[256];
+};
+inline ReplyCache& reply_cache() {
+    static thread_local ReplyCache c;
+    return c;
 }
 }  // namespace chess_detail
 
 struct Chess {
     // square = rank * 8 + file, a1 = 0.  Piece code: +type white, -type black (type 1..6 = P N B R Q K), 0 empty.
     int8_t sq[64] = {};
+    uint64_t colour[2] = {};  // occupancy per colour
+    uint64_t kind[7] = {};    // occupancy per piece type (1..6), both colours
     uint8_t side = 0;        // 0 white to move, 1 black
     uint8_t castle = 0;      // bit 0 white king side, 1 white queen side, 2 black king side, 3 black queen side
     int8_t ep = -1;          // en-passant capture target square, -1 none
     uint8_t halfmove = 0;    // plies without a pawn move or capture
     uint8_t terminal = 0;    // 0 running, 1 side to move is mated, 2 draw
-    uint16_t ply = 0;
     uint8_t reps = 0;        // earlier occurrences of this position since the last irreversible move
     uint8_t king[2] = {4, 60};
-    uint8_t low_material = 0;  // insufficient mating material (recomputed when material changes)
+    uint8_t low_material = 0;  // insufficient mating material
     uint8_t hist_n = 0;
+    uint16_t ply = 0;
     uint64_t key = 0;        // position_key() of the current position
     uint64_t piece_key = 0;  // the placement part of it, kept incrementally
     uint64_t hist[100];      // position keys since the last irreversible move (not including the current one)
@@ -105,6 +210,18 @@ struct Chess {
     static const char* name() { return "chess"; }
     static Chess start(uint64_t /*seed*/) { return from_fen("rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1"); }
 
+    void put(int s, int8_t p) {
+        sq[s] = p;
+        colour[p > 0 ? 0 : 1] |= chess_detail::bit(s);
+        kind[p > 0 ? p : -p] |= chess_detail::bit(s);
+    }
+    void lift(int s) {
+        const int8_t p = sq[s];
+        sq[s] = 0;
+        colour[p > 0 ? 0 : 1] &= ~chess_detail::bit(s);
+        kind[p > 0 ? p : -p] &= ~chess_detail::bit(s);
+    }
+
     static Chess from_fen(const std::string& fen) {
         using namespace chess_detail;
         Chess b;
@@ -122,7 +239,7 @@ struct Chess {
                 int type = 0;
                 for (int k = 0; k < 6; k++)
                     if (names[k] == lower) type = k + 1;
-                b.sq[r * 8 + f] = int8_t(c == lower ? -type : type);
+                b.put(r * 8 + f, int8_t(c == lower ? -type : type));
                 f++;
             }
         }
@@ -159,6 +276,7 @@ struct Chess {
     bool done() const { return terminal != 0; }
     int outcome() const { return terminal == 1 ? (side == 0 ? -1 : 1) : 0; }  // the mated side is the one to move
 
+    uint64_t occupied() const { return colour[0] | colour[1]; }
     uint64_t placement_key() const {
         uint64_t h = 0;
         for (int s = 0; s < 64; s++)
@@ -166,185 +284,118 @@ struct Chess {
         return h;
     }
     uint64_t state_key() const {  // side, castling rights, en-passant square
+        const auto& t = chess_detail::tables();
         uint64_t h = side ? 0x9E3779B97F4A7C15ull : 0;
-        h ^= splitmix64(0xCA57ull + castle);
-        if (ep >= 0) h ^= splitmix64(0xE9ull + uint64_t(ep));
+        h ^= t.zob_castle[castle];
+        if (ep >= 0) h ^= t.zob_ep[ep];
         return h;
     }
     uint64_t position_key() const { return placement_key() ^ state_key(); }  // what repetition compares (from scratch)
     uint64_t hash() const { return splitmix64(key ^ (uint64_t(halfmove) << 8) ^ (uint64_t(reps) << 20)); }  // + what the net sees
 
-    static int colour_of(int8_t p) { return p > 0 ? 0 : 1; }
-    int king_square(int colour) const { return king[colour]; }
+    int king_square(int c) const { return king[c]; }
+    // the pieces of colour `by` that attack square s when the board's occupancy is `occ`
+    uint64_t attackers(int s, int by, uint64_t occ) const {
+        using namespace chess_detail;
+        const Tables& t = tables();
+        const uint64_t them = colour[by];
+        return them & ((t.pawn_att[by ^ 1][s] & kind[kPawn]) | (t.knight[s] & kind[kKnight]) | (t.king[s] & kind[kKing]) |
+                       (bishop_att(t, occ, s) & (kind[kBishop] | kind[kQueen])) | (rook_att(t, occ, s) & (kind[kRook] | kind[kQueen])));
+    }
     // is square s attacked by colour `by`; the square `transparent` counts as empty (a king that steps away does not
     // shelter the squares behind it)
     bool attacked(int s, int by, int transparent = -1) const {
-        using namespace chess_detail;
-        const int r = s / 8, f = s % 8, sign = by == 0 ? 1 : -1;
-        const int pr = r - sign;  // a pawn of colour `by` attacks from the rank behind (from its own side)
-        if (pr >= 0 && pr < 8) {
-            if (f > 0 && sq[pr * 8 + f - 1] == sign * kPawn) return true;
-            if (f < 7 && sq[pr * 8 + f + 1] == sign * kPawn) return true;
-        }
-        static const int kn[8][2] = {{2, 1}, {1, 2}, {-1, 2}, {-2, 1}, {-2, -1}, {-1, -2}, {1, -2}, {2, -1}};
-        for (auto& d : kn) {
-            const int rr = r + d[0], ff = f + d[1];
-            if (rr >= 0 && rr < 8 && ff >= 0 && ff < 8 && sq[rr * 8 + ff] == sign * kKnight) return true;
-        }
-        static const int dirs[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
-        for (int d = 0; d < 8; d++) {
-            int rr = r + dirs[d][0], ff = f + dirs[d][1];
-            for (int dist = 1; rr >= 0 && rr < 8 && ff >= 0 && ff < 8; rr += dirs[d][0], ff += dirs[d][1], dist++) {
-                const int8_t p = sq[rr * 8 + ff];
-                if (!p || rr * 8 + ff == transparent) continue;
-                if (p * sign > 0) {
-                    const int type = p * sign;
-                    if (type == kQueen || (d < 4 && type == kRook) || (d >= 4 && type == kBishop) || (dist == 1 && type == kKing)) return true;
-                }
-                break;
-            }
-        }
-        return false;
+        const uint64_t occ = transparent >= 0 ? occupied() & ~chess_detail::bit(transparent) : occupied();
+        return attackers(s, by, occ) != 0;
     }
-    bool in_check() const { return attacked(king_square(side), side ^ 1); }
+    bool in_check() const { return attacked(king[side], side ^ 1); }
 
+    // every square colour `by` attacks, with `occ` as the blockers
+    uint64_t attack_map(int by, uint64_t occ) const {
+        using namespace chess_detail;
+        const Tables& t = tables();
+        const uint64_t them = colour[by], pawns = them & kind[kPawn];
+        constexpr uint64_t not_a = 0xFEFEFEFEFEFEFEFEull, not_h = 0x7F7F7F7F7F7F7F7Full;
+        uint64_t a = by == 0 ? (((pawns & not_a) << 7) | ((pawns & not_h) << 9)) : (((pawns & not_a) >> 9) | ((pawns & not_h) >> 7));
+        for (uint64_t b = them & kind[kKnight]; b; b &= b - 1) a |= t.knight[lsb(b)];
+        for (uint64_t b = them & (kind[kBishop] | kind[kQueen]); b; b &= b - 1) a |= bishop_att(t, occ, lsb(b));
+        for (uint64_t b = them & (kind[kRook] | kind[kQueen]); b; b &= b - 1) a |= rook_att(t, occ, lsb(b));
+        return a | t.king[king[by]];
+    }
+
+    // the legal moves in canonical order: origins ascending, destinations ascending, promotions Q R B N; emit(Mv) returns false to stop
     template <typename F>
-    void pseudo_moves(F&& emit) const {  // emit(Mv) returns false to stop
+    void legal_moves(F&& emit) const {
         using namespace chess_detail;
-        const int sign = side == 0 ? 1 : -1;
-        for (int s = 0; s < 64; s++) {
-            const int8_t p = sq[s];
-            if (p * sign <= 0) continue;
-            const int type = p * sign, r = s / 8, f = s % 8;
-            if (type == kPawn) {
-                const int fwd = sign, start_rank = side == 0 ? 1 : 6, last = side == 0 ? 7 : 0;
-                const int r1 = r + fwd;
-                if (r1 < 0 || r1 > 7) continue;
-                auto pawn_to = [&](int t) {
-                    if (t / 8 == last) {
-                        for (int8_t pp : {kQueen, kRook, kBishop, kKnight})
-                            if (!emit(Mv{uint8_t(s), uint8_t(t), pp})) return false;
-                        return true;
-                    }
-                    return emit(Mv{uint8_t(s), uint8_t(t), 0});
-                };
-                if (!sq[r1 * 8 + f]) {
-                    if (!pawn_to(r1 * 8 + f)) return;
-                    if (r == start_rank && !sq[(r + 2 * fwd) * 8 + f] && !emit(Mv{uint8_t(s), uint8_t((r + 2 * fwd) * 8 + f), 0})) return;
-                }
-                for (int df : {-1, 1}) {
-                    const int ff = f + df;
-                    if (ff < 0 || ff > 7) continue;
-                    const int t = r1 * 8 + ff;
-                    if ((sq[t] * sign < 0 || t == ep) && !pawn_to(t)) return;
-                }
-            } else if (type == kKnight || type == kKing) {
-                static const int kn[8][2] = {{2, 1}, {1, 2}, {-1, 2}, {-2, 1}, {-2, -1}, {-1, -2}, {1, -2}, {2, -1}};
-                static const int kg[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
-                for (int d = 0; d < 8; d++) {
-                    const int rr = r + (type == kKnight ? kn[d][0] : kg[d][0]), ff = f + (type == kKnight ? kn[d][1] : kg[d][1]);
-                    if (rr < 0 || rr > 7 || ff < 0 || ff > 7 || sq[rr * 8 + ff] * sign > 0) continue;
-                    if (!emit(Mv{uint8_t(s), uint8_t(rr * 8 + ff), 0})) return;
-                }
-                if (type == kKing) {  // castling: rights, empty squares, king not in / through / into check
-                    const int home = side == 0 ? 4 : 60;
-                    if (s == home && !attacked(home, side ^ 1)) {
-                        if ((castle & (side == 0 ? 1 : 4)) && !sq[home + 1] && !sq[home + 2] && sq[home + 3] == sign * kRook &&
-                            !attacked(home + 1, side ^ 1) && !attacked(home + 2, side ^ 1) && !emit(Mv{uint8_t(s), uint8_t(home + 2), 0}))
-                            return;
-                        if ((castle & (side == 0 ? 2 : 8)) && !sq[home - 1] && !sq[home - 2] && !sq[home - 3] && sq[home - 4] == sign * kRook &&
-                            !attacked(home - 1, side ^ 1) && !attacked(home - 2, side ^ 1) && !emit(Mv{uint8_t(s), uint8_t(home - 2), 0}))
-                            return;
-                    }
-                }
-            } else {
-                static const int dirs[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
-                const int d0 = type == kBishop ? 4 : 0, d1 = type == kRook ? 4 : 8;
-                for (int d = d0; d < d1; d++)
-                    for (int rr = r + dirs[d][0], ff = f + dirs[d][1]; rr >= 0 && rr < 8 && ff >= 0 && ff < 8; rr += dirs[d][0], ff += dirs[d][1]) {
-                        const int8_t q = sq[rr * 8 + ff];
-                        if (q * sign > 0) break;
-                        if (!emit(Mv{uint8_t(s), uint8_t(rr * 8 + ff), 0})) return;
-                        if (q) break;
-                    }
-            }
+        const Tables& t = tables();
+        const int us = side, them = side ^ 1, k = king[us];
+        const uint64_t own = colour[us], enemy = colour[them], occ = own | enemy;
+        const uint64_t danger = attack_map(them, occ & ~bit(k));  // with the king lifted: it cannot hide behind itself
+        const uint64_t checkers = attackers(k, them, occ);
+        // non-king moves must end on `target`: anywhere (no check), on the checker or between it and the king (one check), nowhere (two)
+        uint64_t target = ~own;
+        if (checkers) target = (checkers & (checkers - 1)) ? 0 : (checkers | t.between[k][lsb(checkers)]);
+        // own pieces that stand alone between the king and an enemy slider that would otherwise attack it
+        uint64_t pinned = 0;
+        const uint64_t snipers = enemy & ((rook_att(t, 0, k) & (kind[kRook] | kind[kQueen])) | (bishop_att(t, 0, k) & (kind[kBishop] | kind[kQueen])));
+        for (uint64_t b = snipers; b; b &= b - 1) {
+            const uint64_t mid = t.between[k][lsb(b)] & occ;
+            if (mid && !(mid & (mid - 1))) pinned |= mid & own;
         }
-    }
-    // the placement part of a move (no counters, no history): enough to test legality
-    void apply_placement(const Mv& m) {
-        using namespace chess_detail;
-        const int sign = side == 0 ? 1 : -1;
-        const int8_t p = sq[m.from];
-        const int type = p * sign;
-        if (type == kPawn && m.to == ep && !sq[m.to]) sq[(m.from / 8) * 8 + m.to % 8] = 0;  // en passant removes the passed pawn
-        sq[m.to] = m.promo ? int8_t(sign * m.promo) : p;
-        sq[m.from] = 0;
-        if (type == kKing) {
-            king[side] = m.to;
-            if (std::abs(int(m.to) - int(m.from)) == 2) {  // castling moves the rook as well
-                if (m.to > m.from) sq[m.from + 1] = sq[m.from + 3], sq[m.from + 3] = 0;
-                else sq[m.from - 1] = sq[m.from - 4], sq[m.from - 4] = 0;
-            }
-        }
-    }
-    bool legal(const Mv& m) const {  // the full test: make the move on a scratch board, look at the king
-        Chess c;
-        std::memcpy(c.sq, sq, sizeof(sq));
-        c.side = side, c.ep = ep, c.king[0] = king[0], c.king[1] = king[1];
-        c.apply_placement(m);
-        return !c.attacked(c.king_square(side), side ^ 1);
-    }
-    // pin_dir[s] = index (0..7) of the ray from the own king on which the own piece on s is pinned, -1 otherwise
-    void find_pins(int8_t pin_dir[64]) const {
-        using namespace chess_detail;
-        static const int dirs[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
-        std::memset(pin_dir, -1, 64);
-        const int sign = side == 0 ? 1 : -1, k = king[side], kr = k / 8, kf = k % 8;
-        for (int d = 0; d < 8; d++) {
-            int candidate = -1;
-            for (int rr = kr + dirs[d][0], ff = kf + dirs[d][1]; rr >= 0 && rr < 8 && ff >= 0 && ff < 8; rr += dirs[d][0], ff += dirs[d][1]) {
-                const int8_t p = sq[rr * 8 + ff];
-                if (!p) continue;
-                if (p * sign > 0) {
-                    if (candidate >= 0) break;  // two own pieces in a row: nothing is pinned on this ray
-                    candidate = rr * 8 + ff;
-                } else {
-                    const int type = -p * sign;
-                    if (candidate >= 0 && (type == kQueen || (d < 4 && type == kRook) || (d >= 4 && type == kBishop))) pin_dir[candidate] = int8_t(d);
+        const int fwd = us == 0 ? 8 : -8;
+        const uint64_t promo_rank = us == 0 ? 0xFF00000000000000ull : 0xFFull, start_rank = us == 0 ? 0xFF00ull : 0x00FF000000000000ull;
+        for (uint64_t b = own; b; b &= b - 1) {
+            const int s = lsb(b);
+            const int type = sq[s] > 0 ? sq[s] : -sq[s];
+            uint64_t to = 0;
+            switch (type) {
+                case kPawn: {
+                    const uint64_t one = bit(s + fwd) & ~occ;
+                    to = one | (t.pawn_att[us][s] & enemy);
+                    if (one && (bit(s) & start_rank)) to |= bit(s + 2 * fwd) & ~occ;
+                    to &= target;
+                    if (pinned & bit(s)) to &= t.line[k][s];
+                    if (ep >= 0 && (t.pawn_att[us][s] & bit(ep))) {
+                        // en passant: two pawns leave a rank at once -- make the capture on the occupancy and look at the king
+                        const int cap = ep - fwd;
+                        const uint64_t occ2 = (occ ^ bit(s) ^ bit(cap)) | bit(ep);
+                        const uint64_t left = enemy & ~bit(cap);
+                        const uint64_t att = left & ((t.pawn_att[us][k] & kind[kPawn]) | (t.knight[k] & kind[kKnight]) |
+                                                     (bishop_att(t, occ2, k) & (kind[kBishop] | kind[kQueen])) |
+                                                     (rook_att(t, occ2, k) & (kind[kRook] | kind[kQueen])));
+                        if (!att) to |= bit(ep);
+                    }
+                    if (to & promo_rank) {
+                        for (; to; to &= to - 1)
+                            for (int8_t pp : {kQueen, kRook, kBishop, kKnight})
+                                if (!emit(Mv{uint8_t(s), uint8_t(lsb(to)), pp})) return;
+                        continue;
+                    }
+                    break;
+                }
+                case kKnight: to = (pinned & bit(s)) ? 0 : t.knight[s] & target; break;
+                case kBishop: to = bishop_att(t, occ, s) & target; break;
+                case kRook: to = rook_att(t, occ, s) & target; break;
+                case kQueen: to = (bishop_att(t, occ, s) | rook_att(t, occ, s)) & target; break;
+                default: {  // king: any square the other side does not attack; castling: rights, empty squares, not in / through / into check
+                    to = t.king[s] & ~own & ~danger;
+                    const int home = us == 0 ? 4 : 60;
+                    if (s == home && !checkers) {
+                        const int8_t rook = int8_t(us == 0 ? kRook : -kRook);
+                        if ((castle & (us == 0 ? 1 : 4)) && !(occ & (bit(home + 1) | bit(home + 2))) && sq[home + 3] == rook &&
+                            !(danger & (bit(home + 1) | bit(home + 2))))
+                            to |= bit(home + 2);
+                        if ((castle & (us == 0 ? 2 : 8)) && !(occ & (bit(home - 1) | bit(home - 2) | bit(home - 3))) && sq[home - 4] == rook &&
+                            !(danger & (bit(home - 1) | bit(home - 2))))
+                            to |= bit(home - 2);
+                    }
                     break;
                 }
             }
+            if (type >= kBishop && type <= kQueen && (pinned & bit(s))) to &= t.line[k][s];
+            for (; to; to &= to - 1)
+                if (!emit(Mv{uint8_t(s), uint8_t(lsb(to)), 0})) return;
         }
-    }
-    static bool on_ray(int k, int s, int d) {  // is s on ray d (one of the 8 directions) from k
-        const int dr = s / 8 - k / 8, df = s % 8 - k % 8;
-        switch (d) {
-            case 0: return df == 0 && dr > 0;
-            case 1: return df == 0 && dr < 0;
-            case 2: return dr == 0 && df > 0;
-            case 3: return dr == 0 && df < 0;
-            case 4: return dr == df && dr > 0;
-            case 5: return dr == -df && dr > 0;
-            case 6: return dr == -df && dr < 0;
-            default: return dr == df && dr < 0;
-        }
-    }
-    template <typename F>
-    void legal_moves(F&& emit) const {
-        // not in check: a piece other than the king may move unless it is pinned, and a pinned piece may move along its
-        // pin ray; a king may step onto a square the other side does not attack once the king itself is off the board;
-        // en-passant captures and every other move while in check take the full test
-        const bool check = in_check();
-        const int k = king[side];
-        int8_t pin_dir[64];
-        if (!check) find_pins(pin_dir);
-        pseudo_moves([&](const Mv& m) {
-            bool ok;
-            if (m.from == k) ok = !attacked(m.to, side ^ 1, k);  // the squares a castling king crosses were tested by the generator
-            else if (check || (m.to == ep && std::abs(int(sq[m.from])) == chess_detail::kPawn)) ok = legal(m);
-            else ok = pin_dir[m.from] < 0 || on_ray(k, m.to, pin_dir[m.from]);
-            return !ok || emit(m);
-        });
     }
     bool has_legal_move() const {
         bool any = false;
@@ -356,29 +407,38 @@ struct Chess {
     }
     // board-game's Rules::is_draw ends a game on material only when nothing but the two kings is left; K + minor v K plays on --
     // the reference's own tests play knight moves on "8/8/6k1/8/3N4/6K1/8/8 w" (rust/kz-core/tests/mapper/chess/pairs.rs:98-136)
-    bool insufficient_material() const {
-        int pieces = 0;
-        for (int s = 0; s < 64; s++) pieces += sq[s] != 0;
-        return pieces <= 2;
+    bool insufficient_material() const { return __builtin_popcountll(occupied()) <= 2; }
+
+    // the legal replies as policy indices, into the per-thread cache; returns how many
+    int generate_replies() const {
+        chess_detail::ReplyCache& c = chess_detail::reply_cache();
+        int n = 0;
+        const auto& t = chess_detail::flat_moves();
+        const int flip = side == 0 ? 0 : 56;  // pov_square(s) = s ^ 56 for black
+        legal_moves([&](const Mv& m) {
+            c.mv[n++] = uint16_t(t.index[m.from ^ flip][m.to ^ flip][chess_detail::FlatMoves::slot_of(m.promo)]);
+            return true;
+        });
+        c.key = key;
+        c.n = n;
+        return n;
     }
     void update_terminal() {
-        if (!has_legal_move()) terminal = in_check() ? 1 : 2;
+        if (generate_replies() == 0) terminal = in_check() ? 1 : 2;
         else if (halfmove >= 100 || reps >= 2 || low_material) terminal = 2;
         else terminal = 0;
     }
 
     // moves are policy indices from the mover's point of view (ranks flipped for black, move_pov chess.rs:483-497)
-    static int pov_square(int s, int side_) { return side_ == 0 ? s : (7 - s / 8) * 8 + s % 8; }
+    static int pov_square(int s, int side_) { return side_ == 0 ? s : s ^ 56; }
     uint32_t index_of(const Mv& m) const {
         const auto& t = chess_detail::flat_moves();
         return uint32_t(t.index[pov_square(m.from, side)][pov_square(m.to, side)][chess_detail::FlatMoves::slot_of(m.promo)]);
     }
     void moves(std::vector<uint32_t>& out) const {
-        out.clear();
-        legal_moves([&](const Mv& m) {
-            out.push_back(index_of(m));
-            return true;
-        });
+        const chess_detail::ReplyCache& c = chess_detail::reply_cache();
+        if (c.n < 0 || c.key != key) generate_replies();  // the legal moves depend on placement, side, rights and ep square: the key
+        out.assign(c.mv, c.mv + c.n);
     }
     uint32_t move_to_index(uint32_t mv) const { return mv; }
     void play(uint32_t index) {
@@ -393,41 +453,48 @@ struct Chess {
     }
     void apply_move(uint32_t index) {
         using namespace chess_detail;
-        const auto& t = flat_moves();
-        const Mv m{uint8_t(pov_square(t.from[index], side)), uint8_t(pov_square(t.to[index], side)), int8_t(t.promo[index])};
+        const auto& ft = flat_moves();
+        const Tables& t = tables();
+        const int flip = side == 0 ? 0 : 56;
+        const int from = ft.from[index] ^ flip, to = ft.to[index] ^ flip, promo = ft.promo[index];
         const int sign = side == 0 ? 1 : -1;
-        const int type = sq[m.from] * sign;
-        const bool capture = sq[m.to] != 0 || (type == kPawn && m.to == ep);
+        const int8_t p = sq[from];
+        const int type = p * sign;
         const uint64_t key_before = key;
-        {  // placement key: the mover leaves `from`, whatever stood on `to` (or the pawn passed en passant) goes, the mover or
-           // its promotion arrives, a castling rook changes squares
-            const int8_t p = sq[m.from];
-            piece_key ^= zobrist(p, m.from) ^ zobrist(m.promo ? int8_t(sign * m.promo) : p, m.to);
-            if (sq[m.to]) piece_key ^= zobrist(sq[m.to], m.to);
-            else if (type == kPawn && m.to == ep) piece_key ^= zobrist(int8_t(-sign * kPawn), (m.from / 8) * 8 + m.to % 8);
-            if (type == kKing && std::abs(int(m.to) - int(m.from)) == 2) {
-                const int rook_from = m.to > m.from ? m.from + 3 : m.from - 4, rook_to = m.to > m.from ? m.from + 1 : m.from - 1;
-                piece_key ^= zobrist(int8_t(sign * kRook), rook_from) ^ zobrist(int8_t(sign * kRook), rook_to);
+        bool capture = false;
+        if (sq[to]) {
+            capture = true;
+            piece_key ^= t.zob[sq[to] + 6][to];
+            lift(to);
+        } else if (type == kPawn && to == ep) {  // en passant removes the passed pawn
+            capture = true;
+            const int cap = (from & 56) | (to & 7);
+            piece_key ^= t.zob[sq[cap] + 6][cap];
+            lift(cap);
+        }
+        const int8_t arrives = promo ? int8_t(sign * promo) : p;
+        piece_key ^= t.zob[p + 6][from] ^ t.zob[arrives + 6][to];
+        lift(from);
+        put(to, arrives);
+        if (type == kKing) {
+            king[side] = uint8_t(to);
+            if (to - from == 2 || from - to == 2) {  // castling moves the rook as well
+                const int rook_from = to > from ? from + 3 : from - 4, rook_to = to > from ? from + 1 : from - 1;
+                const int8_t rook = sq[rook_from];
+                piece_key ^= t.zob[rook + 6][rook_from] ^ t.zob[rook + 6][rook_to];
+                lift(rook_from);
+                put(rook_to, rook);
             }
         }
-        apply_placement(m);
-        if (capture || m.promo) low_material = insufficient_material();
+        low_material = insufficient_material();
         // castling rights: a king or rook that moves, or a rook that is captured, loses them
-        auto touch = [&](int s) {
-            if (s == 4) castle &= uint8_t(~3);
-            if (s == 60) castle &= uint8_t(~12);
-            if (s == 7) castle &= uint8_t(~1);
-            if (s == 0) castle &= uint8_t(~2);
-            if (s == 63) castle &= uint8_t(~4);
-            if (s == 56) castle &= uint8_t(~8);
-        };
         const uint8_t castle_before = castle;
-        touch(m.from), touch(m.to);
+        castle &= t.castle_keep[from] & t.castle_keep[to];
         // en passant target: only when an enemy pawn stands next to the pawn that just advanced two ranks
         ep = -1;
-        if (type == kPawn && std::abs(int(m.to) - int(m.from)) == 16) {
-            const int f = m.to % 8;
-            if ((f > 0 && sq[m.to - 1] == -sign * kPawn) || (f < 7 && sq[m.to + 1] == -sign * kPawn)) ep = int8_t((int(m.from) + int(m.to)) / 2);
+        if (type == kPawn && (to - from == 16 || from - to == 16)) {
+            const uint64_t beside = (((bit(to) & 0xFEFEFEFEFEFEFEFEull) >> 1) | ((bit(to) & 0x7F7F7F7F7F7F7F7Full) << 1));
+            if (beside & colour[side ^ 1] & kind[kPawn]) ep = int8_t((from + to) / 2);
         }
         const bool irreversible = type == kPawn || capture || castle != castle_before;
         if (type == kPawn || capture) halfmove = 0;
@@ -444,19 +511,19 @@ struct Chess {
 
     void encode(uint8_t* bits, float* scalars) const {  // ChessStdMapper::encode_input, chess.rs:138-170
         using namespace chess_detail;
-        std::memset(bits, 0, 104);
-        const int sign = side == 0 ? 1 : -1;
-        uint64_t planes[12] = {};  // mover's P N B R Q K, then the other side's
-        for (int s = 0; s < 64; s++) {
-            const int p = sq[s] * sign;
-            if (p) planes[(p > 0 ? 0 : 6) + std::abs(p) - 1] |= 1ull << pov_square(s, side);
-        }
-        std::memcpy(bits, planes, sizeof(planes));  // BitBuffer::push_block: little-endian u64 per plane
+        // BitBuffer::push_block: one little-endian u64 per plane; the mover's P N B R Q K, then the other side's.  Black sees the
+        // board with the ranks flipped: a byte swap of the bitboard
+        uint64_t planes[13];
+        for (int c = 0; c < 2; c++)
+            for (int ty = 0; ty < 6; ty++) {
+                const uint64_t b = kind[ty + 1] & colour[c == 0 ? side : side ^ 1];
+                planes[c * 6 + ty] = side == 0 ? b : __builtin_bswap64(b);
+            }
         // `inner.en_passant()` of the `chess` 3.2.0 crate is the square of the PAWN that just advanced two ranks (make_move calls
         // set_ep(dest); the capture's destination is ep_sq.uforward(side_to_move)), not the capture target this struct keeps
         // for move generation: one rank towards the mover's own side of the target
-        const uint64_t epb = ep >= 0 ? 1ull << pov_square(ep + (side == 0 ? -8 : 8), side) : 0;
-        std::memcpy(bits + 12 * 8, &epb, 8);
+        planes[12] = ep >= 0 ? 1ull << pov_square(ep + (side == 0 ? -8 : 8), side) : 0;
+        std::memcpy(bits, planes, sizeof(planes));
         scalars[0] = side == 0 ? 1.0f : 0.0f;
         scalars[1] = side == 1 ? 1.0f : 0.0f;
         const int own_k = side == 0 ? 1 : 4, own_q = side == 0 ? 2 : 8, opp_k = side == 0 ? 4 : 1, opp_q = side == 0 ? 8 : 2;

@@ -330,13 +330,12 @@ class Ataxx7:
 
 class Chess:
     """Twin of kzb::selfplay::Chess (kzero_b200/csrc/selfplay/chess_game.hpp), written independently: a mailbox board,
-    legality by making the move and looking at the king (no pins, no shortcuts).  What the two must share is the
-    SPECIFICATION: moves are policy indices from the mover's side (ranks flipped for black) in the reference's flat table
-    (chess.rs:439-481); they are generated square by square from a1, per piece in the order pawn push (promotions Q R B N),
-    double push, capture towards the a-file, capture towards the h-file; knight / king steps in the orders below, castling
-    king side then queen side; sliders direction by direction, near to far.  The en-passant square exists only while an
-    enemy pawn stands next to the pushed pawn; a position repeats when placement, side, castling rights and en-passant
-    square agree; draw on the third occurrence, after 100 quiet plies, or with bare kings."""
+    legality by making the move and looking at the king (no bitboards, no attack maps, no pins, no shortcuts).  What the two
+    must share is the SPECIFICATION: moves are policy indices from the mover's side (ranks flipped for black) in the
+    reference's flat table (chess.rs:439-481), listed in the canonical order -- origin squares ascending from a1, per piece its
+    destination squares ascending, promotions Q R B N (the search breaks ties by position in this list).  The en-passant
+    square exists only while an enemy pawn stands next to the pushed pawn; a position repeats when placement, side, castling
+    rights and en-passant square agree; draw on the third occurrence, after 100 quiet plies, or with bare kings."""
     KNIGHT = [(2, 1), (1, 2), (-1, 2), (-2, 1), (-2, -1), (-1, -2), (1, -2), (2, -1)]  # (rank, file) steps
     KING = [(1, 0), (-1, 0), (0, 1), (0, -1), (1, 1), (1, -1), (-1, 1), (-1, -1)]
     SLIDES = {3: KING[4:], 4: KING[:4], 5: KING}  # bishop, rook, queen
@@ -521,7 +520,8 @@ class Chess:
 
     def moves(self) -> List[int]:
         index = self.flat()[1]
-        return [index[(self._pov(f), self._pov(t), promo)] for f, t, promo in self._legal()]
+        ordered = sorted(self._legal(), key=lambda m: (m[0], m[1], -m[2]))  # the generator walks piece by piece, direction by direction
+        return [index[(self._pov(f), self._pov(t), promo)] for f, t, promo in ordered]
 
     def play(self, mv: int) -> None:
         f, t, promo = self.flat()[0][mv]

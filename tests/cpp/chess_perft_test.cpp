@@ -5,8 +5,11 @@
 #include <cstdio>
 #include <cstring>
 
+#include <chrono>
+
 #include "../../kzero_b200/csrc/selfplay/chess_game.hpp"
 #include "../../kzero_b200/csrc/selfplay/mcts.hpp"
+#include "chess_mailbox.hpp"
 
 using namespace kzb::selfplay;
 
@@ -66,8 +69,87 @@ static int check_playouts() {
     return 0;
 }
 
+// the bitboard generator against round 1's mailbox generator, move for move over random games: the same legal moves (the mailbox
+// list sorted into the canonical order: origin ascending, destination ascending, promotions Q R B N), the same keys, clocks, rights,
+// repetition counts, terminal flags and encodings
+static int check_against_mailbox() {
+    long positions = 0;
+    for (uint64_t seed = 1000; seed < 1400; seed++) {
+        Chess b = Chess::start(seed);
+        ChessMailbox ref = ChessMailbox::start(seed);
+        Rng rng(seed * 7 + 1);
+        std::vector<uint32_t> m;
+        for (int ply = 0; ply < 300; ply++, positions++) {
+            uint8_t bits[104], ref_bits[104];
+            float sc[8], ref_sc[8];
+            b.encode(bits, sc), ref.encode(ref_bits, ref_sc);
+            if (b.key != ref.key || b.reps != ref.reps || b.halfmove != ref.halfmove || b.castle != ref.castle || b.ep != ref.ep || b.terminal != ref.terminal ||
+                b.side != ref.side || b.hash() != ref.hash() || std::memcmp(b.sq, ref.sq, 64) != 0 || std::memcmp(bits, ref_bits, 104) != 0 ||
+                std::memcmp(sc, ref_sc, sizeof(sc)) != 0)
+                return std::printf("bitboard and mailbox positions differ at seed %llu ply %d\n", (unsigned long long)seed, ply), 1;
+            if (b.done()) break;
+            struct K {
+                int from, to, slot;
+                uint32_t index;
+                bool operator<(const K& o) const { return from != o.from ? from < o.from : to != o.to ? to < o.to : slot < o.slot; }
+            };
+            std::vector<K> want;
+            ref.legal_moves([&](const ChessMailbox::Mv& mv) {
+                want.push_back(K{mv.from, mv.to, mailbox_detail::FlatMoves::slot_of(mv.promo), ref.index_of(mv)});
+                return true;
+            });
+            std::sort(want.begin(), want.end());
+            if (ply % 2) kzb::selfplay::chess_detail::reply_cache().n = -1;  // every other position: generated afresh, not read from the cache
+            b.moves(m);
+            bool same = m.size() == want.size();
+            for (size_t i = 0; same && i < m.size(); i++) same = m[i] == want[i].index;
+            if (!same) return std::printf("legal moves differ at seed %llu ply %d (%zu vs %zu)\n", (unsigned long long)seed, ply, m.size(), want.size()), 1;
+            const uint32_t mv = m[rng.gen_range(uint32_t(m.size()))];
+            b.play(mv), ref.play(mv);
+        }
+    }
+    // play_interior keeps everything but the terminal flag
+    {
+        Chess a = Chess::start(0), c = Chess::start(0);
+        Rng rng(5);
+        std::vector<uint32_t> m;
+        for (int ply = 0; ply < 60 && !a.done(); ply++) {
+            a.moves(m);
+            const uint32_t mv = m[rng.gen_range(uint32_t(m.size()))];
+            a.play(mv), c.play_interior(mv);
+            if (a.key != c.key || a.reps != c.reps || a.halfmove != c.halfmove || a.hash() != c.hash() || std::memcmp(a.sq, c.sq, 64) != 0 || a.colour[0] != c.colour[0] ||
+                a.colour[1] != c.colour[1] || std::memcmp(a.kind, c.kind, sizeof(a.kind)) != 0)
+                return std::printf("play_interior diverges from play at ply %d\n", ply), 1;
+        }
+    }
+    // what the search does per leaf -- play a move into a fresh position, list its replies -- timed for both generators
+    auto time_it = [&](auto start_board, const char* name) {
+        using B = decltype(start_board);
+        const auto t0 = std::chrono::steady_clock::now();
+        long n = 0;
+        uint64_t sink = 0;
+        for (uint64_t seed = 1; seed <= 200; seed++) {
+            B b = start_board;
+            Rng rng(seed);
+            std::vector<uint32_t> m;
+            for (int ply = 0; ply < 200 && !b.done(); ply++, n++) {
+                b.moves(m);
+                b.play(m[rng.gen_range(uint32_t(m.size()))]);
+                sink += m.size();
+            }
+        }
+        const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
+        std::fprintf(stderr, "[chess] %-9s %.0f ns per play + moves (%ld positions, %llu)\n", name, ns / double(n), n, (unsigned long long)sink);
+    };
+    time_it(Chess::start(0), "bitboard");
+    time_it(ChessMailbox::start(0), "mailbox");
+    std::fprintf(stderr, "[chess] %ld positions compared with the mailbox generator\n", positions);
+    return 0;
+}
+
 int main() {
     if (check_playouts()) return 1;
+    if (check_against_mailbox()) return 1;
     struct Case {
         const char* fen;
         int depth;
