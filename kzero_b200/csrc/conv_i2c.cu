@@ -121,7 +121,11 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 // persistent mode: every CTA of the grid has finished `layers_done` layers (its output rows are complete and visible, also to TMA loads)
 __device__ __forceinline__ void grid_barrier_wait(const unsigned* bar, unsigned layers_done) {
     const unsigned target = layers_done * gridDim.x;
-    while (ld_acquire_gpu(bar) < target) __nanosleep(40);
+    unsigned polls = 0;
+    while (ld_acquire_gpu(bar) < target) {
+        __nanosleep(40);
+        if (++polls > (1u << 22)) __trap();  // seconds: a barrier that never opens becomes an error, not a hung device
+    }
     asm volatile("fence.proxy.async;" ::: "memory");  // what the acquire made visible -> visible to the async proxy (TMA loads)
 }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }

@@ -13,6 +13,7 @@
 //   Go9          9x9 go with the reference's GoStdMapper encoding (4 bool + 6 scalar planes) and restated rules, see below.
 //   Chess        legal chess, in chess_game.hpp.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -260,45 +261,63 @@ struct Ataxx {
 // territory = false, the 4 + 6 plane form python/lib/games.py:180-194 describes): bools = (next player's stones, other
 // stones, in-board, empty-but-illegal), scalars = (black to move, white to move, one pass, two passes, komi from the
 // mover's side / 15, multi-stone suicide allowed), policy index 0 = pass, 1 + y * S + x = place (go.rs:26-31).
-// Rules, restated (the `board-game` crate is not vendored): area scoring with komi, suicide is illegal, SIMPLE ko (the
-// immediate recapture of a single stone), two consecutive passes end the game.  No superko: a driver-side
-// max_game_length bounds cycles.  Start positions follow go_start_pos (start_pos.rs:69-88): komi 7.5 most of the time.
+// Rules, restated (the `board-game` crate is not vendored): area scoring with komi, two consecutive passes end the game, positional
+// superko (a placement may not recreate the stones of any earlier position of the game; contains the simple ko rule), a single stone
+// may never kill itself; per game one of the two rule sets go_start_pos draws (start_pos.rs:81-84): Rules::cgos() -- suicide is
+// illegal -- or Rules::tromp_taylor() -- a move may remove its own group of two or more stones (`allow_multi_stone_suicide`, the
+// sixth scalar).  Start positions follow go_start_pos (start_pos.rs:69-88): komi 7.5 most of the time.
 struct Go9 {
     static constexpr int S = 9, A = 81;
+    static constexpr int kHist = 512;  // earlier positions remembered for the superko rule (games are capped far below this)
     uint8_t stones[A] = {};  // 0 empty, 1 player A (black), 2 player B (white)
-    uint32_t ply = 0;
-    int16_t ko = -1;         // point that may not be played this turn
+    uint8_t passes = 0;         // 0 normal, 1 one pass, 2 done
+    uint8_t multi_suicide = 0;  // Rules::tromp_taylor(): a move may remove its own group of two or more stones; Rules::cgos(): it may not
+    mutable uint8_t legal_valid = 0;
     int16_t komi_2 = 15;     // komi in half points, in white's favour
-    uint8_t passes = 0;      // 0 normal, 1 one pass, 2 done
+    uint16_t hist_n = 1;
+    uint32_t ply = 0;
+    mutable uint64_t legal[2] = {};  // the legal placements of the player to move, bit p (computed by play(), or on demand)
+    uint64_t key = 0;                // zobrist key of the stones
+    uint64_t hist[kHist];            // keys of every position of the game so far, the current one included
+
+    Go9() { hist[0] = 0; }  // the empty board is the first position of the game
+    Go9(const Go9& o) { *this = o; }
+    Go9& operator=(const Go9& o) {  // copies only the used part of the history
+        std::memcpy(static_cast<void*>(this), &o, offsetof(Go9, hist) + size_t(o.hist_n) * sizeof(uint64_t));
+        return *this;
+    }
 
     static GameShape shape() { return {4, 6, S, A + 1}; }
     static const char* name() { return "go-9"; }
+    // komi and rule set drawn per game like go_start_pos (rust/kz-selfplay/src/server/start_pos.rs:69-88): komi weights 4 : 4 : 2,
+    // Rules::cgos() or Rules::tromp_taylor() with equal probability
     static Go9 start(uint64_t seed) {
         Go9 g;
         const uint64_t h = splitmix64(seed ^ 0x60B0A4Dull);
-        const uint32_t pick = uint32_t(h % 10);  // weights 4 : 4 : 2 as in go_start_pos
+        const uint32_t pick = uint32_t(h % 10);
         if (pick < 4) g.komi_2 = 15;
         else if (pick < 8) g.komi_2 = int16_t(10 + (h >> 8) % 10);
         else g.komi_2 = int16_t(int((h >> 8) % 60) - 30);
+        g.multi_suicide = uint8_t((h >> 40) & 1);
         return g;
     }
+    static uint64_t zobrist(int colour, int p) { return splitmix64(0x60ull * 1000 + uint64_t(colour) * 128 + uint64_t(p)); }
     int next_player() const { return int(ply & 1); }
     bool done() const { return passes >= 2; }
+    // what the network's answer depends on: stones, side, passes, komi, rule set -- and the set of legal moves, which under superko
+    // depends on the game's history
     uint64_t hash() const {
-        uint64_t h = 0x9E3779B97F4A7C15ull * (uint64_t(ply & 1) + 3) + uint64_t(uint16_t(ko)) * 0x100000001B3ull + passes * 0xD6E8FEB86659FD93ull +
-                     uint64_t(uint16_t(komi_2)) * 0xA0761D6478BD642Full;
-        for (int i = 0; i < A; i += 8) {
-            uint64_t w = 0;
-            std::memcpy(&w, stones + i, size_t(A - i < 8 ? A - i : 8));
-            h = splitmix64(h ^ w);
-        }
-        return h;
+        ensure_legal();
+        uint64_t h = key ^ (0x9E3779B97F4A7C15ull * (uint64_t(ply & 1) + 3)) ^ (passes * 0xD6E8FEB86659FD93ull) ^ (uint64_t(uint16_t(komi_2)) * 0xA0761D6478BD642Full) ^
+                     (multi_suicide ? 0x5851F42D4C957F2Dull : 0);
+        return splitmix64(splitmix64(h ^ legal[0]) ^ legal[1]);
     }
 
-    // groups and their liberties for the whole board: gid[p] (0 = empty), libs[g] = liberty count of group g
+    // groups and their liberties for the whole board: gid[p] (0 = empty), libs[g] = liberty count of group g, zob[g] = key of its stones
     struct Groups {
         uint8_t gid[A];
         uint8_t libs[A + 1];
+        uint64_t zob[A + 1];
         int count = 0;
     };
     template <typename F>
@@ -319,10 +338,12 @@ struct Go9 {
             if (!stones[p0] || g.gid[p0]) continue;
             const int id = ++g.count;
             int top = 0, libs = 0;
+            uint64_t z = 0;
             stack[top++] = p0;
             g.gid[p0] = uint8_t(id);
             while (top) {
                 const int p = stack[--top];
+                z ^= zobrist(stones[p0], p);
                 for_neighbours(p, [&](int q) {
                     if (!stones[q]) {
                         if (seen_lib[q] != id) {
@@ -336,68 +357,100 @@ struct Go9 {
                 });
             }
             g.libs[id] = uint8_t(libs);
+            g.zob[id] = z;
         }
     }
-    // legal placements of the player to move: empty, not the ko point, and the stone ends up with a liberty
-    void legal_mask(bool legal[A]) const {
+    bool seen_before(uint64_t k) const {
+        bool hit = false;
+        for (int i = 0; i < int(hist_n); i++) hit |= hist[i] == k;
+        return hit;
+    }
+    // Legal placements of the player to move (board-game's GoBoard::is_available_move): the point is empty; the stone ends up with a
+    // liberty -- its own, a friendly group's, or by capturing -- or, under Tromp-Taylor rules, takes at least one friendly stone with
+    // it (multi-stone suicide; a single stone may never kill itself); and the stones after the move are not those of any earlier
+    // position of the game (positional superko, which contains the simple ko rule)
+    void compute_legal() const {
         Groups g;
         groups(g);
         const uint8_t me = uint8_t(1 + (ply & 1)), other = uint8_t(3 - me);
+        legal[0] = legal[1] = 0;
         for (int p = 0; p < A; p++) {
-            legal[p] = false;
-            if (stones[p] || p == ko) continue;
-            bool ok = false;
+            if (stones[p]) continue;
+            bool has_empty = false, captures = false, own_safe = false, own_any = false;
+            uint64_t cap_key = 0, own_key = 0;
+            uint8_t seen[4];
+            int n_seen = 0;
             for_neighbours(p, [&](int q) {
-                if (!stones[q]) ok = true;                                            // an empty neighbour
-                else if (stones[q] == me && g.libs[g.gid[q]] >= 2) ok = true;         // joins a group that keeps a liberty
-                else if (stones[q] == other && g.libs[g.gid[q]] == 1) ok = true;      // captures
+                if (!stones[q]) {
+                    has_empty = true;
+                    return;
+                }
+                const uint8_t id = g.gid[q];
+                bool first = true;
+                for (int i = 0; i < n_seen; i++) first &= seen[i] != id;
+                if (first) seen[n_seen++] = id;
+                if (stones[q] == other) {
+                    if (g.libs[id] == 1) {
+                        captures = true;
+                        if (first) cap_key ^= g.zob[id];
+                    }
+                } else {
+                    own_any = true;
+                    if (g.libs[id] >= 2) own_safe = true;
+                    if (first) own_key ^= g.zob[id];
+                }
             });
-            legal[p] = ok;
+            uint64_t after;
+            if (has_empty || captures || own_safe) after = key ^ zobrist(me, p) ^ cap_key;
+            else if (own_any && multi_suicide) after = key ^ own_key;  // the stone and the groups it joined leave the board
+            else continue;
+            if (!seen_before(after)) legal[p >> 6] |= 1ull << (p & 63);
         }
+        legal_valid = 1;
     }
+    void ensure_legal() const {
+        if (!legal_valid) compute_legal();
+    }
+    bool is_legal(int p) const { return (legal[p >> 6] >> (p & 63)) & 1; }
     void moves(std::vector<uint32_t>& out) const {  // a move is its policy index; pass first (available_moves order)
-        bool legal[A];
-        legal_mask(legal);
+        ensure_legal();
         out.clear();
         out.push_back(0);
         for (int p = 0; p < A; p++)
-            if (legal[p]) out.push_back(uint32_t(1 + p));
+            if (is_legal(p)) out.push_back(uint32_t(1 + p));
     }
     uint32_t move_to_index(uint32_t mv) const { return mv; }
     void play(uint32_t mv) {
+        play_interior(mv);
+        if (!done()) compute_legal();  // the search asks for the replies of a new leaf right away; hash() and encode() use them as well
+    }
+    // the move alone: the replies are computed when somebody asks for them (mcts.hpp: interior nodes of a descent never do)
+    void play_interior(uint32_t mv) {
+        legal_valid = 0;
         if (mv == 0) {
             passes++;
-            ko = -1;
             ply++;
             return;
         }
         const int p = int(mv) - 1;
         const uint8_t me = uint8_t(1 + (ply & 1)), other = uint8_t(3 - me);
         stones[p] = me;
+        key ^= zobrist(me, p);
         Groups g;
         groups(g);
-        int captured = 0, last_captured = -1;
         bool dead[A + 1] = {};
+        bool any_dead = false;
         for_neighbours(p, [&](int q) {
-            if (stones[q] == other && g.libs[g.gid[q]] == 0) dead[g.gid[q]] = true;
+            if (stones[q] == other && g.libs[g.gid[q]] == 0) dead[g.gid[q]] = any_dead = true;
         });
-        for (int q = 0; q < A; q++)
-            if (stones[q] == other && dead[g.gid[q]]) {
-                stones[q] = 0;
-                captured++;
-                last_captured = q;
-            }
-        // simple ko: one stone captured by a single stone that now has exactly that one liberty
-        ko = -1;
-        if (captured == 1) {
-            bool single = true;
-            int libs = 0;
-            for_neighbours(p, [&](int q) {
-                if (stones[q] == me) single = false;
-                if (!stones[q]) libs++;
-            });
-            if (single && libs == 1) ko = int16_t(last_captured);
-        }
+        if (!any_dead && g.libs[g.gid[p]] == 0) dead[g.gid[p]] = any_dead = true;  // multi-stone suicide (only ever legal under Tromp-Taylor)
+        if (any_dead)
+            for (int q = 0; q < A; q++)
+                if (stones[q] && dead[g.gid[q]]) {
+                    key ^= zobrist(stones[q], q);
+                    stones[q] = 0;
+                }
+        if (hist_n < kHist) hist[hist_n++] = key;
         passes = 0;
         ply++;
     }
@@ -434,10 +487,12 @@ struct Go9 {
         const int s2 = score_2();
         return (s2 > 0) - (s2 < 0);
     }
-    void encode(uint8_t* bits, float* scalars) const {
+    void encode(uint8_t* bits, float* scalars) const {  // GoStdMapper::encode_input, rust/kz-core/src/mapping/go.rs:62-112
         std::memset(bits, 0, size_t((4 * A + 7) / 8));
-        bool legal[A];
-        legal_mask(legal);
+        // a finished board has no unavailable moves: is_available_move fails on it and the mapper reads that as "available"
+        // (`.unwrap_or(true)`, go.rs:84)
+        const bool running = !done();
+        if (running) ensure_legal();
         const uint8_t me = uint8_t(1 + (ply & 1)), other = uint8_t(3 - me);
         auto set = [&](int plane, int p) {
             const int bit = plane * A + p;
@@ -447,7 +502,7 @@ struct Go9 {
             if (stones[p] == me) set(0, p);
             if (stones[p] == other) set(1, p);
             set(2, p);
-            if (!stones[p] && !legal[p]) set(3, p);
+            if (running && !stones[p] && !is_legal(p)) set(3, p);
         }
         const float komi = float(komi_2) * 0.5f;
         scalars[0] = next_player() == 0 ? 1.0f : 0.0f;
@@ -455,7 +510,7 @@ struct Go9 {
         scalars[2] = passes == 1 ? 1.0f : 0.0f;
         scalars[3] = passes >= 2 ? 1.0f : 0.0f;
         scalars[4] = (next_player() == 0 ? komi : -komi) / 15.0f;
-        scalars[5] = 0.0f;  // multi-stone suicide is not allowed
+        scalars[5] = multi_suicide ? 1.0f : 0.0f;
     }
 };
 

@@ -90,12 +90,16 @@ class SynthChess:
 
 class Go9:
     """Twin of kzb::selfplay::Go9 (kzero_b200/csrc/selfplay/games.hpp), written independently from the rules as stated there:
-    area scoring with komi, no suicide, simple ko, two passes end the game; move 0 = pass, 1 + y * 9 + x = place."""
+    area scoring with komi, two passes end the game, positional superko (the stones after a placement may not be those of any
+    earlier position of the game), a single stone may not kill itself, and per game either no suicide at all (cgos) or suicide of
+    two or more stones allowed (Tromp-Taylor); move 0 = pass, 1 + y * 9 + x = place.  Legality here is "make the move on a copy
+    and look": no group tables, no incremental keys."""
     S, A = 9, 81
 
     def __init__(self):
         self.stones = [0] * self.A  # 0 empty, 1 black (player A), 2 white
-        self.ply, self.ko, self.komi_2, self.passes = 0, -1, 15, 0
+        self.ply, self.komi_2, self.passes, self.multi_suicide = 0, 15, 0, 0
+        self.seen = {tuple(self.stones)}  # the stones of every position so far, the current one included
 
     @staticmethod
     def start(seed: int) -> "Go9":
@@ -108,20 +112,24 @@ class Go9:
             g.komi_2 = 10 + (h >> 8) % 10
         else:
             g.komi_2 = (h >> 8) % 60 - 30
+        g.multi_suicide = (h >> 40) & 1
         return g
 
     def clone(self):
-        g = Go9()
-        g.stones, g.ply, g.ko, g.komi_2, g.passes = list(self.stones), self.ply, self.ko, self.komi_2, self.passes
+        g = Go9.__new__(Go9)
+        g.stones, g.ply, g.komi_2, g.passes, g.multi_suicide = list(self.stones), self.ply, self.komi_2, self.passes, self.multi_suicide
+        g.seen = set(self.seen)
         return g
 
     def hash(self) -> int:
-        h = (0x9E3779B97F4A7C15 * ((self.ply & 1) + 3) + (self.ko & 0xFFFF) * 0x100000001B3 + self.passes * 0xD6E8FEB86659FD93
-             + (self.komi_2 & 0xFFFF) * 0xA0761D6478BD642F) & M64
-        for i in range(0, self.A, 8):
-            w = int.from_bytes(bytes(self.stones[i:i + 8]), "little")
-            h = splitmix64(h ^ w)
-        return h
+        key = 0
+        for p, v in enumerate(self.stones):
+            if v:
+                key ^= splitmix64(0x60 * 1000 + v * 128 + p)
+        legal = sum(1 << p for p in range(self.A) if self._legal(p))
+        h = key ^ ((0x9E3779B97F4A7C15 * ((self.ply & 1) + 3)) & M64) ^ ((self.passes * 0xD6E8FEB86659FD93) & M64) \
+            ^ (((self.komi_2 & 0xFFFF) * 0xA0761D6478BD642F) & M64) ^ (0x5851F42D4C957F2D if self.multi_suicide else 0)
+        return splitmix64(splitmix64(h ^ (legal & M64)) ^ (legal >> 64))
 
     def next_player(self) -> int:
         return self.ply & 1
@@ -140,32 +148,44 @@ class Go9:
         if y < self.S - 1:
             yield p + self.S
 
-    def _group(self, p: int):
+    def _group(self, stones, p: int):
         """-> (stones of the group containing p, its liberties)"""
-        colour, group, libs, todo = self.stones[p], {p}, set(), [p]
+        colour, group, libs, todo = stones[p], {p}, set(), [p]
         while todo:
             q = todo.pop()
             for r in self._neighbours(q):
-                if self.stones[r] == 0:
+                if stones[r] == 0:
                     libs.add(r)
-                elif self.stones[r] == colour and r not in group:
+                elif stones[r] == colour and r not in group:
                     group.add(r)
                     todo.append(r)
         return group, libs
 
-    def _legal(self, p: int) -> bool:
-        if self.stones[p] or p == self.ko:
-            return False
+    def _placed(self, p: int):
+        """The stones after the player to move places on the empty point p, or None when the rules forbid the placement itself
+        (superko is the caller's business)."""
         me = 1 + (self.ply & 1)
+        stones = list(self.stones)
+        stones[p] = me
         for q in self._neighbours(p):
-            if self.stones[q] == 0:
-                return True
-            libs = self._group(q)[1]
-            if self.stones[q] == me and len(libs) >= 2:
-                return True
-            if self.stones[q] != me and len(libs) == 1:
-                return True
-        return False
+            if stones[q] not in (0, me):
+                group, libs = self._group(stones, q)
+                if not libs:
+                    for r in group:
+                        stones[r] = 0
+        group, libs = self._group(stones, p)
+        if not libs:  # nothing was captured (a capture would have freed a point next to p): suicide
+            if len(group) < 2 or not self.multi_suicide:
+                return None
+            for r in group:
+                stones[r] = 0
+        return stones
+
+    def _legal(self, p: int) -> bool:
+        if self.stones[p]:
+            return False
+        after = self._placed(p)
+        return after is not None and tuple(after) not in self.seen
 
     def moves(self) -> List[int]:
         return [0] + [1 + p for p in range(self.A) if self._legal(p)]
@@ -173,25 +193,10 @@ class Go9:
     def play(self, mv: int) -> None:
         if mv == 0:
             self.passes += 1
-            self.ko = -1
             self.ply += 1
             return
-        p = mv - 1
-        me = 1 + (self.ply & 1)
-        self.stones[p] = me
-        captured = []
-        for q in self._neighbours(p):
-            if self.stones[q] not in (0, me):
-                group, libs = self._group(q)
-                if not libs:
-                    for r in group:
-                        self.stones[r] = 0
-                    captured.extend(group)
-        self.ko = -1
-        if len(captured) == 1:
-            group, libs = self._group(p)
-            if len(group) == 1 and len(libs) == 1:
-                self.ko = captured[0]
+        self.stones = self._placed(mv - 1)
+        self.seen.add(tuple(self.stones))
         self.passes = 0
         self.ply += 1
 
@@ -204,10 +209,10 @@ class Go9:
             planes[0, y, x] = v == me
             planes[1, y, x] = v not in (0, me)
             planes[2, y, x] = 1
-            planes[3, y, x] = v == 0 and not self._legal(p)
+            planes[3, y, x] = v == 0 and not self.done() and not self._legal(p)  # a finished board has no unavailable moves (go.rs:84)
         komi = F(self.komi_2) * F(0.5)
         black = self.next_player() == 0
-        return planes, np.array([black, not black, self.passes == 1, self.passes >= 2, (komi if black else -komi) / F(15.0), 0], F)
+        return planes, np.array([black, not black, self.passes == 1, self.passes >= 2, (komi if black else -komi) / F(15.0), self.multi_suicide], F)
 
     def outcome(self) -> int:
         black = sum(1 for v in self.stones if v == 1)

@@ -51,9 +51,9 @@ def test_search_variants_match_oracle(kw):
     assert np.allclose(got.root_values, ref["root_values"], rtol=0, atol=1e-6)
 
 
-@pytest.mark.parametrize("game_seed,plies,rng_seed,eval_kind", [(1, 0, 5, 1), (2, 30, 6, 1), (9, 60, 7, 0)])
+@pytest.mark.parametrize("game_seed,plies,rng_seed,eval_kind", [(1, 0, 5, 1), (2, 30, 6, 1), (9, 60, 7, 0), (3, 120, 8, 1), (5, 100, 9, 1), (33, 140, 10, 1)])
 def test_go_search_matches_oracle(game_seed, plies, rng_seed, eval_kind):
-    """9x9 go: the C++ rules (captures, ko, suicide, passes, scoring inside the search's terminal nodes) and the oracle's
+    """9x9 go: the C++ rules (captures, positional superko, both suicide rule sets, passes, scoring inside the search's terminal nodes) and the oracle's
     independent Python restatement of them must agree for the trees to be identical; 82-way nodes with a pass move."""
     c = _cfg(game=selfplay.GAME_GO9, visits=120, search_batch=8, seed=rng_seed)
     got = selfplay.mcts_trace(c, game_seed, plies, eval_kind)

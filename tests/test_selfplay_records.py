@@ -137,11 +137,12 @@ def replay_under_oracle_rules(prefix, name, twin):
     for g in range(meta["game_count"]):
         first = int(game_starts[g])
         length = int(positions[first]["scalars"][2])
-        # the driver reseeds every new game; go's komi is the only seed-dependent part of a start position and is in the record
+        # the driver reseeds every new game; go's komi and rule set are the seed-dependent parts of a start position and are in the record
         board = getattr(mo, twin).start(0)
         if name == "go-9":
             komi_pov = float(positions[first]["input_scalars"][4]) * 15.0
             board.komi_2 = int(round(2 * komi_pov))  # black moves first: komi from black's side
+            board.multi_suicide = int(positions[first]["input_scalars"][5])
         for k in range(length + 1):
             p = positions[first + k]
             planes, scalars = board.encode()
