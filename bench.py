@@ -302,7 +302,7 @@ def run_reference(args, cfg, spec, onnx_bytes):
     print(json.dumps(line), flush=True)
 
 
-TOWER_STEP = lambda n: n in ("tower8", "tower_i2c") or n.startswith("conv_first") or n.startswith("block")  # noqa: E731
+TOWER_STEP = lambda n: n == "tower8" or n.startswith("conv_first") or n.startswith("block")  # noqa: E731
 
 
 def measure(name, args, ctx, steps, warmup, with_two_threads, sampler=None):

@@ -22,11 +22,6 @@
 // arrives by TMA two chunks ahead, is updated IN PLACE and leaves by TMA store -- no per-thread global loads / stores, and a code
 // body of a few hundred instructions (the shared conv_epilogue_tile unrolls to 90 KB of code and kept the epilogue warps busy 80-90 %
 // of a tile's MMA time: profiles/r02_go_kernels.md).
-// Persistent mode (p.num_layers > 1, small batches): ONE cooperative launch walks consecutive layers -- barriers, TMEM, the stage ring and
-// the staging rings simply keep running -- with a grid-wide barrier between layers: a CTA's epilogue threads wait for their TMA stores,
-// then one of them does fence.proxy.async + __threadfence + atomicAdd on a global counter; before a layer's first activation load (and first
-// residual load) the reader polls the counter with ld.acquire.gpu and issues fence.proxy.async.  A layer's first weight halves are put in
-// flight BEFORE that wait.  Replaces 41 launches (set-up, ramp, drain each) by one for a 20-block go net.
 // p.n_split = 2 (small batches): a work item is one 256-pixel tile x one half of the output channels (M256 N128 MMAs).
 // p.pdl: launched with programmatic stream serialization -- set-up and the first weight tiles overlap the previous layer's tail.
 #include "kernels.cuh"
@@ -53,10 +48,10 @@ struct SmemLayout {
     uint8_t* staging;  // [epilogue warp][kStgBufs][2 KB]
     uint64_t *full, *empty, *tmem_full, *tmem_empty, *res_full;
     uint32_t* tmem_ptr;
-    float* bias;  // two buffers of n floats (layer L uses buffer L & 1)
+    float* bias;
 };
 
-__device__ __forceinline__ SmemLayout carve(uint8_t* base, int stages, int /*n*/) {
+__device__ __forceinline__ SmemLayout carve(uint8_t* base, int stages) {
     SmemLayout s;
     s.stages = base;
     s.staging = base + size_t(stages) * kStageBytes;
@@ -113,40 +108,26 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {  // arrives on `ba
                  : "memory");
 }
 
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-// persistent mode: every CTA of the grid has finished `layers_done` layers (its output rows are complete and visible, also to TMA loads)
-__device__ __forceinline__ void grid_barrier_wait(const unsigned* bar, unsigned layers_done) {
-    const unsigned target = layers_done * gridDim.x;
-    unsigned polls = 0;
-    while (ld_acquire_gpu(bar) < target) {
-        __nanosleep(40);
-        if (++polls > (1u << 22)) __trap();  // seconds: a barrier that never opens becomes an error, not a hung device
-    }
-    asm volatile("fence.proxy.async;" ::: "memory");  // what the acquire made visible -> visible to the async proxy (TMA loads)
-}
-__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-
-__global__ void __launch_bounds__(kThreads, 1) conv_i2c_kernel(const __grid_constant__ I2cMaps maps, const I2cParams p) {
+__global__ void __launch_bounds__(kThreads, 1)
+    conv_i2c_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_bh, const __grid_constant__ CUtensorMap tmap_out,
+                    const __grid_constant__ CUtensorMap tmap_res, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const SmemLayout sm = carve(smem, p.stages, p.n);
+    const SmemLayout sm = carve(smem, p.stages);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int n_eff = p.n / p.n_split;                      // output channels per work item
     const uint32_t b_bytes = uint32_t(n_eff / 2) * 128u;    // this CTA's half of a weight tile
     const int num_pairs = (p.num_tiles + 1) / 2;            // pair tiles of 256 pixels
-    const int num_items = num_pairs * p.n_split;            // per layer
+    const int num_items = num_pairs * p.n_split;
     const int cluster_id = int(blockIdx.x) / 2, num_clusters = int(gridDim.x) / 2;
     const int area = p.lay.W * p.lay.H;
-    const int w_split = p.n_split == 2 ? 1 : 0;             // which weight box: n / 2 or n / 4 rows
-    const I2cLayerDev* layers = p.layers + p.layer0;
+    const int taps = p.taps, pad = p.taps == 9 ? 1 : 0;  // 3x3 with zero padding 1, or 1x1
 
     if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_bh)) : "memory");
         for (int i = 0; i < p.stages; i++) {
             mbar_init(&sm.full[i], 1);
             mbar_init(&sm.empty[i], 1);
@@ -156,11 +137,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i2c_kernel(const __grid_cons
             mbar_init(&sm.tmem_empty[i], 8);  // 4 epilogue warps of each CTA (only the leader's copy is used)
         }
         for (int i = 0; i < 4 * kStgBufs; i++) mbar_init(&sm.res_full[i], 1);
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_out)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_res)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const I2cLayerDev l0 = layers[0];
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.a[l0.a_map])) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.w[l0.w_map][w_split])) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.out[l0.out_map])) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem_ptr)),
@@ -168,6 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i2c_kernel(const __grid_cons
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
+    for (int i = threadIdx.x; i < p.n; i += kThreads) sm.bias[i] = p.bias[i];
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();  // the peer's barriers exist before anything is committed to / completes on them
@@ -181,53 +161,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i2c_kernel(const __grid_cons
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int L = 0; L < p.num_layers; L++) {
-                const I2cLayerDev ly = layers[L];
-                const CUtensorMap* amap = &maps.a[ly.a_map];
-                const CUtensorMap* wmap = &maps.w[ly.w_map][w_split];
-                const int taps = ly.taps, pad = ly.taps == 9 ? 1 : 0, steps = ly.taps * ly.kblocks;
-                // weights do not depend on the previous layer: put this CTA's first weight halves in flight before waiting for it
-                int pre = 0;  // stages whose barrier is armed and whose weight half is in flight already
-                if ((p.pdl || L > 0) && cluster_id < num_items) {
+            int pre = 0;  // stages whose barrier is armed and whose weight half is in flight already
+            if (p.pdl) {
+                // weights do not depend on the previous layer: fill the ring's weight halves before waiting for it
+                if (cluster_id < num_items) {
                     const int n0 = (cluster_id % p.n_split) * n_eff;
-                    int st = stage;
-                    uint32_t ph = phase;
-                    for (; pre < p.stages && pre < steps; pre++) {
-                        mbar_wait(&sm.empty[st], ph ^ 1);
-                        if (leader) mbar_expect_tx(&sm.full[st], 2 * (kABytes + b_bytes));
-                        tma2_load_2d(wmap, &sm.full[st], sm.stages + size_t(st) * kStageBytes + kABytes, (pre % taps) * ly.cin_pad + (pre / taps) * kBlockK,
-                                     ly.w_row0 + n0 + int(rank) * (n_eff / 2));
-                        if (++st == p.stages) {
-                            st = 0;
-                            ph ^= 1;
-                        }
+                    for (; pre < p.stages && pre < taps * p.kblocks; pre++) {
+                        if (leader) mbar_expect_tx(&sm.full[pre], 2 * (kABytes + b_bytes));
+                        tma2_load_2d(&tmap_bh, &sm.full[pre], sm.stages + size_t(pre) * kStageBytes + kABytes, (pre % taps) * p.cin_pad + (pre / taps) * kBlockK,
+                                     n0 + int(rank) * (n_eff / 2));
                     }
                 }
-                if (L == 0) {
-                    if (p.pdl) grid_dep_wait();  // the activations are the previous kernel's output
-                } else {
-                    grid_barrier_wait(p.grid_barrier, unsigned(L));  // ... the previous layer's, written by every CTA of this grid
-                }
-                for (int item = cluster_id; item < num_items; item += num_clusters) {
-                    const int pt = item / p.n_split, n0 = (item % p.n_split) * n_eff;
-                    const int pix = (2 * pt + int(rank)) * kTileM;  // first pixel of this CTA's tile (may lie past the batch: rows never read back)
-                    const int img = pix / area, rem = pix - img * area;
-                    const int h0 = rem / p.lay.W, w0 = rem - h0 * p.lay.W;
-                    for (int kb = 0; kb < ly.kblocks; kb++) {
-                        for (int tap = 0; tap < taps; tap++) {
-                            uint8_t* dst = sm.stages + size_t(stage) * kStageBytes;
-                            if (pre > 0) {
-                                pre--;
-                            } else {
-                                mbar_wait(&sm.empty[stage], phase ^ 1);
-                                if (leader) mbar_expect_tx(&sm.full[stage], 2 * (kABytes + b_bytes));
-                                tma2_load_2d(wmap, &sm.full[stage], dst + kABytes, tap * ly.cin_pad + kb * kBlockK, ly.w_row0 + n0 + int(rank) * (n_eff / 2));
-                            }
-                            tma2_load_im2col(amap, &sm.full[stage], dst, kb * kBlockK, w0 - pad, h0 - pad, img, uint16_t(tap % 3), uint16_t(tap / 3));
-                            if (++stage == p.stages) {
-                                stage = 0;
-                                phase ^= 1;
-                            }
+                grid_dep_wait();  // the activations are the previous layer's output
+            }
+            for (int item = cluster_id; item < num_items; item += num_clusters) {
+                const int pt = item / p.n_split, n0 = (item % p.n_split) * n_eff;
+                const int pix = (2 * pt + int(rank)) * kTileM;  // first pixel of this CTA's tile (may lie past the batch: rows never stored)
+                const int img = pix / area, rem = pix - img * area;
+                const int h0 = rem / p.lay.W, w0 = rem - h0 * p.lay.W;
+                for (int kb = 0; kb < p.kblocks; kb++) {
+                    for (int tap = 0; tap < taps; tap++) {
+                        uint8_t* dst = sm.stages + size_t(stage) * kStageBytes;
+                        if (pre > 0) {
+                            pre--;
+                        } else {
+                            mbar_wait(&sm.empty[stage], phase ^ 1);
+                            if (leader) mbar_expect_tx(&sm.full[stage], 2 * (kABytes + b_bytes));
+                            tma2_load_2d(&tmap_bh, &sm.full[stage], dst + kABytes, tap * p.cin_pad + kb * kBlockK, n0 + int(rank) * (n_eff / 2));
+                        }
+                        tma2_load_im2col(&tmap_a, &sm.full[stage], dst, kb * kBlockK, w0 - pad, h0 - pad, img, uint16_t(tap % 3), uint16_t(tap / 3));
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1;
                         }
                     }
                 }
@@ -240,154 +205,122 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i2c_kernel(const __grid_cons
             const uint64_t hi = umma_desc_sw128_hi();
             int stage = 0;
             uint32_t phase = 0;
-            int local = 0;  // accumulators used so far, over all layers
-            for (int L = 0; L < p.num_layers; L++) {
-                const int steps = layers[L].taps * layers[L].kblocks;
-                for (int item = cluster_id; item < num_items; item += num_clusters, local++) {
-                    const int buf = local & 1;
-                    const uint32_t buf_phase = (local >> 1) & 1;
-                    mbar_wait_cluster(&sm.tmem_empty[buf], buf_phase ^ 1);
+            int local = 0;
+            for (int item = cluster_id; item < num_items; item += num_clusters, local++) {
+                const int buf = local & 1;
+                const uint32_t buf_phase = (local >> 1) & 1;
+                mbar_wait_cluster(&sm.tmem_empty[buf], buf_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * acc_stride;
+                const int steps = taps * p.kblocks;
+                for (int it = 0; it < steps; it++) {
+                    mbar_wait(&sm.full[stage], phase);  // both CTAs' pixels and both halves of the weight tile
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + buf * acc_stride;
-                    for (int it = 0; it < steps; it++) {
-                        mbar_wait(&sm.full[stage], phase);  // both CTAs' pixels and both halves of the weight tile
-                        tc_fence_after();
-                        const uint32_t a_lo = umma_desc_lo(smem_u32(sm.stages + size_t(stage) * kStageBytes));
-                        const uint32_t b_lo = a_lo + (kABytes >> 4);
-                        if (lane == 0) {
+                    const uint32_t a_lo = umma_desc_lo(smem_u32(sm.stages + size_t(stage) * kStageBytes));
+                    const uint32_t b_lo = a_lo + (kABytes >> 4);
+                    if (lane == 0) {
 #pragma unroll
-                            for (int k = 0; k < kBlockK / 16; k++)
-                                umma2_bf16(tmem_d, hi | uint64_t(a_lo + 2 * k), hi | uint64_t(b_lo + 2 * k), idesc, (it != 0 || k != 0) ? 1u : 0u);
-                            umma2_commit(&sm.empty[stage]);
-                        }
-                        __syncwarp();
-                        if (++stage == p.stages) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
+                        for (int k = 0; k < kBlockK / 16; k++)
+                            umma2_bf16(tmem_d, hi | uint64_t(a_lo + 2 * k), hi | uint64_t(b_lo + 2 * k), idesc, (it != 0 || k != 0) ? 1u : 0u);
+                        umma2_commit(&sm.empty[stage]);
                     }
-                    if (lane == 0) umma2_commit(&sm.tmem_full[buf]);  // accumulator complete in both CTAs -> both epilogues
                     __syncwarp();
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
+                if (lane == 0) umma2_commit(&sm.tmem_full[buf]);  // accumulator complete in both CTAs -> both epilogues
+                __syncwarp();
             }
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5), each CTA drains its own 128 rows
         const int quarter = warp % 4;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
-        const int et = int(threadIdx.x) - 64;  // 0..127 among the epilogue threads
         uint8_t* stg = sm.staging + size_t(quarter) * kStgBufs * kStgBytes;
         uint64_t* res_bar = sm.res_full + quarter * kStgBufs;
+        const bool has_res = p.res != nullptr;
+        const bool relu = p.relu_n > 0;  // whole layers only (the executor checks relu_n is 0 or n)
         const uint32_t cpi = uint32_t(n_eff / kChunk);  // chunks per work item
         const uint32_t local_items = cluster_id < num_items ? uint32_t((num_items - cluster_id + num_clusters - 1) / num_clusters) : 0u;
-        const uint32_t total = local_items * cpi;  // chunks per layer
+        const uint32_t total = local_items * cpi;
+        // chunk f of this warp: rows [row0, row0 + 32), output channels [col0, col0 + 32)
+        auto coords = [&](uint32_t f, int& row0, int& col0) {
+            const uint32_t li = f / cpi, c = f - li * cpi;
+            const int item = cluster_id + int(li) * num_clusters;
+            row0 = (2 * (item / p.n_split) + int(rank)) * kTileM + quarter * 32;
+            col0 = (item % p.n_split) * n_eff + int(c) * kChunk;
+        };
+        auto load_res = [&](uint32_t f) {  // lane 0: residual box of chunk f into its staging buffer
+            int row0, col0;
+            coords(f, row0, col0);
+            mbar_expect_tx(&res_bar[f % kStgBufs], kStgBytes);
+            tma_load_2d(&tmap_res, &res_bar[f % kStgBufs], stg + (f % kStgBufs) * kStgBytes, col0, row0);
+        };
+        if (p.pdl) grid_dep_wait();  // the residual rows are the previous layers' output
+        if (has_res && lane == 0) {
+            if (total > 0) load_res(0);
+            if (total > 1) load_res(1);
+        }
         const int sw = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^ bits 7..8 of the address
-        uint32_t g = 0;                  // chunks done so far, over all layers: staging buffer g % 4, its barrier's phase (g / 4) & 1
-        uint32_t acc = 0;                // accumulators drained so far, over all layers
-        for (int L = 0; L < p.num_layers; L++) {
-            const I2cLayerDev ly = layers[L];
-            const CUtensorMap* omap = &maps.out[ly.out_map];
-            const CUtensorMap* rmap = &maps.out[ly.res_map < 0 ? ly.out_map : ly.res_map];
-            const bool has_res = ly.res_map >= 0, relu = ly.relu != 0;
-            float* bias_s = sm.bias + (L & 1) * p.n;
-            for (int i = et; i < p.n; i += 128) bias_s[i] = ly.bias[i];
-            named_bar_sync(1, 128);
-            // chunk f of this layer: rows [row0, row0 + 32), output channels [col0, col0 + 32)
-            auto coords = [&](uint32_t f, int& row0, int& col0) {
-                const uint32_t li = f / cpi, c = f - li * cpi;
-                const int item = cluster_id + int(li) * num_clusters;
-                row0 = (2 * (item / p.n_split) + int(rank)) * kTileM + quarter * 32;
-                col0 = (item % p.n_split) * n_eff + int(c) * kChunk;
-            };
-            if (has_res) {  // the residual rows are earlier layers' output
-                if (L == 0) {
-                    if (p.pdl) grid_dep_wait();
-                } else if (lane == 0) {
-                    grid_barrier_wait(p.grid_barrier, unsigned(L));
-                }
-                __syncwarp();
-            }
-            const uint32_t g0 = g;  // global index of this layer's chunk 0
-            auto issue_res = [&](uint32_t f) {
-                int row0, col0;
-                coords(f, row0, col0);
-                const uint32_t sb = (g0 + f) % kStgBufs;
-                mbar_expect_tx(&res_bar[sb], kStgBytes);
-                tma_load_2d(rmap, &res_bar[sb], stg + sb * kStgBytes, col0, row0);
-            };
-            if (has_res && lane == 0) {
-                if (total > 0) issue_res(0);
-                if (total > 1) issue_res(1);
-            }
 #pragma unroll 1
-            for (uint32_t f = 0; f < total; f++, g++) {
-                const uint32_t li = f / cpi, c = f - li * cpi, a_idx = acc + li, buf = a_idx & 1, sb = g % kStgBufs;
-                if (c == 0) {
-                    mbar_wait(&sm.tmem_full[buf], (a_idx >> 1) & 1);
-                    tc_fence_after();
-                }
-                uint32_t r[32];
-                tmem_ld32(tmem_base + buf * acc_stride + (uint32_t(quarter * 32) << 16) + c * kChunk, r);
-                tmem_ld_wait();
-                if (c == cpi - 1) {  // the accumulator is in registers: the MMAs of the tile after next may overwrite it
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(&sm.tmem_empty[buf], 0);  // the leader's barrier, from either CTA
-                }
-                int row0, col0;
-                coords(f, row0, col0);
-                if (has_res) {
-                    mbar_wait(&res_bar[sb], (g / kStgBufs) & 1);
-                } else {
-                    if (lane == 0) tma_store_wait_read<kStgBufs - 1>();  // the store that last read this buffer (chunk g - 4) is done with it
-                    __syncwarp();
-                }
-                uint8_t* row_ptr = stg + sb * kStgBytes + lane * (kChunk * 2);
-                const float* bias = bias_s + col0;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {  // 8 channels = one 16-byte unit of the row
-                    float v[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        float x = __uint_as_float(r[j * 8 + k]) + bias[j * 8 + k];
-                        v[k] = relu ? (x < 0.0f ? 0.0f : x) : x;  // NaN stays NaN, like torch / ONNX Relu
-                    }
-                    uint4* cell = reinterpret_cast<uint4*>(row_ptr + ((j ^ sw) << 4));
-                    if (has_res) {  // the reference block is x + relu(bn(conv(...))): relu BEFORE the add (post_act.py:218-228)
-                        const uint4 q = *cell;
-                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const float2 t = __bfloat1622float2(h[k]);
-                            v[2 * k] += t.x;
-                            v[2 * k + 1] += t.y;
-                        }
-                    }
-                    *cell = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                }
-                fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(omap, stg + sb * kStgBytes, col0, row0);
-                    tma_store_commit();
-                    if (has_res && f + 2 < total) {
-                        tma_store_wait_read<2>();  // buffer (g + 2) % 4 was last read by the store of chunk g - 2
-                        issue_res(f + 2);
-                    }
-                }
+        for (uint32_t f = 0; f < total; f++) {
+            const uint32_t li = f / cpi, c = f - li * cpi, buf = li & 1, sb = f % kStgBufs;
+            if (c == 0) {
+                mbar_wait(&sm.tmem_full[buf], (li >> 1) & 1);
+                tc_fence_after();
             }
-            acc += local_items;
-            if (lane == 0) tma_store_wait_all();  // this warp's rows of the layer are in global memory
-            if (p.num_layers > 1) {
-                // persistent mode: tell the grid that this CTA is done with the layer -- every later layer reads rows other CTAs wrote
+            uint32_t r[32];
+            tmem_ld32(tmem_base + buf * acc_stride + (uint32_t(quarter * 32) << 16) + c * kChunk, r);
+            tmem_ld_wait();
+            if (c == cpi - 1) {  // the accumulator is in registers: the MMAs of the tile after next may overwrite it
+                tc_fence_before();
                 __syncwarp();
-                named_bar_sync(2, 128);
-                if (et == 0) {
-                    asm volatile("fence.proxy.async;" ::: "memory");  // the TMA stores' writes -> ordered before the generic release below
-                    __threadfence();
-                    atomicAdd(p.grid_barrier, 1u);
+                if (lane == 0) mbar_arrive_remote(&sm.tmem_empty[buf], 0);  // the leader's barrier, from either CTA
+            }
+            int row0, col0;
+            coords(f, row0, col0);
+            if (has_res) {
+                mbar_wait(&res_bar[sb], (f / kStgBufs) & 1);
+            } else {
+                if (lane == 0) tma_store_wait_read<kStgBufs - 1>();  // the store that last read this buffer (chunk f - 4) is done with it
+                __syncwarp();
+            }
+            uint8_t* row_ptr = stg + sb * kStgBytes + lane * (kChunk * 2);
+            const float* bias = sm.bias + col0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {  // 8 channels = one 16-byte unit of the row
+                float v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    float x = __uint_as_float(r[j * 8 + k]) + bias[j * 8 + k];
+                    v[k] = relu ? (x < 0.0f ? 0.0f : x) : x;  // NaN stays NaN, like torch / ONNX Relu
+                }
+                uint4* cell = reinterpret_cast<uint4*>(row_ptr + ((j ^ sw) << 4));
+                if (has_res) {  // the reference block is x + relu(bn(conv(...))): relu BEFORE the add (post_act.py:218-228)
+                    const uint4 q = *cell;
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float2 t = __bfloat1622float2(h[k]);
+                        v[2 * k] += t.x;
+                        v[2 * k + 1] += t.y;
+                    }
+                }
+                *cell = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+            fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&tmap_out, stg + sb * kStgBytes, col0, row0);
+                tma_store_commit();
+                if (has_res && f + 2 < total) {
+                    tma_store_wait_read<2>();  // buffer (f + 2) % 4 was last read by the store of chunk f - 2
+                    load_res(f + 2);
                 }
             }
         }
+        if (lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -403,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i2c_kernel(const __grid_cons
 }  // namespace
 
 size_t conv_i2c_smem_bytes(int n, int stages) {
-    return 1024 /*alignment slack*/ + size_t(stages) * kStageBytes + 4 * kStgBufs * kStgBytes + (2 * stages + 4 + 4 * kStgBufs) * 8 + 16 + 2 * size_t(n) * 4;
+    return 1024 /*alignment slack*/ + size_t(stages) * kStageBytes + 4 * kStgBufs * kStgBytes + (2 * stages + 4 + 4 * kStgBufs) * 8 + 16 + size_t(n) * 4;
 }
 
 int conv_i2c_pick_stages(int n) {
@@ -415,11 +348,12 @@ int conv_i2c_pick_stages(int n) {
 
 void conv_i2c_prepare() { cudaFuncSetAttribute(conv_i2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }
 
-// One launch runs p.num_layers consecutive layers of p.layers starting at p.layer0.  num_layers == 1: an ordinary launch (with
-// programmatic stream serialization when p.pdl).  num_layers > 1: the persistent mode for small batches -- a cooperative launch (all
-// CTAs co-resident) with a grid-wide barrier between layers on p.grid_barrier, which the caller has zeroed on the same stream.
-cudaError_t launch_conv_i2c(const I2cMaps& maps, const I2cParams& p, int grid, cudaStream_t s) {
-    if (p.num_tiles <= 0 || p.num_layers <= 0) return cudaSuccess;
+// tmap_a: im2col map over the dense channels-last activations (C, W, H, boards), 64 channels x 128 pixels per load, SWIZZLE_128B;
+// tmap_bh: weight map whose box holds p.n / p.n_split / 2 rows; tmap_out / tmap_res: output / residual rows, box (32 channels, 32 rows),
+// SWIZZLE_64B (tmap_res is only read when p.res is set)
+void launch_conv_i2c(const CUtensorMap& tmap_a, const CUtensorMap& tmap_bh, const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
+                     const ConvTcParams& p, int grid, cudaStream_t s) {
+    if (p.num_tiles <= 0) return;
     const int items = (p.num_tiles + 1) / 2 * p.n_split;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(2 * std::min(grid / 2, items)));
@@ -431,19 +365,11 @@ cudaError_t launch_conv_i2c(const I2cMaps& maps, const I2cParams& p, int grid, c
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
-    int n_attr = 1;
-    if (p.num_layers > 1) {
-        attr[1].id = cudaLaunchAttributeCooperative;
-        attr[1].val.cooperative = 1;
-        n_attr = 2;
-    } else if (p.pdl) {
-        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[1].val.programmaticStreamSerializationAllowed = 1;
-        n_attr = 2;
-    }
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = unsigned(n_attr);
-    return cudaLaunchKernelEx(&cfg, conv_i2c_kernel, maps, p);
+    cfg.numAttrs = p.pdl ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, conv_i2c_kernel, tmap_a, tmap_bh, tmap_out, tmap_res, p);
 }
 
 }  // namespace kzb

@@ -349,9 +349,26 @@ void Net::build_bf16() {
             uint32_t box[2] = {64, 128};
             st->tmap_a = make_tmap(in.ptr, 2, dims, strides, box);
         }
-        // conv_i2c.cu takes bf16-in / bf16-out layers with whole-layer relu; which of them share a launch table is decided below
-        st->use_i2c = (dense_i2c_ || (mode_ == 1 && i2c_ok_)) && cin_pad % 64 == 0 && n % 32 == 0 && n >= 32 && !out_f32 && (relu_n == 0 || relu_n == n) &&
-                      out_off == 0;
+        if ((dense_i2c_ || (mode_ == 1 && i2c_ok_)) && cin_pad % 64 == 0 && n % 32 == 0 && n >= 32 && !out_f32 && (relu_n == 0 || relu_n == n) && out_off == 0) {
+            st->tmap_i2c = make_tmap_im2col(in.ptr, in_stride, W, H, boards_i2c_, 64, 128, st->taps == 9 ? 1 : 0);
+            auto rows_map = [&](void* ptr, int stride) {
+                uint64_t dims[2] = {uint64_t(stride), uint64_t(rows_alloc_)};
+                uint64_t strides[1] = {uint64_t(stride) * 2};
+                uint32_t box[2] = {32, 32};
+                return make_tmap(ptr, 2, dims, strides, box, false, true);
+            };
+            st->tmap_out = rows_map(out.ptr, out_stride);
+            st->tmap_res = res ? rows_map(res->ptr, c_pad_) : st->tmap_out;
+            st->tmap_bq = st->tmap_bh;
+            if (n % 64 == 0) {
+                uint64_t dims[2] = {uint64_t(ktot), uint64_t(n)};
+                uint64_t strides[1] = {uint64_t(ktot) * 2};
+                uint32_t quarter[2] = {64, uint32_t(n / 4)};
+                st->tmap_bq = make_tmap(st->w_bf16.ptr, 2, dims, strides, quarter);
+            }
+            st->use_i2c = true;
+            st->i2c_stages = conv_i2c_pick_stages(n);
+        }
         if (allow_tc8 && st->taps == 9 && n <= 128 && !out_f32) {
             st->use_i2c = false;  // 8x8 boards, narrow layers: the per-layer 8x8 kernel (it only runs when the whole-tower kernel does not)
             // (c, x, board, y)-ordered view of the same rows, box (64, 8, 4 boards, 10 ranks incl. halo)
@@ -385,6 +402,9 @@ void Net::build_bf16() {
         int cols = 32;
         while (cols < 2 * n) cols *= 2;
         p.tmem_cols = cols;
+        p.n_split = 1;
+        const char* pdl_env = std::getenv("KZB_PDL");  // programmatic dependent launch of consecutive conv_i2c layers (KZB_PDL=0: off)
+        p.pdl = (pdl_env && pdl_env[0] == '0') ? 0 : 1;
         convs_.push_back(std::move(st));
     };
 
@@ -403,8 +423,6 @@ void Net::build_bf16() {
         add("scalar_conv", merged_small_conv(spec_), act_x_, c_pad_, nullptr, act_s1_, s1_stride_, true, 16, spec_.scalar_conv.cout);
         add("policy_conv2", spec_.policy_conv2, act_h1_, cp_pad_, nullptr, act_pm_, pm_stride_, true, pm_stride_, 0);
     }
-
-    build_i2c_tables(W, H);
 
     // fused heads kernel: policy conv1 -> relu -> conv2, scalar conv -> relu -> fc -> relu -> fc, masked softmax (heads8.cu)
     const char* no_h8 = std::getenv("KZB_NO_HEADS8");
@@ -543,87 +561,6 @@ void Net::build_bf16() {
         tp.debug = dbg ? std::atoi(dbg) : 0;
         use_tower8k_ = true;
     }
-}
-
-// conv_i2c.cu: one table of layers + one set of tensor maps for the tower (first layer, 2 * depth block layers) and, where it has the
-// tower's width, the 1x1 policy conv.  Block weights are concatenated so that one map serves every block layer.
-void Net::build_i2c_tables(int W, int H) {
-    const int tower = 1 + 2 * spec_.depth, n = c_pad_;
-    bool all = int(convs_.size()) >= tower;
-    for (int i = 0; all && i < tower; i++) all = convs_[size_t(i)]->use_i2c;
-    for (auto& st : convs_) st->i2c_layer = -1;
-    if (!all) {  // per-layer decisions that do not cover the whole tower are not worth a table: those layers take conv_tc / conv_tc8
-        for (auto& st : convs_) st->use_i2c = false;
-        return;
-    }
-    auto rows_map = [&](void* ptr, int stride) {
-        uint64_t dims[2] = {uint64_t(stride), uint64_t(rows_alloc_)};
-        uint64_t strides[1] = {uint64_t(stride) * 2};
-        uint32_t box[2] = {32, 32};
-        return make_tmap(ptr, 2, dims, strides, box, false, true);
-    };
-    auto w_maps = [&](CUtensorMap* out, void* ptr, int ktot, int rows) {
-        uint64_t dims[2] = {uint64_t(ktot), uint64_t(rows)};
-        uint64_t strides[1] = {uint64_t(ktot) * 2};
-        uint32_t half[2] = {64, uint32_t(n / 2)}, quarter[2] = {64, uint32_t(n % 64 == 0 ? n / 4 : n / 2)};
-        out[0] = make_tmap(ptr, 2, dims, strides, half);
-        out[1] = make_tmap(ptr, 2, dims, strides, quarter);
-    };
-    I2cMaps& m = i2c_maps_;
-    m.a[0] = make_tmap_im2col(act_in_.ptr, cin_pad_, W, H, boards_i2c_, 64, 128, 1);
-    m.a[1] = make_tmap_im2col(act_x_.ptr, c_pad_, W, H, boards_i2c_, 64, 128, 1);
-    m.a[2] = make_tmap_im2col(act_t_.ptr, c_pad_, W, H, boards_i2c_, 64, 128, 1);
-    m.a[3] = make_tmap_im2col(act_x_.ptr, c_pad_, W, H, boards_i2c_, 64, 128, 0);
-    m.out[0] = rows_map(act_x_.ptr, c_pad_);
-    m.out[1] = rows_map(act_t_.ptr, c_pad_);
-    m.out[2] = rows_map(act_h1_.ptr, cp_pad_);
-    w_maps(m.w[0], convs_[0]->w_bf16.ptr, 9 * cin_pad_, n);
-    const size_t layer_w_bytes = size_t(n) * 9 * c_pad_ * 2;
-    w_rows_.alloc(std::max<size_t>(layer_w_bytes * 2 * spec_.depth, 256), true);
-    for (int i = 0; i < 2 * spec_.depth; i++)
-        CK(cudaMemcpy(w_rows_.as<uint8_t>() + layer_w_bytes * i, convs_[size_t(1 + i)]->w_bf16.ptr, layer_w_bytes, cudaMemcpyDeviceToDevice));
-    w_maps(m.w[1], w_rows_.ptr, 9 * c_pad_, std::max(1, 2 * spec_.depth) * n);
-    std::vector<I2cLayerDev> layers;
-    for (int i = 0; i < tower; i++) {
-        const bool first = i == 0, conv2 = !first && (i % 2 == 0);
-        I2cLayerDev l{};
-        l.a_map = first ? 0 : (conv2 ? 2 : 1);
-        l.w_map = first ? 0 : 1;
-        l.w_row0 = first ? 0 : (i - 1) * n;
-        l.out_map = (first || conv2) ? 0 : 1;
-        l.res_map = conv2 ? 0 : -1;
-        l.taps = 9;
-        l.cin_pad = first ? cin_pad_ : c_pad_;
-        l.kblocks = l.cin_pad / 64;
-        l.relu = first ? 0 : 1;
-        l.bias = convs_[size_t(i)]->bias.as<float>();
-        convs_[size_t(i)]->i2c_layer = int(layers.size());
-        layers.push_back(l);
-    }
-    // the head convs: only the 1x1 policy conv qualifies (bf16 out, relu), and only with the tower's width (one n per table)
-    for (size_t si = size_t(tower); si < convs_.size(); si++) {
-        ConvStep& st = *convs_[si];
-        if (st.use_i2c && st.name == "policy_conv1" && st.tc.n == n && cp_pad_ == c_pad_) {
-            w_maps(m.w[2], st.w_bf16.ptr, c_pad_, n);
-            I2cLayerDev l{};
-            l.a_map = 3, l.w_map = 2, l.w_row0 = 0, l.out_map = 2, l.res_map = -1, l.taps = 1, l.cin_pad = c_pad_, l.kblocks = c_pad_ / 64, l.relu = 1;
-            l.bias = st.bias.as<float>();
-            st.i2c_layer = int(layers.size());
-            layers.push_back(l);
-        } else {
-            st.use_i2c = false;
-        }
-    }
-    upload(d_i2c_layers_, layers);
-    d_i2c_barrier_.alloc(64, true);
-    i2c_stages_ = conv_i2c_pick_stages(n);
-    const char* pdl_env = std::getenv("KZB_PDL");  // programmatic dependent launch of consecutive conv_i2c layers (KZB_PDL=0: off)
-    i2c_pdl_ = !(pdl_env && pdl_env[0] == '0');
-    // persistent mode (one cooperative launch for the whole tower) up to this many work items per layer; KZB_I2C_PERSIST=0: never
-    const char* pe = std::getenv("KZB_I2C_PERSIST");
-    i2c_persist_items_ = pe ? std::atoi(pe) : 4 * (num_sms_ / 2);
-    const char* pl = std::getenv("KZB_I2C_PER_LAYER_PROFILE");  // kzb_profile_staged: time every layer by itself
-    hook_per_layer_ = pl && pl[0] == '1';
 }
 
 void Net::build_f32() {
@@ -831,39 +768,11 @@ void Net::run_network(int batch, const StepHook& hook) {
                 p.num_tiles = (p.valid_rows + 127) / 128;
             }
             if (st->use_i2c) {
-                I2cParams ip{};
-                ip.layers = d_i2c_layers_.as<I2cLayerDev>();
-                ip.layer0 = st->i2c_layer;
-                ip.num_layers = 1;
-                ip.num_tiles = p.num_tiles;
-                ip.n = p.n;
-                ip.stages = i2c_stages_;
-                ip.tmem_cols = p.tmem_cols;
-                ip.lay = lay_;
-                ip.grid_barrier = d_i2c_barrier_.as<unsigned>();
+                p.stages = st->i2c_stages;
                 // small batches: split the output channels so that twice as many SM pairs share the layer
                 const char* split = std::getenv("KZB_CONV_SPLIT");
-                const int pairs = (p.num_tiles + 1) / 2;
-                ip.n_split = (!(split && split[0] == '0') && p.n % 64 == 0 && 2 * pairs <= num_sms_ / 2) ? 2 : 1;
-                // the whole tower in ONE persistent launch when a layer is only a few work items per SM pair (launch, set-up and drain
-                // of 2 * depth + 1 launches would dominate); the table's layers are consecutive steps
-                const int tower = 1 + 2 * spec_.depth;
-                if (si == first_step && st->i2c_layer == 0 && tower > 1 && pairs * ip.n_split <= i2c_persist_items_ && !(hook && hook_per_layer_)) {
-                    ip.num_layers = tower;
-                    ip.pdl = 0;
-                    CK(cudaMemsetAsync(d_i2c_barrier_.ptr, 0, 4, stream_));
-                    if (launch_conv_i2c(i2c_maps_, ip, num_sms_, stream_) == cudaSuccess) {
-                        if (hook) hook("tower_i2c");
-                        si += size_t(tower) - 1;
-                        continue;
-                    }
-                    // the grid cannot be made co-resident on this device (cooperative launch refused): one launch per layer from now on
-                    cudaGetLastError();
-                    i2c_persist_items_ = 0;
-                    ip.num_layers = 1;
-                }
-                ip.pdl = i2c_pdl_ ? 1 : 0;
-                CK(launch_conv_i2c(i2c_maps_, ip, num_sms_, stream_));
+                p.n_split = (!(split && split[0] == '0') && p.n % 64 == 0 && p.n_store == p.n && 2 * ((p.num_tiles + 1) / 2) <= num_sms_ / 2) ? 2 : 1;
+                launch_conv_i2c(st->tmap_i2c, p.n_split == 2 ? st->tmap_bq : st->tmap_bh, st->tmap_out, st->tmap_res, p, num_sms_, stream_);
             } else {
                 launch_conv_tc(st->tmap_a, st->tmap_b, p, num_sms_, stream_);
             }

@@ -48,7 +48,9 @@ struct ConvStep {
     // bf16 tensor-core form
     CUtensorMap tmap_a{}, tmap_b{}, tmap_bh{};
     bool use_i2c = false;  // conv_i2c.cu (dense rows, TMA im2col, CTA-pair MMA)
-    int i2c_layer = -1;    // its entry in the network's conv_i2c layer table
+    int i2c_stages = 0;
+    CUtensorMap tmap_out{}, tmap_res{};  // conv_i2c: output / residual rows, box (32 channels, 32 rows), SWIZZLE_64B
+    CUtensorMap tmap_i2c{}, tmap_bq{};  // im2col map of the input rows; weight box of n / 4 rows (output channels split in two)
     ConvTcParams tc{};
     bool use_tc8 = false;  // 8x8-board specialisation (conv_tc8.cu)
     CUtensorMap tmap_a8{};
@@ -93,7 +95,6 @@ private:
     using StepHook = std::function<void(const char*)>;
     void build_bf16();
     void build_f32();
-    void build_i2c_tables(int W, int H);
     void check_batch(int batch) const;
     void require_mapper() const;
     void upload_packed(const uint8_t* bits, const float* scalars, int batch, const uint32_t* mv_idx, const uint32_t* mv_off);
@@ -117,11 +118,6 @@ private:
     bool i2c_ok_ = true;      // conv_i2c.cu may be used (KZB_NO_I2C=1: never)
     bool dense_i2c_ = false;  // boards the 8x8 kernels do not cover: dense rows, 3x3 layers on conv_i2c.cu
     int boards_i2c_ = 0;      // boards covered by the im2col tensor maps (>= every 256-pixel tile of a full batch)
-    I2cMaps i2c_maps_{};
-    DeviceBuffer d_i2c_layers_, w_rows_, d_i2c_barrier_;
-    int i2c_stages_ = 0, i2c_persist_items_ = 0;
-    bool i2c_pdl_ = true;
-    bool hook_per_layer_ = false;  // KZB_I2C_PER_LAYER_PROFILE=1: kzb_profile_staged times every layer of the tower by itself
 
     DeviceBuffer d_bits_, d_scalars_, d_mv_idx_, d_mv_off_, d_nchw_;
     DeviceBuffer act_in_, act_x_, act_t_, act_h1_, act_s1_, act_pm_, act_att_;

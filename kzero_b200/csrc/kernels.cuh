@@ -86,38 +86,15 @@ struct ConvTcParams {
     int n_store;  // channels written per row (multiple of 16, <= n)
     int stages;
     int tmem_cols;
+    int n_split;  // conv_i2c: 1, or 2 = a work item is one 256-pixel tile x one half of the output channels
+    int pdl;      // conv_i2c: launched with programmatic stream serialization (set-up and the first weight tiles overlap the previous layer's tail)
     // development aid: when non-null, each CTA writes 16 clock64() stamps (see conv_tc8.cu) -- KZB_TIMELINE=1
     unsigned long long* timeline;
 };
 void launch_conv_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ConvTcParams& p, int grid, cudaStream_t s);
-// conv_i2c.cu: conv3x3 / conv1x1 on DENSE rows, activation tiles by TMA im2col, CTA-pair MMA, TMA-staged epilogue.  A launch runs
-// `num_layers` consecutive entries of a layer table (1: ordinary launch; > 1: persistent cooperative launch with a grid barrier per layer).
-struct I2cLayerDev {
-    int a_map;    // input activations: index into I2cMaps::a
-    int w_map;    // weight matrix: index into I2cMaps::w
-    int w_row0;   // first output-channel row of this layer inside its weight matrix
-    int out_map;  // output rows: index into I2cMaps::out
-    int res_map;  // residual rows (added after the relu): index into I2cMaps::out, or -1
-    int taps, kblocks, cin_pad, relu;
-    const float* bias;  // [n]
-};
-struct I2cMaps {
-    CUtensorMap a[4];     // im2col maps (64 channels x 128 pixels, SWIZZLE_128B): encoded planes 3x3, X 3x3, T 3x3, X 1x1
-    CUtensorMap w[3][2];  // weight maps [first layer | block layers, concatenated | policy conv1][box of n / 2 | n / 4 rows]
-    CUtensorMap out[3];   // row maps (32 channels x 32 rows, SWIZZLE_64B): X, T, H1
-};
-struct I2cParams {
-    const I2cLayerDev* layers;  // device memory
-    int layer0, num_layers;
-    int num_tiles;  // 128-pixel tiles of the batch
-    int n;          // output channels of every layer in the table (multiple of 32)
-    int n_split;    // 1, or 2 = a work item is one 256-pixel tile x one half of the output channels
-    int stages, tmem_cols;
-    int pdl;        // single-layer launches: programmatic stream serialization
-    RowLayout lay;  // dense
-    unsigned* grid_barrier;  // persistent mode: zeroed by the caller on the same stream before the launch
-};
-cudaError_t launch_conv_i2c(const I2cMaps& maps, const I2cParams& p, int grid, cudaStream_t s);
+// conv_i2c.cu: conv3x3 / conv1x1 (p.taps) on DENSE rows, activation tiles by TMA im2col, CTA-pair MMA (tmap_bh: weight box of p.n / p.n_split / 2 rows)
+void launch_conv_i2c(const CUtensorMap& tmap_a_im2col, const CUtensorMap& tmap_bh, const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
+                     const ConvTcParams& p, int grid, cudaStream_t s);
 size_t conv_i2c_smem_bytes(int n, int stages);
 int conv_i2c_pick_stages(int n);
 void conv_i2c_prepare();

@@ -126,7 +126,7 @@ def test_fp32_packed_vs_oracle(game, depth, ch, n):
     _check_packed(values, probs, ref_values, ref_probs, mv_off, FP32_TOL, FP32_TOL)
 
 
-@pytest.mark.parametrize("variant", ["default", "no_heads8", "no_tower8", "no_conv8", "linear", "no_embed8", "no_persist", "no_pdl", "no_conv_split", "no_i2c"])
+@pytest.mark.parametrize("variant", ["default", "no_heads8", "no_tower8", "no_conv8", "linear", "no_embed8", "no_pdl", "no_conv_split", "no_i2c"])
 @pytest.mark.parametrize("game,depth,ch,n", [("ataxx-7", 8, 64, 256), ("chess", 16, 128, 64), ("go-9", 4, 64, 40),
                                               ("chess", 2, 32, 7), ("chess", 3, 64, 130), ("chess", 2, 256, 12)])
 def test_bf16_packed_vs_oracle(game, depth, ch, n, variant, monkeypatch):
@@ -134,11 +134,10 @@ def test_bf16_packed_vs_oracle(game, depth, ch, n, variant, monkeypatch):
     boards), the same tower with per-op head convs + tail kernel (KZB_NO_HEADS8=1), the per-layer 8x8 specialisation (conv_tc8.cu,
     KZB_NO_TOWER8=1), conv_i2c.cu on 8x8 boards (KZB_NO_CONV8=1, and always for layers wider than 128 channels), and the row kernels of
     every other board (go; KZB_FORCE_LINEAR=1 / KZB_NO_EMBED8=1 push chess / ataxx there): dense rows with TMA im2col loads and the
-    CTA-pair MMA (conv_i2c.cu) -- at these batch sizes the whole tower in ONE persistent cooperative launch with a grid barrier per
-    layer; KZB_I2C_PERSIST=0: one launch per layer, with programmatic dependent launch (KZB_PDL=0: without), sharing a tile's output
-    channels between two SM pairs (KZB_CONV_SPLIT=0: never) -- and the padded-row kernel it replaced (KZB_NO_I2C=1: conv_tc.cu).  Boards
+    CTA-pair MMA (conv_i2c.cu), without programmatic dependent launch (KZB_PDL=0), without sharing a tile's output channels between
+    two SM pairs at small batches (KZB_CONV_SPLIT=0), and the padded-row kernel it replaced (KZB_NO_I2C=1: conv_tc.cu).  Boards
     smaller than 8x8 (ataxx 7x7) are embedded in the 8x8 grid and masked after every layer."""
-    row_variants = ("linear", "no_persist", "no_pdl", "no_conv_split", "no_i2c")  # everything off the 8x8 kernels
+    row_variants = ("linear", "no_pdl", "no_conv_split", "no_i2c")  # everything off the 8x8 kernels
     if variant == "no_embed8":
         if game != "ataxx-7":
             pytest.skip("only boards smaller than 8x8 are embedded")
@@ -151,7 +150,6 @@ def test_bf16_packed_vs_oracle(game, depth, ch, n, variant, monkeypatch):
     force_linear = "1" if variant in row_variants else "0"
     monkeypatch.setenv("KZB_NO_I2C", "1" if variant == "no_i2c" else "0")
     monkeypatch.setenv("KZB_PDL", "0" if variant == "no_pdl" else "1")
-    monkeypatch.setenv("KZB_I2C_PERSIST", "0" if variant in ("no_persist", "no_pdl") else "296")
     monkeypatch.setenv("KZB_CONV_SPLIT", "0" if variant == "no_conv_split" else "1")
     monkeypatch.setenv("KZB_FORCE_LINEAR", force_linear)
     monkeypatch.setenv("KZB_NO_CONV8", "1" if variant == "no_conv8" else "0")
