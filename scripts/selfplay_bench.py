@@ -86,7 +86,7 @@ if ctx.is_root:
                                f"net {depth}x{channels}, gpu batch {args.gpu_batch}",
                    "game": {"chess": "chess-shaped synthetic game (13x8x8 + 8 planes, 1880-move policy, 20-45 legal moves)", "ataxx": "ataxx 7x7",
                             "chess-real": "chess (legal move generation, ChessStdMapper encoding)",
-                            "go": "go 9x9 (area scoring, simple ko, no suicide)"}[args.game],
+                            "go": "go 9x9 (area scoring, positional superko, cgos or Tromp-Taylor suicide rule per game)"}[args.game],
                    "cpu_threads_per_gpu": cpu_threads, "gpu_threads_per_gpu": gpu_threads, "executor_blocking_sync": bool(blocking), "concurrent_games_per_gpu": r.concurrent_games,
                    "host_cores": cores, "pinned": bool(args.pin), **replicas.parallelism_note(ctx)},
         "data": "synthetic"}), flush=True)
