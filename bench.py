@@ -419,7 +419,7 @@ def measure(name, args, ctx, steps, warmup, with_two_threads, sampler=None):
     times = [dev_s, e2e_s, wall_value, e2e2_s if e2e2_s is not None else 0.0, sustained["ms_per_step"] if sustained else 0.0]
     dev_s, e2e_s, wall_value, e2e2_s_max, sus_ms_max = replicas.max_over_ranks(ctx, times, device="cuda")
     bits, scalars, mv_idx, mv_off = inputs[0]
-    return dict(cfg=cfg, spec=spec, onnx_bytes=onnx_bytes, info=info, batch=batch, steps=steps, warmup=warmup, dev_s=dev_s, e2e_s=e2e_s,
+    return dict(name=name, cfg=cfg, spec=spec, onnx_bytes=onnx_bytes, info=info, batch=batch, steps=steps, warmup=warmup, dev_s=dev_s, e2e_s=e2e_s,
                 wall_value=wall_value, e2e2_s=e2e2_s_max if e2e2_s is not None else None, half=half, share=share, tower_ms=tower_ms,
                 tower_launches=tower_launches, launches=launches, clocks=clocks, sustained=sustained, sus_ms=sus_ms_max,
                 comparator=comparator, n_sets=n_sets,
@@ -438,10 +438,15 @@ def rooflines(m, peaks):
         kernel = "tower8k_kernel"
     else:
         kernel = "conv_tc_kernel" if os.environ.get("KZB_NO_I2C") == "1" else "conv_i2c_kernel"
-    traffic = None
-    tpath = ROOT / "profiles" / "tower_dram_traffic.json"
-    if tpath.exists() and "tower8" in share:
-        traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (scripts/ncu_digest.py); only
+    # for the workload the capture was taken on
+    tpath = ROOT / "profiles" / "dram_traffic.json"
+    table = json.loads(tpath.read_text()) if tpath.exists() else {}
+
+    def traffic_of(kern):
+        e = table.get(kern)
+        return e.get("dram_bytes_per_launch") if e and e.get("workload") == m["name"] else None
+    traffic = traffic_of(kernel)
     # the tower is timed launch by launch between L2 flushes with the GPU idle in between: burst denominator
     tower = {"bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
              "frac": achieved / peaks["tflops_burst"],
@@ -462,7 +467,8 @@ def rooflines(m, peaks):
         gbs = enc_bytes / (share["encode"] * 1e-3) / 1e9
         out["roofline_k2"] = {"bound": "hbm", "kernel": "encode_kc_kernel" if "tower8" in share else "encode_nhwc_kernel", "achieved": gbs,
                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "launch_ms": share["encode"],
-                              "algorithmic_bytes_per_launch": enc_bytes, "traffic": None,
+                              "algorithmic_bytes_per_launch": enc_bytes,
+                              "traffic": traffic_of("encode_kc_kernel" if "tower8" in share else "encode_nhwc_kernel"),
                               "note": "a 10 us launch: latency-bound, not bandwidth-bound"}
     # K3: tower output in (C*A*2 B per position), values + legal-move probabilities out
     head_ms = sum(v for n, v in share.items() if not TOWER_STEP(n) and n != "encode")
@@ -471,7 +477,7 @@ def rooflines(m, peaks):
         gbs = head_bytes / (head_ms * 1e-3) / 1e9
         out["roofline_k3"] = {"bound": "hbm", "kernel": "heads8_kernel" if "heads8" in share else "head convs + heads_tail_kernel",
                               "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "launch_ms": head_ms,
-                              "algorithmic_bytes_per_launch": head_bytes, "traffic": None}
+                              "algorithmic_bytes_per_launch": head_bytes, "traffic": traffic_of("heads8_kernel") if "heads8" in share else None}
     return out
 
 

@@ -169,6 +169,7 @@ int kzb_launches_per_eval(const kzb_net* net);
 #define KZB_GAME_ATAXX7 1      /* 7x7 ataxx, AtaxxStdMapper encoding (rust/kz-core/src/mapping/ataxx.rs)                      */
 #define KZB_GAME_GO9 2         /* 9x9 go, GoStdMapper encoding without territory planes (rust/kz-core/src/mapping/go.rs)      */
 #define KZB_GAME_CHESS 3       /* chess with legal move generation, ChessStdMapper encoding and the flat 1880-move policy      */
+#define KZB_GAME_GO9_TERRITORY 4 /* 9x9 go with GoStdMapper::new(9, true): 7 bool planes, what server.rs:193 constructs              */
 
 /* Field for field the reference's settings: StartupSettings (rust/kz-selfplay/src/server/protocol.rs:11-40:
  * cpu_threads_per_device, gpu_threads_per_device, gpu_batch_size, search_batch_size) and Settings (protocol.rs:58-110). */

@@ -487,8 +487,35 @@ struct Go9 {
         const int s2 = score_2();
         return (s2 > 0) - (s2 < 0);
     }
-    void encode(uint8_t* bits, float* scalars) const {  // GoStdMapper::encode_input, rust/kz-core/src/mapping/go.rs:62-112
-        std::memset(bits, 0, size_t((4 * A + 7) / 8));
+    // owner[p]: 1 / 2 = the colour of the stone on p, or of the only colour an empty region touches; 0 = nobody's (`chains().territory()`
+    // + `Territory::player()` of the board-game crate, as GoStdMapper reads them, go.rs:90-98)
+    void territory(uint8_t owner[A]) const {
+        bool seen[A] = {};
+        int stack[A], region[A];
+        for (int p0 = 0; p0 < A; p0++) {
+            if (stones[p0]) owner[p0] = stones[p0];
+            else if (!seen[p0]) {
+                int top = 0, size = 0, touches = 0;
+                stack[top++] = p0;
+                seen[p0] = true;
+                while (top) {
+                    const int p = stack[--top];
+                    region[size++] = p;
+                    for_neighbours(p, [&](int q) {
+                        if (stones[q]) touches |= stones[q];
+                        else if (!seen[q]) {
+                            seen[q] = true;
+                            stack[top++] = q;
+                        }
+                    });
+                }
+                for (int i = 0; i < size; i++) owner[region[i]] = uint8_t(touches == 1 || touches == 2 ? touches : 0);
+            }
+        }
+    }
+    void encode(uint8_t* bits, float* scalars) const { encode_planes(bits, scalars, false); }
+    void encode_planes(uint8_t* bits, float* scalars, bool with_territory) const {  // GoStdMapper::encode_input, rust/kz-core/src/mapping/go.rs:62-112
+        std::memset(bits, 0, size_t(((with_territory ? 7 : 4) * A + 7) / 8));
         // a finished board has no unavailable moves: is_available_move fails on it and the mapper reads that as "available"
         // (`.unwrap_or(true)`, go.rs:84)
         const bool running = !done();
@@ -504,6 +531,11 @@ struct Go9 {
             set(2, p);
             if (running && !stones[p] && !is_legal(p)) set(3, p);
         }
+        if (with_territory) {  // three more planes: owned by the mover, by nobody, by the other side (go.rs:90-98)
+            uint8_t owner[A];
+            territory(owner);
+            for (int p = 0; p < A; p++) set(owner[p] == me ? 4 : owner[p] == 0 ? 5 : 6, p);
+        }
         const float komi = float(komi_2) * 0.5f;
         scalars[0] = next_player() == 0 ? 1.0f : 0.0f;
         scalars[1] = next_player() == 1 ? 1.0f : 0.0f;
@@ -512,6 +544,19 @@ struct Go9 {
         scalars[4] = (next_player() == 0 ? komi : -komi) / 15.0f;
         scalars[5] = multi_suicide ? 1.0f : 0.0f;
     }
+};
+
+// The same game with GoStdMapper::new(size, true) -- the mapper the reference's self-play SERVER constructs (rust/kz-selfplay/src/server/
+// server.rs:193): three territory planes after the four basic ones, 7 + 6 input channels.  (python/lib/games.py:185-186 still declares the
+// 4-plane form, so the reference's Python loader reads Go9's records, not these: SURVEY.md 8 notes the inconsistency at HEAD.)
+struct Go9Territory : Go9 {
+    static GameShape shape() { return {7, 6, S, A + 1}; }
+    static Go9Territory start(uint64_t seed) {
+        Go9Territory g;
+        static_cast<Go9&>(g) = Go9::start(seed);
+        return g;
+    }
+    void encode(uint8_t* bits, float* scalars) const { encode_planes(bits, scalars, true); }
 };
 
 }  // namespace selfplay

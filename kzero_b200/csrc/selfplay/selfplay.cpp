@@ -766,6 +766,7 @@ KZB_API int kzb_selfplay_run(int device, const void* onnx_bytes, size_t onnx_len
         else if (config->game == KZB_GAME_ATAXX7) run_selfplay<MaxMoves<Ataxx>>(device, onnx_bytes, onnx_len, precision, *config, *stats);
         else if (config->game == KZB_GAME_GO9) run_selfplay<MaxMoves<Go9>>(device, onnx_bytes, onnx_len, precision, *config, *stats);
         else if (config->game == KZB_GAME_CHESS) run_selfplay<MaxMoves<Chess>>(device, onnx_bytes, onnx_len, precision, *config, *stats);
+        else if (config->game == KZB_GAME_GO9_TERRITORY) run_selfplay<MaxMoves<Go9Territory>>(device, onnx_bytes, onnx_len, precision, *config, *stats);
         else throw std::runtime_error("unknown game");
     });
 }
@@ -786,6 +787,7 @@ KZB_API int kzb_selfplay_session_create(int game, kzb_selfplay_session** out) {
         else if (game == KZB_GAME_ATAXX7) s->impl = std::make_unique<Session<MaxMoves<Ataxx>>>();
         else if (game == KZB_GAME_GO9) s->impl = std::make_unique<Session<MaxMoves<Go9>>>();
         else if (game == KZB_GAME_CHESS) s->impl = std::make_unique<Session<MaxMoves<Chess>>>();
+        else if (game == KZB_GAME_GO9_TERRITORY) s->impl = std::make_unique<Session<MaxMoves<Go9Territory>>>();
         else throw std::runtime_error("unknown game");
         s->impl->game = game;
         *out = s.release();
@@ -814,6 +816,7 @@ KZB_API int kzb_mcts_trace(const kzb_selfplay_config* config, uint64_t game_seed
         else if (config->game == KZB_GAME_ATAXX7) trace_search<Ataxx>(*config, game_seed, plies, eval_kind, *out);
         else if (config->game == KZB_GAME_GO9) trace_search<Go9>(*config, game_seed, plies, eval_kind, *out);
         else if (config->game == KZB_GAME_CHESS) trace_search<Chess>(*config, game_seed, plies, eval_kind, *out);
+        else if (config->game == KZB_GAME_GO9_TERRITORY) trace_search<Go9Territory>(*config, game_seed, plies, eval_kind, *out);
         else throw std::runtime_error("unknown game");
     });
 }

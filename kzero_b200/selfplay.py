@@ -18,6 +18,7 @@ from ._abi import SelfplayConfig, SelfplayStats
 GAME_SYNTH_CHESS = 0
 GAME_ATAXX7 = 1
 GAME_GO9 = 2
+GAME_GO9_TERRITORY = 4  # go-9 with the three territory planes (GoStdMapper::new(9, true), server.rs:193)
 GAME_CHESS = 3  # real chess; GAME_SYNTH_CHESS is the chess-shaped synthetic game the B200 self-play numbers were taken with
 
 

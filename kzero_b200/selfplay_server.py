@@ -62,9 +62,11 @@ def game_id(name: str) -> int:
         return selfplay.GAME_SYNTH_CHESS
     if name in ("ataxx", "ataxx-7"):
         return selfplay.GAME_ATAXX7
-    if name == "go-9":
+    if name == "go-9":  # the 4-plane encoding python/lib/games.py declares (what the Python loader and trainer read)
         return selfplay.GAME_GO9
-    raise ValueError(f"game {name!r} is not available in this driver (chess, ataxx-7, go-9 and the chess-shaped synthetic game 'chess-synth' are)")
+    if name == "go-9-territory":  # the 7-plane encoding the reference's Rust server constructs (server.rs:193)
+        return selfplay.GAME_GO9_TERRITORY
+    raise ValueError(f"game {name!r} is not available in this driver (chess, ataxx-7, go-9, go-9-territory and the chess-shaped synthetic game 'chess-synth' are)")
 
 
 def config_from(startup: dict, settings: dict, seed: int) -> _abi.SelfplayConfig:

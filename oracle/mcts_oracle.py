@@ -200,16 +200,42 @@ class Go9:
         self.passes = 0
         self.ply += 1
 
+    TERRITORY = False  # Go9Territory: three more planes
+
+    def _owners(self):
+        """Per point: the colour of its stone, or of the only colour its empty region touches, else 0."""
+        owner = list(self.stones)
+        done = set()
+        for p0 in range(self.A):
+            if self.stones[p0] or p0 in done:
+                continue
+            region, touches, todo = {p0}, set(), [p0]
+            while todo:
+                q = todo.pop()
+                for r in self._neighbours(q):
+                    if self.stones[r]:
+                        touches.add(self.stones[r])
+                    elif r not in region:
+                        region.add(r)
+                        todo.append(r)
+            done |= region
+            for q in region:
+                owner[q] = next(iter(touches)) if len(touches) == 1 else 0
+        return owner
+
     def encode(self):
-        """-> (bools [4, 9, 9] u8, scalars f32): GoStdMapper::encode_input without territory, rust/kz-core/src/mapping/go.rs:62-112."""
+        """-> (bools [4 | 7, 9, 9] u8, scalars f32): GoStdMapper::encode_input, rust/kz-core/src/mapping/go.rs:62-112."""
         me = 1 + (self.ply & 1)
-        planes = np.zeros((4, self.S, self.S), np.uint8)
+        planes = np.zeros((7 if self.TERRITORY else 4, self.S, self.S), np.uint8)
+        owner = self._owners() if self.TERRITORY else None
         for p, v in enumerate(self.stones):
             y, x = divmod(p, self.S)
             planes[0, y, x] = v == me
             planes[1, y, x] = v not in (0, me)
             planes[2, y, x] = 1
             planes[3, y, x] = v == 0 and not self.done() and not self._legal(p)  # a finished board has no unavailable moves (go.rs:84)
+            if self.TERRITORY:  # owned by the mover, by nobody, by the other side (go.rs:90-98)
+                planes[4 if owner[p] == me else 5 if owner[p] == 0 else 6, y, x] = 1
         komi = F(self.komi_2) * F(0.5)
         black = self.next_player() == 0
         return planes, np.array([black, not black, self.passes == 1, self.passes >= 2, (komi if black else -komi) / F(15.0), self.multi_suicide], F)
@@ -237,6 +263,22 @@ class Go9:
                 white += len(region)
         score_2 = 2 * (black - white) - self.komi_2
         return (score_2 > 0) - (score_2 < 0)
+
+
+class Go9Territory(Go9):
+    """Go9 with GoStdMapper::new(9, true), the mapper the reference's self-play server constructs (server.rs:193)."""
+    TERRITORY = True
+
+    @staticmethod
+    def start(seed: int) -> "Go9Territory":
+        g = Go9.start(seed)
+        g.__class__ = Go9Territory
+        return g
+
+    def clone(self):
+        g = Go9.clone(self)
+        g.__class__ = Go9Territory
+        return g
 
 
 class Ataxx7:
@@ -733,7 +775,7 @@ def zero_step_apply(tree: Tree, idx: int, next_player: int, values_pov: np.ndarr
 
 def search(game_seed: int, plies: int, rng_seed: int, visits: int, search_batch: int, eval_kind: int, s: Settings, game: str = "chess"):
     """The twin of trace_search in selfplay.cpp: -> dict(child_visits, child_moves, child_policy, root_values, ...)."""
-    board = {"go-9": Go9, "ataxx-7": Ataxx7, "chess": SynthChess, "chess-real": Chess}[game].start(game_seed)
+    board = {"go-9": Go9, "go-9-territory": Go9Territory, "ataxx-7": Ataxx7, "chess": SynthChess, "chess-real": Chess}[game].start(game_seed)
     rng = Rng(rng_seed)
     for _ in range(plies):
         if board.done():

@@ -2,7 +2,7 @@
 """Turn ncu outputs brought back in gpurun_out/ into the small tracked summaries under profiles/.
 
   python scripts/ncu_digest.py launches gpurun_out/launches.csv profiles/r01_chess_b1024_launches.md
-  python scripts/ncu_digest.py kernel   gpurun_out/tower8.ncu-rep profiles/r01_tower8_ncu.md [--traffic-json profiles/tower_dram_traffic.json]
+  python scripts/ncu_digest.py kernel   gpurun_out/tower8.ncu-rep profiles/r01_tower8_ncu.md [--traffic-json profiles/dram_traffic.json --workload chess]
 """
 import collections
 import csv
@@ -71,7 +71,7 @@ def launches(src, dst):
     print(open(dst).read())
 
 
-def kernel(src, dst, traffic_json=None):
+def kernel(src, dst, traffic_json=None, workload=None):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -88,14 +88,27 @@ def kernel(src, dst, traffic_json=None):
                 f.write(f"| {m} | {units[i]} | " + " | ".join(r[i] for r in data) + " |\n")
     print(open(dst).read())
     if traffic_json:
-        def val(m):
+        # per kernel (short name, launches of the same kernel averaged): dram__bytes_read.sum + dram__bytes_write.sum per launch;
+        # merged into the file, which bench.py reads for `roofline*.traffic`
+        import os
+        import re
+
+        def val(r, m):
             i = hdr.index(m)
-            v = float(data[0][i].replace(",", ""))
+            v = float(r[i].replace(",", ""))
             u = units[i].lower()
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
-        rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
-        json.dump({"kernel": data[0][name_col], "source": src, "dram_bytes_read": rd, "dram_bytes_write": wr,
-                   "dram_bytes_per_launch": rd + wr}, open(traffic_json, "w"), indent=1)
+        table = json.load(open(traffic_json)) if os.path.exists(traffic_json) else {}
+        table = {k: v for k, v in table.items() if isinstance(v, dict)}
+        groups = collections.OrderedDict()
+        for r in data:
+            short = re.search(r"(\w+_kernel)", r[name_col])
+            groups.setdefault(short.group(1) if short else r[name_col], []).append(r)
+        for short, rs in groups.items():
+            rd = sum(val(r, "dram__bytes_read.sum") for r in rs) / len(rs)
+            wr = sum(val(r, "dram__bytes_write.sum") for r in rs) / len(rs)
+            table[short] = {"workload": workload, "source": src, "launches_averaged": len(rs), "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr}
+        json.dump(table, open(traffic_json, "w"), indent=1)
         print(open(traffic_json).read())
 
 
@@ -105,4 +118,5 @@ if __name__ == "__main__":
         launches(src, dst)
     else:
         tj = sys.argv[sys.argv.index("--traffic-json") + 1] if "--traffic-json" in sys.argv else None
-        kernel(src, dst, tj)
+        wl = sys.argv[sys.argv.index("--workload") + 1] if "--workload" in sys.argv else None  # bench.py config name the capture was taken on
+        kernel(src, dst, tj, wl)

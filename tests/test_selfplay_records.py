@@ -18,7 +18,7 @@ SCALARS = 26
 
 def _run(tmp_path, game, **kw):
     prefix = str(tmp_path / "games_0")
-    if game in (selfplay.GAME_GO9, selfplay.GAME_CHESS):
+    if game in (selfplay.GAME_GO9, selfplay.GAME_GO9_TERRITORY, selfplay.GAME_CHESS):
         kw.setdefault("max_game_length", 20)  # go games are long: let the length cap end them (max_game_length, generator_alphazero.rs:125)
     cfg = selfplay.default_config(game=game, visits=24, search_batch=4, gpu_batch=32, cpu_threads=2, gpu_threads=1, max_moves=400,
                                   duration_s=30.0, dummy_network=1, output_prefix=prefix, seed=5, **kw)
@@ -56,7 +56,8 @@ def _parse(prefix, bool_count, scalar_count):
 
 @pytest.mark.parametrize("game,name,bool_shape,scalar_count,policy_len", [
     (selfplay.GAME_SYNTH_CHESS, "chess", [13, 8, 8], 8, 1880), (selfplay.GAME_ATAXX7, "ataxx-7", [3, 7, 7], 1, 17 * 49 + 1),
-    (selfplay.GAME_GO9, "go-9", [4, 9, 9], 6, 82), (selfplay.GAME_CHESS, "chess", [13, 8, 8], 8, 1880)])
+    (selfplay.GAME_GO9, "go-9", [4, 9, 9], 6, 82), (selfplay.GAME_GO9_TERRITORY, "go-9", [7, 9, 9], 6, 82),
+    (selfplay.GAME_CHESS, "chess", [13, 8, 8], 8, 1880)])
 def test_record_files_are_self_consistent(tmp_path, game, name, bool_shape, scalar_count, policy_len):
     prefix, r = _run(tmp_path, game)
     meta, positions, game_starts = _parse(prefix, int(np.prod(bool_shape)), scalar_count)
@@ -131,7 +132,7 @@ def replay_under_oracle_rules(prefix, name, twin):
     order, and the recorded played move leads to the next recorded position.  -> number of moves checked."""
     from oracle import mcts_oracle as mo
 
-    shape = {"ataxx-7": (3, 7, 7), "go-9": (4, 9, 9), "chess": (13, 8, 8)}[name]
+    shape = {"ataxx-7": (3, 7, 7), "go-9": (7, 9, 9) if twin == "Go9Territory" else (4, 9, 9), "chess": (13, 8, 8)}[name]
     meta, positions, game_starts = _parse(prefix, int(np.prod(shape)), {"ataxx-7": 1, "go-9": 6, "chess": 8}[name])
     checked = 0
     for g in range(meta["game_count"]):
@@ -168,7 +169,7 @@ def replay_under_oracle_rules(prefix, name, twin):
 
 
 @pytest.mark.parametrize("game,name,twin", [(selfplay.GAME_ATAXX7, "ataxx-7", "Ataxx7"), (selfplay.GAME_GO9, "go-9", "Go9"),
-                                            (selfplay.GAME_CHESS, "chess", "Chess")])
+                                            (selfplay.GAME_GO9_TERRITORY, "go-9", "Go9Territory"), (selfplay.GAME_CHESS, "chess", "Chess")])
 def test_recorded_games_replay_under_the_oracle_rules(tmp_path, game, name, twin):
     """N1 + N2 end to end on the host (DummyNetwork stand-in); tests/test_gpu_selfplay.py does the same with games the GPU played."""
     prefix, r = _run(tmp_path, game)
