@@ -1,7 +1,7 @@
 """Self-play server speaking the reference's TCP / JSON control protocol ("next" row N3), so that the
 UNMODIFIED Python training loop (python/lib/loop.py via python/lib/selfplay_client.py:93-132) can drive the B200 driver.
 
-    python -m kzero_b200.selfplay_server [--port 63105] [--device 0]
+    python -m kzero_b200.selfplay_server [--port 63105] [--device 0 --device 1 ...]
 
 Mirrors `selfplay_server_main` (rust/kz-selfplay/src/server/server.rs:45-101): bind 127.0.0.1:<port>, accept ONE client,
 read one `StartupSettings` line, then
@@ -17,9 +17,10 @@ network or new settings take effect at the next generation boundary, under the r
 as soon as they arrive).  Differences that are deliberate (documented in DESIGN.md): `eval_random_symmetries`, `start_pos`, `top_moves`,
 `saved_state_channels` and `gpu_batch_size_root` are accepted and ignored (muzero-only or above the boundary); `chess`,
 `ataxx-7` and `go-9` are served with this repo's restated rules (`chess-synth` is the chess-shaped synthetic game the
-B200 self-play numbers were taken with); one server process drives ONE device (the reference takes several `--device`
-flags, server.rs:49-51) -- start one process per
-GPU on different ports, the games are independent.
+B200 self-play numbers were taken with).  Several `--device` flags (server.rs:49-51,316-331): one session per device, each with its own
+generator / executor threads and its own games; a generation's `games_per_gen` games are split evenly between the devices, each device
+writes its share, and the parts are joined into the one `games_<gen>` file the loop expects (record_files.merge; the reference's single
+collector takes games from whichever device finishes them, so there a faster device contributes more).
 """
 from __future__ import annotations
 
@@ -31,7 +32,7 @@ import threading
 from pathlib import Path
 from typing import Optional
 
-from . import _abi, selfplay
+from . import _abi, record_files, selfplay
 
 DEFAULT_PORT = 63105  # server.rs:38
 
@@ -94,8 +95,9 @@ def config_from(startup: dict, settings: dict, seed: int) -> _abi.SelfplayConfig
 
 
 class SelfplayServer:
-    def __init__(self, port: int = DEFAULT_PORT, device: int = 0):
-        self.port, self.device = port, device
+    def __init__(self, port: int = DEFAULT_PORT, device: int = 0, devices=None):
+        self.port = port
+        self.devices = list(devices) if devices else [device]
         self.lock = threading.Condition()
         self.settings: Optional[dict] = None
         self.network = None  # None: wait (WaitForNewNetwork); "dummy"; or ONNX bytes
@@ -152,7 +154,12 @@ class SelfplayServer:
             conn.sendall((json.dumps(message) + "\n").encode())
 
         gen = int(startup["first_gen"])
-        session = selfplay.Session(game_id(startup["game"]))
+        sessions = [selfplay.Session(game_id(startup["game"])) for _ in self.devices]
+        n_dev = len(self.devices)
+        games_per_gen = int(startup["games_per_gen"])
+        if games_per_gen < n_dev:
+            raise ValueError(f"games_per_gen = {games_per_gen} cannot be split over {n_dev} devices")
+        quotas = [games_per_gen // n_dev + (1 if d < games_per_gen % n_dev else 0) for d in range(n_dev)]
         try:
             while True:
                 with self.lock:
@@ -163,21 +170,44 @@ class SelfplayServer:
                     settings, network = dict(self.settings), self.network
                     # under the lock the commander also takes: a Stop can no longer slip between this check and the run
                     _abi.lib().kzb_selfplay_clear_stop()
-                cfg = config_from(startup, settings, seed=int(startup["first_gen"]))
-                cfg.output_prefix = str(Path(startup["output_folder"]) / f"games_{gen}").encode()
-                if network == "dummy":
-                    cfg.dummy_network = 1
-                    result = session.run(None, cfg, device=self.device)
+                out_prefix = str(Path(startup["output_folder"]) / f"games_{gen}")
+                results, errors = [None] * n_dev, []
+
+                def run_device(d):
+                    try:
+                        cfg = config_from(startup, settings, seed=int(startup["first_gen"]) * 1000 + d)
+                        cfg.max_games = quotas[d]
+                        cfg.output_prefix = (out_prefix if n_dev == 1 else f"{out_prefix}.dev{d}").encode()
+                        if network == "dummy":
+                            cfg.dummy_network = 1
+                        results[d] = sessions[d].run(None if network == "dummy" else network, cfg, device=self.devices[d])
+                    except Exception as e:  # noqa: BLE001 -- reported below, after the other devices have been stopped
+                        errors.append(e)
+                        _abi.lib().kzb_selfplay_request_stop()
+
+                if n_dev == 1:
+                    run_device(0)
                 else:
-                    result = session.run(network, cfg, device=self.device)
+                    threads = [threading.Thread(target=run_device, args=(d,)) for d in range(n_dev)]
+                    for t in threads:
+                        t.start()
+                    for t in threads:
+                        t.join()
+                if errors:
+                    raise errors[0]
                 if self.stop:
                     break
-                print(f"generation {gen}: {result.games_written} games, {result.moves_played} moves, "
-                      f"{result.mcts_nodes_per_s:,.0f} nodes/s, {result.nn_positions_per_s:,.0f} NN positions/s", flush=True)
+                if n_dev > 1:
+                    record_files.merge([f"{out_prefix}.dev{d}" for d in range(n_dev)], out_prefix)
+                seconds = max(r.seconds for r in results)
+                print(f"generation {gen}: {sum(r.games_written for r in results)} games, {sum(r.moves_played for r in results)} moves, "
+                      f"{sum(r.real_evals + r.cached_evals for r in results) / seconds:,.0f} nodes/s, "
+                      f"{sum(r.real_evals for r in results) / seconds:,.0f} NN positions/s on {n_dev} device(s)", flush=True)
                 send({"FinishedFile": {"index": gen}})  # ServerUpdate::FinishedFile, protocol.rs:80-84
                 gen += 1
         finally:
-            session.close()
+            for session in sessions:
+                session.close()
             try:
                 send("Stopped")
             except OSError:
@@ -189,9 +219,9 @@ class SelfplayServer:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--port", type=int, default=DEFAULT_PORT)
-    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--device", type=int, action="append", help="may be given several times (server.rs:49-51); default: device 0")
     args = ap.parse_args()
-    SelfplayServer(args.port, args.device).serve()
+    SelfplayServer(args.port, devices=args.device or [0]).serve()
 
 
 if __name__ == "__main__":

@@ -379,8 +379,10 @@ class Chess:
     """Twin of kzb::selfplay::Chess (kzero_b200/csrc/selfplay/chess_game.hpp), written independently: a mailbox board,
     legality by making the move and looking at the king (no bitboards, no attack maps, no pins, no shortcuts).  What the two
     must share is the SPECIFICATION: moves are policy indices from the mover's side (ranks flipped for black) in the
-    reference's flat table (chess.rs:439-481), listed in the canonical order -- origin squares ascending from a1, per piece its
-    destination squares ascending, promotions Q R B N (the search breaks ties by position in this list).  The en-passant
+    reference's flat table (chess.rs:439-481), listed in the canonical order (the search breaks ties by position in this list):
+    pawn moves set by set -- pushes, double pushes, captures towards the a-file, captures towards the h-file, each set by
+    destination square and each promotion as Q R B N, then en-passant captures by origin -- then knights, bishops, rooks, queens
+    and the king (castling is a king move), per piece type by origin, per piece by destination.  The en-passant
     square exists only while an enemy pawn stands next to the pushed pawn; a position repeats when placement, side, castling
     rights and en-passant square agree; draw on the third occurrence, after 100 quiet plies, or with bare kings."""
     KNIGHT = [(2, 1), (1, 2), (-1, 2), (-2, 1), (-2, -1), (-1, -2), (1, -2), (2, -1)]  # (rank, file) steps
@@ -567,7 +569,18 @@ class Chess:
 
     def moves(self) -> List[int]:
         index = self.flat()[1]
-        ordered = sorted(self._legal(), key=lambda m: (m[0], m[1], -m[2]))  # the generator walks piece by piece, direction by direction
+        def canonical(m):
+            frm, to, promo = m
+            piece = abs(self.sq[frm])
+            if piece != 1:
+                return piece, 0, frm, to, 0
+            df = to % 8 - frm % 8
+            if df == 0:
+                return 1, (0 if abs(to - frm) == 8 else 1), to, 0, -promo
+            if not self.sq[to]:
+                return 1, 4, frm, 0, 0  # en passant
+            return 1, (2 if df < 0 else 3), to, 0, -promo
+        ordered = sorted(self._legal(), key=canonical)  # the generator below walks square by square, direction by direction
         return [index[(self._pov(f), self._pov(t), promo)] for f, t, promo in ordered]
 
     def play(self, mv: int) -> None:

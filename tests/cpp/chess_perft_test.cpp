@@ -70,7 +70,7 @@ static int check_playouts() {
 }
 
 // the bitboard generator against round 1's mailbox generator, move for move over random games: the same legal moves (the mailbox
-// list sorted into the canonical order: origin ascending, destination ascending, promotions Q R B N), the same keys, clocks, rights,
+// list sorted into the canonical order), the same keys, clocks, rights,
 // repetition counts, terminal flags and encodings
 static int check_against_mailbox() {
     long positions = 0;
@@ -88,14 +88,30 @@ static int check_against_mailbox() {
                 std::memcmp(sc, ref_sc, sizeof(sc)) != 0)
                 return std::printf("bitboard and mailbox positions differ at seed %llu ply %d\n", (unsigned long long)seed, ply), 1;
             if (b.done()) break;
+            // the canonical order (chess_game.hpp): pawn moves set by set -- pushes, double pushes, captures towards the a-file, towards the
+            // h-file, each by destination with promotions Q R B N, then en passant by origin -- then N B R Q K by origin and destination
             struct K {
-                int from, to, slot;
+                int type, cat, a, b, slot;
                 uint32_t index;
-                bool operator<(const K& o) const { return from != o.from ? from < o.from : to != o.to ? to < o.to : slot < o.slot; }
+                bool operator<(const K& o) const {
+                    if (type != o.type) return type < o.type;
+                    if (cat != o.cat) return cat < o.cat;
+                    if (a != o.a) return a < o.a;
+                    if (b != o.b) return b < o.b;
+                    return slot < o.slot;
+                }
             };
             std::vector<K> want;
             ref.legal_moves([&](const ChessMailbox::Mv& mv) {
-                want.push_back(K{mv.from, mv.to, mailbox_detail::FlatMoves::slot_of(mv.promo), ref.index_of(mv)});
+                const int type = std::abs(int(ref.sq[mv.from])), slot = mailbox_detail::FlatMoves::slot_of(mv.promo);
+                K k{type, 0, mv.from, mv.to, slot, ref.index_of(mv)};
+                if (type == 1) {
+                    const int df = mv.to % 8 - mv.from % 8, dist = std::abs(int(mv.to) - int(mv.from));
+                    k.cat = df == 0 ? (dist == 8 ? 0 : 1) : (!ref.sq[mv.to] ? 4 : (df < 0 ? 2 : 3));
+                    k.a = k.cat == 4 ? mv.from : mv.to;
+                    k.b = 0;
+                }
+                want.push_back(k);
                 return true;
             });
             std::sort(want.begin(), want.end());

@@ -23,14 +23,14 @@ def test_selfplay_runs_and_counts_are_consistent(game, game_name, gpu_threads):
 
 
 @pytest.mark.parametrize("game,name,twin", [(selfplay.GAME_ATAXX7, "ataxx-7", "Ataxx7"), (selfplay.GAME_GO9, "go-9", "Go9"),
-                                            (selfplay.GAME_CHESS, "chess", "Chess")])
+                                            (selfplay.GAME_GO9_TERRITORY, "go-9", "Go9Territory"), (selfplay.GAME_CHESS, "chess", "Chess")])
 def test_games_the_gpu_played_replay_under_the_oracle_rules(tmp_path, game, name, twin):
     """What the GPU driver PLAYED, not only how much: every recorded game -- searched with a real network on the B200 evaluator,
     ragged batches, several executors -- is replayed under the oracle's independent restatement of the rules (legal move lists,
     encodings, transitions, outcomes), and the file is read by the same checks as the host-only records."""
     from test_selfplay_records import replay_under_oracle_rules
 
-    spec = netgen.game_spec(name)
+    spec = netgen.game_spec("go-9-territory" if twin == "Go9Territory" else name)  # 13 input channels: GoStdMapper::new(9, true)
     onnx_bytes = netgen.build_onnx(spec, 2, 32, seed=41)
     prefix = str(tmp_path / "games_0")
     cfg = selfplay.default_config(game=game, visits=40, search_batch=8, gpu_batch=64, cpu_threads=2, gpu_threads=2, max_games=6,

@@ -91,3 +91,57 @@ def test_reference_client_drives_the_server(tmp_path):
     # full_search_prob = 0.5: both kinds of searches were recorded, with their visit targets (generator_alphazero.rs:88-94)
     kinds = {(p.is_full_search, p.zero_visits >= 24) for p in positions if not p.is_final}
     assert (True, True) in kinds and any(not full for full, _ in kinds)
+
+
+def test_several_devices_write_one_file_per_generation(tmp_path):
+    """`--device a --device b` (server.rs:49-51,316-331): one session per device, the generation's games split between them, the parts
+    joined into the single games_<gen> file the loop expects.  DummyNetwork evaluations, so both 'devices' are host threads here; the
+    joined file must pass the same checks as a file written by one writer (tests/test_selfplay_records.py) and, when the reference tree
+    is present, load with the reference's DataFile."""
+    import numpy as np
+
+    from test_selfplay_records import SCALARS, _parse
+
+    server = selfplay_server.SelfplayServer(port=0, devices=[0, 1])
+    thread = threading.Thread(target=server.serve, daemon=True)
+    thread.start()
+    s = socket.create_connection(("127.0.0.1", server.port))
+    f = s.makefile("r")
+    for m in ({"StartupSettings": dict(STARTUP, games_per_gen=7, output_folder=str(tmp_path))}, {"NewSettings": SETTINGS}, "UseDummyNetwork"):
+        s.sendall((json.dumps(m) + "\n").encode())
+    assert json.loads(f.readline()) == {"FinishedFile": {"index": 3}}
+    assert json.loads(f.readline()) == {"FinishedFile": {"index": 4}}
+    s.sendall(b'"Stop"\n')
+    assert [json.loads(line) for line in f][-1] == "Stopped"
+    thread.join(timeout=30)
+    assert not thread.is_alive()
+    for gen in (3, 4):
+        prefix = str(tmp_path / f"games_{gen}")
+        assert not list(tmp_path.glob(f"games_{gen}.dev*"))  # the parts are gone
+        meta, positions, starts = _parse(prefix, 3 * 49, 1)
+        # (a device may finish a game or two past its share: generator threads end games concurrently, like the reference's)
+        assert 7 <= meta["game_count"] <= 11 and len(starts) == meta["game_count"] and len(meta["scalar_names"]) == SCALARS
+        assert abs(sum(meta["root_wdl"]) - 1) < 1e-6
+        # python/lib/data/check.py:9-76 on the joined file: games tile the positions, ids count up, per-game indices run 0..length
+        pi = 0
+        for g, start in enumerate(starts):
+            assert int(start) == pi
+            length = int(positions[pi]["scalars"][2])
+            for k in range(length + 1):
+                sc = positions[pi + k]["scalars"]
+                assert int(sc[0]) == g and int(sc[1]) == k and int(sc[2]) == length and bool(sc[5]) == (k == length)
+            pi += length + 1
+        assert pi == meta["position_count"]
+        lengths = [int(positions[int(st)]["scalars"][2]) for st in starts]
+        assert meta["max_game_length"] == max(lengths) and meta["min_game_length"] == min(lengths)
+    if REFERENCE_PY.exists():
+        sys.path.insert(0, str(REFERENCE_PY))
+        try:
+            from lib.data.file import DataFile
+            from lib.games import Game
+        finally:
+            sys.path.pop(0)
+        df = DataFile.open(Game.find("ataxx-7"), str(tmp_path / "games_3"))
+        assert df.info.simulation_count >= 7
+        assert len([df.load_position(i) for i in range(df.info.position_count)]) == df.info.position_count
+    assert np.isfinite(meta["hit_move_limit"])
