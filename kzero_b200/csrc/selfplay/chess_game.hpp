@@ -452,7 +452,9 @@ struct Chess {
     }
     // board-game's Rules::is_draw ends a game on material only when nothing but the two kings is left; K + minor v K plays on --
     // the reference's own tests play knight moves on "8/8/6k1/8/3N4/6K1/8/8 w" (rust/kz-core/tests/mapper/chess/pairs.rs:98-136)
-    bool insufficient_material() const { return __builtin_popcountll(occupied()) <= 2; }
+    bool insufficient_material() const {  // each colour is down to one piece, its king (no popcount: the build targets plain x86-64)
+        return !(colour[0] & (colour[0] - 1)) && !(colour[1] & (colour[1] - 1));
+    }
 
     // the legal replies as policy indices, into the per-thread cache; returns how many
     int generate_replies() const {
