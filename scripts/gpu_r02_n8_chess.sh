@@ -16,11 +16,12 @@ run8() {  # label, args
 }
 {
 nproc
-run8 "real chess, 384 games" --game chess-real --concurrent-games 384
+KZB_SP_PROFILE=1 run8 "real chess, 384 games (profiled)" --game chess-real --concurrent-games 384
+grep -E "gather|apply answers|CPU time" gpurun_out/r02_n8_chess_err.txt | sort | uniq -c | sort -rn | head -12
 run8 "synthetic, 384 games" --game chess --concurrent-games 384
 run8 "real chess, 512 games" --game chess-real --concurrent-games 512
 echo -n "N=1 same box real chess (all cores): "; timeout 100 python scripts/selfplay_bench.py --seconds 6 --game chess-real 2>/dev/null | python -c "$fmt"
 echo -n "N=1 same box synthetic (all cores): "; timeout 100 python scripts/selfplay_bench.py --seconds 6 --game chess 2>/dev/null | python -c "$fmt"
 echo -n "N=1 same box real chess (4 cores, 384 games): "; timeout 100 taskset -c 0-3 python scripts/selfplay_bench.py --seconds 6 --game chess-real --concurrent-games 384 2>/dev/null | python -c "$fmt"
-} | tee gpurun_out/r02_n8_chess.txt
+} | tee gpurun_out/r02_n8_chess_b.txt
 tail -3 gpurun_out/r02_n8_chess_err.txt
