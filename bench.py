@@ -497,9 +497,10 @@ def selfplay_record(ctx, game_name, seconds, dist):
     cpu_threads = share if blocking else share - gpu_threads
     # games in flight per GPU: the reference's formula for three executors, (3 + 1) * 1024 / 16 = 256 (server_alphazero.rs:47), when the
     # replica has plenty of host cores (the loop is GPU-bound; more games only cost cache: 2.04 M -> 1.97 M nodes/s at 384 on a 16-core
-    # box); half as many again when it has few (executors sleep on events): the extra games hide the executor <-> generator wake-up
-    # latency, 6.88x -> 7.15x of one GPU at N = 8 with 4 cores per GPU (profiles/r02_n8_selfplay_ab.txt)
-    concurrent_games = 384 if blocking else 256
+    # box); twice as many when it has few (executors sleep on events): the extra games hide the executor <-> generator wake-up latency
+    # of eight processes sharing one host -- synthetic game 256 -> 320 -> 384 games: 6.88x -> 7.07x -> 7.15x of one GPU at N = 8 with 4
+    # cores per GPU (profiles/r02_n8_selfplay_ab.txt), real chess 384 -> 512: 6.40x -> 6.57x (profiles/r02_n8_chess_b.txt)
+    concurrent_games = 512 if blocking else 256
     cfg = selfplay.default_config(game=game, visits=800, search_batch=16, gpu_batch=1024, cpu_threads=cpu_threads, gpu_threads=gpu_threads,
                                   concurrent_games=concurrent_games, duration_s=seconds, seed=replicas.game_seed(ctx, 1),
                                   executor_blocking_sync=int(blocking))
