@@ -174,3 +174,50 @@ def test_recorded_games_replay_under_the_oracle_rules(tmp_path, game, name, twin
     """N1 + N2 end to end on the host (DummyNetwork stand-in); tests/test_gpu_selfplay.py does the same with games the GPU played."""
     prefix, r = _run(tmp_path, game)
     assert replay_under_oracle_rules(prefix, name, twin) >= 40
+
+
+def test_joined_record_files_hold_exactly_the_parts(tmp_path):
+    """kzero_b200/record_files.merge (several devices per server): the joined file is the parts one after the other -- every position's
+    bytes unchanged except the game id (shifted by the games in front), offsets and per-game start indices consistent, metadata
+    recombined."""
+    from kzero_b200 import record_files
+
+    parts = []
+    for i, seed in enumerate((5, 6, 7)):
+        prefix = str(tmp_path / f"part{i}")
+        cfg = selfplay.default_config(game=selfplay.GAME_ATAXX7, visits=16, search_batch=4, gpu_batch=32, cpu_threads=2, gpu_threads=1,
+                                      max_games=2 + i, duration_s=30.0, dummy_network=1, output_prefix=prefix, seed=seed)
+        assert selfplay.run(None, cfg).games_written >= 2 + i
+        parts.append(prefix)
+    before = [_parse(p, 3 * 49, 1) for p in parts]
+    out = str(tmp_path / "joined")
+    meta = record_files.merge(parts, out)
+    assert not any(Path(p + ext).exists() for p in parts for ext in (".bin", ".off", ".json"))
+    jmeta, positions, starts = _parse(out, 3 * 49, 1)
+    assert jmeta == meta
+    assert jmeta["game_count"] == sum(m["game_count"] for m, _, _ in before) == len(starts)
+    assert jmeta["position_count"] == sum(m["position_count"] for m, _, _ in before) == len(positions)
+    assert jmeta["max_game_length"] == max(m["max_game_length"] for m, _, _ in before)
+    assert jmeta["min_game_length"] == min(m["min_game_length"] for m, _, _ in before)
+    total = jmeta["game_count"]
+    for i in range(3):
+        want = sum(m["root_wdl"][i] * m["game_count"] for m, _, _ in before) / total
+        assert abs(jmeta["root_wdl"][i] - want) < 1e-9
+    pos_base = game_base = 0
+    for m, part_positions, part_starts in before:
+        for k, p in enumerate(part_positions):
+            q = positions[pos_base + k]
+            assert int(q["scalars"][0]) == int(p["scalars"][0]) + game_base
+            assert np.array_equal(q["scalars"][1:], p["scalars"][1:], equal_nan=True)
+            assert np.array_equal(q["bits"], p["bits"]) and np.array_equal(q["input_scalars"], p["input_scalars"])
+            assert np.array_equal(q["indices"], p["indices"]) and np.array_equal(q["values"], p["values"])
+        assert [int(s) for s in starts[game_base:game_base + m["game_count"]]] == [int(s) + pos_base for s in part_starts]
+        pos_base += m["position_count"]
+        game_base += m["game_count"]
+    with pytest.raises(ValueError, match="disagree"):
+        a, b = str(tmp_path / "a"), str(tmp_path / "b")
+        for prefix, game in ((a, selfplay.GAME_ATAXX7), (b, selfplay.GAME_SYNTH_CHESS)):
+            cfg = selfplay.default_config(game=game, visits=8, search_batch=4, gpu_batch=32, cpu_threads=1, gpu_threads=1, max_games=1,
+                                          duration_s=30.0, dummy_network=1, output_prefix=prefix, seed=3)
+            selfplay.run(None, cfg)
+        record_files.merge([a, b], str(tmp_path / "bad"))
