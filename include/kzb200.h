@@ -222,7 +222,10 @@ typedef struct kzb_selfplay_stats {
     uint64_t games_finished, moves_played;
     uint64_t root_visits;     /* sum of root visits of the finished searches                                        */
     uint64_t concurrent_games;
-    uint64_t games_written;   /* games in the record files                                                          */
+    uint64_t games_written;   /* games in the record file (all of it, when the run continued a file left open by an interrupt)  */
+    uint64_t interrupted;     /* 1: a session run returned on kzb_selfplay_request_interrupt before max_games games were in
+                               * its record file; the file stays open in the session and the next run with the same
+                               * output_prefix continues it                                                              */
 } kzb_selfplay_stats;
 
 /* The reference's typical production settings (python/main/loop_main_alpha.py:24-52, UctWeights::default). */
@@ -239,12 +242,22 @@ int kzb_selfplay_run(int device, const void* onnx_bytes, size_t onnx_len, int pr
 void kzb_selfplay_request_stop(void);
 void kzb_selfplay_clear_stop(void);
 
+/* Ask every kzb_selfplay_session_run in this process to return NOW without closing its record file, so that the caller can start
+ * the next run -- with a new network or new settings -- under the same games and into the same file: how a network that arrives in
+ * the middle of a generation is put to work at once, as the reference's executors do (rust/kz-selfplay/src/server/executor.rs:50-65,
+ * 320-342) instead of at the next file boundary.  Sticky like the stop flag, until kzb_selfplay_clear_interrupt; ignored by
+ * kzb_selfplay_run (which has no session to keep the file in). */
+void kzb_selfplay_request_interrupt(void);
+void kzb_selfplay_clear_interrupt(void);
+
 /* A session keeps the concurrent games of one server connection alive BETWEEN runs: every kzb_selfplay_session_run plays until
  * config->max_games more games have finished (one record file = games_per_gen games), writes them to config->output_prefix and
  * returns; the games still in flight -- boards, search trees, per-game caches, the positions recorded so far -- continue in the
  * next run, with that run's network and settings.  This is what the reference's server does: its generators run across file
  * boundaries, the collector only rotates the output file (rust/kz-selfplay/src/server/collector.rs:59-116), and a new network is
  * swapped in under running games (executor.rs:320-342) -- so long games are not dropped and the data has no length bias.
+ * config->max_games counts the games in the record file: a run that continues a file left open by an interrupt (same output_prefix)
+ * returns when the file holds max_games games.  Destroying a session finishes a file it still holds open.
  * The game, cpu_threads and the derived number of concurrent games are fixed by the first run (StartupSettings, protocol.rs:11-28). */
 typedef struct kzb_selfplay_session kzb_selfplay_session;
 int kzb_selfplay_session_create(int game, kzb_selfplay_session** out);

@@ -58,7 +58,7 @@ class SelfplayStats(ctypes.Structure):
     _fields_ = [("seconds", ctypes.c_double), ("real_evals", ctypes.c_uint64), ("cached_evals", ctypes.c_uint64),
                 ("potential_evals", ctypes.c_uint64), ("batches", ctypes.c_uint64), ("max_batch", ctypes.c_uint64),
                 ("games_finished", ctypes.c_uint64), ("moves_played", ctypes.c_uint64), ("root_visits", ctypes.c_uint64),
-                ("concurrent_games", ctypes.c_uint64), ("games_written", ctypes.c_uint64)]
+                ("concurrent_games", ctypes.c_uint64), ("games_written", ctypes.c_uint64), ("interrupted", ctypes.c_uint64)]
 
 
 class MctsTraceOut(ctypes.Structure):
@@ -93,6 +93,8 @@ SYMBOLS = {
     "kzb_selfplay_run": (_i, [_i, _vp, _sz, _i, ctypes.POINTER(SelfplayConfig), ctypes.POINTER(SelfplayStats)]),
     "kzb_selfplay_request_stop": (None, []),
     "kzb_selfplay_clear_stop": (None, []),
+    "kzb_selfplay_request_interrupt": (None, []),
+    "kzb_selfplay_clear_interrupt": (None, []),
     "kzb_selfplay_session_create": (_i, [_i, ctypes.POINTER(_vp)]),
     "kzb_selfplay_session_run": (_i, [_vp, _i, _vp, _sz, _i, ctypes.POINTER(SelfplayConfig), ctypes.POINTER(SelfplayStats)]),
     "kzb_selfplay_session_destroy": (None, [_vp]),

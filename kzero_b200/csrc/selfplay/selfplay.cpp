@@ -50,6 +50,7 @@ namespace selfplay {
 namespace {
 
 std::atomic<bool> g_stop_requested{false};
+std::atomic<bool> g_interrupt_requested{false};  // kzb_selfplay_request_interrupt: session runs return, their record files stay open
 
 // KZB_SP_PROFILE=1: per-section cycle counts of the generator threads, printed when a run ends (host tuning aid)
 enum Section { kSecApply, kSecMove, kSecGather, kSecEncode, kSecQueue, kSecCount };
@@ -523,9 +524,20 @@ using SlotTable = std::vector<std::vector<std::unique_ptr<Slot<Game>>>>;  // [ge
 // `kept`: the games of a session (kzb_selfplay_session_*).  Empty on the first run: filled here; afterwards every game continues
 // where the previous run left it -- board, tree, per-game cache and the positions recorded so far -- like the reference's generators,
 // which run across file boundaries (collector.rs:59-116 only rotates the output file).  nullptr: games live for this run only.
+// a record file that an interrupted session run left open, to be continued by the session's next run with the same prefix
+struct OpenRecordFile {
+    std::unique_ptr<RecordWriter> writer;
+    std::string prefix;
+    void finish() {
+        if (writer) writer->finish();
+        writer.reset();
+        prefix.clear();
+    }
+};
+
 template <typename Game>
 void run_selfplay(int device, const void* onnx, size_t len, int precision, const kzb_selfplay_config& c, kzb_selfplay_stats& out,
-                  SlotTable<Game>* kept = nullptr) {
+                  SlotTable<Game>* kept = nullptr, OpenRecordFile* open_file = nullptr) {
     const GameShape shape = Game::shape();
     if (c.visits < 1 || c.search_batch < 1 || c.gpu_batch < c.search_batch || c.cpu_threads < 1 || c.gpu_threads < 1)
         throw std::runtime_error("selfplay config: need visits >= 1, 1 <= search_batch <= gpu_batch, cpu_threads >= 1, gpu_threads >= 1");
@@ -538,8 +550,13 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
     // server_alphazero.rs:47: concurrent_games = ceil((gpu_threads + 1) * gpu_batch / search_batch)
     int games = c.concurrent_games > 0 ? c.concurrent_games : ((c.gpu_threads + 1) * c.gpu_batch + c.search_batch - 1) / c.search_batch;
     Shared sh;
-    if (c.output_prefix && c.output_prefix[0])
-        sh.writer = std::make_unique<RecordWriter>(c.output_prefix, Game::name(), shape.bool_channels, shape.board, shape.scalar_count, shape.policy_len);
+    const std::string prefix = c.output_prefix ? c.output_prefix : "";
+    if (open_file && open_file->writer && open_file->prefix != prefix) open_file->finish();  // the caller moved on to another file
+    if (!prefix.empty()) {
+        if (open_file && open_file->writer) sh.writer = std::move(open_file->writer);  // continue the file an interrupt left open
+        else sh.writer = std::make_unique<RecordWriter>(prefix, Game::name(), shape.bool_channels, shape.board, shape.scalar_count, shape.policy_len);
+    }
+    const uint64_t games_in_file = sh.writer ? sh.writer->game_count() : 0;  // max_games counts the file's games
     sh.job_count = size_t(std::max(1, c.gpu_batch / std::max(1, c.search_batch)));
     SlotTable<Game> local;
     SlotTable<Game>& per_thread = kept ? *kept : local;
@@ -573,18 +590,32 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
     std::vector<std::thread> threads;
     for (int i = 0; i < c.gpu_threads; i++) threads.emplace_back([&, i] { executor_main(c.dummy_network ? nullptr : nets[size_t(i)].get(), sh, c, shape); });
     for (int t = 0; t < c.cpu_threads; t++) threads.emplace_back([&, t] { generator_main<Game>(t, per_thread[size_t(t)], sh, c); });
+    bool interrupted = false;
     while (!sh.stop.load()) {
         std::this_thread::sleep_for(std::chrono::milliseconds(2));
         const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (el >= c.duration_s || (c.max_moves > 0 && sh.moves.load() >= uint64_t(c.max_moves)) ||
-            (c.max_games > 0 && sh.games.load() >= uint64_t(c.max_games)) || g_stop_requested.load())
+            (c.max_games > 0 && games_in_file + sh.games.load() >= uint64_t(c.max_games)) || g_stop_requested.load())
             sh.stop.store(true);
+        else if (open_file && g_interrupt_requested.load())
+            interrupted = true, sh.stop.store(true);
     }
     sh.cv.notify_all();
     for (auto& cv : sh.gen_cv) cv->notify_all();
     for (auto& t : threads) t.join();
     const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (sh.writer) sh.writer->finish();
+    out.games_written = sh.writer ? sh.writer->game_count() : 0;
+    out.interrupted = 0;
+    if (sh.writer) {
+        // an interrupted run hands its unfinished file to the session: the next run (new network / settings) continues it
+        if (interrupted && sh.error.empty() && (c.max_games <= 0 || sh.writer->game_count() < size_t(c.max_games))) {
+            open_file->writer = std::move(sh.writer);
+            open_file->prefix = prefix;
+            out.interrupted = 1;
+        } else {
+            sh.writer->finish();
+        }
+    }
     if (std::getenv("KZB_SP_PROFILE")) {
         const double nodes = double(sh.real_evals.load() + sh.cached_evals.load());
         for (int i = 0; i < kSecCount; i++)
@@ -594,7 +625,6 @@ void run_selfplay(int device, const void* onnx, size_t len, int precision, const
     }
     if (!sh.error.empty()) throw std::runtime_error(sh.error);
     out.seconds = seconds;
-    out.games_written = sh.writer ? sh.writer->game_count() : 0;
     out.real_evals = sh.real_evals.load();
     out.cached_evals = sh.cached_evals.load();
     out.potential_evals = sh.potential_evals.load();
@@ -696,8 +726,15 @@ struct SessionBase {
 template <typename Game>
 struct Session : SessionBase {
     SlotTable<Game> slots;
+    OpenRecordFile open_file;
+    ~Session() override {
+        try {
+            open_file.finish();  // games already written are not lost when the connection ends in the middle of a file
+        } catch (...) {
+        }
+    }
     void run(int device, const void* onnx, size_t len, int precision, const kzb_selfplay_config& c, kzb_selfplay_stats& out) override {
-        run_selfplay<Game>(device, onnx, len, precision, c, out, &slots);
+        run_selfplay<Game>(device, onnx, len, precision, c, out, &slots, &open_file);
     }
 };
 
@@ -773,6 +810,8 @@ KZB_API int kzb_selfplay_run(int device, const void* onnx_bytes, size_t onnx_len
 
 KZB_API void kzb_selfplay_request_stop(void) { kzb::selfplay::g_stop_requested.store(true); }
 KZB_API void kzb_selfplay_clear_stop(void) { kzb::selfplay::g_stop_requested.store(false); }
+KZB_API void kzb_selfplay_request_interrupt(void) { kzb::selfplay::g_interrupt_requested.store(true); }
+KZB_API void kzb_selfplay_clear_interrupt(void) { kzb::selfplay::g_interrupt_requested.store(false); }
 
 struct kzb_selfplay_session {
     std::unique_ptr<kzb::selfplay::SessionBase> impl;

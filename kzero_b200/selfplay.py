@@ -49,6 +49,7 @@ class SelfplayResult:
     root_visits: int
     concurrent_games: int
     games_written: int = 0
+    interrupted: int = 0  # a session run that returned on kzb_selfplay_request_interrupt with its record file still open
 
     @property
     def nn_positions_per_s(self) -> float:  # "real evals/s" of collector.rs:172-191

@@ -13,8 +13,9 @@ Messages are one JSON value per line, externally tagged like serde's enums (prot
 Games live in a session (kzb_selfplay_session_*): a generation is one run of it, which returns after `games_per_gen` more games
 have been written; the games still in flight at that point -- boards, trees, caches, recorded positions -- continue in the next
 generation, so long games are never dropped (the reference's generators run across file boundaries the same way).  A new
-network or new settings take effect at the next generation boundary, under the running games (the reference swaps them in
-as soon as they arrive).  Differences that are deliberate (documented in DESIGN.md): `eval_random_symmetries`, `start_pos`, `top_moves`,
+network or new settings take effect at once, under the running games and in the middle of a file, like the reference's
+(executor.rs:50-65,320-342): the commander interrupts the running session runs (kzb_selfplay_request_interrupt), which return with
+their record files still open, and the next runs continue the same games into the same files with what arrived.  Differences that are deliberate (documented in DESIGN.md): `eval_random_symmetries`, `start_pos`, `top_moves`,
 `saved_state_channels` and `gpu_batch_size_root` are accepted and ignored (muzero-only or above the boundary); `chess`,
 `ataxx-7` and `go-9` are served with this repo's restated rules (`chess-synth` is the chess-shaped synthetic game the
 B200 self-play numbers were taken with).  Several `--device` flags (server.rs:49-51,316-331): one session per device, each with its own
@@ -121,12 +122,17 @@ class SelfplayServer:
                     _abi.lib().kzb_selfplay_request_stop()
                 elif cmd == "WaitForNewNetwork":
                     self.network = None
+                    _abi.lib().kzb_selfplay_request_interrupt()
                 elif cmd == "UseDummyNetwork":
                     self.network = "dummy"
+                    _abi.lib().kzb_selfplay_request_interrupt()
                 elif isinstance(cmd, dict) and "NewSettings" in cmd:
                     self.settings = cmd["NewSettings"]
+                    _abi.lib().kzb_selfplay_request_interrupt()
                 elif isinstance(cmd, dict) and "NewNetwork" in cmd:
                     self.network = Path(cmd["NewNetwork"]).read_bytes()  # load_graph, server_alphazero.rs:126-128
+                    # put it to work at once, under the running games and into the running file (executor.rs:50-65,320-342)
+                    _abi.lib().kzb_selfplay_request_interrupt()
                 elif isinstance(cmd, dict) and "StartupSettings" in cmd:
                     raise RuntimeError("Already received startup settings")  # commander.rs:30
                 else:
@@ -160,6 +166,8 @@ class SelfplayServer:
         if games_per_gen < n_dev:
             raise ValueError(f"games_per_gen = {games_per_gen} cannot be split over {n_dev} devices")
         quotas = [games_per_gen // n_dev + (1 if d < games_per_gen % n_dev else 0) for d in range(n_dev)]
+        file_done = [False] * n_dev  # devices whose share of the current generation is written
+        totals = [0, 0, 0, 0.0]      # games, moves, nodes, seconds of the current generation (over its runs)
         try:
             while True:
                 with self.lock:
@@ -168,8 +176,9 @@ class SelfplayServer:
                     if self.stop:
                         break
                     settings, network = dict(self.settings), self.network
-                    # under the lock the commander also takes: a Stop can no longer slip between this check and the run
+                    # under the lock the commander also takes: a Stop (or a newer network) can no longer slip between this check and the run
                     _abi.lib().kzb_selfplay_clear_stop()
+                    _abi.lib().kzb_selfplay_clear_interrupt()
                 out_prefix = str(Path(startup["output_folder"]) / f"games_{gen}")
                 results, errors = [None] * n_dev, []
 
@@ -185,10 +194,11 @@ class SelfplayServer:
                         errors.append(e)
                         _abi.lib().kzb_selfplay_request_stop()
 
-                if n_dev == 1:
-                    run_device(0)
+                todo = [d for d in range(n_dev) if not file_done[d]]
+                if len(todo) == 1:
+                    run_device(todo[0])
                 else:
-                    threads = [threading.Thread(target=run_device, args=(d,)) for d in range(n_dev)]
+                    threads = [threading.Thread(target=run_device, args=(d,)) for d in todo]
                     for t in threads:
                         t.start()
                     for t in threads:
@@ -197,14 +207,25 @@ class SelfplayServer:
                     raise errors[0]
                 if self.stop:
                     break
+                for d in todo:
+                    r = results[d]
+                    totals[1] += r.moves_played
+                    totals[2] += r.real_evals + r.cached_evals
+                    file_done[d] = not r.interrupted
+                totals[3] += max(results[d].seconds for d in todo)
+                if not all(file_done):
+                    # a new network / new settings arrived in the middle of the generation: the runs returned with their files open and
+                    # the next round continues them -- same games, same files -- with what arrived
+                    continue
                 if n_dev > 1:
                     record_files.merge([f"{out_prefix}.dev{d}" for d in range(n_dev)], out_prefix)
-                seconds = max(r.seconds for r in results)
-                print(f"generation {gen}: {sum(r.games_written for r in results)} games, {sum(r.moves_played for r in results)} moves, "
-                      f"{sum(r.real_evals + r.cached_evals for r in results) / seconds:,.0f} nodes/s, "
-                      f"{sum(r.real_evals for r in results) / seconds:,.0f} NN positions/s on {n_dev} device(s)", flush=True)
+                games = json.loads(Path(out_prefix + ".json").read_text())["game_count"]
+                print(f"generation {gen}: {games} games, {totals[1]} moves, {totals[2] / max(totals[3], 1e-9):,.0f} nodes/s on {n_dev} device(s)",
+                      flush=True)
                 send({"FinishedFile": {"index": gen}})  # ServerUpdate::FinishedFile, protocol.rs:80-84
                 gen += 1
+                file_done = [False] * n_dev
+                totals = [0, 0, 0, 0.0]
         finally:
             for session in sessions:
                 session.close()

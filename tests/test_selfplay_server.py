@@ -145,3 +145,44 @@ def test_several_devices_write_one_file_per_generation(tmp_path):
         assert df.info.simulation_count >= 7
         assert len([df.load_position(i) for i in range(df.info.position_count)]) == df.info.position_count
     assert np.isfinite(meta["hit_move_limit"])
+
+
+def test_new_settings_take_effect_in_the_middle_of_a_file(tmp_path):
+    """The reference applies new settings / a new network as they arrive (commander.rs:13-61, executor.rs:50-65), not at the next file:
+    NewSettings sent while generation 3 is being played shows up INSIDE games_3 (both visit targets occur in it), the file still holds
+    games_per_gen games, and the FinishedFile sequence is unbroken."""
+    from test_selfplay_records import _parse
+
+    server, thread = _serve()
+    s = socket.create_connection(("127.0.0.1", server.port))
+    f = s.makefile("r")
+
+    def send(m):
+        s.sendall((json.dumps(m) + "\n").encode())
+
+    first = dict(SETTINGS, full_search_prob=1.0, full_iterations=24)
+    send({"StartupSettings": dict(STARTUP, games_per_gen=300, output_folder=str(tmp_path))})
+    send({"NewSettings": first})
+    send("UseDummyNetwork")
+    import time
+
+    time.sleep(0.3)  # two generations of 300 ataxx games take over a second at these settings: the change arrives inside one of them
+    send({"NewSettings": dict(first, full_iterations=40)})
+    assert json.loads(f.readline()) == {"FinishedFile": {"index": 3}}
+    assert json.loads(f.readline()) == {"FinishedFile": {"index": 4}}
+    send("Stop")
+    assert [json.loads(line) for line in f][-1] == "Stopped"
+    thread.join(timeout=30)
+    assert not thread.is_alive()
+    visits = {}
+    for gen in (3, 4):
+        meta, positions, starts = _parse(str(tmp_path / f"games_{gen}"), 3 * 49, 1)
+        assert meta["game_count"] >= 300 and len(starts) == meta["game_count"]
+        targets = set()
+        for p in positions:
+            if not bool(p["scalars"][5]):  # not the final position of a game
+                v = int(p["scalars"][3])   # zero_visits: the search ran to its target, overshooting by less than a search batch
+                targets.add(24 if v < 36 else 40)
+        visits[gen] = targets
+    assert {24, 40} in visits.values(), visits  # the change arrived inside a file ...
+    assert visits[4] == {40} or visits[3] == {24}, visits  # ... and everything after it uses the new target, everything before the old one
