@@ -32,6 +32,7 @@ ap.add_argument("--cpu-threads", type=int, default=0, help="0 = host cores / rep
 ap.add_argument("--gpu-threads", type=int, default=3, help="executor threads, one network instance each")
 ap.add_argument("--concurrent-games", type=int, default=0)
 ap.add_argument("--pin", action="store_true", help="pin each replica to its own contiguous share of the host cores")
+ap.add_argument("--warmup-seconds", type=float, default=0.0, help="play this long on the same games before the timed run (a session keeps them)")
 args = ap.parse_args()
 
 ctx = replicas.context_from_env()
@@ -65,8 +66,16 @@ onnx_bytes = netgen.build_onnx(spec, depth, channels, seed=0)
 cfg = selfplay.default_config(game=game, visits=args.visits, search_batch=args.search_batch, gpu_batch=args.gpu_batch,
                               cpu_threads=cpu_threads, gpu_threads=gpu_threads, concurrent_games=args.concurrent_games,
                               duration_s=args.seconds, seed=replicas.game_seed(ctx, 0), executor_blocking_sync=int(blocking))
-replicas.barrier(ctx)
-r = selfplay.run(onnx_bytes, cfg, device=ctx.local_rank)
+if args.warmup_seconds > 0:  # trees allocated and faulted in, caches warm, games at staggered depths: what a long-running server looks like
+    cfg.duration_s = args.warmup_seconds
+    with selfplay.Session(game) as session:
+        session.run(onnx_bytes, cfg, device=ctx.local_rank)
+        cfg.duration_s = args.seconds
+        replicas.barrier(ctx)
+        r = session.run(onnx_bytes, cfg, device=ctx.local_rank)
+else:
+    replicas.barrier(ctx)
+    r = selfplay.run(onnx_bytes, cfg, device=ctx.local_rank)
 counts = [r.real_evals, r.cached_evals, r.batches, r.moves_played, r.games_finished]
 if dist is not None:
     import torch
@@ -88,7 +97,7 @@ if ctx.is_root:
                             "chess-real": "chess (legal move generation, ChessStdMapper encoding)",
                             "go": "go 9x9 (area scoring, positional superko, cgos or Tromp-Taylor suicide rule per game)"}[args.game],
                    "cpu_threads_per_gpu": cpu_threads, "gpu_threads_per_gpu": gpu_threads, "executor_blocking_sync": bool(blocking), "concurrent_games_per_gpu": r.concurrent_games,
-                   "host_cores": cores, "pinned": bool(args.pin), **replicas.parallelism_note(ctx)},
+                   "host_cores": cores, "pinned": bool(args.pin), "warmup_seconds": args.warmup_seconds, **replicas.parallelism_note(ctx)},
         "data": "synthetic"}), flush=True)
 if dist is not None:
     dist.destroy_process_group()
