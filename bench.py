@@ -504,16 +504,8 @@ def selfplay_record(ctx, game_name, seconds, dist):
     cfg = selfplay.default_config(game=game, visits=800, search_batch=16, gpu_batch=1024, cpu_threads=cpu_threads, gpu_threads=gpu_threads,
                                   concurrent_games=concurrent_games, duration_s=seconds, seed=replicas.game_seed(ctx, 1),
                                   executor_blocking_sync=int(blocking))
-    # warm-up, then the timed run, on the SAME games (a session keeps them between runs): every game starts from the initial position
-    # with an empty evaluation cache, and the cache hit rate -- the difference between nodes/s and network positions/s -- climbs
-    # over a game's first dozens of moves; without a warm-up a replica with few cores and many games is measured in that transient
-    warm_s = max(2.0, seconds / 2)
-    cfg.duration_s = warm_s
-    with selfplay.Session(game) as session:
-        session.run(onnx_bytes, cfg, device=ctx.local_rank)
-        cfg.duration_s = seconds
-        replicas.barrier(ctx)
-        r = session.run(onnx_bytes, cfg, device=ctx.local_rank)
+    replicas.barrier(ctx)
+    r = selfplay.run(onnx_bytes, cfg, device=ctx.local_rank)
     counts = [r.real_evals, r.cached_evals, r.batches, r.moves_played, r.games_finished]
     if dist is not None:
         import torch
@@ -529,7 +521,6 @@ def selfplay_record(ctx, game_name, seconds, dist):
             "game": {"chess-synthetic": "chess-shaped synthetic game (13x8x8 + 8 planes, 1880-move policy, 20-45 legal moves)",
                      "chess": "chess (legal move generation, ChessStdMapper encoding)"}[game_name],
             "settings": "800 visits, search batch 16 with virtual loss, LRU cache 800, net chess 16x128, gpu batch 1024",
-            "warmup_seconds": warm_s,
             "concurrent_games_per_gpu": int(r.concurrent_games),
             "host_cores": cores, "cpu_threads_per_gpu": cpu_threads, "gpu_threads_per_gpu": gpu_threads,
             "executor_blocking_sync": bool(blocking)}
