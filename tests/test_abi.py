@@ -141,3 +141,36 @@ def test_three_output_graphs_are_rejected_with_a_message():
     onnx_bytes = netgen.build_onnx(spec, 1, 16, seed=1, legacy_three_outputs=True)
     with pytest.raises(KzbError, match="3-output"):
         inspect_onnx(onnx_bytes)
+
+
+def test_header_is_plain_c_and_struct_layouts_match_the_ctypes_mirror(tmp_path):
+    """The boundary is a C ABI: include/kzb200.h must compile as C99 (and as C++), a C program must link against the built library
+    and call it, and every struct the Python mirror declares must have the size -- and its last field the offset -- the C compiler
+    gives it (a field added on one side only would silently shift everything behind it)."""
+    import ctypes
+    import subprocess
+
+    from kzero_b200 import _abi
+    from kzero_b200.build import LIB
+
+    pairs = [("kzb_net_info", _abi.NetInfo), ("kzb_conv_weights", _abi.ConvWeights), ("kzb_fc_weights", _abi.FcWeights),
+             ("kzb_net_spec", _abi.NetSpecC), ("kzb_selfplay_config", _abi.SelfplayConfig), ("kzb_selfplay_stats", _abi.SelfplayStats),
+             ("kzb_mcts_trace_out", _abi.MctsTraceOut)]
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "kzb200.h"', 'int main(void) {']
+    for cname, mirror in pairs:
+        last = mirror._fields_[-1][0]
+        lines.append(f'    printf("{cname} %zu %zu\\n", sizeof({cname}), offsetof({cname}, {last}));')
+    lines += ['    printf("devices %d\\n", kzb_device_count());', '    printf("error [%s]\\n", kzb_last_error());', '    return 0;', '}']
+    src = tmp_path / "abi_probe.c"
+    src.write_text("\n".join(lines) + "\n")
+    include = str(ROOT / "include")
+    exe = tmp_path / "abi_probe"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", include, "-o", str(exe), str(src), str(LIB),
+                    f"-Wl,-rpath,{LIB.parent}"], check=True)
+    subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", "-I", include, str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    got = {line.split()[0]: tuple(int(v) for v in line.split()[1:3]) for line in out if line.startswith("kzb_")}
+    for cname, mirror in pairs:
+        last = mirror._fields_[-1][0]
+        assert got[cname] == (ctypes.sizeof(mirror), getattr(mirror, last).offset), (cname, got[cname])
+    assert any(line.startswith("devices ") for line in out)  # the call went through the C ABI (0 devices here, or an error code)
