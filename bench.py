@@ -444,8 +444,8 @@ def rooflines(m, peaks):
     table = json.loads(tpath.read_text()) if tpath.exists() else {}
 
     def traffic_of(kern):
-        e = table.get(kern)
-        return e.get("dram_bytes_per_launch") if e and e.get("workload") == m["name"] else None
+        e = table.get(f"{kern}/{m['name']}")
+        return e.get("dram_bytes_per_launch") if e else None
     traffic = traffic_of(kernel)
     # the tower is timed launch by launch between L2 flushes with the GPU idle in between: burst denominator
     tower = {"bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",

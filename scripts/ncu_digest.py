@@ -88,7 +88,7 @@ def kernel(src, dst, traffic_json=None, workload=None):
                 f.write(f"| {m} | {units[i]} | " + " | ".join(r[i] for r in data) + " |\n")
     print(open(dst).read())
     if traffic_json:
-        # per kernel (short name, launches of the same kernel averaged): dram__bytes_read.sum + dram__bytes_write.sum per launch;
+        # per kernel and workload (key `<kernel>/<bench.py config>`, launches of the same kernel averaged): dram__bytes_read.sum + dram__bytes_write.sum per launch;
         # merged into the file, which bench.py reads for `roofline*.traffic`
         import os
         import re
@@ -107,7 +107,7 @@ def kernel(src, dst, traffic_json=None, workload=None):
         for short, rs in groups.items():
             rd = sum(val(r, "dram__bytes_read.sum") for r in rs) / len(rs)
             wr = sum(val(r, "dram__bytes_write.sum") for r in rs) / len(rs)
-            table[short] = {"workload": workload, "source": src, "launches_averaged": len(rs), "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr}
+            table[f"{short}/{workload}"] = {"workload": workload, "source": src, "launches_averaged": len(rs), "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr}
         json.dump(table, open(traffic_json, "w"), indent=1)
         print(open(traffic_json).read())
 
