@@ -119,8 +119,8 @@ def test_several_devices_write_one_file_per_generation(tmp_path):
         prefix = str(tmp_path / f"games_{gen}")
         assert not list(tmp_path.glob(f"games_{gen}.dev*"))  # the parts are gone
         meta, positions, starts = _parse(prefix, 3 * 49, 1)
-        # (a device may finish a game or two past its share: generator threads end games concurrently, like the reference's)
-        assert 7 <= meta["game_count"] <= 11 and len(starts) == meta["game_count"] and len(meta["scalar_names"]) == SCALARS
+        # (a device may finish a few games past its share -- at most its games in flight: generator threads end games concurrently)
+        assert 7 <= meta["game_count"] <= 7 + 2 * 8 and len(starts) == meta["game_count"] and len(meta["scalar_names"]) == SCALARS
         assert abs(sum(meta["root_wdl"]) - 1) < 1e-6
         # python/lib/data/check.py:9-76 on the joined file: games tile the positions, ids count up, per-game indices run 0..length
         pi = 0
