@@ -296,19 +296,22 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                 }
                 // collect a batch of requests (generator_alphazero.rs:165-201)
                 slot.requests.clear();
+                if (slot.requests.capacity() <= size_t(c.search_batch)) slot.requests.reserve(size_t(c.search_batch) + 1);
                 int terminal_gathers = 0;
                 uint64_t cached = 0;
                 while (int(slot.requests.size()) < c.search_batch && terminal_gathers < c.search_batch) {
-                    Request<Game> req;
+                    // gathered in place: a request holds a whole board, and only requests the cache cannot answer stay in the list
+                    slot.requests.emplace_back();
+                    Request<Game>& req = slot.requests.back();
                     if (zero_step_gather(tree, settings, slot.rng, req, scratch, [&](const Game& b) { slot.cache.prefetch(b.hash()); })) {
                         if (const LruCache::Entry* hit = slot.cache.get(req.board.hash())) {
                             cached++;
                             apply_eval(slot, req, hit->values, hit->policy.data(), hit->policy.size(), c, policy_tmp);
-                        } else {
-                            slot.requests.push_back(std::move(req));
+                            slot.requests.pop_back();
                         }
                     } else {
                         terminal_gathers++;
+                        slot.requests.pop_back();
                     }
                 }
                 if (cached) sh.cached_evals.fetch_add(cached, std::memory_order_relaxed);
