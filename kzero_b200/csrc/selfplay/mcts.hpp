@@ -93,7 +93,9 @@ struct SearchSettings {
 // Node storage.  The reference keeps one 64..88-byte Node per child (node.rs:11-34), and most of them are never visited:
 // a node's children are created together (step.rs:89-97) but a search of V visits touches only about V of them.  So the
 // tree is split in three:
-//   child slots     one per created child, ids consecutive per parent: last_move and net_policy only
+//   child slots     per node ONE slice of `child_data`: the children's net_policy (n floats) with their moves (n uint16) right behind
+//                   it, so that the move of the child a selection step picks lies on the line after the policy slice it has just
+//                   streamed through (two separate arrays cost one more cold line per level)
 //   nodes           one 32-byte entry per node that has been visited at least once: the links (parent, child slots,
 //                   visited block) -- no statistics
 //   visited blocks  per node, the statistics of its VISITED children: one 32-byte row (visit counters, value sums, node
@@ -297,9 +299,9 @@ inline int argmax_random_ties(const float* u, int n, Rng& rng) {
 template <typename Game>
 struct Tree {
     Game root_board;
-    // child slots
-    std::vector<uint32_t> last_move;
-    std::vector<float> net_policy;
+    // child slots: per node `n` policy floats followed by (n + 1) / 2 float-sized words holding the n moves as uint16
+    std::vector<float> child_data;
+    size_t child_slots = 1;  // the root and every created child
     // visited nodes; [0] is the root
     std::vector<Node> nodes;
     ChildStat root_stat;
@@ -313,7 +315,6 @@ struct Tree {
 
     explicit Tree(const Game& root) : root_board(root) {  // tree.rs:31-39
         if (root.done()) throw std::runtime_error("Cannot build tree for done board");
-        last_move.push_back(0), net_policy.push_back(NAN);
         nodes.emplace_back();
         arena.resize(kArenaTail);
     }
@@ -322,24 +323,38 @@ struct Tree {
     void reset(const Game& root) {
         if (root.done()) throw std::runtime_error("Cannot build tree for done board");
         root_board = root;
-        last_move.clear(), net_policy.clear(), nodes.clear();
-        last_move.push_back(0), net_policy.push_back(NAN);
+        child_data.clear(), nodes.clear();
+        child_slots = 1;
         nodes.emplace_back();
         root_stat = ChildStat();
         arena.assign(kArenaTail, ChildStat());
         arena_used = 0;
     }
-    size_t size() const { return last_move.size(); }  // nodes in the reference's sense: the root and every created child
+    size_t size() const { return child_slots; }  // nodes in the reference's sense: the root and every created child
     void reserve(size_t slots, size_t visited) {
-        last_move.reserve(slots), net_policy.reserve(slots);
+        child_data.reserve(slots + slots / 2 + visited);
         nodes.reserve(visited + 1), arena.reserve(5 * visited + 64);
     }
     // all children of a node at once (step.rs:89-97), with a uniform prior
     int push_children(const std::vector<uint32_t>& moves, float p) {
-        const size_t start = last_move.size(), end = start + moves.size();
-        net_policy.resize(end, p);
-        last_move.insert(last_move.end(), moves.begin(), moves.end());
+        const size_t start = child_data.size(), n = moves.size();
+        child_data.resize(start + n + (n + 1) / 2, p);
+        unsigned char* m = reinterpret_cast<unsigned char*>(child_data.data() + start + n);
+        for (size_t i = 0; i < n; i++) {
+            if (moves[i] > 0xFFFFu) throw std::logic_error("move ids are stored in 16 bits");
+            const uint16_t v = uint16_t(moves[i]);
+            std::memcpy(m + 2 * i, &v, 2);
+        }
+        child_slots += n;
         return int(start);
+    }
+    // the children of the node whose slice starts at `child_start` and has `n` children
+    float* policy_of(int child_start) { return child_data.data() + child_start; }
+    const float* policy_of(int child_start) const { return child_data.data() + child_start; }
+    uint32_t move_of(int child_start, int n, int i) const {
+        uint16_t v;
+        std::memcpy(&v, reinterpret_cast<const unsigned char*>(child_data.data() + child_start + n) + 2 * size_t(i), 2);
+        return v;
     }
 
     // block layout: u16 row_pos[cap] | u16 order[cap] | ChildStat rows[cap]
@@ -543,7 +558,7 @@ StepResult descent_step(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Des
         }
     } else {
         const FpuMode fpu = cur == Tree<Game>::kRoot ? s.fpu_root : s.fpu_child;
-        const float* policy = tree.net_policy.data() + c0;
+        const float* policy = tree.policy_of(c0);
         if (tree.uct_scratch.size() < size_t(n) + 8) tree.uct_scratch.resize(size_t(n) + 8), tree.vis_policy.resize(size_t(n) + 8), tree.vis_out.resize(size_t(n) + 8);
         // the policy mass of the visited children is summed in child order, like uct_context (tree.rs:49-66)
         for (int j = 0; j < k; j++) tree.vis_policy[size_t(j)] = policy[vis_pos[j]];
@@ -577,7 +592,7 @@ StepResult descent_step(Tree<Game>& tree, const SearchSettings& s, Rng& rng, Des
     d.cur = row->node;
     d.cur_row = int(row - tree.arena.data());
     // a child that has children of its own was found not to be terminal when it was first reached: the game may skip that test
-    detail::play_move(board, tree.last_move[size_t(c0 + arg)], tree.nodes[size_t(d.cur)].child_start >= 0);
+    detail::play_move(board, tree.move_of(c0, n, arg), tree.nodes[size_t(d.cur)].child_start >= 0);
     return StepResult::kDescend;
 }
 
@@ -602,7 +617,7 @@ void zero_step_apply(Tree<Game>& tree, int node, int next_player, const ValuesPo
     n.has_net_values = 1;
     if (n.child_start < 0) throw std::logic_error("Applied node should have initialized children");
     if (size_t(n.child_count) != n_policy) throw std::logic_error("Wrong children length");
-    std::memcpy(tree.net_policy.data() + n.child_start, policy, n_policy * sizeof(float));
+    std::memcpy(tree.policy_of(n.child_start), policy, n_policy * sizeof(float));
     tree.propagate(node, un_pov(values, next_player));
 }
 

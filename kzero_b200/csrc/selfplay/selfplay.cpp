@@ -222,7 +222,7 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                         const Node& node = slot.tree->nodes[size_t(req.node)];
                         __builtin_prefetch(&node, 1);
                         slot.cache.prefetch(req.board.hash());
-                        prefetch_span(slot.tree->net_policy.data() + req.child_start, size_t(req.child_count) * 4);
+                        prefetch_span(slot.tree->policy_of(req.child_start), size_t(req.child_count) * 4);
                     }
                     // answers are back: cache + apply in request order (generator_alphazero.rs:206-210)
                     for (int i = 0; i < slot.job.n; i++) {
@@ -252,13 +252,13 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                     tree.policy(policy);
                     const size_t pick = select_move(policy.data(), policy.size(), slot.move_count, c.temperature, uint32_t(c.zero_temp_move_count), slot.rng);
                     const size_t c0 = size_t(tree.root().child_start), cn = size_t(tree.root().child_count);
-                    const uint32_t mv = tree.last_move[c0 + pick];
+                    const uint32_t mv = tree.move_of(int(c0), int(cn), int(pick));
                     sh.root_visits.fetch_add(tree.root_visits(), std::memory_order_relaxed);
                     sh.moves.fetch_add(1, std::memory_order_relaxed);
                     if (sh.writer) {  // Position, generator_alphazero.rs:115-123
                         RecordedPosition rp;
                         encode_record(slot.board, shape, rp);
-                        for (size_t k = 0; k < cn; k++) rp.indices.push_back(slot.board.move_to_index(tree.last_move[c0 + k]));
+                        for (size_t k = 0; k < cn; k++) rp.indices.push_back(slot.board.move_to_index(tree.move_of(int(c0), int(cn), int(k))));
                         rp.played_index = slot.board.move_to_index(mv);
                         rp.is_full_search = slot.is_full_search;
                         rp.zero_visits = tree.root_visits();
@@ -333,10 +333,10 @@ void generator_main(int tid, std::vector<std::unique_ptr<Slot<Game>>>& slots, Sh
                     b.encode(job.bits.data() + size_t(i) * bits_bytes, job.scalars.data() + size_t(i) * shape.scalar_count);
                     // the node's children were created from available_moves() in order (step.rs:89-97): their moves ARE the legal list
                     const int node = slot.requests[size_t(i)].node;
-                    const uint32_t* mv = tree.last_move.data() + size_t(tree.nodes[size_t(node)].child_start);
+                    const int c0 = tree.nodes[size_t(node)].child_start;
                     uint32_t* idx = job.mv_idx.data() + job.mv_off[size_t(i)];
                     const size_t cn = size_t(tree.nodes[size_t(node)].child_count);
-                    for (size_t k = 0; k < cn; k++) idx[k] = b.move_to_index(mv[k]);
+                    for (size_t k = 0; k < cn; k++) idx[k] = b.move_to_index(tree.move_of(c0, int(cn), int(k)));
                 }
                 job.values.resize(size_t(job.n) * 5);
                 job.probs.resize(job.mv_idx.size());
@@ -704,10 +704,9 @@ void trace_search(const kzb_selfplay_config& c, uint64_t game_seed, int plies, i
     std::vector<uint32_t> visits;
     tree.child_visits(Tree<Game>::kRoot, visits);
     for (int i = 0; i < n_children; i++) {
-        const size_t ch = size_t(tree.root().child_start + i);
         out.child_visits[i] = visits[size_t(i)];
-        out.child_moves[i] = tree.last_move[ch];
-        out.child_policy[i] = tree.net_policy[ch];
+        out.child_moves[i] = tree.move_of(tree.root().child_start, n_children, i);
+        out.child_policy[i] = tree.policy_of(tree.root().child_start)[i];
     }
     const ValuesPov v = pov(tree.root_values(), board.next_player());
     out.root_values[0] = v.value;

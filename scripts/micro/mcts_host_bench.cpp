@@ -92,7 +92,7 @@ int main(int argc, char** argv) {
                 size_t best = 0;
                 for (size_t i = 1; i < policy.size(); i++)
                     if (policy[i] > policy[best]) best = i;
-                s.board.play(tree.last_move[size_t(tree.root().child_start) + best]);
+                s.board.play(tree.move_of(tree.root().child_start, tree.root().child_count, int(best)));
                 if (s.board.done()) s.board = Game::start(++s.seed * 104729);
                 s.reset();
                 continue;
