@@ -169,7 +169,7 @@ inline uint64_t rook_att(const Tables& t, uint64_t occ, int s) { return hq_line(
 // the replies of the position play() generated last on this thread (its mate / stalemate test): the search asks for exactly
 // that list next (descent_step: done(), then moves())
 struct ReplyCache {
-    uint64_t key = 0;
+    uint64_t key = 0, white = 0, black = 0;  // the position key and, against a key collision, both colours' occupancy
     int n = -1;
     uint16_t mv[256];
 };
@@ -467,7 +467,7 @@ struct Chess {
                                          : t.plain[(m.from ^ flip) * 64 + (m.to ^ flip)]);
             return true;
         });
-        c.key = key;
+        c.key = key, c.white = colour[0], c.black = colour[1];
         c.n = n;
         return n;
     }
@@ -485,7 +485,8 @@ struct Chess {
     }
     void moves(std::vector<uint32_t>& out) const {
         const chess_detail::ReplyCache& c = chess_detail::reply_cache();
-        if (c.n < 0 || c.key != key) generate_replies();  // the legal moves depend on placement, side, rights and ep square: the key
+        // the legal moves depend on placement, side, rights and ep square: the key
+        if (c.n < 0 || c.key != key || c.white != colour[0] || c.black != colour[1]) generate_replies();
         out.assign(c.mv, c.mv + c.n);
     }
     uint32_t move_to_index(uint32_t mv) const { return mv; }
